@@ -1,0 +1,333 @@
+// Fused softmax(scale * Q K^T + key_bias) V for head dim 64 on tcgen05 (sm_100a).
+//
+// Replaces, for every UNet attention (self: attn1 with the trimap key bias, cross: attn2 over the 16 384
+// trimap tokens), the reference chain
+//   custom_prepare_attention_mask  /root/reference/src/utils/replace.py:20-72
+//   custom_get_attention_scores    /root/reference/src/utils/replace.py:75-122  (baddbmm + softmax)
+//   torch.bmm(probs, value) inside diffusers AttnProcessor / SlicedAttnProcessor (sdmatte_nodes.py:331-335)
+// without ever materialising the L x L score matrix: S lives in TMEM, P in shared memory, O in TMEM/registers.
+//
+// CTA = 256 queries (two 128-row tiles A and B) of one (batch, head); it streams 128-key tiles of K and V^T.
+//   warps 0-3  : softmax warpgroup for tile A (thread r owns query row r == TMEM lane r)
+//   warps 4-7  : softmax warpgroup for tile B
+//   warp  8    : TMA producer (Q once; K, V^T and the per-key bias per tile; 3-stage ring)
+//   warp  9    : tcgen05.mma issuer (S_X = Q_X K^T : M128 N128 K64 ; O_X = P_X V : M128 N64 K128) + TMEM alloc
+// The two warpgroups ping-pong: while A does exp/convert on S_A(j) the tensor core computes S_B(j), PV_B(j-1) ...
+// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
+// Softmax statistics are fp32; scores are NOT rounded to fp16 before the softmax (the reference does).
+#include "common.cuh"
+#include "kernels.h"
+#include "tmap.h"
+
+#include <mutex>
+
+namespace sdm {
+
+struct alignas(64) AttnParams {
+  CUtensorMap q_map, k_map, vt_map;
+  const float* bias;
+  long long bias_bstride;
+  __half* out;
+  long long ldo;
+  int Lq, Lk, heads, n_ktiles;
+  float scale;
+};
+
+constexpr int kAttnStages = 3;
+constexpr int kAttnThreads = 320;
+constexpr uint32_t kQBytes = 128 * 128;        // one 128x64 fp16 tile
+constexpr uint32_t kPBytes = 2 * 128 * 128;    // 128 x 128 fp16 as two 64-key blocks
+constexpr uint32_t kKBytes = 128 * 128;        // 128 keys x 64 d
+constexpr uint32_t kVBytes = 2 * 64 * 128;     // 64 d x 128 keys as two 64-key blocks
+constexpr uint32_t kStageBytes = kKBytes + kVBytes;
+constexpr uint32_t kOffQ = 0;
+constexpr uint32_t kOffP = 2 * kQBytes;
+constexpr uint32_t kOffStage = kOffP + 2 * kPBytes;
+constexpr uint32_t kOffBias = kOffStage + kAttnStages * kStageBytes;
+constexpr uint32_t kOffBar = kOffBias + kAttnStages * 512;
+constexpr uint32_t kAttnSmem = kOffBar + 256 + 1024;
+
+template <bool HAS_BIAS>
+__global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar = base + kOffBar;
+  // barriers
+  const uint32_t q_full = bar;
+  auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar + 8u * (4 + s); };
+  auto s_full = [&](int x) { return bar + 8u * (7 + x); };
+  auto p_full = [&](int x) { return bar + 8u * (9 + x); };
+  auto o_full = [&](int x) { return bar + 8u * (11 + x); };
+  const uint32_t tmem_slot = bar + 8u * 13;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kOffBar + 8 * 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n = p.n_ktiles;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kAttnStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int x = 0; x < 2; ++x) { mbar_init(s_full(x), 1); mbar_init(p_full(x), 128); mbar_init(o_full(x), 1); }
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == 8) {
+    // ======================================= TMA producer =======================================
+    if (lane == 0) {
+      tma_prefetch_desc(&p.q_map); tma_prefetch_desc(&p.k_map); tma_prefetch_desc(&p.vt_map);
+      mbar_expect_tx(q_full, 2 * kQBytes);
+      tma_load_3d(base + kOffQ, &p.q_map, q_full, h * 64, q0, b);
+      tma_load_3d(base + kOffQ + kQBytes, &p.q_map, q_full, h * 64, q0 + 128, b);
+      for (int j = 0; j < n; ++j) {
+        const int s = j % kAttnStages;
+        const uint32_t f = (uint32_t)(j / kAttnStages);
+        mbar_wait(kv_empty(s), (f & 1u) ^ 1u);
+        const uint32_t kdst = base + kOffStage + s * kStageBytes;
+        mbar_expect_tx(kv_full(s), kStageBytes + (HAS_BIAS ? 512u : 0u));
+        tma_load_3d(kdst, &p.k_map, kv_full(s), h * 64, j * 128, b);
+        tma_load_3d(kdst + kKBytes, &p.vt_map, kv_full(s), j * 128, h * 64, b);
+        tma_load_3d(kdst + kKBytes + 64 * 128, &p.vt_map, kv_full(s), j * 128 + 64, h * 64, b);
+        if (HAS_BIAS) bulk_load_1d(base + kOffBias + s * 512, p.bias + (long long)b * p.bias_bstride + (long long)j * 128, 512, kv_full(s));
+      }
+    }
+  } else if (warp == 9) {
+    // ======================================= MMA issuer =========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(128);
+      constexpr uint32_t idesc_o = umma_idesc_f16(64);
+      auto issue_s = [&](int x, int stage) {
+        const uint64_t ad = umma_desc_k128(base + kOffQ + x * kQBytes);
+        const uint64_t bd = umma_desc_k128(base + kOffStage + stage * kStageBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem + x * 128, ad + 2 * k, bd + 2 * k, idesc_s, k != 0);
+        umma_commit(s_full(x));
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(kv_full(0), 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < n; ++j) {
+        const int s = j % kAttnStages;
+        const int s1 = (j + 1) % kAttnStages;
+        if (j + 1 < n) mbar_wait(kv_full(s1), (uint32_t)((j + 1) / kAttnStages) & 1u);
+        for (int x = 0; x < 2; ++x) {
+          mbar_wait(p_full(x), (uint32_t)j & 1u);  // P_x(j) in smem, S_x and O_x(j-1) consumed
+          tc_fence_after();
+          if (j + 1 < n) issue_s(x, s1);
+          const uint32_t pa = base + kOffP + x * kPBytes;
+          const uint32_t vb = base + kOffStage + s * kStageBytes + kKBytes;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t ad = umma_desc_k128(pa + (k >> 2) * (128 * 128)) + 2 * (k & 3);
+            const uint64_t bd = umma_desc_k128(vb + (k >> 2) * (64 * 128)) + 2 * (k & 3);
+            umma_f16(tmem + 256 + x * 64, ad, bd, idesc_o, k != 0);
+          }
+          umma_commit(o_full(x));
+        }
+        umma_commit(kv_empty(s));
+      }
+    }
+  } else {
+    // ======================================= softmax warpgroups =================================
+    const int x = warp >> 2;                 // 0: tile A, 1: tile B
+    const int r = (warp & 3) * 32 + lane;    // row within the tile == TMEM lane
+    const uint32_t t_s = tmem + ((uint32_t)((warp & 3) * 32) << 16) + x * 128;
+    const uint32_t t_o = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256 + x * 64;
+    uint8_t* p_row = base_ptr + kOffP + x * kPBytes + (r >> 3) * 1024 + (r & 7) * 128;
+    const float l2e = 1.4426950408889634f;
+    const float sc = p.scale * l2e;
+    float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+
+    for (int j = 0; j < n; ++j) {
+      const int s = j % kAttnStages;
+      const bool tail = (!HAS_BIAS) && (j == n - 1) && ((p.Lk & 127) != 0);
+      const int kbase = j * 128;
+      if (HAS_BIAS) mbar_wait(kv_full(s), (uint32_t)(j / kAttnStages) & 1u);  // bias tile visible to this thread
+      mbar_wait(s_full(x), (uint32_t)j & 1u);
+      tc_fence_after();
+      const float4* bias4 = reinterpret_cast<const float4*>(base_ptr + kOffBias + s * 512);
+      // ---- pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rr[32];
+        tmem_ld32(t_s + c * 32, rr);
+        tmem_ld_wait();
+        if (HAS_BIAS) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 bb = bias4[c * 8 + g];
+            mx = fmaxf(mx, fmaf(__uint_as_float(rr[g * 4 + 0]), p.scale, bb.x));
+            mx = fmaxf(mx, fmaf(__uint_as_float(rr[g * 4 + 1]), p.scale, bb.y));
+            mx = fmaxf(mx, fmaf(__uint_as_float(rr[g * 4 + 2]), p.scale, bb.z));
+            mx = fmaxf(mx, fmaf(__uint_as_float(rr[g * 4 + 3]), p.scale, bb.w));
+          }
+        } else if (tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kbase + c * 32 + i < p.Lk) mx = fmaxf(mx, __uint_as_float(rr[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = HAS_BIAS ? ex2f((m - m_new) * l2e) : ex2f((m - m_new) * sc);
+      // ---- fold in O(j-1) (also guarantees PV(j-1) is done reading P before we overwrite it)
+      if (j > 0) {
+        mbar_wait(o_full(x), (uint32_t)(j - 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t oo[32];
+          tmem_ld32(t_o + c * 32, oo);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha_prev, __uint_as_float(oo[i]));
+        }
+      }
+      // ---- pass 2: probabilities -> fp16 -> swizzled smem (A operand of P·V)
+      float rowsum = 0.f;
+      const float neg_m = HAS_BIAS ? m_new : -m_new * sc;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rr[32];
+        tmem_ld32(t_s + c * 32, rr);
+        tmem_ld_wait();
+        float pv[32];
+        if (HAS_BIAS) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 bb = bias4[c * 8 + g];
+            pv[g * 4 + 0] = ex2f((fmaf(__uint_as_float(rr[g * 4 + 0]), p.scale, bb.x) - neg_m) * l2e);
+            pv[g * 4 + 1] = ex2f((fmaf(__uint_as_float(rr[g * 4 + 1]), p.scale, bb.y) - neg_m) * l2e);
+            pv[g * 4 + 2] = ex2f((fmaf(__uint_as_float(rr[g * 4 + 2]), p.scale, bb.z) - neg_m) * l2e);
+            pv[g * 4 + 3] = ex2f((fmaf(__uint_as_float(rr[g * 4 + 3]), p.scale, bb.w) - neg_m) * l2e);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float e = ex2f(fmaf(__uint_as_float(rr[i]), sc, neg_m));
+            if (tail && (kbase + c * 32 + i >= p.Lk)) e = 0.f;
+            pv[i] = e;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rowsum += pv[i];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = c * 4 + q;  // 16-byte chunk (8 keys) index within the 128-key row
+          const uint4 w = make_uint4(pack_h2(pv[q * 8 + 0], pv[q * 8 + 1]), pack_h2(pv[q * 8 + 2], pv[q * 8 + 3]),
+                                     pack_h2(pv[q * 8 + 4], pv[q * 8 + 5]), pack_h2(pv[q * 8 + 6], pv[q * 8 + 7]));
+          uint8_t* dst = p_row + (chunk >> 3) * (128 * 128) + (((chunk & 7) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = w;
+        }
+      }
+      l = fmaf(l, alpha, rowsum);
+      m = m_new;
+      alpha_prev = alpha;
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_full(x));
+    }
+    // ---- last PV tile and normalisation
+    mbar_wait(o_full(x), (uint32_t)(n - 1) & 1u);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t oo[32];
+      tmem_ld32(t_o + c * 32, oo);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha_prev, __uint_as_float(oo[i]));
+    }
+    const int q = q0 + x * 128 + r;
+    if (q < p.Lq) {
+      const float inv = 1.0f / l;
+      __half* dst = p.out + ((long long)b * p.Lq + q) * p.ldo + h * 64;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        *reinterpret_cast<uint4*>(dst + g * 8) =
+            make_uint4(pack_h2(acc[g * 8 + 0] * inv, acc[g * 8 + 1] * inv), pack_h2(acc[g * 8 + 2] * inv, acc[g * 8 + 3] * inv),
+                       pack_h2(acc[g * 8 + 4] * inv, acc[g * 8 + 5] * inv), pack_h2(acc[g * 8 + 6] * inv, acc[g * 8 + 7] * inv));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+struct AttnLaunch {
+  AttnParams p;
+  dim3 grid;
+  bool has_bias;
+};
+
+std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d) {
+  auto L = std::make_shared<AttnLaunch>();
+  AttnParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  SDM_CHECK(d.Lq > 0 && d.Lk > 0 && d.heads > 0, "attention dims");
+  SDM_CHECK(d.ldq % 8 == 0 && d.ldk % 8 == 0 && d.ldvt % 8 == 0 && d.ldo % 8 == 0, "attention strides must be multiples of 8");
+  {
+    const uint64_t dims[3] = {(uint64_t)d.heads * 64, (uint64_t)d.Lq, (uint64_t)d.B};
+    const uint64_t str[2] = {(uint64_t)d.ldq * 2, (uint64_t)d.Lq * d.ldq * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    make_tmap(&p.q_map, d.q, 3, dims, str, box);
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)d.heads * 64, (uint64_t)d.Lk, (uint64_t)d.B};
+    const uint64_t str[2] = {(uint64_t)d.ldk * 2, (uint64_t)d.Lk * d.ldk * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    make_tmap(&p.k_map, d.k, 3, dims, str, box);
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)d.Lk, (uint64_t)d.heads * 64, (uint64_t)d.B};
+    const uint64_t str[2] = {(uint64_t)d.ldvt * 2, (uint64_t)d.heads * 64 * d.ldvt * 2};
+    const uint32_t box[3] = {64, 64, 1};
+    make_tmap(&p.vt_map, d.vt, 3, dims, str, box);
+  }
+  p.bias = d.bias;
+  p.bias_bstride = d.bias_bstride;
+  if (d.bias) SDM_CHECK(d.bias_bstride % 4 == 0 && d.bias_bstride >= ((d.Lk + 127) / 128) * 128, "bias must be padded to 128 keys");
+  p.out = d.out;
+  p.ldo = d.ldo;
+  p.Lq = d.Lq; p.Lk = d.Lk; p.heads = d.heads;
+  p.n_ktiles = (d.Lk + 127) / 128;
+  p.scale = d.scale;
+  L->grid = dim3((d.Lq + 255) / 256, d.heads, d.B);
+  L->has_bias = d.bias != nullptr;
+  return L;
+}
+
+void attn_run(const AttnLaunch& l, cudaStream_t st) {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+  });
+  if (l.has_bias) attention_kernel<true><<<l.grid, kAttnThreads, kAttnSmem, st>>>(l.p);
+  else attention_kernel<false><<<l.grid, kAttnThreads, kAttnSmem, st>>>(l.p);
+  SDM_CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace sdm

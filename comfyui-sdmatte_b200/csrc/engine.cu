@@ -1,0 +1,930 @@
+// Engine: weight repack + execution plan for the SDMatte single-pass matte path.
+//
+// The op graph follows the reference exactly (citations into /root/reference):
+//   SDMatte.forward                 src/modeling/SDMatte/meta_arch.py:127-261
+//   CustomUNet.forward              src/utils/replace.py:379-549   (module tree built at :184-362)
+//   diffusers internals             restated in SURVEY.md Appendix A (A.2 embeddings, A.3 UNet blocks, A.4 VAE)
+// Data layout: every activation is NHWC fp16 in one caller-provided arena; tokens (B, L, C) alias NHWC.
+// The CLIP text encoder of the reference is dead compute on this path (meta_arch.py:220-234 never reaches
+// the UNet because use_encoder_hidden_states_list=[True]*3, replace.py:414-416) and is not executed.
+#include "engine.h"
+
+#include "common.cuh"
+#include "kernels.h"
+#include "umma_gemm.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace sdm {
+
+// ================================================================================================
+// weights
+// ================================================================================================
+struct HostT {
+  int dtype = 0;
+  std::vector<int64_t> shape;
+  const void* data = nullptr;
+  bool used = false;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+static inline float bf16_to_f(uint16_t v) {
+  uint32_t u = (uint32_t)v << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+struct Weights {
+  std::unordered_map<std::string, HostT> host;  // valid during engine_load only
+  std::unordered_map<std::string, void*> dev;   // packed device buffers
+  std::vector<void*> allocs;
+  std::vector<std::string> missing;
+  bool loading = false;
+  bool loaded = false;
+  size_t bytes = 0;
+  int n_used = 0, n_unexpected = 0;
+
+  const HostT* find(const std::string& name) {
+    auto it = host.find(name);
+    if (it != host.end()) { it->second.used = true; return &it->second; }
+    // legacy VAE attention names (query/key/value/proj_attn)
+    static const char* alias[4][2] = {{".to_q.", ".query."}, {".to_k.", ".key."}, {".to_v.", ".value."}, {".to_out.0.", ".proj_attn."}};
+    for (auto& a : alias) {
+      auto pos = name.find(a[0]);
+      if (pos != std::string::npos) {
+        std::string alt = name;
+        alt.replace(pos, strlen(a[0]), a[1]);
+        auto it2 = host.find(alt);
+        if (it2 != host.end()) { it2->second.used = true; return &it2->second; }
+      }
+    }
+    return nullptr;
+  }
+  // fetch as fp32 host vector; records a missing key (and returns zeros) if absent
+  std::vector<float> fetch(const std::string& name, int64_t expect_numel) {
+    std::vector<float> out((size_t)expect_numel, 0.f);
+    const HostT* t = find(name);
+    if (!t) { missing.push_back(name); return out; }
+    if (t->numel() != expect_numel)
+      throw Error{"shape mismatch for '" + name + "': got " + std::to_string(t->numel()) + " elements, expected " + std::to_string(expect_numel)};
+    if (t->dtype == 0) memcpy(out.data(), t->data, (size_t)expect_numel * 4);
+    else if (t->dtype == 1) { const __half* h = (const __half*)t->data; for (int64_t i = 0; i < expect_numel; ++i) out[i] = __half2float(h[i]); }
+    else if (t->dtype == 2) { const uint16_t* h = (const uint16_t*)t->data; for (int64_t i = 0; i < expect_numel; ++i) out[i] = bf16_to_f(h[i]); }
+    else throw Error{"unsupported dtype for '" + name + "'"};
+    return out;
+  }
+  void* upload(const std::string& key, const void* src, size_t nbytes) {
+    void* d = nullptr;
+    SDM_CUDA_OK(cudaMalloc(&d, std::max<size_t>(nbytes, 16)));
+    SDM_CUDA_OK(cudaMemcpy(d, src, nbytes, cudaMemcpyHostToDevice));
+    dev[key] = d;
+    allocs.push_back(d);
+    bytes += nbytes;
+    return d;
+  }
+  void* get(const std::string& key) {
+    auto it = dev.find(key);
+    return it == dev.end() ? nullptr : it->second;
+  }
+  void require_loading(const std::string& key) {
+    if (!loading) throw Error{"weight '" + key + "' was not packed at load time (internal error)"};
+  }
+
+  // conv weight OIHW -> [O(+pad)][kh*kw][I(+pad)] fp16
+  const __half* conv(const std::string& name, int O, int I, int k, int Ipad = 0, int Opad = 0) {
+    const std::string key = "c:" + name;
+    if (void* p = get(key)) return (const __half*)p;
+    require_loading(key);
+    const int Ip = Ipad ? Ipad : I, Op = Opad ? Opad : O;
+    std::vector<float> w = fetch(name + ".weight", (int64_t)O * I * k * k);
+    std::vector<__half> pk((size_t)Op * k * k * Ip, __float2half_rn(0.f));
+    for (int o = 0; o < O; ++o)
+      for (int i = 0; i < I; ++i)
+        for (int t = 0; t < k * k; ++t) pk[((size_t)o * k * k + t) * Ip + i] = __float2half_rn(w[((size_t)o * I + i) * k * k + t]);
+    return (const __half*)upload(key, pk.data(), pk.size() * 2);
+  }
+  const __half* linear(const std::string& name, int N, int K) {
+    const std::string key = "l:" + name;
+    if (void* p = get(key)) return (const __half*)p;
+    require_loading(key);
+    std::vector<float> w = fetch(name + ".weight", (int64_t)N * K);
+    std::vector<__half> pk(w.size());
+    for (size_t i = 0; i < w.size(); ++i) pk[i] = __float2half_rn(w[i]);
+    return (const __half*)upload(key, pk.data(), pk.size() * 2);
+  }
+  const float* vec(const std::string& name, int n, int npad = 0) {
+    const std::string key = "v:" + name;
+    if (void* p = get(key)) return (const float*)p;
+    require_loading(key);
+    std::vector<float> v = fetch(name, n);
+    if (npad > n) v.resize(npad, 0.f);
+    return (const float*)upload(key, v.data(), v.size() * 4);
+  }
+  // GEGLU projection [8C][C]: rows re-ordered so that every 256-row tile holds 128 value rows followed by the
+  // 128 matching gate rows (reference FeedForward/GEGLU: value = first half, gate = second half)
+  const __half* geglu_w(const std::string& name, int C) {
+    const std::string key = "g:" + name;
+    if (void* p = get(key)) return (const __half*)p;
+    require_loading(key);
+    const int F = 4 * C;
+    std::vector<float> w = fetch(name + ".weight", (int64_t)2 * F * C);
+    std::vector<__half> pk(w.size());
+    for (int t = 0; t < F / 128; ++t)
+      for (int half = 0; half < 2; ++half)
+        for (int r = 0; r < 128; ++r) {
+          const size_t src = (size_t)(half * F + t * 128 + r) * C, dst = (size_t)(t * 256 + half * 128 + r) * C;
+          for (int c = 0; c < C; ++c) pk[dst + c] = __float2half_rn(w[src + c]);
+        }
+    return (const __half*)upload(key, pk.data(), pk.size() * 2);
+  }
+  const float* geglu_b(const std::string& name, int C) {
+    const std::string key = "gb:" + name;
+    if (void* p = get(key)) return (const float*)p;
+    require_loading(key);
+    const int F = 4 * C;
+    std::vector<float> b = fetch(name + ".bias", 2 * F), pk(2 * F);
+    for (int t = 0; t < F / 128; ++t)
+      for (int half = 0; half < 2; ++half)
+        for (int r = 0; r < 128; ++r) pk[t * 256 + half * 128 + r] = b[half * F + t * 128 + r];
+    return (const float*)upload(key, pk.data(), pk.size() * 4);
+  }
+  const float* raw_vec(const std::string& key, const std::vector<float>& v) {
+    if (void* p = get(key)) return (const float*)p;
+    require_loading(key);
+    return (const float*)upload(key, v.data(), v.size() * 4);
+  }
+  void free_all() {
+    for (void* p : allocs) cudaFree(p);
+    allocs.clear();
+    dev.clear();
+    bytes = 0;
+  }
+};
+
+// ================================================================================================
+// plan-time arena: offsets inside the caller's workspace, first-fit free list, explicit free
+// ================================================================================================
+struct Arena {
+  struct Blk { size_t off, size; };
+  std::vector<Blk> free_list;
+  size_t top = 0, peak = 0;
+  static size_t align(size_t x) { return (x + 1023) & ~(size_t)1023; }
+  size_t alloc(size_t bytes) {
+    bytes = align(std::max<size_t>(bytes, 1024));
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < free_list.size(); ++i)
+      if (free_list[i].size >= bytes && (best == (size_t)-1 || free_list[i].size < free_list[best].size)) best = i;
+    if (best != (size_t)-1) {
+      const size_t off = free_list[best].off;
+      if (free_list[best].size == bytes) free_list.erase(free_list.begin() + best);
+      else { free_list[best].off += bytes; free_list[best].size -= bytes; }
+      return off;
+    }
+    // extend the top (absorb a trailing free block if it touches the top)
+    for (size_t i = 0; i < free_list.size(); ++i)
+      if (free_list[i].off + free_list[i].size == top) {
+        const size_t off = free_list[i].off;
+        top = off + bytes;
+        free_list.erase(free_list.begin() + i);
+        peak = std::max(peak, top);
+        return off;
+      }
+    const size_t off = top;
+    top += bytes;
+    peak = std::max(peak, top);
+    return off;
+  }
+  void release(size_t off, size_t bytes) {
+    bytes = align(std::max<size_t>(bytes, 1024));
+    free_list.push_back({off, bytes});
+    std::sort(free_list.begin(), free_list.end(), [](const Blk& a, const Blk& b) { return a.off < b.off; });
+    for (size_t i = 0; i + 1 < free_list.size();) {
+      if (free_list[i].off + free_list[i].size == free_list[i + 1].off) {
+        free_list[i].size += free_list[i + 1].size;
+        free_list.erase(free_list.begin() + i + 1);
+      } else ++i;
+    }
+  }
+};
+
+struct T {  // NHWC fp16 activation
+  __half* p = nullptr;
+  size_t off = 0, bytes = 0;
+  int B = 0, H = 0, W = 0, C = 0;
+  long long ld() const { return C; }
+  long long HW() const { return (long long)H * W; }
+  bool valid() const { return bytes != 0; }
+};
+
+using Op = std::function<void(cudaStream_t)>;
+
+struct Plan {
+  int B = 0, R = 0;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  std::vector<Op> ops;
+  int n_launches = 0;
+  double tensor_flops = 0;
+  // fixed buffers
+  float* d_image = nullptr;   // used by forward_host only
+  float* d_trimap = nullptr;
+  __half* d_alpha = nullptr;
+  const float** image_slot = nullptr;
+  std::map<std::string, T> taps;
+  // run-time argument slots (device pointers change per call without rebuilding the plan)
+  struct Slots { const float* image; const float* trimap; __half* alpha; __half* premean; } slots{};
+  int* d_is_trans = nullptr;
+};
+
+struct Engine {
+  int device = 0;
+  int num_sms = 148;
+  Weights W;
+  std::unique_ptr<Plan> plan;
+  int last_launches = 0;
+  double last_flops = 0;
+};
+
+// ================================================================================================
+// graph builder
+// ================================================================================================
+struct Builder {
+  Engine& E;
+  Weights& W;
+  Plan* plan;       // null in dry mode
+  Arena arena;
+  bool dry;
+  int B, R, S;
+  char* ws;
+  int n_launches = 0;
+  double flops = 0;
+  int* d_is_trans = nullptr;
+
+  Builder(Engine& e, Plan* p, int B_, int R_, void* ws_) : E(e), W(e.W), plan(p), dry(p == nullptr), B(B_), R(R_), S(R_ / 8), ws((char*)ws_) {}
+
+  T alloc(int b, int h, int w, int c) {
+    T t;
+    t.B = b; t.H = h; t.W = w; t.C = c;
+    t.bytes = (size_t)b * h * w * c * 2;
+    t.off = arena.alloc(t.bytes);
+    t.p = dry ? nullptr : (__half*)(ws + t.off);
+    return t;
+  }
+  void* alloc_raw(size_t bytes, size_t* off_out) {
+    const size_t off = arena.alloc(bytes);
+    *off_out = off;
+    return dry ? nullptr : (void*)(ws + off);
+  }
+  void free(T& t) {
+    if (t.valid()) arena.release(t.off, t.bytes);
+    t.bytes = 0;
+  }
+  void push(Op op, int launches = 1) {
+    n_launches += launches;
+    if (!dry) plan->ops.push_back(std::move(op));
+  }
+
+  // ---------------------------------------------------------------- primitive emitters
+  struct GemmOpt {
+    const float* bias = nullptr;
+    const int* bias_sel = nullptr;
+    const T* res = nullptr;
+    int mode = EPI_F16;
+    int ups2 = 0;
+    int stride = 1;
+    int pad = PAD_SAME;
+    float scale = 1.0f;
+  };
+  // generic tensor-core conv (ksize 1/3) over one or two channel-concatenated sources
+  void conv_tc(const T& a, const T* a2, const __half* w, int N, int ksize, const T& out, const GemmOpt& o) {
+    const int Hout = a.H / o.stride, Wout = a.W / o.stride;
+    flops += 2.0 * a.B * Hout * Wout * (double)N * ksize * ksize * (a.C + (a2 ? a2->C : 0));
+    if (dry) { n_launches++; return; }
+    ConvGemmDesc d;
+    d.B = a.B; d.Hin = a.H; d.Win = a.W;
+    d.nsrc = a2 ? 2 : 1;
+    d.src[0] = {a.p, a.C, a.ld()};
+    if (a2) d.src[1] = {a2->p, a2->C, a2->ld()};
+    d.ksize = ksize; d.stride = o.stride; d.pad = o.pad;
+    d.w = w; d.N = N;
+    d.mode = o.mode; d.ups2 = o.ups2;
+    d.out = out.p;
+    if (o.mode == EPI_F16_T) {
+      d.out_ld = out.W;                          // out is [B][N][Lld] stored as T{B, H=N, W=Lld, C=1}
+      d.out_bstride = (long long)out.H * out.W;
+    } else {
+      d.out_ld = out.C;
+      d.out_bstride = out.HW() * out.C;
+    }
+    d.bias = o.bias; d.bias_sel = o.bias_sel;
+    if (o.res) { d.res = o.res->p; d.res_ld = o.res->C; d.res_bstride = o.res->HW() * o.res->C; }
+    d.scale = o.scale;
+    auto l = conv_gemm_build(d, E.num_sms);
+    push([l](cudaStream_t st) { conv_gemm_run(*l, st); });
+  }
+  // token GEMM: x [B][L][K] -> out [B][L][N]
+  void linear(const T& x, const __half* w, int N, const T& out, const GemmOpt& o) {
+    T xv = x; xv.H = 1; xv.W = (int)x.HW();
+    T ov = out;
+    if (o.mode != EPI_F16_T) { ov.H = 1; ov.W = (int)out.HW(); }
+    GemmOpt oo = o;
+    T rv;
+    if (o.res) { rv = *o.res; rv.H = 1; rv.W = (int)o.res->HW(); oo.res = &rv; }
+    conv_tc(xv, nullptr, w, N, 1, ov, oo);
+  }
+  T groupnorm(const T& a, const T* a2, const std::string& name, float eps, int silu) {
+    const int Ctot = a.C + (a2 ? a2->C : 0);
+    T out = alloc(a.B, a.H, a.W, Ctot);
+    const float* gamma = W.vec(name + ".weight", Ctot);
+    const float* beta = W.vec(name + ".bias", Ctot);
+    size_t soff;
+    const size_t sbytes = groupnorm_scratch_floats(a.B, (int)a.HW(), Ctot) * 4;
+    float* scratch = (float*)alloc_raw(sbytes, &soff);
+    if (!dry) {
+      GroupNormDesc d;
+      d.B = a.B; d.HW = (int)a.HW(); d.nsrc = a2 ? 2 : 1;
+      d.src[0] = a.p; d.C[0] = a.C; d.ld[0] = a.ld();
+      if (a2) { d.src[1] = a2->p; d.C[1] = a2->C; d.ld[1] = a2->ld(); }
+      d.gamma = gamma; d.beta = beta; d.eps = eps; d.silu = silu;
+      d.out = out.p; d.scratch = scratch;
+      push([d](cudaStream_t st) { groupnorm_run(d, st); }, 3);
+    } else n_launches += 3;
+    arena.release(soff, sbytes);
+    return out;
+  }
+  T layernorm(const T& x, const std::string& name) {
+    T out = alloc(x.B, x.H, x.W, x.C);
+    const float* g = W.vec(name + ".weight", x.C);
+    const float* b = W.vec(name + ".bias", x.C);
+    if (!dry) {
+      const __half* xp = x.p; __half* yp = out.p;
+      const long long rows = (long long)x.B * x.HW();
+      const int C = x.C;
+      push([=](cudaStream_t st) { layernorm_run(xp, yp, g, b, rows, C, 1e-5f, st); });
+    } else n_launches++;
+    return out;
+  }
+  void direct(const DirectConvDesc& d) {
+    if (!dry) push([d](cudaStream_t st) { direct_conv_run(d, st); });
+    else n_launches++;
+  }
+  void attention(const T& q, const T& k, const T& vt, int heads, const float* bias, long long bias_bs, const T& out) {
+    const int Lq = (int)q.HW(), Lk = (int)k.HW();
+    flops += 4.0 * q.B * heads * (double)Lq * Lk * 64;
+    if (dry) { n_launches++; return; }
+    AttnDesc d;
+    d.B = q.B; d.heads = heads; d.Lq = Lq; d.Lk = Lk;
+    d.q = q.p; d.ldq = q.C; d.k = k.p; d.ldk = k.C;
+    d.vt = vt.p; d.ldvt = vt.W;
+    d.bias = bias; d.bias_bstride = bias_bs;
+    d.out = out.p; d.ldo = out.C; d.scale = 0.125f;
+    auto l = attn_build(d);
+    push([l](cudaStream_t st) { attn_run(*l, st); });
+  }
+
+  // ---------------------------------------------------------------- blocks
+  // ResnetBlock2D.  x2 != null: input is cat([x, x2], channel).  temb_bias: folded
+  // conv1.bias + time_emb_proj(silu(emb)) with two rows (is_transparent = 0 / 1), or null for the VAE.
+  T resnet(const T& x, const T* x2, const std::string& p, int Cout, float eps, bool has_temb, int ups2) {
+    const int Cin = x.C + (x2 ? x2->C : 0);
+    T n1 = groupnorm(x, x2, p + ".norm1", eps, 1);
+    T h = alloc(x.B, x.H, x.W, Cout);
+    {
+      GemmOpt o;
+      if (has_temb) { o.bias = W.raw_vec("temb:" + p, {}); o.bias_sel = d_is_trans; }
+      else o.bias = W.vec(p + ".conv1.bias", Cout);
+      conv_tc(n1, nullptr, W.conv(p + ".conv1", Cout, Cin, 3), Cout, 3, h, o);
+    }
+    free(n1);
+    T n2 = groupnorm(h, nullptr, p + ".norm2", eps, 1);
+    free(h);
+    T sc;
+    const T* resid = &x;
+    if (Cin != Cout) {
+      sc = alloc(x.B, x.H, x.W, Cout);
+      GemmOpt o;
+      o.bias = W.vec(p + ".conv_shortcut.bias", Cout);
+      conv_tc(x, x2, W.conv(p + ".conv_shortcut", Cout, Cin, 1), Cout, 1, sc, o);
+      resid = &sc;
+    } else {
+      SDM_CHECK(x2 == nullptr, "concat input without shortcut conv");
+    }
+    T out = ups2 ? alloc(x.B, x.H * 2, x.W * 2, Cout) : alloc(x.B, x.H, x.W, Cout);
+    {
+      GemmOpt o;
+      o.bias = W.vec(p + ".conv2.bias", Cout);
+      o.res = resid;
+      o.ups2 = ups2;
+      conv_tc(n2, nullptr, W.conv(p + ".conv2", Cout, Cout, 3), Cout, 3, out, o);
+    }
+    free(n2);
+    free(sc);
+    return out;
+  }
+
+  // Transformer2DModel with one BasicTransformerBlock; ctx = trimap tokens [B][Lctx][1024]
+  T transformer(const T& x, const std::string& p, int heads, const T& ctx, const float* key_bias, long long key_bias_bs, int ups2) {
+    const int C = x.C, L = (int)x.HW(), Bq = x.B;
+    const std::string tb = p + ".transformer_blocks.0";
+    T n = groupnorm(x, nullptr, p + ".norm", 1e-6f, 0);
+    T h = alloc(Bq, x.H, x.W, C);
+    { GemmOpt o; o.bias = W.vec(p + ".proj_in.bias", C); linear(n, W.linear(p + ".proj_in", C, C), C, h, o); }
+    free(n);
+    auto attn = [&](const std::string& ap, const T& qsrc, const T& kvsrc, int Ckv, const float* bias, long long bias_bs) {
+      const int Lk = (int)kvsrc.HW();
+      const int Lld = (Lk + 7) & ~7;
+      T q = alloc(Bq, x.H, x.W, C);
+      T k = alloc(Bq, kvsrc.H, kvsrc.W, C);
+      T vt; vt.B = Bq; vt.H = C; vt.W = Lld; vt.C = 1; vt.bytes = (size_t)Bq * C * Lld * 2; vt.off = arena.alloc(vt.bytes);
+      vt.p = dry ? nullptr : (__half*)(ws + vt.off);
+      { GemmOpt o; linear(qsrc, W.linear(ap + ".to_q", C, C), C, q, o); }
+      { GemmOpt o; linear(kvsrc, W.linear(ap + ".to_k", C, Ckv), C, k, o); }
+      { GemmOpt o; o.mode = EPI_F16_T; linear(kvsrc, W.linear(ap + ".to_v", C, Ckv), C, vt, o); }
+      T o_ = alloc(Bq, x.H, x.W, C);
+      attention(q, k, vt, heads, bias, bias_bs, o_);
+      free(q); free(k); free(vt);
+      { GemmOpt o; o.bias = W.vec(ap + ".to_out.0.bias", C); o.res = &h; linear(o_, W.linear(ap + ".to_out.0", C, C), C, h, o); }
+      free(o_);
+    };
+    {  // attn1: self attention with the trimap key bias (replace.py:20-122)
+      T ln = layernorm(h, tb + ".norm1");
+      attn(tb + ".attn1", ln, ln, C, key_bias, key_bias_bs);
+      free(ln);
+    }
+    {  // attn2: cross attention to the trimap tokens, no mask (replace.py:96-98 beta=0)
+      T ln = layernorm(h, tb + ".norm2");
+      attn(tb + ".attn2", ln, ctx, 1024, nullptr, 0);
+      free(ln);
+    }
+    {  // feed-forward (GEGLU)
+      T ln = layernorm(h, tb + ".norm3");
+      T g = alloc(Bq, x.H, x.W, 4 * C);
+      { GemmOpt o; o.mode = EPI_GEGLU; o.bias = W.geglu_b(tb + ".ff.net.0.proj", C); linear(ln, W.geglu_w(tb + ".ff.net.0.proj", C), 8 * C, g, o); }
+      free(ln);
+      { GemmOpt o; o.bias = W.vec(tb + ".ff.net.2.bias", C); o.res = &h; linear(g, W.linear(tb + ".ff.net.2", C, 4 * C), C, h, o); }
+      free(g);
+    }
+    T out = ups2 ? alloc(Bq, x.H * 2, x.W * 2, C) : alloc(Bq, x.H, x.W, C);
+    { GemmOpt o; o.bias = W.vec(p + ".proj_out.bias", C); o.res = &x; o.ups2 = ups2; conv_tc(h, nullptr, W.linear(p + ".proj_out", C, C), C, 1, out, o); }
+    free(h);
+    (void)L;
+    return out;
+  }
+
+  // VAE mid-block attention: single head, d = 512.  Unfused: QK^T -> fp32 scores -> softmax -> P V.
+  T vae_attention(const T& x, const std::string& p) {
+    const int C = 512, L = (int)x.HW(), Bv = x.B;
+    T n = groupnorm(x, nullptr, p + ".group_norm", 1e-6f, 0);
+    T q = alloc(Bv, x.H, x.W, C), k = alloc(Bv, x.H, x.W, C);
+    T vt; vt.B = Bv; vt.H = C; vt.W = L; vt.C = 1; vt.bytes = (size_t)Bv * C * L * 2; vt.off = arena.alloc(vt.bytes);
+    vt.p = dry ? nullptr : (__half*)(ws + vt.off);
+    { GemmOpt o; o.bias = W.vec(p + ".to_q.bias", C); linear(n, W.linear(p + ".to_q", C, C), C, q, o); }
+    { GemmOpt o; o.bias = W.vec(p + ".to_k.bias", C); linear(n, W.linear(p + ".to_k", C, C), C, k, o); }
+    { GemmOpt o; o.bias = W.vec(p + ".to_v.bias", C); o.mode = EPI_F16_T; linear(n, W.linear(p + ".to_v", C, C), C, vt, o); }
+    free(n);
+    T att = alloc(Bv, x.H, x.W, C);
+    const int chunk = std::max(1, std::min(Bv, (int)((6ull << 30) / ((size_t)L * L * 6))));
+    size_t s_off, p_off;
+    const size_t s_bytes = (size_t)chunk * L * L * 4, p_bytes = (size_t)chunk * L * L * 2;
+    float* scores = (float*)alloc_raw(s_bytes, &s_off);
+    __half* probs = (__half*)alloc_raw(p_bytes, &p_off);
+    for (int b0 = 0; b0 < Bv; b0 += chunk) {
+      const int nb = std::min(chunk, Bv - b0);
+      flops += 4.0 * nb * (double)L * L * C;
+      if (dry) { n_launches += 3; continue; }
+      ConvGemmDesc d1;  // scores[b] = scale * Q[b] K[b]^T
+      d1.B = nb; d1.Hin = 1; d1.Win = L; d1.nsrc = 1;
+      d1.src[0] = {q.p + (size_t)b0 * L * C, C, C};
+      d1.ksize = 1; d1.w = k.p + (size_t)b0 * L * C; d1.N = L; d1.w_bstride = (long long)L * C;
+      d1.mode = EPI_F32; d1.out = scores; d1.out_ld = L; d1.out_bstride = (long long)L * L;
+      d1.scale = 1.0f / sqrtf((float)C);
+      auto l1 = conv_gemm_build(d1, E.num_sms);
+      push([l1](cudaStream_t st) { conv_gemm_run(*l1, st); });
+      const long long rows = (long long)nb * L;
+      push([=](cudaStream_t st) { softmax_rows_run(scores, probs, rows, L, st); });
+      ConvGemmDesc d2;  // att[b] = P[b] V[b]   (B operand = V^T [512][L])
+      d2.B = nb; d2.Hin = 1; d2.Win = L; d2.nsrc = 1;
+      d2.src[0] = {probs, L, L};
+      d2.ksize = 1; d2.w = vt.p + (size_t)b0 * C * L; d2.N = C; d2.w_bstride = (long long)C * L;
+      d2.mode = EPI_F16; d2.out = att.p + (size_t)b0 * L * C; d2.out_ld = C; d2.out_bstride = (long long)L * C;
+      auto l2 = conv_gemm_build(d2, E.num_sms);
+      push([l2](cudaStream_t st) { conv_gemm_run(*l2, st); });
+    }
+    arena.release(s_off, s_bytes);
+    arena.release(p_off, p_bytes);
+    free(q); free(k); free(vt);
+    T out = alloc(Bv, x.H, x.W, C);
+    { GemmOpt o; o.bias = W.vec(p + ".to_out.0.bias", C); o.res = &x; linear(att, W.linear(p + ".to_out.0", C, C), C, out, o); }
+    free(att);
+    return out;
+  }
+
+  T conv3_plain(const T& x, const std::string& name, int Cout, int stride, int pad) {
+    T out = alloc(x.B, x.H / stride, x.W / stride, Cout);
+    GemmOpt o;
+    o.bias = W.vec(name + ".bias", Cout);
+    o.stride = stride; o.pad = pad;
+    conv_tc(x, nullptr, W.conv(name, Cout, x.C, 3), Cout, 3, out, o);
+    return out;
+  }
+
+  // ---------------------------------------------------------------- constant folding of the embeddings
+  // emb = time_embedding(time_proj(trans)) + bbox_embedding(emb320([0,0,1,1]))   (replace.py:430-459, meta_arch.py:178-187)
+  void fold_embeddings() {
+    if (W.get("temb:unet.mid_block.resnets.0")) return;
+    W.require_loading("temb");
+    auto sinus = [](float t, std::vector<float>& out) {  // get_timestep_embedding(dim 320, flip_sin_to_cos, shift 0)
+      const int half = 160;
+      for (int i = 0; i < half; ++i) {
+        const float f = expf(-logf(10000.0f) * (float)i / (float)half);
+        out.push_back(cosf(t * f));
+      }
+      for (int i = 0; i < half; ++i) {
+        const float f = expf(-logf(10000.0f) * (float)i / (float)half);
+        out.push_back(sinf(t * f));
+      }
+    };
+    auto matvec = [](const std::vector<float>& w, const std::vector<float>& b, const std::vector<float>& x, int N, int K) {
+      std::vector<float> y(N);
+      for (int n = 0; n < N; ++n) {
+        double a = b[n];
+        for (int k = 0; k < K; ++k) a += (double)w[(size_t)n * K + k] * x[k];
+        y[n] = (float)a;
+      }
+      return y;
+    };
+    auto silu = [](std::vector<float> v) { for (auto& x : v) x = x / (1.0f + expf(-x)); return v; };
+    auto te_w1 = W.fetch("unet.time_embedding.linear_1.weight", 1280 * 320), te_b1 = W.fetch("unet.time_embedding.linear_1.bias", 1280);
+    auto te_w2 = W.fetch("unet.time_embedding.linear_2.weight", 1280 * 1280), te_b2 = W.fetch("unet.time_embedding.linear_2.bias", 1280);
+    auto bb_w1 = W.fetch("unet.bbox_embedding.linear_1.weight", 1280 * 1280), bb_b1 = W.fetch("unet.bbox_embedding.linear_1.bias", 1280);
+    auto bb_w2 = W.fetch("unet.bbox_embedding.linear_2.weight", 1280 * 1280), bb_b2 = W.fetch("unet.bbox_embedding.linear_2.bias", 1280);
+    std::vector<float> coords;
+    for (float c : {0.f, 0.f, 1.f, 1.f}) sinus(c, coords);  // (4, 320) flattened -> 1280
+    auto aug = matvec(bb_w2, bb_b2, silu(matvec(bb_w1, bb_b1, coords, 1280, 1280)), 1280, 1280);
+    std::vector<float> emb[2];
+    for (int is_trans = 0; is_trans < 2; ++is_trans) {
+      std::vector<float> tp;
+      sinus((float)(1 - is_trans), tp);  // trans = 1 - is_trans (meta_arch.py:237-238)
+      auto op = matvec(te_w2, te_b2, silu(matvec(te_w1, te_b1, tp, 1280, 320)), 1280, 1280);
+      emb[is_trans].resize(1280);
+      for (int i = 0; i < 1280; ++i) emb[is_trans][i] = op[i] + aug[i];
+      emb[is_trans] = silu(emb[is_trans]);  // every resnet applies SiLU to emb before time_emb_proj
+    }
+    auto fold = [&](const std::string& p, int C) {
+      auto w = W.fetch(p + ".time_emb_proj.weight", (int64_t)C * 1280), b = W.fetch(p + ".time_emb_proj.bias", C);
+      auto cb = W.fetch(p + ".conv1.bias", C);
+      std::vector<float> out(2 * C);
+      for (int v = 0; v < 2; ++v) {
+        auto t = matvec(w, b, emb[v], C, 1280);
+        for (int i = 0; i < C; ++i) out[v * C + i] = cb[i] + t[i];
+      }
+      W.upload("temb:" + p, out.data(), out.size() * 4);
+    };
+    const int ch[4] = {320, 640, 1280, 1280};
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 2; ++j) fold("unet.down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), ch[i]);
+    for (int j = 0; j < 2; ++j) fold("unet.mid_block.resnets." + std::to_string(j), 1280);
+    const int rch[4] = {1280, 1280, 640, 320};
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 3; ++j) fold("unet.up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), rch[i]);
+  }
+
+  // ---------------------------------------------------------------- the whole path
+  void build() {
+    SDM_CHECK(R % 64 == 0 && R >= 64 && R <= 1024, "inference size must be a multiple of 64 in [64, 1024]");
+    SDM_CHECK(B >= 1, "batch");
+    if (W.loading) fold_embeddings();
+    const int B2 = 2 * B;
+    size_t off;
+    // run-time inputs
+    d_is_trans = (int*)alloc_raw((size_t)B * 4, &off);
+    if (plan) plan->d_is_trans = d_is_trans;
+    Plan::Slots* slots = plan ? &plan->slots : nullptr;
+
+    // ---- a1: input preparation (sdmatte_nodes.py:343,351; meta_arch.py:141)
+    T x0 = alloc(B2, R, R, 4);
+    if (!dry) {
+      __half* xp = x0.p; const int Bc = B, Rc = R;
+      push([=](cudaStream_t st) { prep_inputs_run(slots->image, slots->trimap, xp, 4, Bc, Rc, st); });
+    } else n_launches++;
+    // ---- a4/a6: additive key bias per level
+    int lpad[4];
+    float* kb[4];
+    for (int k = 0; k < 4; ++k) {
+      const int s = S >> k;
+      lpad[k] = (s * s + 127) & ~127;
+      kb[k] = (float*)alloc_raw((size_t)B * lpad[k] * 4, &off);
+    }
+    if (!dry) {
+      const int Bc = B, Rc = R;
+      float* k0 = kb[0]; float* k1 = kb[1]; float* k2 = kb[2]; float* k3 = kb[3];
+      const int l0 = lpad[0], l1 = lpad[1], l2 = lpad[2], l3 = lpad[3];
+      push([=](cudaStream_t st) { const int lp[4] = {l0, l1, l2, l3}; key_bias_run(slots->trimap, Bc, Rc, k0, k1, k2, k3, lp, st); });
+    } else n_launches++;
+
+    // ---- a2: VAE encoder over [rgb ; trimap x3] as one batch of 2B (meta_arch.py:139-145,209-212)
+    T unet_in = alloc(B, S, S, 8);
+    {
+      const std::string e = "vae.encoder";
+      T h = alloc(B2, R, R, 128);
+      { DirectConvDesc d; d.B = B2; d.H = R; d.W = R; d.Cin = 4; d.Cout = 128; d.ksize = 3; d.x = x0.p; d.x_ld = 4;
+        d.w = W.conv(e + ".conv_in", 128, 3, 3, 4); d.bias = W.vec(e + ".conv_in.bias", 128); d.out = h.p; d.out_ld = 128; direct(d); }
+      free(x0);
+      const int ch[4] = {128, 256, 512, 512};
+      for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 2; ++j) {
+          T o = resnet(h, nullptr, e + ".down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), ch[i], 1e-6f, false, 0);
+          free(h); h = o;
+        }
+        if (i < 3) {
+          T o = conv3_plain(h, e + ".down_blocks." + std::to_string(i) + ".downsamplers.0.conv", ch[i], 2, PAD_VAE_DOWN);
+          free(h); h = o;
+        }
+      }
+      { T o = resnet(h, nullptr, e + ".mid_block.resnets.0", 512, 1e-6f, false, 0); free(h); h = o; }
+      { T o = vae_attention(h, e + ".mid_block.attentions.0"); free(h); h = o; }
+      { T o = resnet(h, nullptr, e + ".mid_block.resnets.1", 512, 1e-6f, false, 0); free(h); h = o; }
+      T n = groupnorm(h, nullptr, e + ".conv_norm_out", 1e-6f, 1);
+      free(h);
+      T mom = alloc(B2, S, S, 8);
+      { DirectConvDesc d; d.B = B2; d.H = S; d.W = S; d.Cin = 512; d.Cout = 8; d.ksize = 3; d.x = n.p; d.x_ld = 512;
+        d.w = W.conv(e + ".conv_out", 8, 512, 3); d.bias = W.vec(e + ".conv_out.bias", 8); d.out = mom.p; d.out_ld = 8; direct(d); }
+      free(n);
+      // quant_conv 1x1 (8->8), keep the mean half (channels 0..3), * scaling_factor; rgb -> ch 0..3, trimap -> ch 4..7
+      for (int part = 0; part < 2; ++part) {
+        DirectConvDesc d; d.B = B; d.H = S; d.W = S; d.Cin = 8; d.Cout = 8; d.ksize = 1;
+        d.x = dry ? nullptr : mom.p + (size_t)part * B * S * S * 8; d.x_ld = 8;
+        d.w = W.conv("vae.quant_conv", 8, 8, 1); d.bias = W.vec("vae.quant_conv.bias", 8);
+        d.out = unet_in.p; d.out_ld = 8; d.out_coff = part * 4; d.out_scale = 0.18215f; d.cout_limit = 4;
+        direct(d);
+      }
+      free(mom);
+    }
+    if (plan) plan->taps["unet_in"] = unet_in;
+
+    // ---- a5: trimap tokens = aux_conv_in(trimap latent) (meta_arch.py:215-218, utils.py:33-41)
+    T ctx = alloc(B, S, S, 1024);
+    { DirectConvDesc d; d.B = B; d.H = S; d.W = S; d.Cin = 4; d.Cout = 1024; d.ksize = 3; d.x = dry ? nullptr : unet_in.p + 4; d.x_ld = 8;
+      d.w = W.conv("unet.aux_conv_in", 1024, 4, 3); d.bias = W.vec("unet.aux_conv_in.bias", 1024); d.out = ctx.p; d.out_ld = 1024; direct(d); }
+    if (plan) plan->taps["ctx"] = ctx;
+
+    // ---- a7..a14: UNet (replace.py:462-544)
+    T unet_out = alloc(B, S, S, 4);
+    {
+      const int ch[4] = {320, 640, 1280, 1280};
+      const int heads[4] = {5, 10, 20, 20};
+      std::vector<T> skips;
+      T h = alloc(B, S, S, 320);
+      { DirectConvDesc d; d.B = B; d.H = S; d.W = S; d.Cin = 8; d.Cout = 320; d.ksize = 3; d.x = unet_in.p; d.x_ld = 8;
+        d.w = W.conv("unet.conv_in", 320, 8, 3); d.bias = W.vec("unet.conv_in.bias", 320); d.out = h.p; d.out_ld = 320; direct(d); }
+      skips.push_back(h);
+      for (int i = 0; i < 4; ++i) {
+        const std::string bp = "unet.down_blocks." + std::to_string(i);
+        for (int j = 0; j < 2; ++j) {
+          T o = resnet(h, nullptr, bp + ".resnets." + std::to_string(j), ch[i], 1e-5f, true, 0);
+          if (i < 3) {
+            T o2 = transformer(o, bp + ".attentions." + std::to_string(j), heads[i], ctx, kb[i], lpad[i], 0);
+            free(o); o = o2;
+          }
+          h = o;
+          skips.push_back(h);
+        }
+        if (i < 3) {
+          h = conv3_plain(h, bp + ".downsamplers.0.conv", ch[i], 2, PAD_SAME);
+          skips.push_back(h);
+        }
+      }
+      // mid (h is the last skip; it stays alive as a skip)
+      {
+        T o = resnet(h, nullptr, "unet.mid_block.resnets.0", 1280, 1e-5f, true, 0);
+        T o2 = transformer(o, "unet.mid_block.attentions.0", 20, ctx, kb[3], lpad[3], 0);
+        free(o);
+        T o3 = resnet(o2, nullptr, "unet.mid_block.resnets.1", 1280, 1e-5f, true, 0);
+        free(o2);
+        h = o3;
+      }
+      const int rch[4] = {1280, 1280, 640, 320};
+      const int rheads[4] = {20, 20, 10, 5};
+      for (int i = 0; i < 4; ++i) {
+        const std::string bp = "unet.up_blocks." + std::to_string(i);
+        const int level = 3 - i;
+        for (int j = 0; j < 3; ++j) {
+          T skip = skips.back();
+          skips.pop_back();
+          const bool last = (j == 2) && (i < 3);
+          const bool has_attn = i > 0;
+          T o = resnet(h, &skip, bp + ".resnets." + std::to_string(j), rch[i], 1e-5f, true, (last && !has_attn) ? 1 : 0);
+          free(h); free(skip);
+          if (has_attn) {
+            T o2 = transformer(o, bp + ".attentions." + std::to_string(j), rheads[i], ctx, kb[level], lpad[level], last ? 1 : 0);
+            free(o); o = o2;
+          }
+          h = o;
+        }
+        if (i < 3) {  // Upsample2D: nearest x2 (fused into the producer's store) + conv3x3
+          T o = conv3_plain(h, bp + ".upsamplers.0.conv", rch[i], 1, PAD_SAME);
+          free(h); h = o;
+        }
+      }
+      T n = groupnorm(h, nullptr, "unet.conv_norm_out", 1e-5f, 1);
+      free(h);
+      // conv_out (320->4), then label_latent / scaling_factor (meta_arch.py:254)
+      { DirectConvDesc d; d.B = B; d.H = S; d.W = S; d.Cin = 320; d.Cout = 4; d.ksize = 3; d.x = n.p; d.x_ld = 320;
+        d.w = W.conv("unet.conv_out", 4, 320, 3); d.bias = W.vec("unet.conv_out.bias", 4); d.out = unet_out.p; d.out_ld = 4; d.out_div = 0.18215f; direct(d); }
+      free(n);
+      SDM_CHECK(skips.empty(), "skip bookkeeping");
+    }
+    // ctx / unet_in / unet_out stay allocated: they are small and double as parity-test taps
+    if (plan) plan->taps["unet_out_scaled"] = unet_out;
+
+    // ---- a15: VAE decode (meta_arch.py:255-256)
+    {
+      const std::string dcd = "vae.decoder";
+      T z = alloc(B, S, S, 4);
+      { DirectConvDesc d; d.B = B; d.H = S; d.W = S; d.Cin = 4; d.Cout = 8; d.ksize = 1; d.x = unet_out.p; d.x_ld = 4;
+        d.w = W.conv("vae.post_quant_conv", 4, 4, 1, 0, 8); d.bias = W.vec("vae.post_quant_conv.bias", 4, 8); d.out = z.p; d.out_ld = 4; d.cout_limit = 4; direct(d); }
+      T h = alloc(B, S, S, 512);
+      { DirectConvDesc d; d.B = B; d.H = S; d.W = S; d.Cin = 4; d.Cout = 512; d.ksize = 3; d.x = z.p; d.x_ld = 4;
+        d.w = W.conv(dcd + ".conv_in", 512, 4, 3); d.bias = W.vec(dcd + ".conv_in.bias", 512); d.out = h.p; d.out_ld = 512; direct(d); }
+      free(z);
+      { T o = resnet(h, nullptr, dcd + ".mid_block.resnets.0", 512, 1e-6f, false, 0); free(h); h = o; }
+      { T o = vae_attention(h, dcd + ".mid_block.attentions.0"); free(h); h = o; }
+      { T o = resnet(h, nullptr, dcd + ".mid_block.resnets.1", 512, 1e-6f, false, 0); free(h); h = o; }
+      const int ch[4] = {512, 512, 256, 128};
+      for (int i = 0; i < 4; ++i) {
+        const std::string bp = dcd + ".up_blocks." + std::to_string(i);
+        for (int j = 0; j < 3; ++j) {
+          T o = resnet(h, nullptr, bp + ".resnets." + std::to_string(j), ch[i], 1e-6f, false, (j == 2 && i < 3) ? 1 : 0);
+          free(h); h = o;
+        }
+        if (i < 3) { T o = conv3_plain(h, bp + ".upsamplers.0.conv", ch[i], 1, PAD_SAME); free(h); h = o; }
+      }
+      T n = groupnorm(h, nullptr, dcd + ".conv_norm_out", 1e-6f, 1);
+      free(h);
+      // ---- a16: conv_out (128->3) + channel mean + clip + (x+1)/2 (meta_arch.py:258-260)
+      const __half* wco = W.conv(dcd + ".conv_out", 3, 128, 3);
+      const float* bco = W.vec(dcd + ".conv_out.bias", 3);
+      if (!dry) {
+        const __half* np_ = n.p; const int Bc = B, Rc = R;
+        push([=](cudaStream_t st) { alpha_head_run(np_, 128, Bc, Rc, Rc, 128, wco, bco, slots->alpha, slots->premean, st); });
+      } else n_launches++;
+      free(n);
+    }
+  }
+};
+
+// ================================================================================================
+// engine API
+// ================================================================================================
+Engine* engine_create(int device) {
+  SDM_CUDA_OK(cudaSetDevice(device));
+  Engine* e = new Engine();
+  e->device = device;
+  SDM_CUDA_OK(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device));
+  int major = 0, minor = 0;
+  SDM_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  SDM_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  if (major != 10) {
+    delete e;
+    throw Error{"sdmatte_b200 requires an sm_100a (B200) device; found sm_" + std::to_string(major) + std::to_string(minor) + " — there is no fallback path"};
+  }
+  return e;
+}
+
+void engine_destroy(Engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  e->W.free_all();
+  delete e;
+}
+
+void engine_load(Engine* e, const sdm_tensor_desc* tensors, int n) {
+  SDM_CUDA_OK(cudaSetDevice(e->device));
+  Weights& W = e->W;
+  W.free_all();
+  W.host.clear();
+  W.missing.clear();
+  e->plan.reset();
+  for (int i = 0; i < n; ++i) {
+    HostT t;
+    t.dtype = tensors[i].dtype;
+    for (int d = 0; d < tensors[i].ndim; ++d) t.shape.push_back(tensors[i].shape[d]);
+    t.data = tensors[i].data;
+    W.host[tensors[i].name] = t;
+  }
+  W.loading = true;
+  try {
+    Builder b(*e, nullptr, 1, 64, nullptr);
+    b.build();
+  } catch (...) {
+    W.loading = false;
+    W.host.clear();
+    throw;
+  }
+  W.loading = false;
+  W.n_used = 0;
+  W.n_unexpected = 0;
+  for (auto& kv : W.host) (kv.second.used ? W.n_used : W.n_unexpected)++;
+  W.host.clear();
+  if (!W.missing.empty()) {
+    std::string msg = std::to_string(W.missing.size()) + " required checkpoint keys are missing, e.g.:";
+    for (size_t i = 0; i < std::min<size_t>(W.missing.size(), 8); ++i) msg += " " + W.missing[i];
+    W.free_all();
+    throw Error{msg};
+  }
+  W.loaded = true;
+}
+
+void engine_load_report(Engine* e, int* n_used, int* n_unexpected) {
+  if (n_used) *n_used = e->W.n_used;
+  if (n_unexpected) *n_unexpected = e->W.n_unexpected;
+}
+
+size_t engine_workspace_bytes(Engine* e, int B, int R) {
+  SDM_CHECK(e->W.loaded, "weights not loaded");
+  Builder b(*e, nullptr, B, R, nullptr);
+  b.build();
+  return b.arena.peak + 4096;
+}
+
+static Plan& get_plan(Engine* e, int B, int R, void* ws, size_t ws_bytes) {
+  SDM_CHECK(e->W.loaded, "weights not loaded");
+  SDM_CHECK((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
+  if (e->plan && e->plan->B == B && e->plan->R == R && e->plan->ws == ws && e->plan->ws_bytes == ws_bytes) return *e->plan;
+  const size_t need = engine_workspace_bytes(e, B, R);
+  if (ws_bytes < need) throw Error{"workspace too small: need " + std::to_string(need) + " bytes, got " + std::to_string(ws_bytes)};
+  auto plan = std::make_unique<Plan>();
+  plan->B = B; plan->R = R; plan->ws = ws; plan->ws_bytes = ws_bytes;
+  Builder b(*e, plan.get(), B, R, ws);
+  b.build();
+  plan->n_launches = b.n_launches;
+  plan->tensor_flops = b.flops;
+  e->plan = std::move(plan);
+  return *e->plan;
+}
+
+void engine_forward(Engine* e, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
+                    void* alpha_dev, void* premean_dev, void* ws, size_t ws_bytes, cudaStream_t st) {
+  SDM_CUDA_OK(cudaSetDevice(e->device));
+  Plan& p = get_plan(e, B, R, ws, ws_bytes);
+  p.slots.image = image_dev;
+  p.slots.trimap = trimap_dev;
+  p.slots.alpha = (__half*)alpha_dev;
+  p.slots.premean = (__half*)premean_dev;
+  for (int i = 0; i < B; ++i) SDM_CHECK(is_trans[i] == 0 || is_trans[i] == 1, "is_trans must be 0/1");
+  SDM_CUDA_OK(cudaMemcpyAsync(p.d_is_trans, is_trans, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  for (auto& op : p.ops) op(st);
+  e->last_launches = p.n_launches;
+  e->last_flops = p.tensor_flops;
+}
+
+void engine_forward_host(Engine* e, const float* image_host, const float* trimap_host, int B, int R, const int32_t* is_trans,
+                         void* alpha_host_f16, void* ws, size_t ws_bytes, cudaStream_t st) {
+  SDM_CUDA_OK(cudaSetDevice(e->device));
+  // staging buffers live at the tail of the workspace: image, trimap, alpha
+  const size_t img_b = (size_t)B * R * R * 3 * 4, tri_b = (size_t)B * R * R * 4, al_b = (size_t)B * R * R * 2;
+  const size_t stage = ((img_b + tri_b + al_b) + 4095) & ~(size_t)4095;
+  SDM_CHECK(ws_bytes > stage, "workspace too small for host staging");
+  const size_t main_bytes = (ws_bytes - stage) & ~(size_t)1023;
+  char* tail = (char*)ws + main_bytes;
+  float* d_img = (float*)tail;
+  float* d_tri = (float*)(tail + img_b);
+  __half* d_alpha = (__half*)(tail + img_b + tri_b);
+  SDM_CUDA_OK(cudaMemcpyAsync(d_img, image_host, img_b, cudaMemcpyHostToDevice, st));
+  SDM_CUDA_OK(cudaMemcpyAsync(d_tri, trimap_host, tri_b, cudaMemcpyHostToDevice, st));
+  engine_forward(e, d_img, d_tri, B, R, is_trans, d_alpha, nullptr, ws, main_bytes, st);
+  SDM_CUDA_OK(cudaMemcpyAsync(alpha_host_f16, d_alpha, al_b, cudaMemcpyDeviceToHost, st));
+  SDM_CUDA_OK(cudaStreamSynchronize(st));
+}
+
+void engine_stats(Engine* e, int* n_launches, double* tensor_flops) {
+  if (n_launches) *n_launches = e->last_launches;
+  if (tensor_flops) *tensor_flops = e->last_flops;
+}
+
+void engine_debug_tensor(Engine* e, const char* name, void* dst_dev, size_t dst_bytes, int64_t* shape4, int* dtype) {
+  SDM_CHECK(e->plan != nullptr, "no forward has run yet");
+  auto it = e->plan->taps.find(name);
+  if (it == e->plan->taps.end()) throw Error{std::string("unknown debug tensor '") + name + "'"};
+  const T& t = it->second;
+  const size_t bytes = (size_t)t.B * t.H * t.W * t.C * 2;
+  SDM_CHECK(dst_bytes >= bytes, "debug tensor destination too small");
+  SDM_CUDA_OK(cudaMemcpy(dst_dev, (const char*)e->plan->ws + t.off, bytes, cudaMemcpyDeviceToDevice));
+  if (shape4) { shape4[0] = t.B; shape4[1] = t.H; shape4[2] = t.W; shape4[3] = t.C; }
+  if (dtype) *dtype = 1;
+}
+
+}  // namespace sdm

@@ -1,0 +1,22 @@
+// Engine: weight store + execution plan for the SDMatte single-pass matte path.
+#pragma once
+#include "sdmatte_b200.h"
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace sdm {
+struct Engine;
+Engine* engine_create(int device);
+void engine_destroy(Engine* e);
+void engine_load(Engine* e, const sdm_tensor_desc* tensors, int n);
+void engine_load_report(Engine* e, int* n_used, int* n_unexpected);
+size_t engine_workspace_bytes(Engine* e, int B, int R);
+void engine_forward(Engine* e, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
+                    void* alpha_dev, void* premean_dev, void* ws, size_t ws_bytes, cudaStream_t st);
+void engine_forward_host(Engine* e, const float* image_host, const float* trimap_host, int B, int R, const int32_t* is_trans,
+                         void* alpha_host_f16, void* ws, size_t ws_bytes, cudaStream_t st);
+void engine_stats(Engine* e, int* n_launches, double* tensor_flops);
+void engine_debug_tensor(Engine* e, const char* name, void* dst_dev, size_t dst_bytes, int64_t* shape4, int* dtype);
+}  // namespace sdm

@@ -1,0 +1,122 @@
+// Host-callable launchers for the sm_100a kernels of the SDMatte matte path.
+// Plain C++ (no torch). Every launcher enqueues on the given stream and never synchronises.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <memory>
+
+namespace sdm {
+
+// ------------------------------------------------------------------ tcgen05 conv / GEMM
+struct ActSrc {
+  const __half* ptr = nullptr;  // NHWC activation (or [B][L][C] tokens)
+  int C = 0;                    // channels used from this source (multiple of 64)
+  long long ld = 0;             // elements between consecutive pixels (>= C)
+};
+
+enum ConvPad { PAD_SAME = 0, PAD_VAE_DOWN = 1 };  // PAD_VAE_DOWN: F.pad(0,1,0,1) + stride 2 + pad 0
+
+struct ConvGemmDesc {
+  int B = 1, Hin = 1, Win = 1;  // input spatial dims (tokens: Hin = 1, Win = L)
+  int nsrc = 1;
+  ActSrc src[2];
+  long long src_bstride[2] = {0, 0};  // elements per batch element (0 -> Hin*Win*ld)
+  int ksize = 1;                      // 1 or 3
+  int stride = 1;                     // 1 or 2 (2 only with ksize 3, nsrc 1)
+  int pad = PAD_SAME;
+  const __half* w = nullptr;  // [N][ksize*ksize*cin_total], K contiguous
+  int N = 0;
+  long long w_bstride = 0;  // != 0: per-batch weights (batched GEMM), elements
+  int mode = 0;             // EpiMode
+  int ups2 = 0;
+  void* out = nullptr;
+  long long out_ld = 0, out_bstride = 0;
+  const float* bias = nullptr;
+  const int* bias_sel = nullptr;
+  const __half* res = nullptr;
+  long long res_ld = 0, res_bstride = 0;
+  float scale = 1.0f;
+  int force_block_n = 0;  // tests only
+};
+
+struct ConvGemmLaunch;  // opaque: prebuilt tensor maps + params
+std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_sms);
+void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st);
+double conv_gemm_flops(const ConvGemmLaunch& l);
+
+// ------------------------------------------------------------------ flash attention (d = 64)
+struct AttnDesc {
+  int B = 1, heads = 1, Lq = 0, Lk = 0;
+  const __half* q = nullptr;   // [B][Lq][ldq], head h at columns h*64..
+  long long ldq = 0;
+  const __half* k = nullptr;   // [B][Lk][ldk]
+  long long ldk = 0;
+  const __half* vt = nullptr;  // [B][heads*64][Lk_ld]  (V transposed: keys contiguous)
+  long long ldvt = 0;          // row length (>= Lk, multiple of 8)
+  const float* bias = nullptr; // [B][Lk_pad] additive per-key bias (padded with -inf to a multiple of 128) or null
+  long long bias_bstride = 0;
+  __half* out = nullptr;       // [B][Lq][ldo]
+  long long ldo = 0;
+  float scale = 0.125f;
+};
+struct AttnLaunch;
+std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d);
+void attn_run(const AttnLaunch& l, cudaStream_t st);
+
+// ------------------------------------------------------------------ norms / softmax
+// GroupNorm(32 groups) over NHWC input given as up to two channel-concatenated sources.
+// stats: per-(b, channel) partial sums -> per-(b, group) mean/rstd; apply: y = silu?((x-mean)*rstd*gamma+beta) fp16.
+struct GroupNormDesc {
+  int B = 1, HW = 0;
+  int nsrc = 1;
+  const __half* src[2] = {nullptr, nullptr};
+  int C[2] = {0, 0};
+  long long ld[2] = {0, 0};
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float eps = 1e-5f;
+  int silu = 1;
+  __half* out = nullptr;   // [B][HW][C0+C1]
+  float* scratch = nullptr;  // >= groupnorm_scratch_floats(...) floats
+};
+size_t groupnorm_scratch_floats(int B, int HW, int Ctot);
+void groupnorm_run(const GroupNormDesc& d, cudaStream_t st);
+
+void layernorm_run(const __half* x, __half* y, const float* gamma, const float* beta, long long rows, int C, float eps,
+                   cudaStream_t st);
+// rows of fp32 scores -> fp16 probabilities (softmax over the last dim)
+void softmax_rows_run(const float* s, __half* p, long long rows, int L, cudaStream_t st);
+
+// ------------------------------------------------------------------ small direct convs (Cin <= 8 or Cout <= 8)
+struct DirectConvDesc {
+  int B = 1, H = 0, W = 0;          // stride 1, pad (k-1)/2
+  int Cin = 0, Cout = 0, ksize = 3;
+  const __half* x = nullptr; long long x_ld = 0;   // NHWC, pixel stride
+  const __half* w = nullptr;   // [Cout][k*k][Cin] fp16
+  const float* bias = nullptr; // [Cout]
+  __half* out = nullptr; long long out_ld = 0; int out_coff = 0;  // writes channels [out_coff, out_coff+Cout)
+  float out_scale = 1.0f;      // applied after fp16 rounding of conv+bias (fp16 multiply), 1 = none
+  __half* out2 = nullptr; long long out2_ld = 0; int out2_coff = 0;  // optional second copy
+  int cout_limit = 0;          // if >0 only the first cout_limit channels are stored (VAE "mean" half)
+  float out_div = 1.0f;        // small-Cout path only: fp16(out) / out_div, rounded to fp16 (latent / scaling_factor)
+};
+void direct_conv_run(const DirectConvDesc& d, cudaStream_t st);
+
+// decoder head: conv3x3 (C->3) on an already normalised/activated input, then mean over the 3 channels,
+// clip(-1,1), (x+1)/2 -> alpha fp16 [B][H][W]   (reference meta_arch.py:256-260)
+void alpha_head_run(const __half* x, long long x_ld, int B, int H, int W, int Cin, const __half* w, const float* bias,
+                    __half* alpha, __half* premean /*nullable: pre-clip mean, fp16*/, cudaStream_t st);
+
+// ------------------------------------------------------------------ elementwise
+// image [B][R][R][3] fp32 in [0,1] -> (x-0.5)/0.5 fp16 NHWC with 3 channels padded to ldc
+// trimap [B][R][R] fp32 in [0,1] -> t*2-1 replicated to 3 channels
+void prep_inputs_run(const float* image, const float* trimap, __half* out /*[2B][R][R][ldc]*/, int ldc, int B, int R,
+                     cudaStream_t st);
+// key-bias vectors for the 4 UNet levels: bias_k[b][i*s+j] = (1 - trimap[b][8*2^k*i][8*2^k*j]) * -10000,
+// padded to lpad[k] (multiple of 128) with -inf.   (reference meta_arch.py:200-204, replace.py:56-63,401-403)
+void key_bias_run(const float* trimap, int B, int R, float* bias0, float* bias1, float* bias2, float* bias3,
+                  const int* lpad, cudaStream_t st);
+
+int device_sm_count();
+}  // namespace sdm

@@ -1,0 +1,305 @@
+// HBM-bound normalisation kernels: GroupNorm(32)(+SiLU), LayerNorm, row softmax.
+// Reference ops: nn.GroupNorm inside diffusers ResnetBlock2D / Transformer2DModel / VAE (eps 1e-5 / 1e-6),
+// nn.LayerNorm in BasicTransformerBlock, softmax in the VAE mid-block attention.
+// All statistics are fp32/fp64; inputs and outputs are fp16 NHWC (the reference's autocast rounding points, A.6).
+#include "common.cuh"
+#include "kernels.h"
+
+#include <algorithm>
+
+namespace sdm {
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm
+// ------------------------------------------------------------------------------------------------
+static int gn_ny(int nvec) { return std::max(1, 256 / nvec); }
+static int gn_nslab(int B, int HW, int Ctot) {
+  const int ny = gn_ny(Ctot / 8);
+  const int by_rows = (HW + ny - 1) / ny;
+  const int target = std::max(1, (148 * 8 + B - 1) / B);
+  return std::max(1, std::min(by_rows, target));
+}
+size_t groupnorm_scratch_floats(int B, int HW, int Ctot) {
+  return (size_t)B * gn_nslab(B, HW, Ctot) * Ctot * 2 + (size_t)B * Ctot * 2;
+}
+
+// partial[b][slab][c][2] = (sum, sumsq) over the slab's pixels
+__global__ void gn_stats_kernel(const __half* __restrict__ s0, const __half* __restrict__ s1, int C0, int Ctot, long long ld0,
+                                long long ld1, int HW, int pix_per_slab, float* __restrict__ partial) {
+  extern __shared__ float red[];  // [ny][nvec*16]
+  const int nvec = Ctot >> 3;
+  const int v = threadIdx.x, y = threadIdx.y, ny = blockDim.y;
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int p0 = slab * pix_per_slab;
+  const int p1 = min(HW, p0 + pix_per_slab);
+  const int c = v * 8;
+  const __half* base;
+  long long ld;
+  if (c < C0) { base = s0 + (long long)b * HW * ld0 + c; ld = ld0; }
+  else { base = s1 + (long long)b * HW * ld1 + (c - C0); ld = ld1; }
+  float sum[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sum[i] = 0.f; sq[i] = 0.f; }
+  for (int p = p0 + y; p < p1; p += ny) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + (long long)p * ld));
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      sum[2 * j] += f.x; sq[2 * j] += f.x * f.x;
+      sum[2 * j + 1] += f.y; sq[2 * j + 1] += f.y * f.y;
+    }
+  }
+  float* mine = red + ((size_t)y * nvec + v) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mine[i] = sum[i]; mine[8 + i] = sq[i]; }
+  __syncthreads();
+  if (y == 0) {
+    for (int yy = 1; yy < ny; ++yy) {
+      const float* o = red + ((size_t)yy * nvec + v) * 16;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sum[i] += o[i]; sq[i] += o[8 + i]; }
+    }
+    float* dst = partial + (((size_t)b * gridDim.x + slab) * Ctot + c) * 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dst[2 * i] = sum[i]; dst[2 * i + 1] = sq[i]; }
+  }
+}
+
+// one warp per (b, group): reduce partials in fp64, emit per-channel scale/shift
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int nslab, int Ctot, int HW, float eps,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ab,
+                                   int total_groups) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= total_groups) return;
+  const int b = wid >> 5, g = wid & 31;
+  const int gs = Ctot >> 5;
+  double s = 0.0, q = 0.0;
+  const int n = nslab * gs;
+  for (int i = lane; i < n; i += 32) {
+    const int slab = i / gs, cc = i % gs;
+    const float* src = partial + (((size_t)b * nslab + slab) * Ctot + g * gs + cc) * 2;
+    s += (double)src[0];
+    q += (double)src[1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const double cnt = (double)HW * gs;
+  const double mean = s / cnt;
+  double var = q / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float fmean = (float)mean;
+  for (int cc = lane; cc < gs; cc += 32) {
+    const int c = g * gs + cc;
+    const float a = rstd * gamma[c];
+    ab[((size_t)b * Ctot + c) * 2] = a;
+    ab[((size_t)b * Ctot + c) * 2 + 1] = beta[c] - fmean * a;
+  }
+}
+
+__global__ void gn_apply_kernel(const __half* __restrict__ s0, const __half* __restrict__ s1, int C0, int Ctot, long long ld0,
+                                long long ld1, int HW, const float* __restrict__ ab, int silu, __half* __restrict__ out,
+                                long long total_vec) {
+  const int nvec = Ctot >> 3;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_vec;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % nvec);
+    const long long bp = idx / nvec;  // b*HW + p
+    const int b = (int)(bp / HW);
+    const int c = v * 8;
+    const __half* src = (c < C0) ? s0 + bp * ld0 + c : s1 + bp * ld1 + (c - C0);
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src));
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    const float4* abp = reinterpret_cast<const float4*>(ab + ((size_t)b * Ctot + c) * 2);
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 k = __ldg(abp + j);  // (a0, s0, a1, s1)
+      const float2 f = __half22float2(h[j]);
+      float y0 = fmaf(f.x, k.x, k.y);
+      float y1 = fmaf(f.y, k.z, k.w);
+      if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+      w[j] = pack_h2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(out + bp * Ctot + c) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+void groupnorm_run(const GroupNormDesc& d, cudaStream_t st) {
+  const int C0 = d.C[0];
+  const int Ctot = d.C[0] + (d.nsrc > 1 ? d.C[1] : 0);
+  SDM_CHECK(Ctot % 32 == 0 && C0 % 8 == 0 && Ctot % 8 == 0, "GroupNorm channel constraints");
+  const int nvec = Ctot / 8;
+  SDM_CHECK(nvec <= 1024, "GroupNorm: too many channels");
+  const int ny = gn_ny(nvec);
+  const int nslab = gn_nslab(d.B, d.HW, Ctot);
+  const int pps = (d.HW + nslab - 1) / nslab;
+  float* partial = d.scratch;
+  float* ab = d.scratch + (size_t)d.B * nslab * Ctot * 2;
+  const __half* s1 = d.nsrc > 1 ? d.src[1] : d.src[0];
+  const long long ld1 = d.nsrc > 1 ? d.ld[1] : d.ld[0];
+  const size_t smem = (size_t)ny * nvec * 16 * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDM_CUDA_OK(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  gn_stats_kernel<<<dim3(nslab, d.B), dim3(nvec, ny), smem, st>>>(d.src[0], s1, C0, Ctot, d.ld[0], ld1, d.HW, pps, partial);
+  SDM_CUDA_OK(cudaGetLastError());
+  const int groups = d.B * 32;
+  gn_finalize_kernel<<<(groups * 32 + 127) / 128, 128, 0, st>>>(partial, nslab, Ctot, d.HW, d.eps, d.gamma, d.beta, ab, groups);
+  SDM_CUDA_OK(cudaGetLastError());
+  const long long total_vec = (long long)d.B * d.HW * nvec;
+  const int blocks = (int)std::min<long long>((total_vec + 255) / 256, 148ll * 16);
+  gn_apply_kernel<<<blocks, 256, 0, st>>>(d.src[0], s1, C0, Ctot, d.ld[0], ld1, d.HW, ab, d.silu, d.out, total_vec);
+  SDM_CUDA_OK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the channel dim: one warp per token row, two-pass from registers
+// ------------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, long long rows, int C, float eps) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nvec = C >> 3;
+  const uint4* src = reinterpret_cast<const uint4*>(x + row * C);
+  float v[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint4 raw = __ldg(src + vi);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        v[i][2 * j] = f.x; v[i][2 * j + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float dlt = v[i][j] - mean; sq += dlt * dlt; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+  uint4* dst = reinterpret_cast<uint4*>(y + row * C);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const float4* g = reinterpret_cast<const float4*>(gamma + vi * 8);
+      const float4* bt = reinterpret_cast<const float4*>(beta + vi * 8);
+      const float4 g0 = __ldg(g), g1 = __ldg(g + 1), b0 = __ldg(bt), b1 = __ldg(bt + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        w[j] = pack_h2((v[i][2 * j] - mean) * rstd * gg[2 * j] + bb[2 * j],
+                       (v[i][2 * j + 1] - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1]);
+      dst[vi] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+void layernorm_run(const __half* x, __half* y, const float* gamma, const float* beta, long long rows, int C, float eps,
+                   cudaStream_t st) {
+  SDM_CHECK(C % 8 == 0 && C <= 8 * 32 * 5, "LayerNorm: C must be a multiple of 8 and <= 1280");
+  const int wpb = 8;
+  const unsigned blocks = (unsigned)((rows + wpb - 1) / wpb);
+  const int nvec = C / 8;
+  if (nvec <= 64) layernorm_kernel<2><<<blocks, wpb * 32, 0, st>>>(x, y, gamma, beta, rows, C, eps);
+  else if (nvec <= 96) layernorm_kernel<3><<<blocks, wpb * 32, 0, st>>>(x, y, gamma, beta, rows, C, eps);
+  else layernorm_kernel<5><<<blocks, wpb * 32, 0, st>>>(x, y, gamma, beta, rows, C, eps);
+  SDM_CUDA_OK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row softmax fp32 -> fp16 (VAE mid-block attention probabilities). One CTA per row, row kept in registers.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, __half* __restrict__ p, int L) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const long long row = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(s + row * L);
+  const int nv = L >> 2;
+  float4 v[16];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int vi = threadIdx.x + i * 256;
+    if (vi < nv) {
+      v[i] = __ldg(src + vi);
+      mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    bcast = m;
+  }
+  __syncthreads();
+  mx = bcast;
+  float sum = 0.f;
+  const float l2e = 1.4426950408889634f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int vi = threadIdx.x + i * 256;
+    if (vi < nv) {
+      v[i].x = ex2f((v[i].x - mx) * l2e); v[i].y = ex2f((v[i].y - mx) * l2e);
+      v[i].z = ex2f((v[i].z - mx) * l2e); v[i].w = ex2f((v[i].w - mx) * l2e);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    bcast = 1.0f / t;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  uint2* dst = reinterpret_cast<uint2*>(p + row * L);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int vi = threadIdx.x + i * 256;
+    if (vi < nv) dst[vi] = make_uint2(pack_h2(v[i].x * inv, v[i].y * inv), pack_h2(v[i].z * inv, v[i].w * inv));
+  }
+}
+
+void softmax_rows_run(const float* s, __half* p, long long rows, int L, cudaStream_t st) {
+  SDM_CHECK(L % 4 == 0 && L <= 16384, "softmax_rows: L must be a multiple of 4 and <= 16384");
+  SDM_CHECK(rows < (1ll << 31), "softmax_rows: too many rows");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(s, p, L);
+  SDM_CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace sdm

@@ -1,0 +1,258 @@
+// HBM-bound "skinny" ops of the matte path: convs with <= 8 input or output channels, input preparation,
+// per-level attention key-bias vectors, the alpha head.  (a1, a4, a5, a7, a14, a16.)
+#include "common.cuh"
+#include "kernels.h"
+
+#include <algorithm>
+
+namespace sdm {
+
+// ------------------------------------------------------------------------------------------------
+// conv with small Cin (4 or 8): thread -> (pixel, 8 output channels)
+//   VAE conv_in (3->128, input padded to 4 ch), UNet conv_in (8->320), aux_conv_in (4->1024, utils.py:33-41),
+//   decoder conv_in (4->512), quant/post_quant 1x1 convs.
+// ------------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void conv_small_cin_kernel(const __half* __restrict__ x, long long x_ld, const __half* __restrict__ w,
+                                      const float* __restrict__ bias, __half* __restrict__ out, long long out_ld, int out_coff,
+                                      float out_scale, int cout_store, int B, int H, int W, int Cout, int ksize) {
+  const int cg = Cout >> 3;
+  const long long total = (long long)B * H * W * cg;
+  const int taps = ksize * ksize;
+  const int r = ksize >> 1;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % cg);
+    const long long pix = idx / cg;
+    const int xx = (int)(pix % W);
+    const int yy = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = bias ? bias[g * 8 + i] : 0.f;
+    for (int t = 0; t < taps; ++t) {
+      const int iy = yy + t / ksize - r, ix = xx + t % ksize - r;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      const __half* xp = x + (((long long)b * H + iy) * W + ix) * x_ld;
+      float xv[CIN];
+      if (CIN == 4) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(xp));
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+        const float2 a = __half22float2(h[0]), c = __half22float2(h[1]);
+        xv[0] = a.x; xv[1] = a.y; xv[2] = c.x; xv[3] = c.y;
+      } else {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xp));
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); xv[2 * j] = f.x; xv[2 * j + 1] = f.y; }
+      }
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const __half* wp = w + ((long long)(g * 8 + o) * taps + t) * CIN;
+        if (CIN == 4) {
+          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(wp));
+          const __half2* h = reinterpret_cast<const __half2*>(&raw);
+          const float2 a = __half22float2(h[0]), c = __half22float2(h[1]);
+          acc[o] += xv[0] * a.x + xv[1] * a.y + xv[2] * c.x + xv[3] * c.y;
+        } else {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(wp));
+          const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); acc[o] += xv[2 * j] * f.x + xv[2 * j + 1] * f.y; }
+        }
+      }
+    }
+    __half hv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __half h = __float2half_rn(acc[i]);
+      if (out_scale != 1.0f) h = __float2half_rn(__half2float(h) * out_scale);  // fp16 * python scalar -> fp16
+      hv[i] = h;
+    }
+    __half* op = out + pix * out_ld + out_coff + g * 8;
+    if (cout_store >= (g + 1) * 8) {
+      *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(hv);
+    } else {
+      for (int i = 0; i < 8; ++i)
+        if (g * 8 + i < cout_store) op[i] = hv[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv 3x3 with small Cout (<= 8): thread -> one pixel, all outputs.  Weights [COUT][9][Cin].
+//   UNet conv_out (320->4), VAE encoder conv_out (512->8), decoder conv_out (128->3, via alpha head).
+// ------------------------------------------------------------------------------------------------
+template <int COUT>
+__device__ __forceinline__ void small_cout_accumulate(const __half* __restrict__ x, long long x_ld, const __half* __restrict__ w,
+                                                      int b, int yy, int xx, int H, int W, int Cin, float (&acc)[COUT]) {
+  for (int t = 0; t < 9; ++t) {
+    const int iy = yy + t / 3 - 1, ix = xx + t % 3 - 1;
+    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+    const uint4* xp = reinterpret_cast<const uint4*>(x + (((long long)b * H + iy) * W + ix) * x_ld);
+    for (int c8 = 0; c8 < (Cin >> 3); ++c8) {
+      const uint4 raw = __ldg(xp + c8);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+      float xv[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); xv[2 * j] = f.x; xv[2 * j + 1] = f.y; }
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        const uint4 wr = __ldg(reinterpret_cast<const uint4*>(w + ((long long)o * 9 + t) * Cin) + c8);
+        const __half2* wh = reinterpret_cast<const __half2*>(&wr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(wh[j]); acc[o] += xv[2 * j] * f.x + xv[2 * j + 1] * f.y; }
+      }
+    }
+  }
+}
+
+template <int COUT>
+__global__ void conv_small_cout_kernel(const __half* __restrict__ x, long long x_ld, const __half* __restrict__ w,
+                                       const float* __restrict__ bias, __half* __restrict__ out, long long out_ld, int out_coff,
+                                       float out_div, int B, int H, int W, int Cin) {
+  const long long total = (long long)B * H * W;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(pix % W);
+    const int yy = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = bias ? bias[o] : 0.f;
+    small_cout_accumulate<COUT>(x, x_ld, w, b, yy, xx, H, W, Cin, acc);
+    __half* op = out + pix * out_ld + out_coff;
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      __half hv = __float2half_rn(acc[o]);
+      if (out_div != 1.0f) hv = __float2half_rn(__half2float(hv) / out_div);  // fp16 / python scalar -> fp16
+      op[o] = hv;
+    }
+  }
+}
+
+void direct_conv_run(const DirectConvDesc& d, cudaStream_t st) {
+  SDM_CHECK(d.ksize == 1 || d.ksize == 3, "direct conv ksize");
+  const long long npix = (long long)d.B * d.H * d.W;
+  if (d.Cin <= 8) {
+    SDM_CHECK((d.Cin == 4 || d.Cin == 8) && d.Cout % 8 == 0, "small-Cin conv: Cin in {4,8}, Cout % 8 == 0");
+    const int store = d.cout_limit > 0 ? d.cout_limit : d.Cout;
+    const long long total = npix * (d.Cout / 8);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148ll * 32);
+    if (d.Cin == 4)
+      conv_small_cin_kernel<4><<<blocks, 256, 0, st>>>(d.x, d.x_ld, d.w, d.bias, d.out, d.out_ld, d.out_coff, d.out_scale, store,
+                                                      d.B, d.H, d.W, d.Cout, d.ksize);
+    else
+      conv_small_cin_kernel<8><<<blocks, 256, 0, st>>>(d.x, d.x_ld, d.w, d.bias, d.out, d.out_ld, d.out_coff, d.out_scale, store,
+                                                      d.B, d.H, d.W, d.Cout, d.ksize);
+  } else {
+    SDM_CHECK(d.ksize == 3 && d.Cin % 8 == 0 && (d.Cout == 4 || d.Cout == 8), "small-Cout conv: 3x3, Cout in {4,8}");
+    SDM_CHECK(d.out_scale == 1.0f && d.cout_limit == 0, "small-Cout conv has no scale/limit");
+    const int blocks = (int)std::min<long long>((npix + 127) / 128, 148ll * 32);
+    if (d.Cout == 4)
+      conv_small_cout_kernel<4><<<blocks, 128, 0, st>>>(d.x, d.x_ld, d.w, d.bias, d.out, d.out_ld, d.out_coff, d.out_div, d.B, d.H, d.W, d.Cin);
+    else
+      conv_small_cout_kernel<8><<<blocks, 128, 0, st>>>(d.x, d.x_ld, d.w, d.bias, d.out, d.out_ld, d.out_coff, d.out_div, d.B, d.H, d.W, d.Cin);
+  }
+  SDM_CUDA_OK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// alpha head: decoder conv_out (Cin->3) + mean over channels + clip + (x+1)/2   (meta_arch.py:256-260)
+// rounding points as on the reference fp16 path: conv outputs fp16, mean fp16, (clip(x)+1) fp16, /2 exact
+// ------------------------------------------------------------------------------------------------
+__global__ void alpha_head_kernel(const __half* __restrict__ x, long long x_ld, const __half* __restrict__ w,
+                                  const float* __restrict__ bias, __half* __restrict__ alpha, __half* __restrict__ premean, int B,
+                                  int H, int W, int Cin) {
+  const long long total = (long long)B * H * W;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(pix % W);
+    const int yy = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    float acc[3] = {bias[0], bias[1], bias[2]};
+    small_cout_accumulate<3>(x, x_ld, w, b, yy, xx, H, W, Cin, acc);
+    const float c0 = __half2float(__float2half_rn(acc[0]));
+    const float c1 = __half2float(__float2half_rn(acc[1]));
+    const float c2 = __half2float(__float2half_rn(acc[2]));
+    const __half m = __float2half_rn((c0 + c1 + c2) / 3.0f);
+    if (premean) premean[pix] = m;
+    const float cl = fminf(fmaxf(__half2float(m), -1.0f), 1.0f);
+    const __half p1 = __float2half_rn(cl + 1.0f);
+    alpha[pix] = __float2half_rn(__half2float(p1) * 0.5f);
+  }
+}
+
+void alpha_head_run(const __half* x, long long x_ld, int B, int H, int W, int Cin, const __half* w, const float* bias,
+                    __half* alpha, __half* premean, cudaStream_t st) {
+  SDM_CHECK(Cin % 8 == 0, "alpha head Cin");
+  const long long npix = (long long)B * H * W;
+  const int blocks = (int)std::min<long long>((npix + 127) / 128, 148ll * 32);
+  alpha_head_kernel<<<blocks, 128, 0, st>>>(x, x_ld, w, bias, alpha, premean, B, H, W, Cin);
+  SDM_CUDA_OK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// input preparation (sdmatte_nodes.py:343,351 at native resolution; meta_arch.py:141)
+// ------------------------------------------------------------------------------------------------
+__global__ void prep_inputs_kernel(const float* __restrict__ image, const float* __restrict__ trimap, __half* __restrict__ out,
+                                   int ldc, long long npix_b /* B*R*R */) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * npix_b; i += (long long)gridDim.x * blockDim.x) {
+    float a, b, c;
+    if (i < npix_b) {
+      a = (image[i * 3] - 0.5f) / 0.5f;
+      b = (image[i * 3 + 1] - 0.5f) / 0.5f;
+      c = (image[i * 3 + 2] - 0.5f) / 0.5f;
+    } else {
+      a = b = c = trimap[i - npix_b] * 2.0f - 1.0f;
+    }
+    __half* o = out + i * ldc;
+    *reinterpret_cast<uint2*>(o) = make_uint2(pack_h2(a, b), pack_h2(c, 0.f));
+  }
+}
+void prep_inputs_run(const float* image, const float* trimap, __half* out, int ldc, int B, int R, cudaStream_t st) {
+  SDM_CHECK(ldc % 4 == 0 && ldc >= 4, "prep ldc");
+  const long long n = (long long)B * R * R;
+  const int blocks = (int)std::min<long long>((2 * n + 255) / 256, 148ll * 16);
+  prep_inputs_kernel<<<blocks, 256, 0, st>>>(image, trimap, out, ldc, n);
+  SDM_CUDA_OK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// additive key bias per UNet level (meta_arch.py:200-204 -> replace.py:401-403 -> replace.py:56-63)
+// ------------------------------------------------------------------------------------------------
+struct KeyBiasArgs {
+  float* dst[4];
+  int lpad[4];
+};
+__global__ void key_bias_kernel(const float* __restrict__ trimap, int B, int R, KeyBiasArgs a) {
+  const int S = R >> 3;
+  const int level = blockIdx.y;
+  const int s = S >> level;
+  const int step = 8 << level;
+  const int lp = a.lpad[level];
+  const long long total = (long long)B * lp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / lp);
+    const int k = (int)(i % lp);
+    float v = -INFINITY;
+    if (k < s * s) {
+      const int yy = (k / s) * step, xx = (k % s) * step;
+      const float t = trimap[((long long)b * R + yy) * R + xx];
+      const float tri = t * 2.0f - 1.0f;
+      const float m = (tri + 1.0f) / 2.0f;
+      v = (1.0f - m) * -10000.0f;
+    }
+    a.dst[level][i] = v;
+  }
+}
+void key_bias_run(const float* trimap, int B, int R, float* bias0, float* bias1, float* bias2, float* bias3, const int* lpad,
+                  cudaStream_t st) {
+  KeyBiasArgs a;
+  a.dst[0] = bias0; a.dst[1] = bias1; a.dst[2] = bias2; a.dst[3] = bias3;
+  for (int i = 0; i < 4; ++i) a.lpad[i] = lpad[i];
+  const long long n = (long long)B * lpad[0];
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 1024);
+  key_bias_kernel<<<dim3(blocks, 4), 256, 0, st>>>(trimap, B, R, a);
+  SDM_CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace sdm

@@ -1,0 +1,175 @@
+// Host side of the tcgen05 implicit-GEMM kernel: tensor-map construction, tile-shape selection, launch.
+#include "kernels.h"
+#include "umma_gemm.cuh"
+#include "tmap.h"
+
+#include <mutex>
+
+namespace sdm {
+
+struct ConvGemmLaunch {
+  ConvGemmParams p;
+  int block_n = 0;
+  int grid = 0;
+  double flops = 0;
+};
+
+static void pick_patch(int H, int W, int& tw, int& th) {
+  // 128-pixel patch tw x th minimising wasted (out-of-image) pixels; prefer long rows on ties
+  long long best = -1;
+  for (int cand = 128; cand >= 8; cand >>= 1) {
+    const int ch = 128 / cand;
+    if (ch > 1 && H == 1) continue;
+    const long long tiles = (long long)((W + cand - 1) / cand) * ((H + ch - 1) / ch);
+    if (best < 0 || tiles < best) {
+      best = tiles;
+      tw = cand;
+      th = ch;
+    }
+  }
+}
+
+static int pick_block_n(int N, int mode, long long m_tiles, int num_sms) {
+  if (mode == EPI_GEGLU) return 256;
+  int bn;
+  if (N % 256 == 0) bn = 256;
+  else if (N % 160 == 0) bn = 160;
+  else if (N % 128 == 0) bn = 128;
+  else if (N > 128) bn = (N % 64 == 0) ? 64 : 128;
+  else bn = (N > 64) ? 128 : 64;
+  // small problems: trade tile size for parallelism (one wave should cover the SMs)
+  while (bn == 256 && m_tiles * (N / bn) < num_sms && N % 128 == 0) bn = 128;
+  if (bn == 128 && m_tiles * (N / bn) < num_sms && N % 64 == 0) bn = 64;
+  return bn;
+}
+
+template <int BN>
+static void launch_bn(const ConvGemmLaunch& l, cudaStream_t st) {
+  using Cfg = ConvGemmCfg<BN>;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    SDM_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  });
+  conv_gemm_kernel<BN><<<l.grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(l.p);
+  SDM_CUDA_OK(cudaGetLastError());
+}
+
+std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_sms) {
+  auto L = std::make_shared<ConvGemmLaunch>();
+  ConvGemmParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  SDM_CHECK(d.ksize == 1 || d.ksize == 3, "ksize");
+  SDM_CHECK(d.stride == 1 || (d.stride == 2 && d.ksize == 3 && d.nsrc == 1), "stride");
+  SDM_CHECK(d.nsrc == 1 || d.nsrc == 2, "nsrc");
+  SDM_CHECK(d.N % 8 == 0, "N must be a multiple of 8");
+  int cin_total = 0;
+  for (int s = 0; s < d.nsrc; ++s) {
+    SDM_CHECK(d.src[s].C % 64 == 0 && d.src[s].C > 0, "source channels must be a multiple of 64");
+    SDM_CHECK(d.src[s].ld % 8 == 0, "pixel stride must be a multiple of 8 elements");
+    cin_total += d.src[s].C;
+  }
+  const int Hout = d.Hin / d.stride, Wout = d.Win / d.stride;
+  if (d.stride == 2) SDM_CHECK(d.Hin % 2 == 0 && d.Win % 2 == 0, "stride-2 conv needs even input dims");
+  p.B = d.B; p.H = Hout; p.W = Wout;
+  pick_patch(Hout, Wout, p.tw, p.th);
+  p.tiles_x = (Wout + p.tw - 1) / p.tw;
+  p.tiles_y = (Hout + p.th - 1) / p.th;
+  const long long m_tiles = (long long)p.tiles_x * p.tiles_y * d.B;
+  p.N = d.N;
+  const int bn = d.force_block_n ? d.force_block_n : pick_block_n(d.N, d.mode, m_tiles, num_sms);
+  if (d.mode == EPI_GEGLU) SDM_CHECK(bn == 256 && d.N % 256 == 0, "GEGLU needs N % 256 == 0");
+  L->block_n = bn;
+  p.n_tiles = (d.N + bn - 1) / bn;
+  const long long total = m_tiles * p.n_tiles;
+  SDM_CHECK(total < (1ll << 31), "too many tiles");
+  p.total_tiles = (int)total;
+  p.ntaps = d.ksize * d.ksize;
+  p.nsrc = d.nsrc;
+  p.cin_total = cin_total;
+  for (int s = 0; s < d.nsrc; ++s) p.src_c[s] = d.src[s].C;
+
+  // ---- A tensor maps
+  const uint32_t box[4] = {64u, (uint32_t)p.tw, (uint32_t)p.th, 1u};
+  if (d.stride == 1) {
+    for (int s = 0; s < d.nsrc; ++s) {
+      const long long bs = d.src_bstride[s] ? d.src_bstride[s] : (long long)d.Hin * d.Win * d.src[s].ld;
+      const uint64_t dims[4] = {(uint64_t)d.src[s].C, (uint64_t)d.Win, (uint64_t)d.Hin, (uint64_t)d.B};
+      const uint64_t strides[3] = {(uint64_t)d.src[s].ld * 2, (uint64_t)d.Win * d.src[s].ld * 2, (uint64_t)bs * 2};
+      make_tmap(&p.a_map[s], d.src[s].ptr, 4, dims, strides, box);
+    }
+    for (int s = d.nsrc; s < 4; ++s) p.a_map[s] = p.a_map[0];
+    for (int t = 0; t < p.ntaps; ++t) {
+      p.tap_map[t] = 0;
+      p.tap_dx[t] = (d.ksize == 3) ? (t % 3) - 1 : 0;
+      p.tap_dy[t] = (d.ksize == 3) ? (t / 3) - 1 : 0;
+    }
+  } else {
+    // stride 2: four parity views of the input (py, px); each is a plain strided 4-D tensor
+    const long long ld = d.src[0].ld;
+    const long long bs = d.src_bstride[0] ? d.src_bstride[0] : (long long)d.Hin * d.Win * ld;
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const uint64_t dims[4] = {(uint64_t)d.src[0].C, (uint64_t)(d.Win / 2), (uint64_t)(d.Hin / 2), (uint64_t)d.B};
+        const uint64_t strides[3] = {(uint64_t)ld * 2 * 2, (uint64_t)d.Win * ld * 2 * 2, (uint64_t)bs * 2};
+        make_tmap(&p.a_map[py * 2 + px], d.src[0].ptr + ((long long)py * d.Win + px) * ld, 4, dims, strides, box);
+      }
+    for (int t = 0; t < 9; ++t) {
+      const int ky = t / 3, kx = t % 3;
+      int py, dy, px, dx;
+      if (d.pad == PAD_SAME) {  // iy = 2*oy + ky - 1
+        py = (ky == 1) ? 0 : 1; dy = (ky == 0) ? -1 : 0;
+        px = (kx == 1) ? 0 : 1; dx = (kx == 0) ? -1 : 0;
+      } else {  // iy = 2*oy + ky, zero row/col past the bottom/right edge
+        py = (ky == 1) ? 1 : 0; dy = (ky == 2) ? 1 : 0;
+        px = (kx == 1) ? 1 : 0; dx = (kx == 2) ? 1 : 0;
+      }
+      p.tap_map[t] = (signed char)(py * 2 + px);
+      p.tap_dx[t] = (signed char)dx;
+      p.tap_dy[t] = (signed char)dy;
+    }
+  }
+  // ---- B tensor map
+  const long long ktot = (long long)p.ntaps * cin_total;
+  if (d.w_bstride) {
+    SDM_CHECK(d.w_bstride % 8 == 0, "weight batch stride alignment");
+    const uint64_t dims[3] = {(uint64_t)ktot, (uint64_t)d.N, (uint64_t)d.B};
+    const uint64_t strides[2] = {(uint64_t)ktot * 2, (uint64_t)d.w_bstride * 2};
+    const uint32_t bbox[3] = {64u, (uint32_t)bn, 1u};
+    make_tmap(&p.b_map, d.w, 3, dims, strides, bbox);
+    p.b_batched = 1;
+  } else {
+    const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d.N};
+    const uint64_t strides[1] = {(uint64_t)ktot * 2};
+    const uint32_t bbox[2] = {64u, (uint32_t)bn};
+    make_tmap(&p.b_map, d.w, 2, dims, strides, bbox);
+  }
+  // ---- epilogue
+  p.mode = d.mode;
+  p.ups2 = d.ups2;
+  SDM_CHECK(!(d.ups2 && (d.res || d.mode != EPI_F16)) || d.mode == EPI_F16, "ups2 only with EPI_F16");
+  p.out = d.out;
+  p.out_ld = d.out_ld;
+  p.out_bstride = d.out_bstride;
+  p.bias = d.bias;
+  p.bias_sel = d.bias_sel;
+  p.res = d.res;
+  p.res_ld = d.res_ld;
+  p.res_bstride = d.res_bstride;
+  p.scale = d.scale;
+  L->grid = (int)std::min<long long>(total, num_sms);
+  L->flops = 2.0 * (double)d.B * Hout * Wout * (double)d.N * (double)ktot;
+  return L;
+}
+
+void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
+  switch (l.block_n) {
+    case 256: launch_bn<256>(l, st); break;
+    case 160: launch_bn<160>(l, st); break;
+    case 128: launch_bn<128>(l, st); break;
+    case 64: launch_bn<64>(l, st); break;
+    default: throw Error{"unsupported BLOCK_N"};
+  }
+}
+double conv_gemm_flops(const ConvGemmLaunch& l) { return l.flops; }
+
+}  // namespace sdm

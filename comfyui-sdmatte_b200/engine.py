@@ -1,0 +1,312 @@
+"""ctypes binding of libsdmatte_b200.so (include/sdmatte_b200.h) + a thin torch-tensor convenience layer.
+
+PyTorch is used for device memory and streams only; every computation happens inside the C-ABI library.
+There is no CPU fallback: if the CUDA extension is missing or the device is not sm_100, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libsdmatte_b200.so")
+_lib = None
+
+
+class sdm_tensor_desc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("dtype", C.c_int), ("ndim", C.c_int), ("shape", C.c_int64 * 4), ("data", C.c_void_p)]
+
+
+class sdm_conv_gemm_args(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("Hin", C.c_int), ("Win", C.c_int), ("nsrc", C.c_int),
+        ("src0", C.c_void_p), ("c0", C.c_int), ("ld0", C.c_int64),
+        ("src1", C.c_void_p), ("c1", C.c_int), ("ld1", C.c_int64),
+        ("ksize", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
+        ("w", C.c_void_p), ("N", C.c_int), ("w_bstride", C.c_int64),
+        ("mode", C.c_int), ("ups2", C.c_int),
+        ("out", C.c_void_p), ("out_ld", C.c_int64), ("out_bstride", C.c_int64),
+        ("bias", C.c_void_p), ("bias_sel", C.c_void_p),
+        ("res", C.c_void_p), ("res_ld", C.c_int64), ("res_bstride", C.c_int64),
+        ("scale", C.c_float), ("force_block_n", C.c_int),
+    ]
+
+
+class sdm_attn_args(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("heads", C.c_int), ("Lq", C.c_int), ("Lk", C.c_int),
+        ("q", C.c_void_p), ("ldq", C.c_int64), ("k", C.c_void_p), ("ldk", C.c_int64),
+        ("vt", C.c_void_p), ("ldvt", C.c_int64), ("bias", C.c_void_p), ("bias_bstride", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("scale", C.c_float),
+    ]
+
+
+class sdm_groupnorm_args(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("HW", C.c_int), ("nsrc", C.c_int),
+        ("src0", C.c_void_p), ("c0", C.c_int), ("ld0", C.c_int64),
+        ("src1", C.c_void_p), ("c1", C.c_int), ("ld1", C.c_int64),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("silu", C.c_int),
+        ("out", C.c_void_p), ("scratch", C.c_void_p), ("scratch_floats", C.c_size_t),
+    ]
+
+
+class sdm_direct_conv_args(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int), ("ksize", C.c_int),
+        ("x", C.c_void_p), ("x_ld", C.c_int64), ("w", C.c_void_p), ("bias", C.c_void_p),
+        ("out", C.c_void_p), ("out_ld", C.c_int64), ("out_coff", C.c_int), ("out_scale", C.c_float), ("cout_limit", C.c_int),
+    ]
+
+
+EXPORTS = [
+    "sdm_version", "sdm_last_error", "sdm_create", "sdm_destroy", "sdm_load_weights", "sdm_load_report",
+    "sdm_workspace_bytes", "sdm_forward", "sdm_forward_host", "sdm_last_forward_stats", "sdm_debug_tensor",
+    "sdm_k_conv_gemm", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
+    "sdm_k_softmax_rows", "sdm_k_direct_conv",
+]
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen the CUDA library (building it first if a toolkit is present). Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("_sdm_build_ext", os.path.join(_HERE, "build_ext.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    lib = C.CDLL(_LIB_PATH)
+    lib.sdm_version.restype = C.c_int
+    lib.sdm_last_error.restype = C.c_char_p
+    lib.sdm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.sdm_destroy.argtypes = [C.c_void_p]
+    lib.sdm_destroy.restype = None
+    lib.sdm_load_weights.argtypes = [C.c_void_p, C.POINTER(sdm_tensor_desc), C.c_int]
+    lib.sdm_load_report.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.sdm_workspace_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.sdm_workspace_bytes.restype = C.c_size_t
+    lib.sdm_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sdm_forward_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_void_p,
+                                     C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sdm_last_forward_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    lib.sdm_debug_tensor.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+    lib.sdm_k_conv_gemm.argtypes = [C.POINTER(sdm_conv_gemm_args), C.c_void_p]
+    lib.sdm_k_attention.argtypes = [C.POINTER(sdm_attn_args), C.c_void_p]
+    lib.sdm_k_groupnorm_scratch_floats.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.sdm_k_groupnorm_scratch_floats.restype = C.c_size_t
+    lib.sdm_k_groupnorm.argtypes = [C.POINTER(sdm_groupnorm_args), C.c_void_p]
+    lib.sdm_k_layernorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_void_p]
+    lib.sdm_k_softmax_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    lib.sdm_k_direct_conv.argtypes = [C.POINTER(sdm_direct_conv_args), C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise RuntimeError("sdmatte_b200: " + load_library().sdm_last_error().decode("utf-8", "replace"))
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+class Engine:
+    """One handle per device. `forward` takes/returns CUDA tensors; `forward_host` takes/returns host tensors."""
+
+    def __init__(self, device: int | str | torch.device = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("sdmatte_b200 needs a CUDA (sm_100a / B200) device; there is no CPU fallback")
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib.sdm_create(C.byref(h), self.device.index or 0))
+        self.h = h
+        self._ws: Optional[torch.Tensor] = None
+        self.load_report = (0, 0)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sdm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights (replaces load_state_dict + .to(device), sdmatte_nodes.py:298-323)
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        keep = []
+        descs = (sdm_tensor_desc * len(sd))()
+        n = 0
+        for k, v in sd.items():
+            if not (k.startswith("unet.") or k.startswith("vae.")):
+                continue  # text_encoder.* is dead on this path
+            if v.dtype not in _DTYPES:
+                continue
+            t = v.detach().to("cpu").contiguous()
+            if t.dim() > 4:
+                continue
+            keep.append(t)
+            d = descs[n]
+            d.name = k.encode()
+            d.dtype = _DTYPES[t.dtype]
+            d.ndim = t.dim()
+            for i, s in enumerate(t.shape):
+                d.shape[i] = s
+            d.data = t.data_ptr()
+            n += 1
+        _check(self.lib.sdm_load_weights(self.h, descs, n))
+        used, unexpected = C.c_int(), C.c_int()
+        _check(self.lib.sdm_load_report(self.h, C.byref(used), C.byref(unexpected)))
+        self.load_report = (used.value, unexpected.value)
+        self._ws = None
+        return self.load_report
+
+    # ---- workspace (caller-owned arena: torch allocates, the engine never cudaMallocs per call)
+    def workspace(self, B: int, R: int, host_staging: bool = False) -> torch.Tensor:
+        need = self.lib.sdm_workspace_bytes(self.h, B, R)
+        if need == 0:
+            _check(1)
+        if host_staging:
+            need += B * R * R * (12 + 4 + 2) + 8192
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def forward(self, image: torch.Tensor, trimap: torch.Tensor, is_transparent=False, want_premean: bool = False):
+        """image [B,R,R,3] fp32 cuda, trimap [B,R,R] fp32 cuda -> alpha [B,R,R] fp16 cuda (and pre-clip mean)."""
+        B, R = image.shape[0], image.shape[1]
+        assert image.shape == (B, R, R, 3) and trimap.shape == (B, R, R), "inputs must already be R x R"
+        assert image.dtype == torch.float32 and trimap.dtype == torch.float32
+        assert image.is_cuda and trimap.is_cuda
+        image = image.contiguous()
+        trimap = trimap.contiguous()
+        ws = self.workspace(B, R)
+        alpha = torch.empty((B, R, R), dtype=torch.float16, device=self.device)
+        pre = torch.empty((B, R, R), dtype=torch.float16, device=self.device) if want_premean else None
+        flags = is_transparent if isinstance(is_transparent, (list, tuple)) else [is_transparent] * B
+        it = (C.c_int32 * B)(*[1 if f else 0 for f in flags])
+        with torch.cuda.device(self.device):
+            _check(self.lib.sdm_forward(self.h, image.data_ptr(), trimap.data_ptr(), B, R, it, alpha.data_ptr(),
+                                        pre.data_ptr() if pre is not None else None, ws.data_ptr(), ws.numel(),
+                                        _stream_ptr(self.device)))
+        return (alpha, pre) if want_premean else alpha
+
+    def forward_host(self, image: torch.Tensor, trimap: torch.Tensor, is_transparent=False, out: Optional[torch.Tensor] = None):
+        """Host tensors in, host fp16 alpha out; H2D + D2H happen inside the library call (and it synchronises)."""
+        B, R = image.shape[0], image.shape[1]
+        assert image.shape == (B, R, R, 3) and trimap.shape == (B, R, R)
+        assert not image.is_cuda and not trimap.is_cuda
+        image = image.contiguous().float()
+        trimap = trimap.contiguous().float()
+        ws = self.workspace(B, R, host_staging=True)
+        if out is None:
+            out = torch.empty((B, R, R), dtype=torch.float16)
+        flags = is_transparent if isinstance(is_transparent, (list, tuple)) else [is_transparent] * B
+        it = (C.c_int32 * B)(*[1 if f else 0 for f in flags])
+        with torch.cuda.device(self.device):
+            _check(self.lib.sdm_forward_host(self.h, image.data_ptr(), trimap.data_ptr(), B, R, it, out.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+        return out
+
+    def stats(self):
+        n, f = C.c_int(), C.c_double()
+        _check(self.lib.sdm_last_forward_stats(self.h, C.byref(n), C.byref(f)))
+        return {"launches": n.value, "tensor_flops": f.value}
+
+    def debug_tensor(self, name: str) -> torch.Tensor:
+        shape = (C.c_int64 * 4)()
+        dt = C.c_int()
+        buf = torch.empty(64 << 20, dtype=torch.float16, device=self.device)
+        _check(self.lib.sdm_debug_tensor(self.h, name.encode(), buf.data_ptr(), buf.numel() * 2, shape, C.byref(dt)))
+        n = shape[0] * shape[1] * shape[2] * shape[3]
+        return buf[:n].view(shape[0], shape[1], shape[2], shape[3]).clone()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# kernel-level entry points (used by tests/bench only)
+# ---------------------------------------------------------------------------------------------------------------
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def k_conv_gemm(srcs, w, N, out, *, B, Hin, Win, ksize=1, stride=1, pad=0, mode=0, ups2=0, bias=None, bias_sel=None,
+                res=None, scale=1.0, w_bstride=0, out_ld=None, out_bstride=None, force_block_n=0):
+    lib = load_library()
+    a = sdm_conv_gemm_args()
+    a.B, a.Hin, a.Win, a.nsrc = B, Hin, Win, len(srcs)
+    a.src0, a.c0, a.ld0 = srcs[0][0].data_ptr(), srcs[0][1], srcs[0][2]
+    if len(srcs) > 1:
+        a.src1, a.c1, a.ld1 = srcs[1][0].data_ptr(), srcs[1][1], srcs[1][2]
+    a.ksize, a.stride, a.pad = ksize, stride, pad
+    a.w, a.N, a.w_bstride = w.data_ptr(), N, w_bstride
+    a.mode, a.ups2 = mode, ups2
+    a.out, a.out_ld, a.out_bstride = out.data_ptr(), out_ld, out_bstride
+    a.bias, a.bias_sel = _p(bias), _p(bias_sel)
+    if res is not None:
+        a.res, a.res_ld, a.res_bstride = res[0].data_ptr(), res[1], res[2]
+    a.scale, a.force_block_n = scale, force_block_n
+    _check(lib.sdm_k_conv_gemm(C.byref(a), _stream_ptr(out.device)))
+
+
+def k_attention(q, k, vt, out, *, B, heads, Lq, Lk, ldq, ldk, ldvt, ldo, bias=None, bias_bstride=0, scale=0.125):
+    lib = load_library()
+    a = sdm_attn_args()
+    a.B, a.heads, a.Lq, a.Lk = B, heads, Lq, Lk
+    a.q, a.ldq, a.k, a.ldk, a.vt, a.ldvt = q.data_ptr(), ldq, k.data_ptr(), ldk, vt.data_ptr(), ldvt
+    a.bias, a.bias_bstride = _p(bias), bias_bstride
+    a.out, a.ldo, a.scale = out.data_ptr(), ldo, scale
+    _check(lib.sdm_k_attention(C.byref(a), _stream_ptr(out.device)))
+
+
+def k_groupnorm(srcs, gamma, beta, out, *, B, HW, eps, silu):
+    lib = load_library()
+    a = sdm_groupnorm_args()
+    a.B, a.HW, a.nsrc = B, HW, len(srcs)
+    a.src0, a.c0, a.ld0 = srcs[0][0].data_ptr(), srcs[0][1], srcs[0][2]
+    ctot = srcs[0][1]
+    if len(srcs) > 1:
+        a.src1, a.c1, a.ld1 = srcs[1][0].data_ptr(), srcs[1][1], srcs[1][2]
+        ctot += srcs[1][1]
+    n = lib.sdm_k_groupnorm_scratch_floats(B, HW, ctot)
+    scratch = torch.empty(n, dtype=torch.float32, device=out.device)
+    a.gamma, a.beta, a.eps, a.silu = gamma.data_ptr(), beta.data_ptr(), eps, int(silu)
+    a.out, a.scratch, a.scratch_floats = out.data_ptr(), scratch.data_ptr(), n
+    _check(lib.sdm_k_groupnorm(C.byref(a), _stream_ptr(out.device)))
+    return scratch
+
+
+def k_layernorm(x, y, gamma, beta, rows, Cc, eps=1e-5):
+    _check(load_library().sdm_k_layernorm(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, Cc, eps,
+                                          _stream_ptr(x.device)))
+
+
+def k_softmax_rows(s, p, rows, L):
+    _check(load_library().sdm_k_softmax_rows(s.data_ptr(), p.data_ptr(), rows, L, _stream_ptr(s.device)))
+
+
+def k_direct_conv(x, w, bias, out, *, B, H, W, Cin, Cout, ksize, x_ld, out_ld, out_coff=0, out_scale=1.0, cout_limit=0):
+    a = sdm_direct_conv_args()
+    a.B, a.H, a.W, a.Cin, a.Cout, a.ksize = B, H, W, Cin, Cout, ksize
+    a.x, a.x_ld, a.w, a.bias = x.data_ptr(), x_ld, w.data_ptr(), _p(bias)
+    a.out, a.out_ld, a.out_coff, a.out_scale, a.cout_limit = out.data_ptr(), out_ld, out_coff, out_scale, cout_limit
+    _check(load_library().sdm_k_direct_conv(C.byref(a), _stream_ptr(out.device)))

@@ -1,0 +1,119 @@
+/* sdmatte_b200 — C ABI of the B200-native SDMatte matte engine (libsdmatte_b200.so).
+ *
+ * The reference (flybirdxx/ComfyUI-SDMatte) has no FFI boundary of its own: the path sits behind the
+ * ComfyUI node protocol (sdmatte_nodes.py:217-405).  This header is the boundary the replacement
+ * exports; each entry point cites the reference code it replaces.  Conventions:
+ *   - return 0 = OK, non-zero = error; sdm_last_error() gives the message (thread-local).
+ *   - every pointer is caller-owned memory; "dev" = device pointer on the handle's device.
+ *   - nothing here synchronises the stream unless stated; `stream` is a cudaStream_t cast to uintptr_t.
+ *   - no torch / C++ types cross this boundary.
+ */
+#ifndef SDMATTE_B200_H
+#define SDMATTE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sdm_handle sdm_handle;
+
+typedef struct {
+  const char* name;      /* state-dict key with the reference's names, e.g. "unet.conv_in.weight"  */
+  int dtype;             /* 0 = fp32, 1 = fp16, 2 = bf16 */
+  int ndim;
+  int64_t shape[4];
+  const void* data;      /* HOST pointer, contiguous, borrowed for the duration of the call */
+} sdm_tensor_desc;
+
+int sdm_version(void);
+const char* sdm_last_error(void);
+
+/* Replaces SDMatteCore(...) construction, sdmatte_nodes.py:286-296 (architecture is fixed: SD-2.1 CustomUNet + SD VAE). */
+int sdm_create(sdm_handle** out, int device);
+void sdm_destroy(sdm_handle* h);
+
+/* Replaces load_state_dict(strict=False) + .to(device), sdmatte_nodes.py:298-323.  Repacks to fp16 device buffers,
+ * constant-folds the time/opacity/bbox embeddings (replace.py:430-459).  Fails loudly on missing keys;
+ * unexpected keys are counted (sdm_load_report). */
+int sdm_load_weights(sdm_handle* h, const sdm_tensor_desc* tensors, int n);
+int sdm_load_report(sdm_handle* h, int* n_used, int* n_unexpected);
+
+/* Workspace the caller must provide for a (B, R) forward; R in {64k}, multiples of 64. */
+size_t sdm_workspace_bytes(sdm_handle* h, int B, int R);
+
+/* Replaces SDMatte.forward (meta_arch.py:127-261) incl. CustomUNet.forward (replace.py:379-549) and the
+ * pre-processing normalisation of sdmatte_nodes.py:343,351 for inputs already at R x R.
+ *   image_dev  : [B][R][R][3] fp32 in [0,1]   (ComfyUI IMAGE layout)
+ *   trimap_dev : [B][R][R]    fp32 in [0,1]   (ComfyUI MASK layout)
+ *   is_trans   : HOST int32[B] (sdmatte_nodes.py:345)
+ *   alpha_dev  : [B][R][R] fp16 in [0,1] (reference returns fp16 on its CUDA path)
+ *   premean_dev: optional [B][R][R] fp16, decoder channel-mean before clip (parity diagnostics), may be NULL */
+int sdm_forward(sdm_handle* h, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
+                void* alpha_dev, void* premean_dev, void* workspace_dev, size_t workspace_bytes, uintptr_t stream);
+
+/* Same, with HOST buffers (pinned or pageable): H2D of image/trimap and D2H of alpha on `stream`, then a stream sync.
+ * This is the call the node makes (replaces the .to(device) / .cpu() pair at sdmatte_nodes.py:342,349,363). */
+int sdm_forward_host(sdm_handle* h, const float* image_host, const float* trimap_host, int B, int R, const int32_t* is_trans,
+                     void* alpha_host_f16, void* workspace_dev, size_t workspace_bytes, uintptr_t stream);
+
+/* Counters for the last forward: number of kernel launches, algorithmic tensor FLOPs issued by the tcgen05 kernels. */
+int sdm_last_forward_stats(sdm_handle* h, int* n_launches, double* tensor_flops);
+
+/* Intermediate taps for block-level parity tests: copies the named activation of the LAST forward into dst (device).
+ * Names: "rgb_latent", "tri_latent", "ctx", "unet_out", "emb_bias0" ... returns element count via *n. */
+int sdm_debug_tensor(sdm_handle* h, const char* name, void* dst_dev, size_t dst_bytes, int64_t* shape4, int* dtype);
+
+/* ---- single-kernel entry points (parity tests at the kernel level; all pointers are device pointers) ---- */
+typedef struct {
+  int B, Hin, Win;
+  int nsrc;
+  const void* src0; int c0; int64_t ld0;
+  const void* src1; int c1; int64_t ld1;
+  int ksize, stride, pad;       /* pad: 0 = same, 1 = VAE down (0,1,0,1) */
+  const void* w; int N; int64_t w_bstride;
+  int mode; int ups2;           /* mode: 0 f16, 1 f16 transposed, 2 GEGLU, 3 f32 */
+  void* out; int64_t out_ld; int64_t out_bstride;
+  const float* bias; const int32_t* bias_sel;
+  const void* res; int64_t res_ld; int64_t res_bstride;
+  float scale;
+  int force_block_n;
+} sdm_conv_gemm_args;
+int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream);
+
+typedef struct {
+  int B, heads, Lq, Lk;
+  const void* q; int64_t ldq;
+  const void* k; int64_t ldk;
+  const void* vt; int64_t ldvt;
+  const float* bias; int64_t bias_bstride;
+  void* out; int64_t ldo;
+  float scale;
+} sdm_attn_args;
+int sdm_k_attention(const sdm_attn_args* a, uintptr_t stream);
+
+typedef struct {
+  int B, HW, nsrc;
+  const void* src0; int c0; int64_t ld0;
+  const void* src1; int c1; int64_t ld1;
+  const float* gamma; const float* beta; float eps; int silu;
+  void* out; float* scratch; size_t scratch_floats;
+} sdm_groupnorm_args;
+size_t sdm_k_groupnorm_scratch_floats(int B, int HW, int C);
+int sdm_k_groupnorm(const sdm_groupnorm_args* a, uintptr_t stream);
+int sdm_k_layernorm(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int C, float eps, uintptr_t stream);
+int sdm_k_softmax_rows(const float* s, void* p, int64_t rows, int L, uintptr_t stream);
+
+typedef struct {
+  int B, H, W, Cin, Cout, ksize;
+  const void* x; int64_t x_ld;
+  const void* w; const float* bias;
+  void* out; int64_t out_ld; int out_coff; float out_scale; int cout_limit;
+} sdm_direct_conv_args;
+int sdm_k_direct_conv(const sdm_direct_conv_args* a, uintptr_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

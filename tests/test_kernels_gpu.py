@@ -1,0 +1,298 @@
+"""Kernel-level parity (GPU): every sm_100a kernel against the same op in plain torch fp32 on the same inputs.
+
+All calls go through the C ABI (ctypes); torch is only the checker here.  Tolerances are written per test: the
+kernels accumulate in fp32 and round once to fp16, so the bound is a few fp16 ulps of the output magnitude.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def _pack_conv_w(w):  # OIHW -> [O][kh*kw][I] fp16
+    O, I, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(O, kh * kw * I).contiguous().half()
+
+
+def _close(got, ref, rtol, atol, what=""):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    bound = atol + rtol * ref.abs()
+    bad = (err > bound).sum().item()
+    assert bad == 0, f"{what}: {bad} / {err.numel()} elements out of tolerance, max err {err.max().item():.4e}, ref max {ref.abs().max().item():.3e}"
+
+
+# ------------------------------------------------------------------------------------------------ GEMM / linear
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (256, 128, 128, 128), (1000, 320, 320, 0), (4096, 640, 1024, 0),
+                                      (300, 1280, 640, 0), (512, 256, 512, 256), (130, 160, 192, 160)])
+def test_linear(eng_mod, M, N, K, bn):
+    x = _rand(1, M, K, seed=1).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).half()
+    b = _rand(N, seed=3).float()
+    out = torch.zeros(1, M, N, dtype=torch.float16, device=DEV)
+    eng_mod.k_conv_gemm([(x, K, K)], w, N, out, B=1, Hin=1, Win=M, bias=b, out_ld=N, out_bstride=M * N, force_block_n=bn)
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t() + b
+    _close(out, ref, 2e-3, 2e-3, f"linear {M}x{N}x{K}")
+
+
+def test_linear_residual_batched_inplace(eng_mod):
+    B, M, N, K = 3, 200, 320, 1280
+    x = _rand(B, M, K, seed=1).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).half()
+    b = _rand(N, seed=3).float()
+    h = _rand(B, M, N, seed=4).half()
+    ref = (x.float() @ w.float().t() + b).half().float() + h.float()
+    eng_mod.k_conv_gemm([(x, K, K)], w, N, h, B=B, Hin=1, Win=M, bias=b, out_ld=N, out_bstride=M * N, res=(h, N, M * N))
+    torch.cuda.synchronize()
+    _close(h, ref, 2e-3, 2e-3, "linear+res in place")
+
+
+def test_linear_transposed_store(eng_mod):
+    B, M, N, K = 2, 328, 320, 1024
+    x = _rand(B, M, K, seed=1).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).half()
+    out = torch.zeros(B, N, M, dtype=torch.float16, device=DEV)
+    eng_mod.k_conv_gemm([(x, K, K)], w, N, out, B=B, Hin=1, Win=M, mode=1, out_ld=M, out_bstride=N * M)
+    torch.cuda.synchronize()
+    ref = (x.float() @ w.float().t()).transpose(1, 2)
+    _close(out, ref, 2e-3, 2e-3, "V^T store")
+
+
+def test_geglu(eng_mod):
+    B, M, C = 2, 300, 320
+    F4 = 4 * C
+    x = _rand(B, M, C, seed=1).half()
+    w = _rand(2 * F4, C, scale=C ** -0.5, seed=2).half()
+    b = _rand(2 * F4, seed=3).float()
+    # interleave rows in 128-blocks: [value block t | gate block t]
+    idx = []
+    for t in range(F4 // 128):
+        idx += list(range(t * 128, t * 128 + 128)) + list(range(F4 + t * 128, F4 + t * 128 + 128))
+    idx = torch.tensor(idx, device=DEV)
+    wp, bp = w[idx].contiguous(), b[idx].contiguous()
+    out = torch.zeros(B, M, F4, dtype=torch.float16, device=DEV)
+    eng_mod.k_conv_gemm([(x, C, C)], wp, 2 * F4, out, B=B, Hin=1, Win=M, mode=2, bias=bp, out_ld=F4, out_bstride=M * F4)
+    torch.cuda.synchronize()
+    y = (x.float() @ w.float().t() + b).half()
+    ref = y[..., :F4].float() * F.gelu(y[..., F4:].float()).half().float()
+    _close(out, ref, 3e-3, 3e-3, "GEGLU")
+
+
+def test_batched_scores_f32(eng_mod):
+    B, L, D = 2, 320, 512
+    q = _rand(B, L, D, seed=1).half()
+    k = _rand(B, L, D, seed=2).half()
+    out = torch.zeros(B, L, L, dtype=torch.float32, device=DEV)
+    sc = 1.0 / math.sqrt(D)
+    eng_mod.k_conv_gemm([(q, D, D)], k, L, out, B=B, Hin=1, Win=L, mode=3, scale=sc, w_bstride=L * D, out_ld=L, out_bstride=L * L)
+    torch.cuda.synchronize()
+    ref = torch.einsum("bld,bmd->blm", q.float(), k.float()) * sc
+    _close(out, ref, 1e-4, 1e-3, "QK^T fp32")
+
+
+# ------------------------------------------------------------------------------------------------ conv 3x3
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 16, 16, 64, 64), (2, 32, 32, 128, 128), (1, 128, 128, 128, 256), (2, 40, 40, 320, 320),
+                                            (1, 10, 10, 1280, 1280), (1, 8, 8, 64, 160), (1, 4, 4, 128, 64), (1, 2, 2, 64, 64), (1, 1, 1, 64, 64)])
+def test_conv3x3(eng_mod, B, H, W, Cin, Cout):
+    x = _rand(B, H, W, Cin, seed=1).half()
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2).half()
+    b = _rand(Cout, seed=3).float()
+    out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    eng_mod.k_conv_gemm([(x, Cin, Cin)], _pack_conv_w(w), Cout, out, B=B, Hin=H, Win=W, ksize=3, bias=b, out_ld=Cout,
+                        out_bstride=H * W * Cout)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1)
+    _close(out, ref, 2e-3, 2e-3, f"conv3x3 {B}x{H}x{W} {Cin}->{Cout}")
+
+
+@pytest.mark.parametrize("pad", [0, 1])
+@pytest.mark.parametrize("H,W,C", [(32, 32, 128), (16, 16, 320), (8, 8, 64), (2, 2, 64)])
+def test_conv3x3_stride2(eng_mod, pad, H, W, C):
+    B = 2
+    x = _rand(B, H, W, C, seed=1).half()
+    w = _rand(C, C, 3, 3, scale=(9 * C) ** -0.5, seed=2).half()
+    b = _rand(C, seed=3).float()
+    out = torch.zeros(B, H // 2, W // 2, C, dtype=torch.float16, device=DEV)
+    eng_mod.k_conv_gemm([(x, C, C)], _pack_conv_w(w), C, out, B=B, Hin=H, Win=W, ksize=3, stride=2, pad=pad, bias=b, out_ld=C,
+                        out_bstride=(H // 2) * (W // 2) * C)
+    torch.cuda.synchronize()
+    xin = x.float().permute(0, 3, 1, 2)
+    if pad == 0:
+        ref = F.conv2d(xin, w.float(), b, stride=2, padding=1)
+    else:  # VAE Downsample2D: F.pad (0,1,0,1) then stride-2 conv without padding
+        ref = F.conv2d(F.pad(xin, (0, 1, 0, 1)), w.float(), b, stride=2, padding=0)
+    _close(out, ref.permute(0, 2, 3, 1), 2e-3, 2e-3, "conv s2")
+
+
+def test_conv1x1_concat_two_sources(eng_mod):
+    B, H, W, C0, C1, Cout = 2, 16, 16, 640, 320, 640
+    a = _rand(B, H, W, C0, seed=1).half()
+    s = _rand(B, H, W, C1, seed=2).half()
+    w = _rand(Cout, C0 + C1, 1, 1, scale=(C0 + C1) ** -0.5, seed=3).half()
+    b = _rand(Cout, seed=4).float()
+    out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    eng_mod.k_conv_gemm([(a, C0, C0), (s, C1, C1)], _pack_conv_w(w), Cout, out, B=B, Hin=H, Win=W, ksize=1, bias=b, out_ld=Cout,
+                        out_bstride=H * W * Cout)
+    torch.cuda.synchronize()
+    ref = F.conv2d(torch.cat([a, s], -1).float().permute(0, 3, 1, 2), w.float(), b).permute(0, 2, 3, 1)
+    _close(out, ref, 2e-3, 2e-3, "1x1 concat")
+
+
+def test_conv3x3_residual_upsample_store(eng_mod):
+    B, H, W, C = 1, 16, 16, 128
+    x = _rand(B, H, W, C, seed=1).half()
+    r = _rand(B, H, W, C, seed=5).half()
+    w = _rand(C, C, 3, 3, scale=(9 * C) ** -0.5, seed=2).half()
+    b = _rand(C, seed=3).float()
+    out = torch.zeros(B, 2 * H, 2 * W, C, dtype=torch.float16, device=DEV)
+    eng_mod.k_conv_gemm([(x, C, C)], _pack_conv_w(w), C, out, B=B, Hin=H, Win=W, ksize=3, bias=b, ups2=1, out_ld=C,
+                        out_bstride=4 * H * W * C, res=(r, C, H * W * C))
+    torch.cuda.synchronize()
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).half().float() + r.float().permute(0, 3, 1, 2)
+    ref = F.interpolate(y, scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    _close(out, ref, 2e-3, 2e-3, "conv+res+ups2")
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_ref(q, k, v, heads, bias, scale):
+    B, Lq, C = q.shape
+    Lk = k.shape[1]
+    qh = q.float().view(B, Lq, heads, 64).transpose(1, 2)
+    kh = k.float().view(B, Lk, heads, 64).transpose(1, 2)
+    vh = v.float().view(B, Lk, heads, 64).transpose(1, 2)
+    s = torch.matmul(qh, kh.transpose(-1, -2)) * scale
+    if bias is not None:
+        s = s + bias[:, None, None, :Lk]
+    p = s.softmax(-1)
+    return torch.matmul(p, vh).transpose(1, 2).reshape(B, Lq, C)
+
+
+@pytest.mark.parametrize("B,heads,Lq,Lk,with_bias", [(1, 1, 256, 256, False), (2, 5, 1024, 1024, True), (1, 10, 400, 1600, False),
+                                                     (1, 20, 64, 64, True), (1, 2, 100, 4096, False), (2, 5, 1600, 1600, True),
+                                                     (1, 1, 128, 128, True)])
+def test_attention(eng_mod, B, heads, Lq, Lk, with_bias):
+    C = heads * 64
+    q = _rand(B, Lq, C, seed=1).half()
+    k = _rand(B, Lk, C, seed=2).half()
+    v = _rand(B, Lk, C, seed=3).half()
+    ldvt = (Lk + 7) // 8 * 8
+    vt = torch.zeros(B, C, ldvt, dtype=torch.float16, device=DEV)
+    vt[:, :, :Lk] = v.transpose(1, 2)
+    bias = None
+    lpad = (Lk + 127) // 128 * 128
+    if with_bias:
+        g = torch.Generator().manual_seed(7)
+        lv = torch.randint(0, 3, (B, Lk), generator=g).float()  # 0: fg, 1: unknown, 2: bg
+        lv[:, 0] = 0  # at least one foreground key per sample
+        bias = torch.full((B, lpad), float("-inf"))
+        bias[:, :Lk] = lv * -5000.0
+        bias = bias.to(DEV)
+    out = torch.zeros(B, Lq, C, dtype=torch.float16, device=DEV)
+    eng_mod.k_attention(q, k, vt, out, B=B, heads=heads, Lq=Lq, Lk=Lk, ldq=C, ldk=C, ldvt=ldvt, ldo=C, bias=bias, bias_bstride=lpad)
+    torch.cuda.synchronize()
+    ref = _attn_ref(q, k, v, heads, bias, 0.125)
+    _close(out, ref, 4e-3, 2e-3, f"attention B{B} h{heads} {Lq}x{Lk} bias={with_bias}")
+
+
+def test_attention_soft_bias_no_foreground(eng_mod):
+    """All keys unknown/background (bias -5000/-10000): softmax renormalises over the least-negative keys."""
+    B, heads, L = 1, 2, 256
+    C = heads * 64
+    q, k, v = _rand(B, L, C, seed=1).half(), _rand(B, L, C, seed=2).half(), _rand(B, L, C, seed=3).half()
+    vt = v.transpose(1, 2).contiguous()
+    bias = torch.full((B, L), -10000.0)
+    bias[:, ::3] = -5000.0
+    bias = bias.to(DEV)
+    out = torch.zeros(B, L, C, dtype=torch.float16, device=DEV)
+    eng_mod.k_attention(q, k, vt, out, B=B, heads=heads, Lq=L, Lk=L, ldq=C, ldk=C, ldvt=L, ldo=C, bias=bias, bias_bstride=L)
+    torch.cuda.synchronize()
+    ref = _attn_ref(q, k, v, heads, bias, 0.125)
+    _close(out, ref, 6e-3, 3e-3, "attention soft bias")
+
+
+# ------------------------------------------------------------------------------------------------ norms / softmax
+@pytest.mark.parametrize("B,HW,C,silu,eps", [(2, 4096, 128, 1, 1e-6), (1, 1600, 320, 1, 1e-5), (2, 256, 1280, 0, 1e-6), (1, 64, 512, 1, 1e-6),
+                                             (3, 1, 320, 1, 1e-5)])
+def test_groupnorm(eng_mod, B, HW, C, silu, eps):
+    x = (_rand(B, HW, C, seed=1) * 2 + 0.5).half()
+    g = _rand(C, seed=2).float() * 0.2 + 1.0
+    b = _rand(C, seed=3).float() * 0.2
+    out = torch.zeros(B, HW, C, dtype=torch.float16, device=DEV)
+    eng_mod.k_groupnorm([(x, C, C)], g, b, out, B=B, HW=HW, eps=eps, silu=silu)
+    torch.cuda.synchronize()
+    ref = F.group_norm(x.float().transpose(1, 2), 32, g, b, eps)
+    if silu:
+        ref = F.silu(ref)
+    _close(out, ref.transpose(1, 2), 2e-3, 2e-3, "groupnorm")
+
+
+def test_groupnorm_concat_straddling_groups(eng_mod):
+    B, HW, C0, C1 = 2, 1024, 1280, 640  # 1920 channels: 60 per group, groups straddle the source boundary
+    a = _rand(B, HW, C0, seed=1).half()
+    s = (_rand(B, HW, C1, seed=2) * 3).half()
+    g = _rand(C0 + C1, seed=3).float() * 0.2 + 1.0
+    b = _rand(C0 + C1, seed=4).float() * 0.2
+    out = torch.zeros(B, HW, C0 + C1, dtype=torch.float16, device=DEV)
+    eng_mod.k_groupnorm([(a, C0, C0), (s, C1, C1)], g, b, out, B=B, HW=HW, eps=1e-5, silu=1)
+    torch.cuda.synchronize()
+    ref = F.silu(F.group_norm(torch.cat([a, s], -1).float().transpose(1, 2), 32, g, b, 1e-5)).transpose(1, 2)
+    _close(out, ref, 2e-3, 2e-3, "groupnorm concat")
+
+
+@pytest.mark.parametrize("rows,C", [(1000, 320), (512, 640), (77, 1280)])
+def test_layernorm(eng_mod, rows, C):
+    x = (_rand(rows, C, seed=1) * 1.5 + 0.3).half()
+    g = _rand(C, seed=2).float() * 0.2 + 1.0
+    b = _rand(C, seed=3).float() * 0.2
+    y = torch.zeros_like(x)
+    eng_mod.k_layernorm(x, y, g, b, rows, C)
+    torch.cuda.synchronize()
+    _close(y, F.layer_norm(x.float(), (C,), g, b, 1e-5), 2e-3, 2e-3, "layernorm")
+
+
+@pytest.mark.parametrize("rows,L", [(64, 4096), (7, 16384), (33, 1024), (5, 64)])
+def test_softmax_rows(eng_mod, rows, L):
+    s = _rand(rows, L, seed=1).float() * 4
+    p = torch.zeros(rows, L, dtype=torch.float16, device=DEV)
+    eng_mod.k_softmax_rows(s, p, rows, L)
+    torch.cuda.synchronize()
+    _close(p, s.softmax(-1), 2e-3, 1e-6, "softmax rows")
+
+
+# ------------------------------------------------------------------------------------------------ small convs
+@pytest.mark.parametrize("Cin,Cout,k", [(4, 128, 3), (8, 320, 3), (4, 1024, 3), (8, 8, 1)])
+def test_small_cin_conv(eng_mod, Cin, Cout, k):
+    B, H, W = 2, 24, 24
+    x = _rand(B, H, W, Cin, seed=1).half()
+    w = _rand(Cout, Cin, k, k, scale=(k * k * Cin) ** -0.5, seed=2).half()
+    b = _rand(Cout, seed=3).float()
+    out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    eng_mod.k_direct_conv(x, _pack_conv_w(w), b, out, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=k, x_ld=Cin, out_ld=Cout)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=k // 2).permute(0, 2, 3, 1)
+    _close(out, ref, 2e-3, 2e-3, "small-cin conv")
+
+
+@pytest.mark.parametrize("Cin,Cout", [(320, 4), (512, 8)])
+def test_small_cout_conv(eng_mod, Cin, Cout):
+    B, H, W = 2, 16, 16
+    x = _rand(B, H, W, Cin, seed=1).half()
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2).half()
+    b = _rand(Cout, seed=3).float()
+    out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    eng_mod.k_direct_conv(x, _pack_conv_w(w), b, out, B=B, H=H, W=W, Cin=Cin, Cout=Cout, ksize=3, x_ld=Cin, out_ld=Cout)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1)
+    _close(out, ref, 2e-3, 2e-3, "small-cout conv")
