@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — mattes/sec of the SDMatte single-pass matte path at 1024^2, bs=8 per GPU (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # B200 engine (this repo)
+  python bench.py --impl reference [--gpus N] --steps K --warmup W   # the reference graph on the host CPU (oracle port)
+
+One "step" = one pass of the hot path over one batch of 8 synthetic 1024x1024 RGB+trimap inputs per GPU.
+N > 1: launched by torchrun, one rank per GPU, batch-sharded (weak scaling: 8 mattes per GPU), one NCCL all-gather of
+the fp16 alpha per step (north_star); timing = CUDA events, barrier + synchronize on both sides, max over ranks.
+
+JSON keys beyond the base contract:
+  roofline     : the dominant kernel family (tcgen05 implicit-GEMM conv/linear): achieved = algorithmic FLOPs / CUDA-event time
+                 of those launches inside one profiled step; peak = MEASURED_PEAKS.json bf16 sustained TFLOP/s.
+  path_roofline: whole step: B * 28.785 TFLOP (SURVEY.md §8d, R=1024) / step time / sustained peak.
+  kernel_breakdown: per kernel family ms / share / achieved TFLOP/s or GB/s (from the same profiled step).
+  cpu_baseline : the oracle (torch fp32 restatement of the reference graph, kind "port") timed on the host cores.
+  e2e          : same metric through the host-buffer C-ABI call (pinned host inputs, H2D + forward + D2H of alpha).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TFLOP_PER_MATTE = {512: 5.952, 640: 9.664, 768: 14.558, 896: 20.848, 1024: 28.785}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops_sustained": d.get("bf16_tflops_sustained", 1438.8), "tflops_burst": d.get("bf16_tflops", 1677.1),
+                "hbm_gbs": d.get("hbm_gbs", 6566.1), "source": "measured"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}",
+                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def shard_range(total: int, rank: int, world: int):
+    """Batch shard of rank `rank`: samples [lo, hi). Samples are independent, so this is the whole partitioning."""
+    per = total // world
+    assert per * world == total, "global batch must divide by the number of GPUs"
+    return rank * per, (rank + 1) * per
+
+
+def cpu_oracle_rate(R: int, n_mattes: int, threads: int, sd=None):
+    """Time the oracle (fp32, sliced attention at large R) on the host: returns (mattes/s, seconds, description)."""
+    import torch
+    from oracle import sdmatte_oracle as orc
+    from oracle import synth
+
+    torch.set_num_threads(threads)
+    if sd is None:
+        sd = synth.make_checkpoint(seed=1234)
+    image, trimap = synth.make_inputs(1, R, seed=0)
+    t0 = time.perf_counter()
+    for _ in range(n_mattes):
+        orc.forward(sd, image, trimap, is_transparent=False, sliced=R > 512)
+    dt = time.perf_counter() - t0
+    return n_mattes / dt, dt, f"{n_mattes} matte(s) at {R}x{R}, fp32 torch CPU, {threads} threads"
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path does not run (hard-coded .cuda(), meta_arch.py:128; diffusers absent),
+    so this times the oracle port of the same graph on the host cores.  Each step = ONE matte (a bounded sample of the
+    bs=8 workload); if 1024^2 would not finish in a few minutes the sample resolution is reduced and the rate is converted
+    to 1024^2-equivalent mattes by the FLOP ratio of SURVEY.md §8(d) (stated in `sample`)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import synth
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = synth.make_checkpoint(seed=1234)
+    # probe at 256^2 to size the sample
+    _, probe_s, _ = cpu_oracle_rate(256, 1, threads, sd)
+    est_1024 = probe_s * (TFLOP_PER_MATTE[1024] / (TFLOP_PER_MATTE[512] / 4.0)) * 0.6  # large convs run nearer peak than 256^2
+    budget = 150.0
+    R = 1024
+    for cand in (1024, 768, 512):
+        R = cand
+        if (args.steps + args.warmup) * est_1024 * TFLOP_PER_MATTE[cand] / TFLOP_PER_MATTE[1024] <= budget:
+            break
+    cpu_oracle_rate(R, args.warmup, threads, sd) if args.warmup > 0 else None
+    rate, dt, desc = cpu_oracle_rate(R, args.steps, threads, sd)
+    equiv = rate * TFLOP_PER_MATTE[R] / TFLOP_PER_MATTE[1024]
+    sample = desc + ("" if R == 1024 else f"; converted to 1024^2-equivalent mattes by the FLOP ratio {TFLOP_PER_MATTE[R]}/{TFLOP_PER_MATTE[1024]}")
+    line = {
+        "impl": "reference", "metric": "mattes/sec @1024^2 bs=8", "value": equiv, "unit": "mattes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "bs=8 1024x1024 synthetic RGB+trimap, synthetic SDMatte checkpoint (seed 1234), is_transparent=False"},
+        "cpu_baseline": {"value": equiv, "unit": "mattes/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": equiv, "unit": "mattes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+    from oracle import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pkg = ge.load_package()
+
+    R, B = args.size, args.batch
+    sd = synth.make_checkpoint(seed=1234)
+    eng = pkg.engine.Engine(dev)
+    eng.load_state_dict(sd)
+    del sd
+    # global batch = world*B; this rank's shard (weak scaling: B per GPU)
+    lo, hi = shard_range(world * B, rank, world)
+    image, trimap = synth.make_inputs(B, R, seed=1000 + lo)
+    img_d, tri_d = image.to(dev), trimap.to(dev)
+    img_h, tri_h = image.pin_memory(), trimap.pin_memory()
+    alpha_h = torch.empty((B, R, R), dtype=torch.float16).pin_memory()
+    gathered = torch.empty((world * B, R, R), dtype=torch.float16, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB)
+    eng.workspace(B, R, host_staging=True)
+
+    def step_device():
+        flush.zero_()  # L2 flush between iterations (inside the loop; ~0.1 ms of a >100 ms step)
+        a = eng.forward(img_d, tri_d, False)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, a)
+        return a
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step_device()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    stats = eng.stats()
+
+    # ---- end to end through the host-buffer call (pinned host inputs -> H2D -> forward -> D2H alpha), same K steps
+    for _ in range(min(2, args.warmup)):
+        eng.forward_host(img_h, tri_h, False, out=alpha_h)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        eng.forward_host(img_h, tri_h, False, out=alpha_h)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, alpha_h.to(dev, non_blocking=True))
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = t.item()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = measured_peaks()
+    # ---- per-kernel-family breakdown from one profiled step (CUDA events around every launch)
+    prof = eng.forward_profiled(img_d, tri_d, False)
+    fam = {}
+    for kind, kms, fl, by in prof:
+        f = fam.setdefault(kind, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        f["ms"] += kms; f["flops"] += fl; f["bytes"] += by; f["launches"] += 1
+    tot_ms = sum(f["ms"] for f in fam.values())
+    breakdown = {}
+    for k, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+        e = {"ms": round(f["ms"], 3), "share": round(f["ms"] / tot_ms, 4), "launches": f["launches"]}
+        if f["flops"] > 0:
+            e["tflops"] = round(f["flops"] / (f["ms"] * 1e-3) / 1e12, 1)
+        elif f["bytes"] > 0:
+            e["gbs"] = round(f["bytes"] / (f["ms"] * 1e-3) / 1e9, 1)
+        breakdown[k] = e
+    gemm_ms = sum(f["ms"] for k, f in fam.items() if k.startswith("tc:") and "attention" not in k)
+    gemm_fl = sum(f["flops"] for k, f in fam.items() if k.startswith("tc:") and "attention" not in k)
+    gemm_launches = sum(f["launches"] for k, f in fam.items() if k.startswith("tc:") and "attention" not in k)
+    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    path_tflops = B * TFLOP_PER_MATTE.get(R, 0.0) / (ms_step * 1e-3)
+
+    # ---- CPU baseline: the oracle on the host cores, bounded sample (N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        Rc = 1024 if threads >= 64 else 512
+        rate, dt, desc = cpu_oracle_rate(Rc, 1, threads)
+        equiv = rate * TFLOP_PER_MATTE[Rc] / TFLOP_PER_MATTE[1024]
+        cpu = {"value": equiv, "unit": "mattes/s", "cores": threads, "kind": "port",
+               "sample": desc + ("" if Rc == 1024 else "; converted to 1024^2-equivalent by FLOP ratio") + f"; {dt:.1f} s"}
+
+    line = {
+        "metric": "mattes/sec @1024^2 bs=8", "value": value, "unit": "mattes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"bs={B} per GPU, {R}x{R} synthetic RGB+trimap, synthetic SDMatte checkpoint (seed 1234), is_transparent=False",
+                   "global_batch": world * B, "resolution": R, "parallelism": f"dp{world} batch shard + one NCCL all-gather of alpha" if world > 1 else "single GPU",
+                   "l2": "256 MiB buffer written between timed iterations (inside the loop)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "mattes/s", "h2d_bytes_per_step": B * R * R * 16, "d2h_bytes_per_step": B * R * R * 2,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": stats["launches"] * args.steps,
+        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel<BLOCK_N> (tcgen05 implicit-GEMM conv/linear, all launches of one step)",
+                     "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
+                     "traffic": None, "launches_per_step": gemm_launches, "share_of_step": gemm_ms / tot_ms if tot_ms else None,
+                     "peak_source": peaks["source"] + " (bf16 sustained)"},
+        "path_roofline": {"algorithmic_tflop_per_matte": TFLOP_PER_MATTE.get(R), "achieved_tflops": path_tflops,
+                          "frac_of_sustained_peak": path_tflops / peaks["tflops_sustained"]},
+        "kernel_breakdown": breakdown,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=8, help="mattes per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

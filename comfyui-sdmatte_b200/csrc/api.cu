@@ -75,6 +75,19 @@ int sdm_forward_host(sdm_handle* h, const float* image_host, const float* trimap
                            workspace_dev, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
   SDM_API_END
 }
+int sdm_forward_profiled(sdm_handle* h, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
+                         void* alpha_dev, void* workspace_dev, size_t workspace_bytes, uintptr_t stream) {
+  SDM_API_BEGIN
+  sdm::engine_forward_profiled(reinterpret_cast<sdm::Engine*>(h), image_dev, trimap_dev, B, R, is_trans, alpha_dev, workspace_dev,
+                               workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+  SDM_API_END
+}
+int sdm_profile_count(sdm_handle* h) { return sdm::engine_profile_count(reinterpret_cast<sdm::Engine*>(h)); }
+int sdm_profile_entry(sdm_handle* h, int i, char* kind, int kind_len, float* ms, double* flops, double* bytes) {
+  SDM_API_BEGIN
+  sdm::engine_profile_entry(reinterpret_cast<sdm::Engine*>(h), i, kind, kind_len, ms, flops, bytes);
+  SDM_API_END
+}
 int sdm_last_forward_stats(sdm_handle* h, int* n_launches, double* tensor_flops) {
   SDM_API_BEGIN
   sdm::engine_stats(reinterpret_cast<sdm::Engine*>(h), n_launches, tensor_flops);

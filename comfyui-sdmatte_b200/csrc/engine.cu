@@ -230,12 +230,23 @@ struct T {  // NHWC fp16 activation
 };
 
 using Op = std::function<void(cudaStream_t)>;
+struct OpRec {
+  Op fn;
+  std::string kind;
+  double flops = 0;   // algorithmic tensor FLOPs (0 for HBM-bound ops)
+  double bytes = 0;   // algorithmic HBM bytes (inputs read once + outputs written once)
+};
+struct ProfRec {
+  std::string kind;
+  float ms;
+  double flops, bytes;
+};
 
 struct Plan {
   int B = 0, R = 0;
   void* ws = nullptr;
   size_t ws_bytes = 0;
-  std::vector<Op> ops;
+  std::vector<OpRec> ops;
   int n_launches = 0;
   double tensor_flops = 0;
   // fixed buffers
@@ -256,6 +267,7 @@ struct Engine {
   std::unique_ptr<Plan> plan;
   int last_launches = 0;
   double last_flops = 0;
+  std::vector<ProfRec> prof;
 };
 
 // ================================================================================================
@@ -292,9 +304,9 @@ struct Builder {
     if (t.valid()) arena.release(t.off, t.bytes);
     t.bytes = 0;
   }
-  void push(Op op, int launches = 1) {
+  void push(Op op, int launches = 1, const std::string& kind = "misc", double fl = 0, double by = 0) {
     n_launches += launches;
-    if (!dry) plan->ops.push_back(std::move(op));
+    if (!dry) plan->ops.push_back(OpRec{std::move(op), kind, fl, by});
   }
 
   // ---------------------------------------------------------------- primitive emitters
@@ -307,11 +319,13 @@ struct Builder {
     int stride = 1;
     int pad = PAD_SAME;
     float scale = 1.0f;
+    const char* label = nullptr;
   };
   // generic tensor-core conv (ksize 1/3) over one or two channel-concatenated sources
   void conv_tc(const T& a, const T* a2, const __half* w, int N, int ksize, const T& out, const GemmOpt& o) {
     const int Hout = a.H / o.stride, Wout = a.W / o.stride;
-    flops += 2.0 * a.B * Hout * Wout * (double)N * ksize * ksize * (a.C + (a2 ? a2->C : 0));
+    const double fl = 2.0 * a.B * Hout * Wout * (double)N * ksize * ksize * (a.C + (a2 ? a2->C : 0));
+    flops += fl;
     if (dry) { n_launches++; return; }
     ConvGemmDesc d;
     d.B = a.B; d.Hin = a.H; d.Win = a.W;
@@ -333,7 +347,12 @@ struct Builder {
     if (o.res) { d.res = o.res->p; d.res_ld = o.res->C; d.res_bstride = o.res->HW() * o.res->C; }
     d.scale = o.scale;
     auto l = conv_gemm_build(d, E.num_sms);
-    push([l](cudaStream_t st) { conv_gemm_run(*l, st); });
+    const double by = 2.0 * a.B * ((double)a.HW() * (a.C + (a2 ? a2->C : 0)) + (double)Hout * Wout * N * (o.ups2 ? 4 : 1) * (o.mode == EPI_GEGLU ? 0.5 : 1.0) +
+                                   (o.res ? (double)Hout * Wout * N : 0.0)) + 2.0 * N * ksize * ksize * (a.C + (a2 ? a2->C : 0));
+    std::string kind = o.label ? o.label : (ksize == 3 ? (o.stride == 2 ? "conv3x3_s2" : "conv3x3") : (a.H == 1 ? "linear" : "conv1x1"));
+    if (o.mode == EPI_GEGLU) kind = "linear_geglu";
+    if (o.mode == EPI_F16_T) kind = "linear_vT";
+    push([l](cudaStream_t st) { conv_gemm_run(*l, st); }, 1, "tc:" + kind, fl, by);
   }
   // token GEMM: x [B][L][K] -> out [B][L][N]
   void linear(const T& x, const __half* w, int N, const T& out, const GemmOpt& o) {
@@ -360,7 +379,7 @@ struct Builder {
       if (a2) { d.src[1] = a2->p; d.C[1] = a2->C; d.ld[1] = a2->ld(); }
       d.gamma = gamma; d.beta = beta; d.eps = eps; d.silu = silu;
       d.out = out.p; d.scratch = scratch;
-      push([d](cudaStream_t st) { groupnorm_run(d, st); }, 3);
+      push([d](cudaStream_t st) { groupnorm_run(d, st); }, 3, "groupnorm", 0, 4.0 * a.B * (double)a.HW() * Ctot);
     } else n_launches += 3;
     arena.release(soff, sbytes);
     return out;
@@ -373,17 +392,18 @@ struct Builder {
       const __half* xp = x.p; __half* yp = out.p;
       const long long rows = (long long)x.B * x.HW();
       const int C = x.C;
-      push([=](cudaStream_t st) { layernorm_run(xp, yp, g, b, rows, C, 1e-5f, st); });
+      push([=](cudaStream_t st) { layernorm_run(xp, yp, g, b, rows, C, 1e-5f, st); }, 1, "layernorm", 0, 4.0 * rows * C);
     } else n_launches++;
     return out;
   }
   void direct(const DirectConvDesc& d) {
-    if (!dry) push([d](cudaStream_t st) { direct_conv_run(d, st); });
+    if (!dry) push([d](cudaStream_t st) { direct_conv_run(d, st); }, 1, "direct_conv", 0, 2.0 * d.B * (double)d.H * d.W * (d.Cin + (d.cout_limit ? d.cout_limit : d.Cout)));
     else n_launches++;
   }
   void attention(const T& q, const T& k, const T& vt, int heads, const float* bias, long long bias_bs, const T& out) {
     const int Lq = (int)q.HW(), Lk = (int)k.HW();
-    flops += 4.0 * q.B * heads * (double)Lq * Lk * 64;
+    const double fl = 4.0 * q.B * heads * (double)Lq * Lk * 64;
+    flops += fl;
     if (dry) { n_launches++; return; }
     AttnDesc d;
     d.B = q.B; d.heads = heads; d.Lq = Lq; d.Lk = Lk;
@@ -392,7 +412,7 @@ struct Builder {
     d.bias = bias; d.bias_bstride = bias_bs;
     d.out = out.p; d.ldo = out.C; d.scale = 0.125f;
     auto l = attn_build(d);
-    push([l](cudaStream_t st) { attn_run(*l, st); });
+    push([l](cudaStream_t st) { attn_run(*l, st); }, 1, bias ? "tc:attention_self" : "tc:attention_cross", fl, 2.0 * q.B * heads * 64.0 * (2.0 * Lq + 2.0 * Lk));
   }
 
   // ---------------------------------------------------------------- blocks
@@ -512,16 +532,16 @@ struct Builder {
       d1.mode = EPI_F32; d1.out = scores; d1.out_ld = L; d1.out_bstride = (long long)L * L;
       d1.scale = 1.0f / sqrtf((float)C);
       auto l1 = conv_gemm_build(d1, E.num_sms);
-      push([l1](cudaStream_t st) { conv_gemm_run(*l1, st); });
+      push([l1](cudaStream_t st) { conv_gemm_run(*l1, st); }, 1, "tc:vae_qk", 2.0 * nb * (double)L * L * C, nb * ((double)L * L * 4 + 4.0 * L * C));
       const long long rows = (long long)nb * L;
-      push([=](cudaStream_t st) { softmax_rows_run(scores, probs, rows, L, st); });
+      push([=](cudaStream_t st) { softmax_rows_run(scores, probs, rows, L, st); }, 1, "softmax_rows", 0, 6.0 * rows * L);
       ConvGemmDesc d2;  // att[b] = P[b] V[b]   (B operand = V^T [512][L])
       d2.B = nb; d2.Hin = 1; d2.Win = L; d2.nsrc = 1;
       d2.src[0] = {probs, L, L};
       d2.ksize = 1; d2.w = vt.p + (size_t)b0 * C * L; d2.N = C; d2.w_bstride = (long long)C * L;
       d2.mode = EPI_F16; d2.out = att.p + (size_t)b0 * L * C; d2.out_ld = C; d2.out_bstride = (long long)L * C;
       auto l2 = conv_gemm_build(d2, E.num_sms);
-      push([l2](cudaStream_t st) { conv_gemm_run(*l2, st); });
+      push([l2](cudaStream_t st) { conv_gemm_run(*l2, st); }, 1, "tc:vae_pv", 2.0 * nb * (double)L * L * C, nb * ((double)L * L * 2 + 4.0 * L * C));
     }
     arena.release(s_off, s_bytes);
     arena.release(p_off, p_bytes);
@@ -618,7 +638,7 @@ struct Builder {
     T x0 = alloc(B2, R, R, 4);
     if (!dry) {
       __half* xp = x0.p; const int Bc = B, Rc = R;
-      push([=](cudaStream_t st) { prep_inputs_run(slots->image, slots->trimap, xp, 4, Bc, Rc, st); });
+      push([=](cudaStream_t st) { prep_inputs_run(slots->image, slots->trimap, xp, 4, Bc, Rc, st); }, 1, "prep_inputs", 0, (double)Bc * Rc * Rc * (16 + 16));
     } else n_launches++;
     // ---- a4/a6: additive key bias per level
     int lpad[4];
@@ -632,7 +652,7 @@ struct Builder {
       const int Bc = B, Rc = R;
       float* k0 = kb[0]; float* k1 = kb[1]; float* k2 = kb[2]; float* k3 = kb[3];
       const int l0 = lpad[0], l1 = lpad[1], l2 = lpad[2], l3 = lpad[3];
-      push([=](cudaStream_t st) { const int lp[4] = {l0, l1, l2, l3}; key_bias_run(slots->trimap, Bc, Rc, k0, k1, k2, k3, lp, st); });
+      push([=](cudaStream_t st) { const int lp[4] = {l0, l1, l2, l3}; key_bias_run(slots->trimap, Bc, Rc, k0, k1, k2, k3, lp, st); }, 1, "key_bias");
     } else n_launches++;
 
     // ---- a2: VAE encoder over [rgb ; trimap x3] as one batch of 2B (meta_arch.py:139-145,209-212)
@@ -779,7 +799,7 @@ struct Builder {
       const float* bco = W.vec(dcd + ".conv_out.bias", 3);
       if (!dry) {
         const __half* np_ = n.p; const int Bc = B, Rc = R;
-        push([=](cudaStream_t st) { alpha_head_run(np_, 128, Bc, Rc, Rc, 128, wco, bco, slots->alpha, slots->premean, st); });
+        push([=](cudaStream_t st) { alpha_head_run(np_, 128, Bc, Rc, Rc, 128, wco, bco, slots->alpha, slots->premean, st); }, 1, "alpha_head", 0, (double)Bc * Rc * Rc * (256 + 2));
       } else n_launches++;
       free(n);
     }
@@ -886,9 +906,41 @@ void engine_forward(Engine* e, const float* image_dev, const float* trimap_dev, 
   p.slots.premean = (__half*)premean_dev;
   for (int i = 0; i < B; ++i) SDM_CHECK(is_trans[i] == 0 || is_trans[i] == 1, "is_trans must be 0/1");
   SDM_CUDA_OK(cudaMemcpyAsync(p.d_is_trans, is_trans, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  for (auto& op : p.ops) op(st);
+  for (auto& op : p.ops) op.fn(st);
   e->last_launches = p.n_launches;
   e->last_flops = p.tensor_flops;
+}
+
+void engine_forward_profiled(Engine* e, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
+                             void* alpha_dev, void* ws, size_t ws_bytes, cudaStream_t st) {
+  SDM_CUDA_OK(cudaSetDevice(e->device));
+  Plan& p = get_plan(e, B, R, ws, ws_bytes);
+  p.slots.image = image_dev;
+  p.slots.trimap = trimap_dev;
+  p.slots.alpha = (__half*)alpha_dev;
+  p.slots.premean = nullptr;
+  SDM_CUDA_OK(cudaMemcpyAsync(p.d_is_trans, is_trans, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  std::vector<cudaEvent_t> ev(p.ops.size() + 1);
+  for (auto& x : ev) SDM_CUDA_OK(cudaEventCreate(&x));
+  SDM_CUDA_OK(cudaEventRecord(ev[0], st));
+  for (size_t i = 0; i < p.ops.size(); ++i) {
+    p.ops[i].fn(st);
+    SDM_CUDA_OK(cudaEventRecord(ev[i + 1], st));
+  }
+  SDM_CUDA_OK(cudaStreamSynchronize(st));
+  e->prof.clear();
+  for (size_t i = 0; i < p.ops.size(); ++i) {
+    float ms = 0;
+    SDM_CUDA_OK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+    e->prof.push_back({p.ops[i].kind, ms, p.ops[i].flops, p.ops[i].bytes});
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+}
+int engine_profile_count(Engine* e) { return (int)e->prof.size(); }
+void engine_profile_entry(Engine* e, int i, char* kind, int kind_len, float* ms, double* flops, double* bytes) {
+  SDM_CHECK(i >= 0 && i < (int)e->prof.size(), "profile index");
+  snprintf(kind, kind_len, "%s", e->prof[i].kind.c_str());
+  *ms = e->prof[i].ms; *flops = e->prof[i].flops; *bytes = e->prof[i].bytes;
 }
 
 void engine_forward_host(Engine* e, const float* image_host, const float* trimap_host, int B, int R, const int32_t* is_trans,

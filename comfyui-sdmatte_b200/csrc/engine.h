@@ -17,6 +17,10 @@ void engine_forward(Engine* e, const float* image_dev, const float* trimap_dev, 
                     void* alpha_dev, void* premean_dev, void* ws, size_t ws_bytes, cudaStream_t st);
 void engine_forward_host(Engine* e, const float* image_host, const float* trimap_host, int B, int R, const int32_t* is_trans,
                          void* alpha_host_f16, void* ws, size_t ws_bytes, cudaStream_t st);
+void engine_forward_profiled(Engine* e, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
+                             void* alpha_dev, void* ws, size_t ws_bytes, cudaStream_t st);
+int engine_profile_count(Engine* e);
+void engine_profile_entry(Engine* e, int i, char* kind, int kind_len, float* ms, double* flops, double* bytes);
 void engine_stats(Engine* e, int* n_launches, double* tensor_flops);
 void engine_debug_tensor(Engine* e, const char* name, void* dst_dev, size_t dst_bytes, int64_t* shape4, int* dtype);
 }  // namespace sdm

@@ -64,7 +64,8 @@ class sdm_direct_conv_args(C.Structure):
 
 EXPORTS = [
     "sdm_version", "sdm_last_error", "sdm_create", "sdm_destroy", "sdm_load_weights", "sdm_load_report",
-    "sdm_workspace_bytes", "sdm_forward", "sdm_forward_host", "sdm_last_forward_stats", "sdm_debug_tensor",
+    "sdm_workspace_bytes", "sdm_forward", "sdm_forward_host", "sdm_forward_profiled", "sdm_profile_count", "sdm_profile_entry",
+    "sdm_last_forward_stats", "sdm_debug_tensor",
     "sdm_k_conv_gemm", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
     "sdm_k_softmax_rows", "sdm_k_direct_conv",
 ]
@@ -100,6 +101,11 @@ def load_library():
                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.sdm_forward_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_void_p,
                                      C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sdm_forward_profiled.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_void_p,
+                                         C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sdm_profile_count.argtypes = [C.c_void_p]
+    lib.sdm_profile_entry.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double)]
     lib.sdm_last_forward_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     lib.sdm_debug_tensor.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
     lib.sdm_k_conv_gemm.argtypes = [C.POINTER(sdm_conv_gemm_args), C.c_void_p]
@@ -226,6 +232,23 @@ class Engine:
         with torch.cuda.device(self.device):
             _check(self.lib.sdm_forward_host(self.h, image.data_ptr(), trimap.data_ptr(), B, R, it, out.data_ptr(),
                                              ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+        return out
+
+    def forward_profiled(self, image: torch.Tensor, trimap: torch.Tensor, is_transparent=False):
+        """One forward with CUDA events around every op; returns [(kind, ms, flops, bytes), ...] (measurement aid)."""
+        B, R = image.shape[0], image.shape[1]
+        ws = self.workspace(B, R)
+        alpha = torch.empty((B, R, R), dtype=torch.float16, device=self.device)
+        it = (C.c_int32 * B)(*[1 if is_transparent else 0] * B)
+        with torch.cuda.device(self.device):
+            _check(self.lib.sdm_forward_profiled(self.h, image.data_ptr(), trimap.data_ptr(), B, R, it, alpha.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+        out = []
+        buf = C.create_string_buffer(64)
+        ms, fl, by = C.c_float(), C.c_double(), C.c_double()
+        for i in range(self.lib.sdm_profile_count(self.h)):
+            _check(self.lib.sdm_profile_entry(self.h, i, buf, 64, C.byref(ms), C.byref(fl), C.byref(by)))
+            out.append((buf.value.decode(), ms.value, fl.value, by.value))
         return out
 
     def stats(self):

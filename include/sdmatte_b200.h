@@ -58,11 +58,20 @@ int sdm_forward(sdm_handle* h, const float* image_dev, const float* trimap_dev, 
 int sdm_forward_host(sdm_handle* h, const float* image_host, const float* trimap_host, int B, int R, const int32_t* is_trans,
                      void* alpha_host_f16, void* workspace_dev, size_t workspace_bytes, uintptr_t stream);
 
+/* Measurement aid (bench.py roofline): one forward with a CUDA-event pair around every op of the plan (synchronises).
+ * sdm_profile_entry returns, per op: kind ("tc:conv3x3", "tc:attention_self", "groupnorm", ...), device ms,
+ * algorithmic FLOPs and algorithmic HBM bytes. */
+int sdm_forward_profiled(sdm_handle* h, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
+                         void* alpha_dev, void* workspace_dev, size_t workspace_bytes, uintptr_t stream);
+int sdm_profile_count(sdm_handle* h);
+int sdm_profile_entry(sdm_handle* h, int i, char* kind, int kind_len, float* ms, double* flops, double* bytes);
+
 /* Counters for the last forward: number of kernel launches, algorithmic tensor FLOPs issued by the tcgen05 kernels. */
 int sdm_last_forward_stats(sdm_handle* h, int* n_launches, double* tensor_flops);
 
 /* Intermediate taps for block-level parity tests: copies the named activation of the LAST forward into dst (device).
- * Names: "rgb_latent", "tri_latent", "ctx", "unet_out", "emb_bias0" ... returns element count via *n. */
+ * Names: "unet_in" [B,S,S,8] (rgb latent | trimap latent), "ctx" [B,S,S,1024] (trimap tokens),
+ * "unet_out_scaled" [B,S,S,4] (UNet output / scaling_factor).  shape4 receives (B,H,W,C); dtype 1 = fp16. */
 int sdm_debug_tensor(sdm_handle* h, const char* name, void* dst_dev, size_t dst_bytes, int64_t* shape4, int* dtype);
 
 /* ---- single-kernel entry points (parity tests at the kernel level; all pointers are device pointers) ---- */

@@ -1,0 +1,316 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  CPU/torch restatement of the reference SDMatte matte path.
+
+Nothing on the product path may import this module; only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs do (as the checker / the timed CPU baseline).
+
+PARITY STATUS: *partially pinned*.  The reference (flybirdxx/ComfyUI-SDMatte @ /root/reference) ships no tests, no
+golden vectors and no checkpoints, and its arithmetic lives in the un-vendored dependency `diffusers>=0.25.0`
+(requirements.txt:1; not installed here, no network).  What IS pinned against the reference's own code, executed in
+this container from /root/reference (see oracle/ref_lifted.py and tests/golden/make_golden.py):
+  * custom_prepare_attention_mask / custom_get_attention_scores  (src/utils/replace.py:20-122)
+  * replace_unet_conv_in / add_aux_conv_in                       (src/utils/utils.py:13-41)
+  * _resize_norm_image_bchw / _resize_mask_b1hw, mask_refine + output composition (sdmatte_nodes.py:204-214,365-397)
+What is restated from the published diffusers algorithm and therefore "parity unpinned":
+  ResnetBlock2D, Transformer2DModel/BasicTransformerBlock/Attention/GEGLU, Down/Upsample2D, AutoencoderKL
+  encoder/decoder, get_timestep_embedding/TimestepEmbedding.  Structural self-check available without diffusers:
+  the enumerated parameter shapes reproduce the published counts (SD-2.1 UNet 865.91 M, SD VAE 83.65 M), see
+  tests/test_oracle_cpu.py::test_parameter_counts.
+
+The functions below follow, line by line:
+  SDMatte.forward        /root/reference/src/modeling/SDMatte/meta_arch.py:127-261
+  CustomUNet.forward     /root/reference/src/utils/replace.py:379-549 (module tree :184-362)
+with node flags frozen as sdmatte_nodes.py:286-296 sets them (aux_input="trimap", use_coor_input=True, ...).
+State-dict keys are the reference's (`unet.*`, `vae.*`), so a real SDMatte.safetensors drops in.
+
+mode="fp32"   : everything in fp32 (what the reference's CPU branch computes, sdmatte_nodes.py:359-360)
+mode="fp16sim": fp32 math with the fp16 rounding points of the reference's CUDA autocast path emulated
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+SCALING_FACTOR = 0.18215
+UNET_CH = (320, 640, 1280, 1280)
+UNET_HEADS = (5, 10, 20, 20)
+VAE_CH = (128, 256, 512, 512)
+
+
+class _Ctx:
+    def __init__(self, sd, mode, sliced):
+        self.sd = sd
+        self.mode = mode
+        self.sliced = sliced
+
+    def r(self, x):  # fp16 rounding point of the autocast path
+        return x.half().float() if self.mode == "fp16sim" else x
+
+    def w(self, name):
+        t = self.sd[name]
+        t = t.float()
+        return t.half().float() if self.mode == "fp16sim" else t
+
+
+def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    """diffusers get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0) as called at meta_arch.py:181-186."""
+    half = dim // 2
+    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half
+    emb = t[:, None].float() * torch.exp(exponent)[None, :]
+    return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
+
+
+def _linear(c, x, name, bias=True):
+    return c.r(F.linear(c.r(x), c.w(name + ".weight"), c.sd[name + ".bias"].float() if bias else None))
+
+
+def _conv(c, x, name, stride=1, padding=1):
+    return c.r(F.conv2d(c.r(x), c.w(name + ".weight"), c.sd[name + ".bias"].float(), stride=stride, padding=padding))
+
+
+def _gn(c, x, name, eps):
+    return F.group_norm(x, 32, c.sd[name + ".weight"].float(), c.sd[name + ".bias"].float(), eps)
+
+
+def _ln(c, x, name):
+    return F.layer_norm(x, (x.shape[-1],), c.sd[name + ".weight"].float(), c.sd[name + ".bias"].float(), 1e-5)
+
+
+def _time_mlp(c, x, name):  # TimestepEmbedding: linear_2(silu(linear_1(x)))
+    return _linear(c, F.silu(_linear(c, x, name + ".linear_1")), name + ".linear_2")
+
+
+def _resnet(c, x, p, emb, eps):
+    """diffusers ResnetBlock2D."""
+    h = _conv(c, F.silu(_gn(c, x, p + ".norm1", eps)), p + ".conv1")
+    if emb is not None:
+        t = _linear(c, F.silu(emb), p + ".time_emb_proj")
+        h = c.r(h + t[:, :, None, None])
+    h = _conv(c, F.silu(_gn(c, h, p + ".norm2", eps)), p + ".conv2")
+    if (p + ".conv_shortcut.weight") in c.sd:
+        x = _conv(c, x, p + ".conv_shortcut", padding=0)
+    return c.r(x + h)
+
+
+def prepare_key_bias(attention_mask: torch.Tensor, target_length: int) -> torch.Tensor:
+    """custom_prepare_attention_mask (replace.py:20-72) for out_dim=3: nearest resize of the (B,1,L0) additive bias."""
+    current = attention_mask.shape[-1]
+    if current != target_length:
+        B = attention_mask.shape[0]
+        cs, ts = int(math.sqrt(current)), int(math.sqrt(target_length))
+        assert cs * cs == current and ts * ts == target_length
+        attention_mask = F.interpolate(attention_mask.view(B, -1, cs, cs), size=(ts, ts), mode="nearest").view(B, 1, target_length)
+    return attention_mask
+
+
+def _attention(c, x, ctx, p, heads, key_bias):
+    """diffusers Attention with AttnProcessor + custom_get_attention_scores (replace.py:75-122)."""
+    B, L, C = x.shape
+    q = _linear(c, x, p + ".to_q", bias=False)
+    k = _linear(c, ctx, p + ".to_k", bias=False)
+    v = _linear(c, ctx, p + ".to_v", bias=False)
+    Lk = k.shape[1]
+    d = C // heads
+    q = q.view(B, L, heads, d).transpose(1, 2)
+    k = k.view(B, Lk, heads, d).transpose(1, 2)
+    v = v.view(B, Lk, heads, d).transpose(1, 2)
+    scale = d ** -0.5
+    bias = None
+    if key_bias is not None:
+        bias = prepare_key_bias(key_bias, Lk)[:, :, None, :]  # (B,1,1,Lk) -> every head, every query row
+    out = torch.empty(B, heads, L, d)
+    for b in range(B):
+        for h in range(heads if c.sliced else 1):
+            hs = slice(h, h + 1) if c.sliced else slice(None)
+            s = torch.matmul(q[b, hs], k[b, hs].transpose(-1, -2)) * scale  # baddbmm(beta, alpha=scale)
+            if bias is not None:
+                s = s + bias[b]
+            s = c.r(s)
+            pr = c.r(s.softmax(dim=-1))
+            out[b, hs] = c.r(torch.matmul(pr, v[b, hs]))
+    out = out.transpose(1, 2).reshape(B, L, C)
+    return _linear(c, out, p + ".to_out.0")
+
+
+def _transformer(c, x, p, heads, ctx, key_bias):
+    """Transformer2DModel(use_linear_projection=True) with one BasicTransformerBlock."""
+    B, C, H, W = x.shape
+    res = x
+    h = _gn(c, x, p + ".norm", 1e-6).permute(0, 2, 3, 1).reshape(B, H * W, C)
+    h = _linear(c, h, p + ".proj_in")
+    t = p + ".transformer_blocks.0"
+    h = c.r(_attention(c, _ln(c, h, t + ".norm1"), _ln(c, h, t + ".norm1"), t + ".attn1", heads, key_bias) + h)
+    h = c.r(_attention(c, _ln(c, h, t + ".norm2"), ctx, t + ".attn2", heads, None) + h)
+    g = _linear(c, _ln(c, h, t + ".norm3"), t + ".ff.net.0.proj")
+    a, gate = g.chunk(2, dim=-1)
+    ff = c.r(a * c.r(F.gelu(gate)))
+    h = c.r(_linear(c, ff, t + ".ff.net.2") + h)
+    h = _linear(c, h, p + ".proj_out").reshape(B, H, W, C).permute(0, 3, 1, 2)
+    return c.r(h + res)
+
+
+def unet_forward(c, sample, trans, ctx, bbox_coords_emb, attention_mask, capture=None):
+    """CustomUNet.forward (replace.py:379-549) with timestep=None."""
+    B = sample.shape[0]
+    key_bias = ((1 - attention_mask) * -10000.0).unsqueeze(1)  # replace.py:401-403
+    op_emb = _time_mlp(c, timestep_embedding(trans.float(), 320), "unet.time_embedding")  # :430-435
+    aug_emb = _time_mlp(c, bbox_coords_emb.reshape(B, -1), "unet.bbox_embedding")  # :451-455
+    emb = c.r(op_emb + aug_emb)  # :459
+    x = _conv(c, sample, "unet.conv_in")  # :462
+    skips = [x]
+    for i in range(4):
+        bp = f"unet.down_blocks.{i}"
+        for j in range(2):
+            x = _resnet(c, x, f"{bp}.resnets.{j}", emb, 1e-5)
+            if i < 3:
+                x = _transformer(c, x, f"{bp}.attentions.{j}", UNET_HEADS[i], ctx, key_bias)
+            skips.append(x)
+        if i < 3:
+            x = _conv(c, x, f"{bp}.downsamplers.0.conv", stride=2, padding=1)
+            skips.append(x)
+    x = _resnet(c, x, "unet.mid_block.resnets.0", emb, 1e-5)
+    x = _transformer(c, x, "unet.mid_block.attentions.0", 20, ctx, key_bias)
+    x = _resnet(c, x, "unet.mid_block.resnets.1", emb, 1e-5)
+    rheads = (20, 20, 10, 5)
+    for i in range(4):
+        bp = f"unet.up_blocks.{i}"
+        for j in range(3):
+            x = torch.cat([x, skips.pop()], dim=1)
+            x = _resnet(c, x, f"{bp}.resnets.{j}", emb, 1e-5)
+            if i > 0:
+                x = _transformer(c, x, f"{bp}.attentions.{j}", rheads[i], ctx, key_bias)
+        if i < 3:
+            x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+            x = _conv(c, x, f"{bp}.upsamplers.0.conv")
+    assert not skips
+    x = F.silu(_gn(c, x, "unet.conv_norm_out", 1e-5))
+    return _conv(c, x, "unet.conv_out")
+
+
+def _vae_attention(c, x, p):
+    """diffusers Attention(heads=1, residual_connection=True, norm_num_groups=32) in the VAE mid block."""
+    B, C, H, W = x.shape
+    h = _gn(c, x, p + ".group_norm", 1e-6).view(B, C, H * W).transpose(1, 2)
+    q, k, v = _linear(c, h, p + ".to_q"), _linear(c, h, p + ".to_k"), _linear(c, h, p + ".to_v")
+    out = torch.empty_like(q)
+    for b in range(B):
+        s = torch.matmul(q[b], k[b].transpose(0, 1)) * (C ** -0.5)
+        out[b] = c.r(torch.matmul(s.softmax(dim=-1), v[b]))
+    out = _linear(c, out, p + ".to_out.0").transpose(1, 2).reshape(B, C, H, W)
+    return c.r(out + x)
+
+
+def vae_encode(c, x):
+    """AutoencoderKL.encoder + quant_conv, mean half, * scaling_factor (meta_arch.py:142-145,209-212)."""
+    e = "vae.encoder"
+    h = _conv(c, x, e + ".conv_in")
+    for i in range(4):
+        for j in range(2):
+            h = _resnet(c, h, f"{e}.down_blocks.{i}.resnets.{j}", None, 1e-6)
+        if i < 3:
+            h = _conv(c, F.pad(h, (0, 1, 0, 1)), f"{e}.down_blocks.{i}.downsamplers.0.conv", stride=2, padding=0)
+    h = _resnet(c, h, e + ".mid_block.resnets.0", None, 1e-6)
+    h = _vae_attention(c, h, e + ".mid_block.attentions.0")
+    h = _resnet(c, h, e + ".mid_block.resnets.1", None, 1e-6)
+    h = _conv(c, F.silu(_gn(c, h, e + ".conv_norm_out", 1e-6)), e + ".conv_out")
+    moments = _conv(c, h, "vae.quant_conv", padding=0)
+    mean, _ = torch.chunk(moments, 2, dim=1)
+    return c.r(mean * SCALING_FACTOR)
+
+
+def vae_decode(c, z):
+    """post_quant_conv + AutoencoderKL.decoder (meta_arch.py:255-256)."""
+    d = "vae.decoder"
+    h = _conv(c, z, "vae.post_quant_conv", padding=0)
+    h = _conv(c, h, d + ".conv_in")
+    h = _resnet(c, h, d + ".mid_block.resnets.0", None, 1e-6)
+    h = _vae_attention(c, h, d + ".mid_block.attentions.0")
+    h = _resnet(c, h, d + ".mid_block.resnets.1", None, 1e-6)
+    for i in range(4):
+        for j in range(3):
+            h = _resnet(c, h, f"{d}.up_blocks.{i}.resnets.{j}", None, 1e-6)
+        if i < 3:
+            h = F.interpolate(h, scale_factor=2.0, mode="nearest")
+            h = _conv(c, h, f"{d}.up_blocks.{i}.upsamplers.0.conv")
+    return _conv(c, F.silu(_gn(c, h, d + ".conv_norm_out", 1e-6)), d + ".conv_out")
+
+
+@torch.no_grad()
+def forward(sd: Dict[str, torch.Tensor], image: torch.Tensor, trimap: torch.Tensor, is_transparent=False,
+            mode: str = "fp32", sliced: bool = False, capture: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+    """image (B,R,R,3) fp32 in [0,1] and trimap (B,R,R) fp32 in [0,1], both ALREADY at inference size R.
+
+    Returns {"alpha": (B,1,R,R) in [0,1], "label_mean": pre-clip decoder channel mean, + intermediates}.
+    Follows sdmatte_nodes.py:339-360 (pre-processing at native size) then meta_arch.py:127-261.
+    """
+    c = _Ctx(sd, mode, sliced)
+    B = image.shape[0]
+    rgb = (image.permute(0, 3, 1, 2).float() - 0.5) / 0.5  # Normalize(0.5, 0.5), sdmatte_nodes.py:204-209
+    tri = trimap.unsqueeze(1).float() * 2 - 1  # sdmatte_nodes.py:351
+    flags = is_transparent if isinstance(is_transparent, (list, tuple)) else [is_transparent] * B
+    is_trans = torch.tensor([1 if f else 0 for f in flags])
+
+    aux_latent = vae_encode(c, tri.repeat(1, 3, 1, 1))  # meta_arch.py:139-145
+    coor = torch.tensor([[0.0, 0.0, 1.0, 1.0]] * B)  # sdmatte_nodes.py:353
+    coor_emb = timestep_embedding(coor.flatten(), 320)  # meta_arch.py:181-187
+    attention_mask = (tri + 1) / 2  # meta_arch.py:200-204
+    attention_mask = F.interpolate(attention_mask, scale_factor=1 / 8, mode="nearest").flatten(start_dim=1)
+    rgb_latent = vae_encode(c, rgb)  # meta_arch.py:209-212
+    ehs = _conv(c, aux_latent, "unet.aux_conv_in")  # meta_arch.py:215-218
+    ehs = ehs.view(B, 1024, -1).permute(0, 2, 1)
+    trans = 1 - is_trans  # meta_arch.py:237-238
+    unet_input = torch.cat([rgb_latent, aux_latent], dim=1)  # meta_arch.py:244
+    label_latent = unet_forward(c, unet_input, trans, ehs, coor_emb, attention_mask)
+    label_latent = c.r(label_latent / SCALING_FACTOR)  # meta_arch.py:254
+    stacked = vae_decode(c, label_latent)
+    label_mean = c.r(stacked.mean(dim=1, keepdim=True))  # meta_arch.py:258
+    output = torch.clip(label_mean, -1.0, 1.0)
+    output = c.r(c.r(output + 1.0) / 2.0)  # meta_arch.py:259-260
+    res = {"alpha": output, "label_mean": label_mean, "unet_in": unet_input, "ctx": ehs, "unet_out_scaled": label_latent}
+    if capture is not None:
+        capture.update(res)
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# node-level pre/post-processing (sdmatte_nodes.py:339-353, 362-397) — restated; pinned against the lifted
+# reference code in tests/test_oracle_cpu.py
+# ---------------------------------------------------------------------------------------------------------------
+def preprocess(image_bhwc: torch.Tensor, trimap_bhw: torch.Tensor, size: int):
+    from torchvision import transforms
+
+    img = transforms.Resize((size, size), antialias=True)(image_bhwc.permute(0, 3, 1, 2).contiguous())
+    tri = transforms.Resize((size, size))(trimap_bhw.unsqueeze(1).contiguous())
+    return img.permute(0, 2, 3, 1).contiguous(), tri.squeeze(1).contiguous()
+
+
+def postprocess(pred_alpha_b1rr: torch.Tensor, image: torch.Tensor, trimap: torch.Tensor, output_mode: str, mask_refine: bool,
+                trimap_constraint: float):
+    from torchvision import transforms
+
+    orig_h, orig_w = image.shape[1], image.shape[2]
+    out = transforms.Resize((orig_h, orig_w))(pred_alpha_b1rr)
+    out = out.squeeze(1).clamp(0, 1).detach().cpu()
+    if mask_refine:
+        trimap_cpu = trimap.cpu()
+        fg = trimap_cpu > trimap_constraint
+        bg = trimap_cpu < (1.0 - trimap_constraint)
+        unknown = ~(fg | bg)
+        refined = out.clone()
+        refined[bg] = 0.0
+        refined[fg] = torch.clamp(refined[fg] * 1.2, 0, 1)
+        refined[(refined < 0.3) & unknown] = 0.0
+        out = refined
+    ae = out.unsqueeze(-1)
+    if output_mode == "alpha_only":
+        matted = torch.zeros_like(image.cpu())
+    elif output_mode == "matted_rgba":
+        matted = torch.cat([image.cpu(), ae.expand(-1, -1, -1, 1)], dim=-1)
+    elif output_mode == "matted_rgb":
+        fgm = (trimap.cpu().unsqueeze(-1) > 0.2) & (ae > 0.1)
+        matted = image.cpu() * fgm.float()
+    else:
+        matted = image.cpu() * ae
+    return out, matted
