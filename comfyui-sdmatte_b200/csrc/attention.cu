@@ -13,7 +13,8 @@
 //   warp  8    : TMA producer (Q once; K, V^T and the per-key bias per tile; 3-stage ring)
 //   warp  9    : tcgen05.mma issuer (S_X = Q_X K^T : M128 N128 K64 ; O_X = P_X V : M128 N64 K128) + TMEM alloc
 // The two warpgroups ping-pong: while A does exp/convert on S_A(j) the tensor core computes S_B(j), PV_B(j-1) ...
-// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
+// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384); O accumulates in TMEM over all key tiles.
+// The per-key bias is expected pre-multiplied by log2(e).
 // Softmax statistics are fp32; scores are NOT rounded to fp16 before the softmax (the reference does).
 #include "common.cuh"
 #include "kernels.h"
@@ -131,26 +132,28 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
           for (int k = 0; k < 8; ++k) {
             const uint64_t ad = umma_desc_k128(pa + (k >> 2) * (128 * 128)) + 2 * (k & 3);
             const uint64_t bd = umma_desc_k128(vb + (k >> 2) * (64 * 128)) + 2 * (k & 3);
-            umma_f16(tmem + 256 + x * 64, ad, bd, idesc_o, k != 0);
+            umma_f16(tmem + 256 + x * 64, ad, bd, idesc_o, (j | k) != 0);
           }
           umma_commit(o_full(x));
         }
         umma_commit(kv_empty(s));
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ======================================= softmax warpgroups =================================
+    // O_x accumulates in TMEM across key tiles (the P·V MMAs run with accumulate=1); the softmax reference m2 is only
+    // raised when a new score exceeds it by more than 2^8 ("lazy rescale"), in which case the warp multiplies its O
+    // rows in TMEM by alpha (tcgen05.ld / st) before the next P·V is issued.  Scores are handled in the log2 domain.
     const int x = warp >> 2;                 // 0: tile A, 1: tile B
     const int r = (warp & 3) * 32 + lane;    // row within the tile == TMEM lane
-    const uint32_t t_s = tmem + ((uint32_t)((warp & 3) * 32) << 16) + x * 128;
-    const uint32_t t_o = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256 + x * 64;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem + lane_base + x * 128;
+    const uint32_t t_o = tmem + lane_base + 256 + x * 64;
     uint8_t* p_row = base_ptr + kOffP + x * kPBytes + (r >> 3) * 1024 + (r & 7) * 128;
-    const float l2e = 1.4426950408889634f;
-    const float sc = p.scale * l2e;
-    float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
-    float acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    const uint32_t rx = (uint32_t)(r & 7) << 4;
+    const float sc = p.scale * 1.4426950408889634f;
+    constexpr float kTau = 8.0f;
+    float m2 = -INFINITY, l = 0.f;
 
     for (int j = 0; j < n; ++j) {
       const int s = j % kAttnStages;
@@ -160,110 +163,103 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       mbar_wait(s_full(x), (uint32_t)j & 1u);
       tc_fence_after();
       const float4* bias4 = reinterpret_cast<const float4*>(base_ptr + kOffBias + s * 512);
-      // ---- pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t rr[32];
-        tmem_ld32(t_s + c * 32, rr);
-        tmem_ld_wait();
-        if (HAS_BIAS) {
+      uint32_t P[64];   // the 128 probabilities of this row, packed fp16x2
+      float rowsum, mx;
+      // one pass over S: e = 2^(x - m2), row sum, row max of x
+      auto pass = [&](float mref) {
+        rowsum = 0.f;
+        mx = -INFINITY;
+        const float neg_m = -mref;
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 bb = bias4[c * 8 + g];
-            mx = fmaxf(mx, fmaf(__uint_as_float(rr[g * 4 + 0]), p.scale, bb.x));
-            mx = fmaxf(mx, fmaf(__uint_as_float(rr[g * 4 + 1]), p.scale, bb.y));
-            mx = fmaxf(mx, fmaf(__uint_as_float(rr[g * 4 + 2]), p.scale, bb.z));
-            mx = fmaxf(mx, fmaf(__uint_as_float(rr[g * 4 + 3]), p.scale, bb.w));
-          }
-        } else if (tail) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kbase + c * 32 + i < p.Lk) mx = fmaxf(mx, __uint_as_float(rr[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
-        }
-      }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = HAS_BIAS ? ex2f((m - m_new) * l2e) : ex2f((m - m_new) * sc);
-      // ---- fold in O(j-1) (also guarantees PV(j-1) is done reading P before we overwrite it)
-      if (j > 0) {
-        mbar_wait(o_full(x), (uint32_t)(j - 1) & 1u);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t oo[32];
-          tmem_ld32(t_o + c * 32, oo);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t rr[32];
+          tmem_ld32(t_s + c * 32, rr);
           tmem_ld_wait();
+          if (!HAS_BIAS && tail) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha_prev, __uint_as_float(oo[i]));
-        }
-      }
-      // ---- pass 2: probabilities -> fp16 -> swizzled smem (A operand of P·V)
-      float rowsum = 0.f;
-      const float neg_m = HAS_BIAS ? m_new : -m_new * sc;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t rr[32];
-        tmem_ld32(t_s + c * 32, rr);
-        tmem_ld_wait();
-        float pv[32];
-        if (HAS_BIAS) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 bb = bias4[c * 8 + g];
-            pv[g * 4 + 0] = ex2f((fmaf(__uint_as_float(rr[g * 4 + 0]), p.scale, bb.x) - neg_m) * l2e);
-            pv[g * 4 + 1] = ex2f((fmaf(__uint_as_float(rr[g * 4 + 1]), p.scale, bb.y) - neg_m) * l2e);
-            pv[g * 4 + 2] = ex2f((fmaf(__uint_as_float(rr[g * 4 + 2]), p.scale, bb.z) - neg_m) * l2e);
-            pv[g * 4 + 3] = ex2f((fmaf(__uint_as_float(rr[g * 4 + 3]), p.scale, bb.w) - neg_m) * l2e);
+            for (int i = 0; i < 32; ++i)
+              if (kbase + c * 32 + i >= p.Lk) rr[i] = 0xff800000u;  // -inf
           }
-        } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float e = ex2f(fmaf(__uint_as_float(rr[i]), sc, neg_m));
-            if (tail && (kbase + c * 32 + i >= p.Lk)) e = 0.f;
-            pv[i] = e;
+          for (int q = 0; q < 4; ++q) {
+            float e[8];
+            if (HAS_BIAS) {
+              const float4 b0 = bias4[c * 8 + q * 2], b1 = bias4[c * 8 + q * 2 + 1];
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              float xs[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) xs[i] = fmaf(__uint_as_float(rr[q * 8 + i]), sc, bb[i]);
+              mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(xs[0], xs[1]), fmaxf(xs[2], xs[3])), fmaxf(fmaxf(xs[4], xs[5]), fmaxf(xs[6], xs[7]))));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) e[i] = ex2f(xs[i] + neg_m);
+            } else {
+              float cm = fmaxf(fmaxf(fmaxf(__uint_as_float(rr[q * 8 + 0]), __uint_as_float(rr[q * 8 + 1])),
+                                     fmaxf(__uint_as_float(rr[q * 8 + 2]), __uint_as_float(rr[q * 8 + 3]))),
+                               fmaxf(fmaxf(__uint_as_float(rr[q * 8 + 4]), __uint_as_float(rr[q * 8 + 5])),
+                                     fmaxf(__uint_as_float(rr[q * 8 + 6]), __uint_as_float(rr[q * 8 + 7]))));
+              mx = fmaxf(mx, cm * sc);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) e[i] = ex2f(fmaf(__uint_as_float(rr[q * 8 + i]), sc, neg_m));
+            }
+            rowsum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+            P[(c * 4 + q) * 4 + 0] = pack_h2(e[0], e[1]);
+            P[(c * 4 + q) * 4 + 1] = pack_h2(e[2], e[3]);
+            P[(c * 4 + q) * 4 + 2] = pack_h2(e[4], e[5]);
+            P[(c * 4 + q) * 4 + 3] = pack_h2(e[6], e[7]);
           }
         }
+      };
+      pass(m2);
+      // P(j) overwrites the smem buffer PV(j-1) reads, and a rescale touches O: wait for that MMA first
+      if (j > 0) mbar_wait(o_full(x), (uint32_t)(j - 1) & 1u);
+      if (__any_sync(0xffffffffu, mx > m2 + kTau)) {
+        const float m_new = fmaxf(m2, mx);
+        const float alpha = ex2f(m2 - m_new);  // 0 on the first tile (m2 = -inf)
+        if (j > 0) {
+          tc_fence_after();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) rowsum += pv[i];
+          for (int c = 0; c < 2; ++c) {
+            uint32_t oo[32];
+            tmem_ld32(t_o + c * 32, oo);
+            tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = c * 4 + q;  // 16-byte chunk (8 keys) index within the 128-key row
-          const uint4 w = make_uint4(pack_h2(pv[q * 8 + 0], pv[q * 8 + 1]), pack_h2(pv[q * 8 + 2], pv[q * 8 + 3]),
-                                     pack_h2(pv[q * 8 + 4], pv[q * 8 + 5]), pack_h2(pv[q * 8 + 6], pv[q * 8 + 7]));
-          uint8_t* dst = p_row + (chunk >> 3) * (128 * 128) + (((chunk & 7) ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(dst) = w;
+            for (int i = 0; i < 32; ++i) oo[i] = __float_as_uint(__uint_as_float(oo[i]) * alpha);
+            tmem_st32(t_o + c * 32, oo);
+          }
+          tmem_st_wait();
         }
+        l *= alpha;
+        m2 = m_new;
+        pass(m2);
       }
-      l = fmaf(l, alpha, rowsum);
-      m = m_new;
-      alpha_prev = alpha;
+      l += rowsum;
+#pragma unroll
+      for (int chunk = 0; chunk < 16; ++chunk)
+        *reinterpret_cast<uint4*>(p_row + (chunk >> 3) * (128 * 128) + ((uint32_t)((chunk & 7) << 4) ^ rx)) =
+            make_uint4(P[chunk * 4], P[chunk * 4 + 1], P[chunk * 4 + 2], P[chunk * 4 + 3]);
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_full(x));
     }
-    // ---- last PV tile and normalisation
+    // ---- normalise and store
     mbar_wait(o_full(x), (uint32_t)(n - 1) & 1u);
     tc_fence_after();
+    const int q = q0 + x * 128 + r;
+    const float inv = 1.0f / l;
+    __half* dst = p.out + ((long long)b * p.Lq + q) * p.ldo + h * 64;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t oo[32];
       tmem_ld32(t_o + c * 32, oo);
       tmem_ld_wait();
+      if (q < p.Lq) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(acc[c * 32 + i], alpha_prev, __uint_as_float(oo[i]));
-    }
-    const int q = q0 + x * 128 + r;
-    if (q < p.Lq) {
-      const float inv = 1.0f / l;
-      __half* dst = p.out + ((long long)b * p.Lq + q) * p.ldo + h * 64;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        *reinterpret_cast<uint4*>(dst + g * 8) =
-            make_uint4(pack_h2(acc[g * 8 + 0] * inv, acc[g * 8 + 1] * inv), pack_h2(acc[g * 8 + 2] * inv, acc[g * 8 + 3] * inv),
-                       pack_h2(acc[g * 8 + 4] * inv, acc[g * 8 + 5] * inv), pack_h2(acc[g * 8 + 6] * inv, acc[g * 8 + 7] * inv));
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) =
+              make_uint4(pack_h2(__uint_as_float(oo[g * 8 + 0]) * inv, __uint_as_float(oo[g * 8 + 1]) * inv),
+                         pack_h2(__uint_as_float(oo[g * 8 + 2]) * inv, __uint_as_float(oo[g * 8 + 3]) * inv),
+                         pack_h2(__uint_as_float(oo[g * 8 + 4]) * inv, __uint_as_float(oo[g * 8 + 5]) * inv),
+                         pack_h2(__uint_as_float(oo[g * 8 + 6]) * inv, __uint_as_float(oo[g * 8 + 7]) * inv));
       }
     }
   }

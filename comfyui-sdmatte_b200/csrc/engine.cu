@@ -319,6 +319,9 @@ struct Builder {
     int stride = 1;
     int pad = PAD_SAME;
     float scale = 1.0f;
+    float post_div = 1.0f;
+    int n_store = 0;
+    bool alpha_slots = false;  // EPI_ALPHA: outputs come from the per-call slots
     const char* label = nullptr;
   };
   // generic tensor-core conv (ksize 1/3) over one or two channel-concatenated sources
@@ -346,13 +349,21 @@ struct Builder {
     d.bias = o.bias; d.bias_sel = o.bias_sel;
     if (o.res) { d.res = o.res->p; d.res_ld = o.res->C; d.res_bstride = o.res->HW() * o.res->C; }
     d.scale = o.scale;
+    d.post_div = o.post_div;
+    d.n_store = o.n_store;
+    if (o.mode == EPI_ALPHA) { d.out_ld = 1; d.out_bstride = (long long)Hout * Wout; }
     auto l = conv_gemm_build(d, E.num_sms);
     const double by = 2.0 * a.B * ((double)a.HW() * (a.C + (a2 ? a2->C : 0)) + (double)Hout * Wout * N * (o.ups2 ? 4 : 1) * (o.mode == EPI_GEGLU ? 0.5 : 1.0) +
                                    (o.res ? (double)Hout * Wout * N : 0.0)) + 2.0 * N * ksize * ksize * (a.C + (a2 ? a2->C : 0));
     std::string kind = o.label ? o.label : (ksize == 3 ? (o.stride == 2 ? "conv3x3_s2" : "conv3x3") : (a.H == 1 ? "linear" : "conv1x1"));
     if (o.mode == EPI_GEGLU) kind = "linear_geglu";
     if (o.mode == EPI_F16_T) kind = "linear_vT";
-    push([l](cudaStream_t st) { conv_gemm_run(*l, st); }, 1, "tc:" + kind, fl, by);
+    if (o.alpha_slots) {
+      Plan::Slots* slots = &plan->slots;
+      push([l, slots](cudaStream_t st) { conv_gemm_set_outputs(*l, slots->alpha, slots->premean); conv_gemm_run(*l, st); }, 1, "tc:" + kind, fl, by);
+    } else {
+      push([l](cudaStream_t st) { conv_gemm_run(*l, st); }, 1, "tc:" + kind, fl, by);
+    }
   }
   // token GEMM: x [B][L][K] -> out [B][L][N]
   void linear(const T& x, const __half* w, int N, const T& out, const GemmOpt& o) {
@@ -680,8 +691,8 @@ struct Builder {
       T n = groupnorm(h, nullptr, e + ".conv_norm_out", 1e-6f, 1);
       free(h);
       T mom = alloc(B2, S, S, 8);
-      { DirectConvDesc d; d.B = B2; d.H = S; d.W = S; d.Cin = 512; d.Cout = 8; d.ksize = 3; d.x = n.p; d.x_ld = 512;
-        d.w = W.conv(e + ".conv_out", 8, 512, 3); d.bias = W.vec(e + ".conv_out.bias", 8); d.out = mom.p; d.out_ld = 8; direct(d); }
+      { GemmOpt o; o.bias = W.vec(e + ".conv_out.bias", 8); o.label = "conv3x3_skinny";
+        conv_tc(n, nullptr, W.conv(e + ".conv_out", 8, 512, 3), 8, 3, mom, o); }
       free(n);
       // quant_conv 1x1 (8->8), keep the mean half (channels 0..3), * scaling_factor; rgb -> ch 0..3, trimap -> ch 4..7
       for (int part = 0; part < 2; ++part) {
@@ -762,8 +773,8 @@ struct Builder {
       T n = groupnorm(h, nullptr, "unet.conv_norm_out", 1e-5f, 1);
       free(h);
       // conv_out (320->4), then label_latent / scaling_factor (meta_arch.py:254)
-      { DirectConvDesc d; d.B = B; d.H = S; d.W = S; d.Cin = 320; d.Cout = 4; d.ksize = 3; d.x = n.p; d.x_ld = 320;
-        d.w = W.conv("unet.conv_out", 4, 320, 3); d.bias = W.vec("unet.conv_out.bias", 4); d.out = unet_out.p; d.out_ld = 4; d.out_div = 0.18215f; direct(d); }
+      { GemmOpt o; o.bias = W.vec("unet.conv_out.bias", 4, 8); o.post_div = 0.18215f; o.n_store = 4; o.label = "conv3x3_skinny";
+        conv_tc(n, nullptr, W.conv("unet.conv_out", 4, 320, 3, 0, 8), 8, 3, unet_out, o); }
       free(n);
       SDM_CHECK(skips.empty(), "skip bookkeeping");
     }
@@ -795,12 +806,9 @@ struct Builder {
       T n = groupnorm(h, nullptr, dcd + ".conv_norm_out", 1e-6f, 1);
       free(h);
       // ---- a16: conv_out (128->3) + channel mean + clip + (x+1)/2 (meta_arch.py:258-260)
-      const __half* wco = W.conv(dcd + ".conv_out", 3, 128, 3);
-      const float* bco = W.vec(dcd + ".conv_out.bias", 3);
-      if (!dry) {
-        const __half* np_ = n.p; const int Bc = B, Rc = R;
-        push([=](cudaStream_t st) { alpha_head_run(np_, 128, Bc, Rc, Rc, 128, wco, bco, slots->alpha, slots->premean, st); }, 1, "alpha_head", 0, (double)Bc * Rc * Rc * (256 + 2));
-      } else n_launches++;
+      { GemmOpt o; o.bias = W.vec(dcd + ".conv_out.bias", 3, 8); o.mode = EPI_ALPHA; o.alpha_slots = true; o.label = "conv3x3_alpha_head";
+        T dummy; dummy.B = B; dummy.H = R; dummy.W = R; dummy.C = 1;
+        conv_tc(n, nullptr, W.conv(dcd + ".conv_out", 3, 128, 3, 0, 8), 8, 3, dummy, o); }
       free(n);
     }
   }

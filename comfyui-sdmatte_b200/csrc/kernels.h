@@ -37,12 +37,16 @@ struct ConvGemmDesc {
   const __half* res = nullptr;
   long long res_ld = 0, res_bstride = 0;
   float scale = 1.0f;
+  float post_div = 1.0f;   // EPI_F16: fp16(result) / post_div (rounded again)
+  int n_store = 0;         // EPI_F16: store only the first n_store (< 8) columns; 0 = all N
+  void* out2 = nullptr;    // EPI_ALPHA: optional pre-clip channel mean
   int force_block_n = 0;  // tests only
 };
 
 struct ConvGemmLaunch;  // opaque: prebuilt tensor maps + params
 std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_sms);
 void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st);
+void conv_gemm_set_outputs(ConvGemmLaunch& l, void* out, void* out2);  // run-time output slots (EPI_ALPHA)
 double conv_gemm_flops(const ConvGemmLaunch& l);
 
 // ------------------------------------------------------------------ flash attention (d = 64)
@@ -54,7 +58,7 @@ struct AttnDesc {
   long long ldk = 0;
   const __half* vt = nullptr;  // [B][heads*64][Lk_ld]  (V transposed: keys contiguous)
   long long ldvt = 0;          // row length (>= Lk, multiple of 8)
-  const float* bias = nullptr; // [B][Lk_pad] additive per-key bias (padded with -inf to a multiple of 128) or null
+  const float* bias = nullptr; // [B][Lk_pad] additive per-key bias * log2(e) (padded with -inf to a multiple of 128) or null
   long long bias_bstride = 0;
   __half* out = nullptr;       // [B][Lq][ldo]
   long long ldo = 0;

@@ -14,10 +14,12 @@ namespace sdm {
 // ------------------------------------------------------------------------------------------------
 static int gn_ny(int nvec) { return std::max(1, 256 / nvec); }
 static int gn_nslab(int B, int HW, int Ctot) {
+  // The slab partition must NOT depend on the batch size: the fp32 partial sums of a sample are then identical
+  // whether it runs alone or inside a batch (bit-exact batch sharding across GPUs).
+  (void)B;
   const int ny = gn_ny(Ctot / 8);
-  const int by_rows = (HW + ny - 1) / ny;
-  const int target = std::max(1, (148 * 8 + B - 1) / B);
-  return std::max(1, std::min(by_rows, target));
+  const int by_rows = (HW + ny * 64 - 1) / (ny * 64);  // >= 64 pixels per thread
+  return std::max(1, std::min(by_rows, 512));
 }
 size_t groupnorm_scratch_floats(int B, int HW, int Ctot) {
   return (size_t)B * gn_nslab(B, HW, Ctot) * Ctot * 2 + (size_t)B * Ctot * 2;
@@ -66,35 +68,39 @@ __global__ void gn_stats_kernel(const __half* __restrict__ s0, const __half* __r
   }
 }
 
-// one warp per (b, group): reduce partials in fp64, emit per-channel scale/shift
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, int nslab, int Ctot, int HW, float eps,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ ab,
-                                   int total_groups) {
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (wid >= total_groups) return;
-  const int b = wid >> 5, g = wid & 31;
+// one 128-thread CTA per (b, group): reduce the slab partials in fp64 (fixed order => deterministic), emit per-channel
+// scale/shift
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ partial, int nslab, int Ctot, int HW, float eps,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ ab) {
+  __shared__ double red[2][4];
+  const int b = blockIdx.x >> 5, g = blockIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gs = Ctot >> 5;
   double s = 0.0, q = 0.0;
   const int n = nslab * gs;
-  for (int i = lane; i < n; i += 32) {
+  for (int i = threadIdx.x; i < n; i += 128) {
     const int slab = i / gs, cc = i % gs;
-    const float* src = partial + (((size_t)b * nslab + slab) * Ctot + g * gs + cc) * 2;
-    s += (double)src[0];
-    q += (double)src[1];
+    const float2 v = *reinterpret_cast<const float2*>(partial + (((size_t)b * nslab + slab) * Ctot + g * gs + cc) * 2);
+    s += (double)v.x;
+    q += (double)v.y;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
   }
+  if (lane == 0) { red[0][warp] = s; red[1][warp] = q; }
+  __syncthreads();
+  s = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+  q = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
   const double cnt = (double)HW * gs;
   const double mean = s / cnt;
   double var = q / cnt - mean * mean;
   if (var < 0.0) var = 0.0;
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
   const float fmean = (float)mean;
-  for (int cc = lane; cc < gs; cc += 32) {
+  for (int cc = threadIdx.x; cc < gs; cc += 128) {
     const int c = g * gs + cc;
     const float a = rstd * gamma[c];
     ab[((size_t)b * Ctot + c) * 2] = a;
@@ -151,8 +157,7 @@ void groupnorm_run(const GroupNormDesc& d, cudaStream_t st) {
   }
   gn_stats_kernel<<<dim3(nslab, d.B), dim3(nvec, ny), smem, st>>>(d.src[0], s1, C0, Ctot, d.ld[0], ld1, d.HW, pps, partial);
   SDM_CUDA_OK(cudaGetLastError());
-  const int groups = d.B * 32;
-  gn_finalize_kernel<<<(groups * 32 + 127) / 128, 128, 0, st>>>(partial, nslab, Ctot, d.HW, d.eps, d.gamma, d.beta, ab, groups);
+  gn_finalize_kernel<<<d.B * 32, 128, 0, st>>>(partial, nslab, Ctot, d.HW, d.eps, d.gamma, d.beta, ab);
   SDM_CUDA_OK(cudaGetLastError());
   const long long total_vec = (long long)d.B * d.HW * nvec;
   const int blocks = (int)std::min<long long>((total_vec + 255) / 256, 148ll * 16);

@@ -31,6 +31,7 @@ static void pick_patch(int H, int W, int& tw, int& th) {
 
 static int pick_block_n(int N, int mode, long long m_tiles, int num_sms) {
   if (mode == EPI_GEGLU) return 256;
+  if (N <= 16) return 16;
   int bn;
   if (N % 256 == 0) bn = 256;
   else if (N % 160 == 0) bn = 160;
@@ -156,6 +157,10 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   p.res_ld = d.res_ld;
   p.res_bstride = d.res_bstride;
   p.scale = d.scale;
+  p.post_div = d.post_div;
+  p.n_store = d.n_store > 0 ? d.n_store : d.N;
+  p.out2 = d.out2;
+  if (d.mode == EPI_ALPHA) SDM_CHECK(d.N >= 3 && d.N <= 16 && d.bias != nullptr, "EPI_ALPHA needs 3..16 columns and a bias");
   L->grid = (int)std::min<long long>(total, num_sms);
   L->flops = 2.0 * (double)d.B * Hout * Wout * (double)d.N * (double)ktot;
   return L;
@@ -167,9 +172,14 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
     case 160: launch_bn<160>(l, st); break;
     case 128: launch_bn<128>(l, st); break;
     case 64: launch_bn<64>(l, st); break;
+    case 16: launch_bn<16>(l, st); break;
     default: throw Error{"unsupported BLOCK_N"};
   }
 }
 double conv_gemm_flops(const ConvGemmLaunch& l) { return l.flops; }
+void conv_gemm_set_outputs(ConvGemmLaunch& l, void* out, void* out2) {
+  l.p.out = out;
+  l.p.out2 = out2;
+}
 
 }  // namespace sdm

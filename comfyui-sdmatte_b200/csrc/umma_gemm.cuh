@@ -26,6 +26,7 @@ enum EpiMode : int {
   EPI_F16_T = 1,  // out[b][n][pixel] fp16 (transposed; used for V^T)
   EPI_GEGLU = 2,  // out[pixel][n/2] = fp16(v) * gelu(fp16(g)), tile = [BLOCK_N/2 value | BLOCK_N/2 gate]
   EPI_F32 = 3,    // out[pixel][n] fp32 = scale * acc
+  EPI_ALPHA = 4,  // N>=3: alpha[pixel] = (clip(mean(fp16(c0..c2)), -1, 1) + 1) / 2 ; out2[pixel] = pre-clip mean (meta_arch.py:258-260)
 };
 
 struct alignas(64) ConvGemmParams {
@@ -52,6 +53,9 @@ struct alignas(64) ConvGemmParams {
   const __half* res;      // residual, same indexing as out (never with ups2)
   long long res_ld, res_bstride;
   float scale;
+  float post_div;   // EPI_F16: fp16(result) / post_div, rounded again (label_latent / scaling_factor); 1 = off
+  int n_store;      // EPI_F16: number of output columns actually stored (< 8 => scalar stores)
+  void* out2;       // EPI_ALPHA: optional pre-clip mean
 };
 
 template <int BLOCK_N>
@@ -59,8 +63,9 @@ struct ConvGemmCfg {
   static constexpr int kABytes = 128 * 128;          // 128 rows x 64 fp16
   static constexpr int kBBytes = BLOCK_N * 128;      // BLOCK_N rows x 64 fp16
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kStageBytes * 6 <= 200 * 1024) ? 6 : (kStageBytes * 5 <= 200 * 1024 ? 5 : 4);
-  static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+  static constexpr int kAccStride = BLOCK_N < 32 ? 32 : BLOCK_N;  // TMEM columns between the two accumulators
+  static constexpr int kTmemCols = (2 * kAccStride <= 64) ? 64 : (2 * kAccStride <= 128) ? 128 : (2 * kAccStride <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kThreads = 192;
 };
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
         for (int ks = 0; ks < num_ksteps; ++ks) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BLOCK_N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * Cfg::kAccStride;
 
       if (p.mode == EPI_GEGLU) {
         constexpr int HALF = BLOCK_N / 2;
@@ -234,6 +239,23 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
               }
             }
           }
+        }
+      } else if (p.mode == EPI_ALPHA) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(taddr, r);
+        tmem_ld_wait();
+        if (valid) {
+          // rounding points of the reference fp16 path: conv outputs fp16, channel mean fp16, (clip+1) fp16, /2 exact
+          const float c0 = __half2float(__float2half_rn(__uint_as_float(r[0]) + bias[0]));
+          const float c1 = __half2float(__float2half_rn(__uint_as_float(r[1]) + bias[1]));
+          const float c2 = __half2float(__float2half_rn(__uint_as_float(r[2]) + bias[2]));
+          const __half m = __float2half_rn((c0 + c1 + c2) / 3.0f);
+          const long long o = (long long)b * p.out_bstride + pix;
+          if (p.out2) reinterpret_cast<__half*>(p.out2)[o] = m;
+          const float cl = fminf(fmaxf(__half2float(m), -1.0f), 1.0f);
+          const __half p1 = __float2half_rn(cl + 1.0f);
+          reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(__half2float(p1) * 0.5f);
         }
       } else {
 #pragma unroll 1
@@ -284,12 +306,21 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
                 }
               }
             }
+            if (p.post_div != 1.0f) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __half2float(__float2half_rn(v[i])) / p.post_div;
+            }
             uint4 w[4];
 #pragma unroll
             for (int g = 0; g < 4; ++g)
               w[g] = make_uint4(pack_h2(v[g * 8], v[g * 8 + 1]), pack_h2(v[g * 8 + 2], v[g * 8 + 3]),
                                 pack_h2(v[g * 8 + 4], v[g * 8 + 5]), pack_h2(v[g * 8 + 6], v[g * 8 + 7]));
-            if (!p.ups2) {
+            if (p.n_store < 8) {
+              __half* out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + pix * p.out_ld;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < p.n_store) out[i] = __float2half_rn(v[i]);
+            } else if (!p.ups2) {
               __half* out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + pix * p.out_ld + n0 + c;
 #pragma unroll
               for (int g = 0; g < 4; ++g)

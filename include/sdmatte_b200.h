@@ -82,12 +82,15 @@ typedef struct {
   const void* src1; int c1; int64_t ld1;
   int ksize, stride, pad;       /* pad: 0 = same, 1 = VAE down (0,1,0,1) */
   const void* w; int N; int64_t w_bstride;
-  int mode; int ups2;           /* mode: 0 f16, 1 f16 transposed, 2 GEGLU, 3 f32 */
+  int mode; int ups2;           /* mode: 0 f16, 1 f16 transposed, 2 GEGLU, 3 f32, 4 alpha head */
   void* out; int64_t out_ld; int64_t out_bstride;
   const float* bias; const int32_t* bias_sel;
   const void* res; int64_t res_ld; int64_t res_bstride;
   float scale;
   int force_block_n;
+  float post_div;               /* mode 0: fp16(result) / post_div, rounded again; 1 = off */
+  int n_store;                  /* mode 0: store only the first n_store (< 8) columns; 0 = all */
+  void* out2;                   /* mode 4 (alpha head): optional pre-clip mean */
 } sdm_conv_gemm_args;
 int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream);
 
@@ -96,7 +99,7 @@ typedef struct {
   const void* q; int64_t ldq;
   const void* k; int64_t ldk;
   const void* vt; int64_t ldvt;
-  const float* bias; int64_t bias_bstride;
+  const float* bias; int64_t bias_bstride;   /* additive per-key bias * log2(e), padded with -inf to 128 keys */
   void* out; int64_t ldo;
   float scale;
 } sdm_attn_args;

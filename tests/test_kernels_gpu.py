@@ -200,7 +200,9 @@ def test_attention(eng_mod, B, heads, Lq, Lk, with_bias):
         bias[:, :Lk] = lv * -5000.0
         bias = bias.to(DEV)
     out = torch.zeros(B, Lq, C, dtype=torch.float16, device=DEV)
-    eng_mod.k_attention(q, k, vt, out, B=B, heads=heads, Lq=Lq, Lk=Lk, ldq=C, ldk=C, ldvt=ldvt, ldo=C, bias=bias, bias_bstride=lpad)
+    # the kernel takes the additive key bias pre-multiplied by log2(e)
+    bias_l2 = None if bias is None else (bias * math.log2(math.e)).contiguous()
+    eng_mod.k_attention(q, k, vt, out, B=B, heads=heads, Lq=Lq, Lk=Lk, ldq=C, ldk=C, ldvt=ldvt, ldo=C, bias=bias_l2, bias_bstride=lpad)
     torch.cuda.synchronize()
     ref = _attn_ref(q, k, v, heads, bias, 0.125)
     _close(out, ref, 4e-3, 2e-3, f"attention B{B} h{heads} {Lq}x{Lk} bias={with_bias}")
@@ -216,7 +218,7 @@ def test_attention_soft_bias_no_foreground(eng_mod):
     bias[:, ::3] = -5000.0
     bias = bias.to(DEV)
     out = torch.zeros(B, L, C, dtype=torch.float16, device=DEV)
-    eng_mod.k_attention(q, k, vt, out, B=B, heads=heads, Lq=L, Lk=L, ldq=C, ldk=C, ldvt=L, ldo=C, bias=bias, bias_bstride=L)
+    eng_mod.k_attention(q, k, vt, out, B=B, heads=heads, Lq=L, Lk=L, ldq=C, ldk=C, ldvt=L, ldo=C, bias=(bias * math.log2(math.e)).contiguous(), bias_bstride=L)
     torch.cuda.synchronize()
     ref = _attn_ref(q, k, v, heads, bias, 0.125)
     _close(out, ref, 6e-3, 3e-3, "attention soft bias")
@@ -296,3 +298,86 @@ def test_small_cout_conv(eng_mod, Cin, Cout):
     torch.cuda.synchronize()
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1)
     _close(out, ref, 2e-3, 2e-3, "small-cout conv")
+
+
+def test_attention_late_rescale(eng_mod):
+    """Keys whose scores grow along the sequence force the lazy-rescale path (O rows rescaled in TMEM) on late tiles."""
+    B, heads, Lq, Lk = 1, 2, 256, 1024
+    C = heads * 64
+    q = _rand(B, Lq, C, seed=1).half()
+    k = _rand(B, Lk, C, seed=2)
+    ramp = torch.linspace(0.2, 3.0, Lk, device=DEV)[None, :, None]
+    k = (k * ramp).half()
+    v = _rand(B, Lk, C, seed=3).half()
+    vt = v.transpose(1, 2).contiguous()
+    out = torch.zeros(B, Lq, C, dtype=torch.float16, device=DEV)
+    eng_mod.k_attention(q, k, vt, out, B=B, heads=heads, Lq=Lq, Lk=Lk, ldq=C, ldk=C, ldvt=Lk, ldo=C)
+    torch.cuda.synchronize()
+    _close(out, _attn_ref(q, k, v, heads, None, 0.125), 4e-3, 2e-3, "attention late rescale")
+
+
+def test_attention_bias_background_first(eng_mod):
+    """First key tiles are all background (-10000), foreground keys only appear later: the reference max jumps by ~14 000
+    (log2 units) and everything accumulated so far must vanish."""
+    B, heads, L = 1, 1, 512
+    C = 64
+    q, k, v = _rand(B, L, C, seed=1).half(), _rand(B, L, C, seed=2).half(), _rand(B, L, C, seed=3).half()
+    vt = v.transpose(1, 2).contiguous()
+    bias = torch.full((B, L), -10000.0)
+    bias[:, 300:340] = 0.0
+    bias = bias.to(DEV)
+    out = torch.zeros(B, L, C, dtype=torch.float16, device=DEV)
+    eng_mod.k_attention(q, k, vt, out, B=B, heads=heads, Lq=L, Lk=L, ldq=C, ldk=C, ldvt=L, ldo=C, bias=(bias * math.log2(math.e)).contiguous(), bias_bstride=L)
+    torch.cuda.synchronize()
+    _close(out, _attn_ref(q, k, v, heads, bias, 0.125), 4e-3, 2e-3, "attention bg-first")
+
+
+def test_skinny_cout_conv_tensor_path(eng_mod):
+    """3x3 conv with 4 output channels on the tcgen05 path (BLOCK_N=16), narrow store + fp16 division (UNet conv_out / 0.18215)."""
+    B, H, W, Cin = 2, 16, 16, 320
+    x = _rand(B, H, W, Cin, seed=1).half()
+    w = _rand(4, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2).half()
+    b = _rand(4, seed=3).float()
+    wp = torch.zeros(8, 9 * Cin, dtype=torch.float16, device=DEV)
+    wp[:4] = _pack_conv_w(w)
+    bp = torch.zeros(8, device=DEV)
+    bp[:4] = b
+    out = torch.zeros(B, H, W, 4, dtype=torch.float16, device=DEV)
+    eng_mod.k_conv_gemm([(x, Cin, Cin)], wp, 8, out, B=B, Hin=H, Win=W, ksize=3, bias=bp, out_ld=4, out_bstride=H * W * 4, n_store=4,
+                        post_div=0.18215)
+    torch.cuda.synchronize()
+    ref = (F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).half().float() / 0.18215).permute(0, 2, 3, 1)
+    _close(out, ref, 2e-3, 2e-3, "skinny conv")
+
+
+def test_alpha_head_epilogue(eng_mod):
+    B, H, W, Cin = 1, 32, 32, 128
+    x = _rand(B, H, W, Cin, seed=1).half()
+    w = _rand(3, Cin, 3, 3, scale=(9 * Cin) ** -0.5 * 1.5, seed=2).half()
+    b = _rand(3, seed=3).float() * 0.1
+    wp = torch.zeros(8, 9 * Cin, dtype=torch.float16, device=DEV)
+    wp[:3] = _pack_conv_w(w)
+    bp = torch.zeros(8, device=DEV)
+    bp[:3] = b
+    alpha = torch.zeros(B, H, W, dtype=torch.float16, device=DEV)
+    pre = torch.zeros(B, H, W, dtype=torch.float16, device=DEV)
+    eng_mod.k_conv_gemm([(x, Cin, Cin)], wp, 8, alpha, B=B, Hin=H, Win=W, ksize=3, bias=bp, mode=4, out_ld=1, out_bstride=H * W, out2=pre)
+    torch.cuda.synchronize()
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).half()
+    m = y.float().mean(1).half()
+    ref = ((m.float().clamp(-1, 1) + 1).half().float() / 2).half()
+    _close(pre, m, 2e-3, 2e-3, "alpha head pre-clip mean")
+    _close(alpha, ref, 2e-3, 1e-3, "alpha head")
+
+
+def test_silu_accuracy_via_groupnorm(eng_mod):
+    """The one-MUFU SiLU (bit-trick reciprocal + 2 Newton steps) stays within 1 fp16 ulp of torch's SiLU."""
+    B, HW, C = 1, 4096, 128
+    x = (_rand(B, HW, C, seed=1) * 4).half()
+    g = torch.ones(C, device=DEV) * 3.0
+    b = torch.zeros(C, device=DEV)
+    out = torch.zeros(B, HW, C, dtype=torch.float16, device=DEV)
+    eng_mod.k_groupnorm([(x, C, C)], g, b, out, B=B, HW=HW, eps=1e-6, silu=1)
+    torch.cuda.synchronize()
+    ref = F.silu(F.group_norm(x.float().transpose(1, 2), 32, g, b, 1e-6)).transpose(1, 2)
+    _close(out, ref, 1.2e-3, 2e-4, "silu")
