@@ -113,11 +113,13 @@ int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream) {
   d.bias = a->bias; d.bias_sel = a->bias_sel;
   d.res = reinterpret_cast<const __half*>(a->res); d.res_ld = a->res_ld; d.res_bstride = a->res_bstride;
   d.scale = a->scale; d.force_block_n = a->force_block_n;
-  d.post_div = a->post_div == 0.f ? 1.f : a->post_div; d.n_store = a->n_store; d.out2 = a->out2;
+  d.post_div = a->post_div == 0.f ? 1.f : a->post_div; d.n_store = a->n_store; d.out2 = a->out2; d.force_mt = a->force_mt; d.stats = a->stats;
   auto l = sdm::conv_gemm_build(d, sdm::device_sm_count());
   sdm::conv_gemm_run(*l, reinterpret_cast<cudaStream_t>(stream));
   SDM_API_END
 }
+
+int sdm_k_conv_tiles_per_image(int Hout, int Wout) { return sdm::conv_gemm_tiles_per_image(Hout, Wout); }
 
 int sdm_k_attention(const sdm_attn_args* a, uintptr_t stream) {
   SDM_API_BEGIN
@@ -142,6 +144,7 @@ int sdm_k_groupnorm(const sdm_groupnorm_args* a, uintptr_t stream) {
   d.src[1] = reinterpret_cast<const __half*>(a->src1); d.C[1] = a->c1; d.ld[1] = a->ld1;
   d.gamma = a->gamma; d.beta = a->beta; d.eps = a->eps; d.silu = a->silu;
   d.out = reinterpret_cast<__half*>(a->out); d.scratch = a->scratch;
+  d.pre_partial[0] = a->pre0; d.pre_partial[1] = a->pre1; d.pre_slots = a->pre_slots;
   SDM_CHECK(a->scratch_floats >= sdm::groupnorm_scratch_floats(a->B, a->HW, a->c0 + (a->nsrc > 1 ? a->c1 : 0)), "scratch too small");
   sdm::groupnorm_run(d, reinterpret_cast<cudaStream_t>(stream));
   SDM_API_END

@@ -224,6 +224,10 @@ struct T {  // NHWC fp16 activation
   __half* p = nullptr;
   size_t off = 0, bytes = 0;
   int B = 0, H = 0, W = 0, C = 0;
+  // GroupNorm partial statistics written by the producing conv's epilogue (optional)
+  float* stats = nullptr;
+  size_t stats_off = 0, stats_bytes = 0;
+  int stat_slots = 0;
   long long ld() const { return C; }
   long long HW() const { return (long long)H * W; }
   bool valid() const { return bytes != 0; }
@@ -302,7 +306,9 @@ struct Builder {
   }
   void free(T& t) {
     if (t.valid()) arena.release(t.off, t.bytes);
+    if (t.stats_bytes) arena.release(t.stats_off, t.stats_bytes);
     t.bytes = 0;
+    t.stats_bytes = 0;
   }
   void push(Op op, int launches = 1, const std::string& kind = "misc", double fl = 0, double by = 0) {
     n_launches += launches;
@@ -322,6 +328,7 @@ struct Builder {
     float post_div = 1.0f;
     int n_store = 0;
     bool alpha_slots = false;  // EPI_ALPHA: outputs come from the per-call slots
+    T* stats_for = nullptr;    // EPI_F16 (no ups2): attach GroupNorm partial statistics of the output to this tensor
     const char* label = nullptr;
   };
   // generic tensor-core conv (ksize 1/3) over one or two channel-concatenated sources
@@ -329,6 +336,14 @@ struct Builder {
     const int Hout = a.H / o.stride, Wout = a.W / o.stride;
     const double fl = 2.0 * a.B * Hout * Wout * (double)N * ksize * ksize * (a.C + (a2 ? a2->C : 0));
     flops += fl;
+    float* stats_ptr = nullptr;
+    if (o.stats_for && o.mode == EPI_F16 && !o.ups2) {
+      T& st_t = *o.stats_for;
+      st_t.stat_slots = conv_gemm_tiles_per_image(Hout, Wout);
+      st_t.stats_bytes = (size_t)a.B * st_t.stat_slots * N * 2 * sizeof(float);
+      stats_ptr = (float*)alloc_raw(st_t.stats_bytes, &st_t.stats_off);
+      st_t.stats = dry ? (float*)1 : stats_ptr;  // non-null marker in dry mode
+    }
     if (dry) { n_launches++; return; }
     ConvGemmDesc d;
     d.B = a.B; d.Hin = a.H; d.Win = a.W;
@@ -351,6 +366,7 @@ struct Builder {
     d.scale = o.scale;
     d.post_div = o.post_div;
     d.n_store = o.n_store;
+    d.stats = stats_ptr;
     if (o.mode == EPI_ALPHA) { d.out_ld = 1; d.out_bstride = (long long)Hout * Wout; }
     auto l = conv_gemm_build(d, E.num_sms);
     const double by = 2.0 * a.B * ((double)a.HW() * (a.C + (a2 ? a2->C : 0)) + (double)Hout * Wout * N * (o.ups2 ? 4 : 1) * (o.mode == EPI_GEGLU ? 0.5 : 1.0) +
@@ -390,6 +406,11 @@ struct Builder {
       if (a2) { d.src[1] = a2->p; d.C[1] = a2->C; d.ld[1] = a2->ld(); }
       d.gamma = gamma; d.beta = beta; d.eps = eps; d.silu = silu;
       d.out = out.p; d.scratch = scratch;
+      if (a.stats && (!a2 || (a2->stats && a2->stat_slots == a.stat_slots))) {
+        d.pre_partial[0] = a.stats;
+        d.pre_partial[1] = a2 ? a2->stats : nullptr;
+        d.pre_slots = a.stat_slots;
+      }
       push([d](cudaStream_t st) { groupnorm_run(d, st); }, 3, "groupnorm", 0, 4.0 * a.B * (double)a.HW() * Ctot);
     } else n_launches += 3;
     arena.release(soff, sbytes);
@@ -437,6 +458,7 @@ struct Builder {
       GemmOpt o;
       if (has_temb) { o.bias = W.raw_vec("temb:" + p, {}); o.bias_sel = d_is_trans; }
       else o.bias = W.vec(p + ".conv1.bias", Cout);
+      o.stats_for = &h;  // norm2 statistics come out of this conv's epilogue
       conv_tc(n1, nullptr, W.conv(p + ".conv1", Cout, Cin, 3), Cout, 3, h, o);
     }
     free(n1);
@@ -459,6 +481,7 @@ struct Builder {
       o.bias = W.vec(p + ".conv2.bias", Cout);
       o.res = resid;
       o.ups2 = ups2;
+      o.stats_for = ups2 ? nullptr : &out;
       conv_tc(n2, nullptr, W.conv(p + ".conv2", Cout, Cout, 3), Cout, 3, out, o);
     }
     free(n2);
@@ -509,7 +532,8 @@ struct Builder {
       free(g);
     }
     T out = ups2 ? alloc(Bq, x.H * 2, x.W * 2, C) : alloc(Bq, x.H, x.W, C);
-    { GemmOpt o; o.bias = W.vec(p + ".proj_out.bias", C); o.res = &x; o.ups2 = ups2; conv_tc(h, nullptr, W.linear(p + ".proj_out", C, C), C, 1, out, o); }
+    { GemmOpt o; o.bias = W.vec(p + ".proj_out.bias", C); o.res = &x; o.ups2 = ups2; o.stats_for = ups2 ? nullptr : &out;
+      conv_tc(h, nullptr, W.linear(p + ".proj_out", C, C), C, 1, out, o); }
     free(h);
     (void)L;
     return out;
@@ -558,7 +582,7 @@ struct Builder {
     arena.release(p_off, p_bytes);
     free(q); free(k); free(vt);
     T out = alloc(Bv, x.H, x.W, C);
-    { GemmOpt o; o.bias = W.vec(p + ".to_out.0.bias", C); o.res = &x; linear(att, W.linear(p + ".to_out.0", C, C), C, out, o); }
+    { GemmOpt o; o.bias = W.vec(p + ".to_out.0.bias", C); o.res = &x; o.stats_for = &out; linear(att, W.linear(p + ".to_out.0", C, C), C, out, o); }
     free(att);
     return out;
   }
@@ -568,6 +592,7 @@ struct Builder {
     GemmOpt o;
     o.bias = W.vec(name + ".bias", Cout);
     o.stride = stride; o.pad = pad;
+    o.stats_for = &out;
     conv_tc(x, nullptr, W.conv(name, Cout, x.C, 3), Cout, 3, out, o);
     return out;
   }

@@ -40,7 +40,9 @@ struct ConvGemmDesc {
   float post_div = 1.0f;   // EPI_F16: fp16(result) / post_div (rounded again)
   int n_store = 0;         // EPI_F16: store only the first n_store (< 8) columns; 0 = all N
   void* out2 = nullptr;    // EPI_ALPHA: optional pre-clip channel mean
+  float* stats = nullptr;  // EPI_F16 without ups2: GroupNorm partials [B][tiles_per_image][N][2] (see conv_gemm_tiles_per_image)
   int force_block_n = 0;  // tests only
+  int force_mt = 0;       // tests only: 1 / 2 = force the number of M sub-tiles per CTA tile
 };
 
 struct ConvGemmLaunch;  // opaque: prebuilt tensor maps + params
@@ -48,6 +50,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
 void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st);
 void conv_gemm_set_outputs(ConvGemmLaunch& l, void* out, void* out2);  // run-time output slots (EPI_ALPHA)
 double conv_gemm_flops(const ConvGemmLaunch& l);
+int conv_gemm_tiles_per_image(int Hout, int Wout);  // number of 128-pixel M tiles per batch element
 
 // ------------------------------------------------------------------ flash attention (d = 64)
 struct AttnDesc {
@@ -83,6 +86,9 @@ struct GroupNormDesc {
   int silu = 1;
   __half* out = nullptr;   // [B][HW][C0+C1]
   float* scratch = nullptr;  // >= groupnorm_scratch_floats(...) floats
+  // optional: per-(image tile, channel) partial sums written by the producing conv's epilogue (one buffer per source)
+  const float* pre_partial[2] = {nullptr, nullptr};
+  int pre_slots = 0;
 };
 size_t groupnorm_scratch_floats(int B, int HW, int Ctot);
 void groupnorm_run(const GroupNormDesc& d, cudaStream_t st);

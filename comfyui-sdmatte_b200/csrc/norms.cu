@@ -70,18 +70,21 @@ __global__ void gn_stats_kernel(const __half* __restrict__ s0, const __half* __r
 
 // one 128-thread CTA per (b, group): reduce the slab partials in fp64 (fixed order => deterministic), emit per-channel
 // scale/shift
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ partial, int nslab, int Ctot, int HW, float eps,
-                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          float* __restrict__ ab) {
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ part0, const float* __restrict__ part1, int C0,
+                                                          int nslab, int Ctot, int HW, float eps, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ ab) {
   __shared__ double red[2][4];
   const int b = blockIdx.x >> 5, g = blockIdx.x & 31;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gs = Ctot >> 5;
+  const int C1 = Ctot - C0;
   double s = 0.0, q = 0.0;
   const int n = nslab * gs;
   for (int i = threadIdx.x; i < n; i += 128) {
-    const int slab = i / gs, cc = i % gs;
-    const float2 v = *reinterpret_cast<const float2*>(partial + (((size_t)b * nslab + slab) * Ctot + g * gs + cc) * 2);
+    const int slab = i / gs, c = g * gs + i % gs;
+    const float* src = (c < C0) ? part0 + (((size_t)b * nslab + slab) * C0 + c) * 2
+                                : part1 + (((size_t)b * nslab + slab) * C1 + (c - C0)) * 2;
+    const float2 v = *reinterpret_cast<const float2*>(src);
     s += (double)v.x;
     q += (double)v.y;
   }
@@ -108,32 +111,53 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
   }
 }
 
+// apply: same (channel-vector, pixel-row) thread layout as the stats kernel, so each thread keeps the scale/shift of its
+// 8 channels in registers and streams pixels with 4 independent 16-byte loads in flight (r1c ncu: the grid-stride version
+// was latency/issue-bound at 3.4 TB/s: one load in flight per thread, 64 B of scale/shift re-fetched per vector).
 __global__ void gn_apply_kernel(const __half* __restrict__ s0, const __half* __restrict__ s1, int C0, int Ctot, long long ld0,
-                                long long ld1, int HW, const float* __restrict__ ab, int silu, __half* __restrict__ out,
-                                long long total_vec) {
-  const int nvec = Ctot >> 3;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_vec;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(idx % nvec);
-    const long long bp = idx / nvec;  // b*HW + p
-    const int b = (int)(bp / HW);
-    const int c = v * 8;
-    const __half* src = (c < C0) ? s0 + bp * ld0 + c : s1 + bp * ld1 + (c - C0);
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src));
-    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+                                long long ld1, int HW, int pix_per_slab, const float* __restrict__ ab, int silu,
+                                __half* __restrict__ out) {
+  const int v = threadIdx.x, y = threadIdx.y, ny = blockDim.y;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_slab;
+  const int p1 = min(HW, p0 + pix_per_slab);
+  const int c = v * 8;
+  const __half* base;
+  long long ld;
+  if (c < C0) { base = s0 + (long long)b * HW * ld0 + c; ld = ld0; }
+  else { base = s1 + (long long)b * HW * ld1 + (c - C0); ld = ld1; }
+  __half* obase = out + (long long)b * HW * Ctot + c;
+  float ka[8], ks[8];
+  {
     const float4* abp = reinterpret_cast<const float4*>(ab + ((size_t)b * Ctot + c) * 2);
-    uint32_t w[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float4 k = __ldg(abp + j);  // (a0, s0, a1, s1)
+      ka[2 * j] = k.x; ks[2 * j] = k.y; ka[2 * j + 1] = k.z; ks[2 * j + 1] = k.w;
+    }
+  }
+  auto emit = [&](const uint4& raw, int p) {
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
       const float2 f = __half22float2(h[j]);
-      float y0 = fmaf(f.x, k.x, k.y);
-      float y1 = fmaf(f.y, k.z, k.w);
+      float y0 = fmaf(f.x, ka[2 * j], ks[2 * j]);
+      float y1 = fmaf(f.y, ka[2 * j + 1], ks[2 * j + 1]);
       if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
       w[j] = pack_h2(y0, y1);
     }
-    *reinterpret_cast<uint4*>(out + bp * Ctot + c) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(obase + (long long)p * Ctot) = make_uint4(w[0], w[1], w[2], w[3]);
+  };
+  int p = p0 + y;
+  for (; p + 3 * ny < p1; p += 4 * ny) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = __ldg(reinterpret_cast<const uint4*>(base + (long long)(p + u * ny) * ld));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(r[u], p + u * ny);
   }
+  for (; p < p1; p += ny) emit(__ldg(reinterpret_cast<const uint4*>(base + (long long)p * ld)), p);
 }
 
 void groupnorm_run(const GroupNormDesc& d, cudaStream_t st) {
@@ -155,13 +179,19 @@ void groupnorm_run(const GroupNormDesc& d, cudaStream_t st) {
     SDM_CUDA_OK(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
-  gn_stats_kernel<<<dim3(nslab, d.B), dim3(nvec, ny), smem, st>>>(d.src[0], s1, C0, Ctot, d.ld[0], ld1, d.HW, pps, partial);
+  if (d.pre_partial[0] && (d.nsrc == 1 || d.pre_partial[1])) {
+    // statistics were produced by the epilogue of the conv(s) that wrote the input: only reduce them
+    gn_finalize_kernel<<<d.B * 32, 128, 0, st>>>(d.pre_partial[0], d.nsrc > 1 ? d.pre_partial[1] : d.pre_partial[0], C0, d.pre_slots, Ctot,
+                                                 d.HW, d.eps, d.gamma, d.beta, ab);
+  } else {
+    gn_stats_kernel<<<dim3(nslab, d.B), dim3(nvec, ny), smem, st>>>(d.src[0], s1, C0, Ctot, d.ld[0], ld1, d.HW, pps, partial);
+    SDM_CUDA_OK(cudaGetLastError());
+    gn_finalize_kernel<<<d.B * 32, 128, 0, st>>>(partial, partial, Ctot, nslab, Ctot, d.HW, d.eps, d.gamma, d.beta, ab);
+  }
   SDM_CUDA_OK(cudaGetLastError());
-  gn_finalize_kernel<<<d.B * 32, 128, 0, st>>>(partial, nslab, Ctot, d.HW, d.eps, d.gamma, d.beta, ab);
-  SDM_CUDA_OK(cudaGetLastError());
-  const long long total_vec = (long long)d.B * d.HW * nvec;
-  const int blocks = (int)std::min<long long>((total_vec + 255) / 256, 148ll * 16);
-  gn_apply_kernel<<<blocks, 256, 0, st>>>(d.src[0], s1, C0, Ctot, d.ld[0], ld1, d.HW, ab, d.silu, d.out, total_vec);
+  const int app_pps = ny * 16;  // 16 pixels per thread
+  const int app_slabs = (d.HW + app_pps - 1) / app_pps;
+  gn_apply_kernel<<<dim3(app_slabs, d.B), dim3(nvec, ny), 0, st>>>(d.src[0], s1, C0, Ctot, d.ld[0], ld1, d.HW, app_pps, ab, d.silu, d.out);
   SDM_CUDA_OK(cudaGetLastError());
 }
 

@@ -86,7 +86,7 @@ __global__ void conv_small_cin_kernel(const __half* __restrict__ x, long long x_
 // conv_small_cin_kernel for the heavy cases (VAE conv_in 3->128 @1024^2 was 8.7 ms per launch, ncu r1a).
 // ------------------------------------------------------------------------------------------------
 template <int CIN>
-__global__ void __launch_bounds__(256) conv_small_cin_tiled_kernel(const __half* __restrict__ x, long long x_ld,
+__global__ void __launch_bounds__(128) conv_small_cin_tiled_kernel(const __half* __restrict__ x, long long x_ld,
                                                                    const __half* __restrict__ w, const float* __restrict__ bias,
                                                                    __half* __restrict__ out, long long out_ld, int out_coff, int B,
                                                                    int H, int W, int Cout, int tiles_x, int tiles_y) {
@@ -97,11 +97,11 @@ __global__ void __launch_bounds__(256) conv_small_cin_tiled_kernel(const __half*
   const int tx0 = (tile % tiles_x) * 16, ty0 = ((tile / tiles_x) % tiles_y) * 16, b = tile / (tiles_x * tiles_y);
   const int c0 = blockIdx.y * 64;
   const int tid = threadIdx.x;
-  for (int i = tid; i < K * 64; i += 256) {
+  for (int i = tid; i < K * 64; i += 128) {
     const int k = i / 64, c = i % 64;
     sW[k][c] = (c0 + c < Cout) ? __half2float(w[(long long)(c0 + c) * K + k]) : 0.f;
   }
-  for (int i = tid; i < 18 * 18; i += 256) {
+  for (int i = tid; i < 18 * 18; i += 128) {
     const int yy = ty0 + i / 18 - 1, xx = tx0 + i % 18 - 1;
     const bool in = (yy >= 0 && yy < H && xx >= 0 && xx < W);
     const __half* src = x + (((long long)b * H + (in ? yy : 0)) * W + (in ? xx : 0)) * x_ld;
@@ -114,18 +114,22 @@ __global__ void __launch_bounds__(256) conv_small_cin_tiled_kernel(const __half*
     }
   }
   __syncthreads();
+  // each thread: 2 pixels (rows py and py+8 of the tile) x 64 output channels -> every weight LDS.128 feeds 8 FMAs
   const int px = tid & 15, py = tid >> 4;
-  float acc[64];
+  float acc[2][64];
 #pragma unroll
-  for (int c = 0; c < 64; ++c) acc[c] = (bias && c0 + c < Cout) ? bias[c0 + c] : 0.f;
+  for (int c = 0; c < 64; ++c) acc[0][c] = acc[1][c] = (bias && c0 + c < Cout) ? bias[c0 + c] : 0.f;
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
-    const __half* ip = &sIn[(py + t / 3) * 18 + px + t % 3][0];
-    float xv[CIN];
+    float xv[2][CIN];
 #pragma unroll
-    for (int j = 0; j < CIN / 2; ++j) {
-      const float2 f = __half22float2(reinterpret_cast<const __half2*>(ip)[j]);
-      xv[2 * j] = f.x; xv[2 * j + 1] = f.y;
+    for (int u = 0; u < 2; ++u) {
+      const __half* ip = &sIn[(py + u * 8 + t / 3) * 18 + px + t % 3][0];
+#pragma unroll
+      for (int j = 0; j < CIN / 2; ++j) {
+        const float2 f = __half22float2(reinterpret_cast<const __half2*>(ip)[j]);
+        xv[u][2 * j] = f.x; xv[u][2 * j + 1] = f.y;
+      }
     }
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) {
@@ -133,21 +137,28 @@ __global__ void __launch_bounds__(256) conv_small_cin_tiled_kernel(const __half*
 #pragma unroll
       for (int c4 = 0; c4 < 16; ++c4) {
         const float4 w4 = wr[c4];
-        acc[c4 * 4 + 0] = fmaf(xv[ci], w4.x, acc[c4 * 4 + 0]);
-        acc[c4 * 4 + 1] = fmaf(xv[ci], w4.y, acc[c4 * 4 + 1]);
-        acc[c4 * 4 + 2] = fmaf(xv[ci], w4.z, acc[c4 * 4 + 2]);
-        acc[c4 * 4 + 3] = fmaf(xv[ci], w4.w, acc[c4 * 4 + 3]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          acc[u][c4 * 4 + 0] = fmaf(xv[u][ci], w4.x, acc[u][c4 * 4 + 0]);
+          acc[u][c4 * 4 + 1] = fmaf(xv[u][ci], w4.y, acc[u][c4 * 4 + 1]);
+          acc[u][c4 * 4 + 2] = fmaf(xv[u][ci], w4.z, acc[u][c4 * 4 + 2]);
+          acc[u][c4 * 4 + 3] = fmaf(xv[u][ci], w4.w, acc[u][c4 * 4 + 3]);
+        }
       }
     }
   }
-  const int ox = tx0 + px, oy = ty0 + py;
-  if (ox < W && oy < H) {
-    __half* op = out + (((long long)b * H + oy) * W + ox) * out_ld + out_coff + c0;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (c0 + g * 8 < Cout)
-        *reinterpret_cast<uint4*>(op + g * 8) = make_uint4(pack_h2(acc[g * 8 + 0], acc[g * 8 + 1]), pack_h2(acc[g * 8 + 2], acc[g * 8 + 3]),
-                                                          pack_h2(acc[g * 8 + 4], acc[g * 8 + 5]), pack_h2(acc[g * 8 + 6], acc[g * 8 + 7]));
+  for (int u = 0; u < 2; ++u) {
+    const int ox = tx0 + px, oy = ty0 + py + u * 8;
+    if (ox < W && oy < H) {
+      __half* op = out + (((long long)b * H + oy) * W + ox) * out_ld + out_coff + c0;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (c0 + g * 8 < Cout)
+          *reinterpret_cast<uint4*>(op + g * 8) =
+              make_uint4(pack_h2(acc[u][g * 8 + 0], acc[u][g * 8 + 1]), pack_h2(acc[u][g * 8 + 2], acc[u][g * 8 + 3]),
+                         pack_h2(acc[u][g * 8 + 4], acc[u][g * 8 + 5]), pack_h2(acc[u][g * 8 + 6], acc[u][g * 8 + 7]));
+      }
     }
   }
 }
@@ -213,9 +224,9 @@ void direct_conv_run(const DirectConvDesc& d, cudaStream_t st) {
       const int tiles_x = (d.W + 15) / 16, tiles_y = (d.H + 15) / 16;
       const dim3 grid((unsigned)(tiles_x * tiles_y * d.B), (unsigned)((d.Cout + 63) / 64));
       if (d.Cin == 4)
-        conv_small_cin_tiled_kernel<4><<<grid, 256, 0, st>>>(d.x, d.x_ld, d.w, d.bias, d.out, d.out_ld, d.out_coff, d.B, d.H, d.W, d.Cout, tiles_x, tiles_y);
+        conv_small_cin_tiled_kernel<4><<<grid, 128, 0, st>>>(d.x, d.x_ld, d.w, d.bias, d.out, d.out_ld, d.out_coff, d.B, d.H, d.W, d.Cout, tiles_x, tiles_y);
       else
-        conv_small_cin_tiled_kernel<8><<<grid, 256, 0, st>>>(d.x, d.x_ld, d.w, d.bias, d.out, d.out_ld, d.out_coff, d.B, d.H, d.W, d.Cout, tiles_x, tiles_y);
+        conv_small_cin_tiled_kernel<8><<<grid, 128, 0, st>>>(d.x, d.x_ld, d.w, d.bias, d.out, d.out_ld, d.out_coff, d.B, d.H, d.W, d.Cout, tiles_x, tiles_y);
       SDM_CUDA_OK(cudaGetLastError());
       return;
     }

@@ -1,7 +1,9 @@
 // Host side of the tcgen05 implicit-GEMM kernel: tensor-map construction, tile-shape selection, launch.
 #include "kernels.h"
-#include "umma_gemm.cuh"
+#include "umma_launch.h"
 #include "tmap.h"
+
+#include <map>
 
 #include <mutex>
 
@@ -10,6 +12,7 @@ namespace sdm {
 struct ConvGemmLaunch {
   ConvGemmParams p;
   int block_n = 0;
+  int mt = 1;
   int grid = 0;
   double flops = 0;
 };
@@ -32,6 +35,7 @@ static void pick_patch(int H, int W, int& tw, int& th) {
 static int pick_block_n(int N, int mode, long long m_tiles, int num_sms) {
   if (mode == EPI_GEGLU) return 256;
   if (N <= 16) return 16;
+  if (mode == EPI_F32) return (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
   int bn;
   if (N % 256 == 0) bn = 256;
   else if (N % 160 == 0) bn = 160;
@@ -44,15 +48,28 @@ static int pick_block_n(int N, int mode, long long m_tiles, int num_sms) {
   return bn;
 }
 
-template <int BN>
-static void launch_bn(const ConvGemmLaunch& l, cudaStream_t st) {
-  using Cfg = ConvGemmCfg<BN>;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    SDM_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  });
-  conv_gemm_kernel<BN><<<l.grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(l.p);
+// identity matrix [kIdentityN][kIdentityN] fp16, one per device: B operand of the residual K steps
+constexpr int kIdentityN = 2048;
+__global__ void identity_init_kernel(__half* m, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) m[(size_t)i * n + i] = __float2half_rn(1.0f);
+}
+static const __half* identity_matrix() {
+  static std::mutex mu;
+  static std::map<int, __half*> per_device;
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  SDM_CUDA_OK(cudaGetDevice(&dev));
+  auto it = per_device.find(dev);
+  if (it != per_device.end()) return it->second;
+  __half* m = nullptr;
+  SDM_CUDA_OK(cudaMalloc(&m, (size_t)kIdentityN * kIdentityN * 2));
+  SDM_CUDA_OK(cudaMemset(m, 0, (size_t)kIdentityN * kIdentityN * 2));
+  identity_init_kernel<<<(kIdentityN + 255) / 256, 256>>>(m, kIdentityN);
   SDM_CUDA_OK(cudaGetLastError());
+  SDM_CUDA_OK(cudaDeviceSynchronize());
+  per_device[dev] = m;
+  return m;
 }
 
 std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_sms) {
@@ -81,7 +98,10 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   if (d.mode == EPI_GEGLU) SDM_CHECK(bn == 256 && d.N % 256 == 0, "GEGLU needs N % 256 == 0");
   L->block_n = bn;
   p.n_tiles = (d.N + bn - 1) / bn;
-  const long long total = m_tiles * p.n_tiles;
+  // 256 x 128 CTA tiles (two M sub-tiles per B tile) when there is enough work to keep every SM busy
+  L->mt = (bn == 128 && d.mode == EPI_F16 && d.force_mt != 1 && (d.force_mt == 2 || (m_tiles / 2) * p.n_tiles >= 2 * num_sms)) ? 2 : 1;
+  p.m_tiles = (int)m_tiles;
+  const long long total = ((m_tiles + L->mt - 1) / L->mt) * p.n_tiles;
   SDM_CHECK(total < (1ll << 31), "too many tiles");
   p.total_tiles = (int)total;
   p.ntaps = d.ksize * d.ksize;
@@ -144,6 +164,23 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
     const uint32_t bbox[2] = {64u, (uint32_t)bn};
     make_tmap(&p.b_map, d.w, 2, dims, strides, bbox);
   }
+  // ---- residual: extra K steps  A = residual tile, B = identity columns
+  if (d.res) {
+    SDM_CHECK(d.mode == EPI_F16, "residual only with EPI_F16");
+    SDM_CHECK(d.N <= kIdentityN && d.res_ld % 8 == 0, "residual constraints");
+    const long long bs = d.res_bstride ? d.res_bstride : (long long)Hout * Wout * d.res_ld;
+    const uint64_t dims[4] = {(uint64_t)d.N, (uint64_t)Wout, (uint64_t)Hout, (uint64_t)d.B};
+    const uint64_t strides[3] = {(uint64_t)d.res_ld * 2, (uint64_t)Wout * d.res_ld * 2, (uint64_t)bs * 2};
+    make_tmap(&p.r_map, d.res, 4, dims, strides, box);
+    const uint64_t idims[2] = {(uint64_t)kIdentityN, (uint64_t)kIdentityN};
+    const uint64_t istr[1] = {(uint64_t)kIdentityN * 2};
+    const uint32_t ibox[2] = {64u, (uint32_t)bn};
+    make_tmap(&p.i_map, identity_matrix(), 2, idims, istr, ibox);
+    p.has_res = 1;
+  } else {
+    p.r_map = p.a_map[0];
+    p.i_map = p.b_map;
+  }
   // ---- epilogue
   p.mode = d.mode;
   p.ups2 = d.ups2;
@@ -153,13 +190,13 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   p.out_bstride = d.out_bstride;
   p.bias = d.bias;
   p.bias_sel = d.bias_sel;
-  p.res = d.res;
-  p.res_ld = d.res_ld;
-  p.res_bstride = d.res_bstride;
   p.scale = d.scale;
   p.post_div = d.post_div;
   p.n_store = d.n_store > 0 ? d.n_store : d.N;
+  if (p.mode == EPI_F16 && p.n_store < 8) p.mode = EPI_SKINNY;
+  if (p.mode == EPI_SKINNY) SDM_CHECK(bn == 16 && !d.res && !d.ups2, "skinny output needs N <= 16 and no residual");
   p.out2 = d.out2;
+  p.stats = (d.mode == EPI_F16 && !d.ups2) ? d.stats : nullptr;
   if (d.mode == EPI_ALPHA) SDM_CHECK(d.N >= 3 && d.N <= 16 && d.bias != nullptr, "EPI_ALPHA needs 3..16 columns and a bias");
   L->grid = (int)std::min<long long>(total, num_sms);
   L->flops = 2.0 * (double)d.B * Hout * Wout * (double)d.N * (double)ktot;
@@ -167,16 +204,57 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
 }
 
 void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
-  switch (l.block_n) {
-    case 256: launch_bn<256>(l, st); break;
-    case 160: launch_bn<160>(l, st); break;
-    case 128: launch_bn<128>(l, st); break;
-    case 64: launch_bn<64>(l, st); break;
-    case 16: launch_bn<16>(l, st); break;
-    default: throw Error{"unsupported BLOCK_N"};
+  const ConvGemmParams& p = l.p;
+  const int bn = l.block_n, mt = l.mt, g = l.grid;
+#define SDM_GO(BN, MT, MODE, UPS2) return conv_gemm_launch<BN, MT, MODE, UPS2>(p, g, st)
+  switch (p.mode) {
+    case EPI_F16:
+      if (!p.ups2) {
+        if (bn == 256) SDM_GO(256, 1, EPI_F16, false);
+        if (bn == 160) SDM_GO(160, 1, EPI_F16, false);
+        if (bn == 128 && mt == 2) SDM_GO(128, 2, EPI_F16, false);
+        if (bn == 128) SDM_GO(128, 1, EPI_F16, false);
+        if (bn == 64) SDM_GO(64, 1, EPI_F16, false);
+        if (bn == 16) SDM_GO(16, 1, EPI_F16, false);
+      } else {
+        if (bn == 256) SDM_GO(256, 1, EPI_F16, true);
+        if (bn == 160) SDM_GO(160, 1, EPI_F16, true);
+        if (bn == 128 && mt == 2) SDM_GO(128, 2, EPI_F16, true);
+        if (bn == 128) SDM_GO(128, 1, EPI_F16, true);
+        if (bn == 64) SDM_GO(64, 1, EPI_F16, true);
+      }
+      break;
+    case EPI_F16_T:
+      if (bn == 256) SDM_GO(256, 1, EPI_F16_T, false);
+      if (bn == 160) SDM_GO(160, 1, EPI_F16_T, false);
+      if (bn == 128) SDM_GO(128, 1, EPI_F16_T, false);
+      if (bn == 64) SDM_GO(64, 1, EPI_F16_T, false);
+      break;
+    case EPI_GEGLU:
+      if (bn == 256) SDM_GO(256, 1, EPI_GEGLU, false);
+      break;
+    case EPI_F32:
+      if (bn == 256) SDM_GO(256, 1, EPI_F32, false);
+      if (bn == 128) SDM_GO(128, 1, EPI_F32, false);
+      if (bn == 64) SDM_GO(64, 1, EPI_F32, false);
+      break;
+    case EPI_ALPHA:
+      if (bn == 16) SDM_GO(16, 1, EPI_ALPHA, false);
+      break;
+    case EPI_SKINNY:
+      if (bn == 16) SDM_GO(16, 1, EPI_SKINNY, false);
+      break;
   }
+#undef SDM_GO
+  throw Error{"conv_gemm: no kernel instantiation for mode " + std::to_string(p.mode) + " BLOCK_N " + std::to_string(bn) + " MT " +
+              std::to_string(mt) + (p.ups2 ? " ups2" : "")};
 }
 double conv_gemm_flops(const ConvGemmLaunch& l) { return l.flops; }
+int conv_gemm_tiles_per_image(int Hout, int Wout) {
+  int tw = 128, th = 1;
+  pick_patch(Hout, Wout, tw, th);
+  return ((Wout + tw - 1) / tw) * ((Hout + th - 1) / th);
+}
 void conv_gemm_set_outputs(ConvGemmLaunch& l, void* out, void* out2) {
   l.p.out = out;
   l.p.out2 = out2;

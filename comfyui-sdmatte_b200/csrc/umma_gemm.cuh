@@ -1,48 +1,58 @@
 // Implicit-GEMM convolution / linear kernel on tcgen05 (sm_100a).
 //
-// One kernel covers every dense contraction of the matte path except attention:
+// One kernel template covers every dense contraction of the matte path except the d=64 attention:
 //   * Conv2d 3x3 stride 1 (pad 1), stride 2 (UNet pad 1 / VAE asymmetric pad), 1x1 shortcut convs
 //     (reference: diffusers ResnetBlock2D / Downsample2D / Upsample2D built at
 //      /root/reference/src/utils/replace.py:239,268,321)
 //   * nn.Linear (proj_in/out, to_q/k/v/out, GEGLU, FF-out; reference Attention/FeedForward)
-//   * the VAE mid-block attention GEMMs (QK^T -> fp32 scores, P·V)
+//   * the VAE mid-block attention GEMMs (QK^T -> fp32 scores, P·V), the skinny output convs and the alpha head
 //
-// A operand ("activation"): NHWC fp16 tensor(s) read through up-to-4 TMA tensor maps (C, W, H, B).
+// A operand ("activation"): NHWC fp16 tensor(s) read through TMA tensor maps (C, W, H, B).
 //   A tile of 128 output pixels is a (tw x th) patch of one image; for tap (dy,dx) the producer
 //   issues ONE 4-D TMA box load at (c0, x0+dx, y0+dy, b): out-of-image coordinates are zero-filled
 //   by the TMA unit, which *is* the convolution padding.  Box rows land in shared memory as
 //   128 rows x 128 B with the 128-byte swizzle, exactly the K-major layout tcgen05.mma expects.
 // B operand ("weight"): [N][Ktot] fp16, K contiguous, Ktot ordered (tap, cin); 2-D map (or 3-D batched).
-// D: 128 x BLOCK_N fp32 accumulator in TMEM, double buffered so the epilogue of tile i overlaps
+// Residual: "+ x" of ResnetBlock2D / Attention / FeedForward / Transformer2DModel is folded into the contraction as
+//   extra K steps  A = residual tile (TMA, 64 channels),  B = the matching 64 columns of an identity matrix:
+//   the add costs N/64 MMA steps and no epilogue work or uncoalesced loads (fp32 accumulate of fp16 * 1.0 is exact).
+// D: MT x (128 x BLOCK_N) fp32 accumulators in TMEM, double buffered so the epilogue of tile i overlaps
 //   the main loop of tile i+1.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
-//   alloc), warps 2..5 = epilogue (TMEM -> registers -> bias/residual/activation -> global).
+//   alloc), warps 2..5 = epilogue (TMEM -> registers -> bias/activation -> smem staging -> row-contiguous stores).
+// The epilogue flavour is a template parameter: one instantiation contains one code path (the all-in-one version
+// had grown to 135 KB of SASS per kernel and thrashed the instruction cache, r1d).
 #pragma once
 #include "common.cuh"
 
 namespace sdm {
 
 enum EpiMode : int {
-  EPI_F16 = 0,    // out[pixel][n] fp16  (+bias, +residual, optional 2x nearest-upsample scatter)
-  EPI_F16_T = 1,  // out[b][n][pixel] fp16 (transposed; used for V^T)
-  EPI_GEGLU = 2,  // out[pixel][n/2] = fp16(v) * gelu(fp16(g)), tile = [BLOCK_N/2 value | BLOCK_N/2 gate]
-  EPI_F32 = 3,    // out[pixel][n] fp32 = scale * acc
-  EPI_ALPHA = 4,  // N>=3: alpha[pixel] = (clip(mean(fp16(c0..c2)), -1, 1) + 1) / 2 ; out2[pixel] = pre-clip mean (meta_arch.py:258-260)
+  EPI_F16 = 0,     // out[pixel][n] fp16  (+bias, optional 2x nearest-upsample scatter, optional fp16 division)
+  EPI_F16_T = 1,   // out[b][n][pixel] fp16 (transposed; used for V^T)
+  EPI_GEGLU = 2,   // out[pixel][n/2] = fp16(v) * gelu(fp16(g)), tile = [BLOCK_N/2 value | BLOCK_N/2 gate]
+  EPI_F32 = 3,     // out[pixel][n] fp32 = scale * acc
+  EPI_ALPHA = 4,   // N>=3: alpha[pixel] = (clip(mean(fp16(c0..c2)), -1, 1) + 1) / 2 ; out2[pixel] = pre-clip mean (meta_arch.py:258-260)
+  EPI_SKINNY = 5,  // out[pixel][0..n_store) fp16, n_store < 8 (scalar stores), optional fp16 division
 };
 
 struct alignas(64) ConvGemmParams {
   CUtensorMap a_map[4];
   CUtensorMap b_map;
+  CUtensorMap r_map;  // residual activation (same geometry as a_map[0]) or unused
+  CUtensorMap i_map;  // identity matrix [NI][NI] fp16 (B operand of the residual K steps)
   int B, H, W;        // output pixel grid (per batch element)
   int tw, th;         // tile patch, tw*th == 128
   int tiles_x, tiles_y;
   int N;              // GEMM N (output channels before GEGLU halving)
   int n_tiles;
   int total_tiles;
+  int m_tiles;        // number of 128-pixel M tiles (all batch elements)
   int ntaps, nsrc;
   int src_c[2];       // channels per A source (multiples of 64)
   int cin_total;      // weight K per tap
   signed char tap_map[9], tap_dx[9], tap_dy[9];
   int b_batched;      // weight map has a batch coordinate
+  int has_res;        // residual K steps present
   int mode;
   int ups2;           // EPI_F16 only: write each pixel to the 2x2 block of a (2H,2W) output
   void* out;
@@ -50,29 +60,39 @@ struct alignas(64) ConvGemmParams {
   long long out_bstride;  // elements per batch element
   const float* bias;      // [nsel][N] fp32 or null
   const int* bias_sel;    // per-batch row selector into bias, or null
-  const __half* res;      // residual, same indexing as out (never with ups2)
-  long long res_ld, res_bstride;
   float scale;
-  float post_div;   // EPI_F16: fp16(result) / post_div, rounded again (label_latent / scaling_factor); 1 = off
-  int n_store;      // EPI_F16: number of output columns actually stored (< 8 => scalar stores)
+  float post_div;   // EPI_F16 / EPI_SKINNY: fp16(result) / post_div, rounded again (label_latent / scaling_factor); 1 = off
+  int n_store;      // EPI_SKINNY: number of output columns stored
   void* out2;       // EPI_ALPHA: optional pre-clip mean
+  float* stats;     // EPI_F16 (no ups2): per-(M tile, channel) partial (sum, sumsq) of the STORED fp16 values for the next GroupNorm:
+                    // stats[((b * tiles_per_image + tile_in_image) * N + col) * 2 + {0,1}]  (deterministic: one writer per slot)
 };
 
-template <int BLOCK_N>
+// MT = number of 128-row M sub-tiles a CTA processes against ONE B tile (MT=2 halves the weight traffic per FLOP:
+// the N=128 VAE convs were L2->SM bandwidth bound at 128 B/clk/SM with MT=1, r1c: 545-885 TFLOP/s vs 1300-1440 for N=256)
+template <int BLOCK_N, int MT = 1>
 struct ConvGemmCfg {
-  static constexpr int kABytes = 128 * 128;          // 128 rows x 64 fp16
+  static constexpr int kABytes = 128 * 128;          // 128 rows x 64 fp16 (per M sub-tile)
   static constexpr int kBBytes = BLOCK_N * 128;      // BLOCK_N rows x 64 fp16
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
-  static constexpr int kAccStride = BLOCK_N < 32 ? 32 : BLOCK_N;  // TMEM columns between the two accumulators
+  static constexpr int kStageBytes = MT * kABytes + kBBytes;
+  static constexpr int kStages = (206 * 1024 / kStageBytes) > 8 ? 8 : (206 * 1024 / kStageBytes);
+  static constexpr int kSubStride = BLOCK_N < 32 ? 32 : BLOCK_N;  // TMEM columns per M sub-tile accumulator
+  static constexpr int kAccStride = MT * kSubStride;              // TMEM columns between the two accumulator stages
   static constexpr int kTmemCols = (2 * kAccStride <= 64) ? 64 : (2 * kAccStride <= 128) ? 128 : (2 * kAccStride <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 4096 /*epilogue staging*/ + 2048 /*GroupNorm partials*/;
   static constexpr int kThreads = 192;
 };
 
+// number of residual K steps of the tile starting at output column n0 (64-channel chunks overlapping [n0, n0+BLOCK_N))
 template <int BLOCK_N>
+__device__ __forceinline__ void residual_chunks(int n0, int N, int& c_begin, int& c_end) {
+  c_begin = (n0 >> 6) << 6;
+  c_end = min(n0 + BLOCK_N, N);
+}
+
+template <int BLOCK_N, int MT, int MODE, bool UPS2>
 __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BLOCK_N>;
+  using Cfg = ConvGemmCfg<BLOCK_N, MT>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -120,11 +140,16 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
-        const int mt = tile / p.n_tiles;
-        const int tx = mt % p.tiles_x;
-        const int ty = (mt / p.tiles_x) % p.tiles_y;
-        const int b = mt / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * p.tw, y0 = ty * p.th, n0 = nt * BLOCK_N;
+        const int n0 = nt * BLOCK_N;
+        int x0[MT], y0[MT], bb[MT];
+#pragma unroll
+        for (int u = 0; u < MT; ++u) {
+          const int mt = (tile / p.n_tiles) * MT + u;
+          const int tx = mt % p.tiles_x;
+          const int ty = (mt / p.tiles_x) % p.tiles_y;
+          x0[u] = tx * p.tw; y0[u] = ty * p.th;
+          bb[u] = mt < p.m_tiles ? mt / (p.tiles_x * p.tiles_y) : p.B;  // past-the-end sub-tile: batch index out of range -> zero fill
+        }
         for (int tap = 0; tap < p.ntaps; ++tap) {
           int koff = tap * p.cin_total;
           for (int s = 0; s < p.nsrc; ++s) {
@@ -132,16 +157,32 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
             for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
-              const uint32_t b_dst = a_dst + Cfg::kABytes;
+              const uint32_t b_dst = a_dst + MT * Cfg::kABytes;
               mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-              tma_load_4d(a_dst, amap, full_bar(stage), c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b);
+#pragma unroll
+              for (int u = 0; u < MT; ++u)
+                tma_load_4d(a_dst + u * Cfg::kABytes, amap, full_bar(stage), c0, x0[u] + p.tap_dx[tap], y0[u] + p.tap_dy[tap], bb[u]);
               if (p.b_batched)
-                tma_load_3d(b_dst, &p.b_map, full_bar(stage), koff + c0, n0, b);
+                tma_load_3d(b_dst, &p.b_map, full_bar(stage), koff + c0, n0, bb[0]);
               else
                 tma_load_2d(b_dst, &p.b_map, full_bar(stage), koff + c0, n0);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
             koff += p.src_c[s];
+          }
+        }
+        if (p.has_res) {  // residual as K steps against the identity
+          int cb, ce;
+          residual_chunks<BLOCK_N>(n0, p.N, cb, ce);
+          for (int c0 = cb; c0 < ce; c0 += 64) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+            const uint32_t b_dst = a_dst + MT * Cfg::kABytes;
+            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+#pragma unroll
+            for (int u = 0; u < MT; ++u) tma_load_4d(a_dst + u * Cfg::kABytes, &p.r_map, full_bar(stage), c0, x0[u], y0[u], bb[u]);
+            tma_load_2d(b_dst, &p.i_map, full_bar(stage), c0, n0);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -155,19 +196,28 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int nks = num_ksteps;
+        if (p.has_res) {
+          int cb, ce;
+          residual_chunks<BLOCK_N>((tile % p.n_tiles) * BLOCK_N, p.N, cb, ce);
+          nks += (ce - cb + 63) >> 6;
+        }
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
-        for (int ks = 0; ks < num_ksteps; ++ks) {
+        for (int ks = 0; ks < nks; ++ks) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
-          const uint64_t adesc = umma_desc_k128(a_addr);
-          const uint64_t bdesc = umma_desc_k128(a_addr + Cfg::kABytes);
+          const uint64_t bdesc = umma_desc_k128(a_addr + MT * Cfg::kABytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // +32 B per 16-element K step (start-address field is in 16-byte units)
-            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+          for (int u = 0; u < MT; ++u) {
+            const uint64_t adesc = umma_desc_k128(a_addr + u * Cfg::kABytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // +32 B per 16-element K step (start-address field is in 16-byte units)
+              umma_f16(d_tmem + u * Cfg::kSubStride, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+            }
           }
           umma_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -178,169 +228,269 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
     }
   } else {
     // ============================== epilogue (4 warps, one TMEM lane quadrant each) ==============
+    // Thread `lane` of quadrant `quad` owns accumulator row quad*32+lane (TMEM lane).  Global stores are made
+    // row-contiguous through a per-warp 32 x 128 B staging tile in shared memory (XOR-swizzled 16-byte pieces):
+    // a warp-wide 16-byte store then covers 4 rows x 128 contiguous bytes (4 L2 lines) instead of 32 rows x 16 bytes.
     const int quad = warp & 3;
     const int row = quad * 32 + lane;  // row of the 128-row tile == TMEM lane
+    uint8_t* stg = smem_raw + (bar_base - smem_u32(smem_raw)) + 256 + (warp - 2) * 4096;
+    const int t_row0 = lane >> 3, t_piece = lane & 7;
+    int ltw = 0;
+    while ((1 << ltw) < p.tw) ++ltw;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      const int mt = tile / p.n_tiles;
-      const int tx = mt % p.tiles_x;
-      const int ty = (mt / p.tiles_x) % p.tiles_y;
-      const int b = mt / (p.tiles_x * p.tiles_y);
-      const int x = tx * p.tw + (row % p.tw);
-      const int y = ty * p.th + (row / p.tw);
-      const bool valid = (x < p.W) && (y < p.H);
-      const int n0 = nt * BLOCK_N;
-      const long long pix = (long long)y * p.W + x;
-      const float* bias = p.bias ? p.bias + (p.bias_sel ? (long long)p.bias_sel[b] * p.N : 0) : nullptr;
-
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * Cfg::kAccStride;
+      const int nt = tile % p.n_tiles;
+      const int n0 = nt * BLOCK_N;
+#pragma unroll 1
+      for (int u = 0; u < MT; ++u) {
+        const int mt = (tile / p.n_tiles) * MT + u;
+        if (mt >= p.m_tiles) break;  // warp-uniform
+        const int tx = mt % p.tiles_x;
+        const int ty = (mt / p.tiles_x) % p.tiles_y;
+        const int b = mt / (p.tiles_x * p.tiles_y);
+        const float* bias = p.bias ? p.bias + (p.bias_sel ? (long long)p.bias_sel[b] * p.N : 0) : nullptr;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * Cfg::kAccStride + u * Cfg::kSubStride;
 
-      if (p.mode == EPI_GEGLU) {
-        constexpr int HALF = BLOCK_N / 2;
-        __half* out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + pix * p.out_ld + (n0 >> 1);
+        if constexpr (MODE == EPI_F16 || MODE == EPI_GEGLU || MODE == EPI_F32) {
+          // ---- staged, row-contiguous store path -------------------------------------------------
+          constexpr int ES = (MODE == EPI_F32) ? 4 : 2;       // output element size
+          constexpr int CPP = 16 / ES;                        // columns per 16-byte piece
+          constexpr int SLAB = 128 / ES;                      // output columns per 128-byte staging row
+          constexpr int OUT_COLS = (MODE == EPI_GEGLU) ? BLOCK_N / 2 : BLOCK_N;
+          const int ocol0 = (MODE == EPI_GEGLU) ? (n0 >> 1) : n0;
+          const int o_lim = (MODE == EPI_GEGLU) ? min(p.N >> 1, ocol0 + OUT_COLS) : min(p.N, n0 + BLOCK_N);
+          uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + (long long)b * p.out_bstride * ES;
+          // pixel offsets of the 8 rows this lane serves in the transposed phase; -1 = outside the image
+          long long tpix[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rg = quad * 32 + i * 4 + t_row0;
+            const int xx = tx * p.tw + (rg & (p.tw - 1)), yy = ty * p.th + (rg >> ltw);
+            tpix[i] = (xx < p.W && yy < p.H) ? (UPS2 ? (long long)(2 * yy) * (2 * p.W) + 2 * xx : (long long)yy * p.W + xx) : -1;
+          }
 #pragma unroll 1
-        for (int c = 0; c < HALF; c += 32) {
-          uint32_t rv[32], rg[32];
-          __syncwarp();
-          tmem_ld32(taddr + c, rv);
-          tmem_ld32(taddr + HALF + c, rg);
-          tmem_ld_wait();
-          if (valid) {
+          for (int c = 0; c < OUT_COLS; c += SLAB) {
+            uint4 pc[8];
+            if constexpr (MODE == EPI_F32) {
+              uint32_t r[32];
+              __syncwarp();
+              tmem_ld32(taddr + c, r);
+              tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (n0 + c + g * 8 < p.N) {  // N counts value+gate columns; tiles never straddle
-                uint32_t w[4];
+              for (int g = 0; g < 8; ++g) {
+                float v[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float o[2];
-#pragma unroll
-                  for (int e = 0; e < 2; ++e) {
-                    const int i = g * 8 + j * 2 + e;
-                    float v = __uint_as_float(rv[i]);
-                    float gt = __uint_as_float(rg[i]);
-                    if (bias) {
-                      v += bias[n0 + c + i];
-                      gt += bias[n0 + HALF + c + i];
-                    }
-                    // reference rounding points: proj output fp16, gelu(gate) fp16, product fp16
-                    v = __half2float(__float2half_rn(v));
-                    gt = __half2float(__float2half_rn(gt));
-                    float ge = 0.5f * gt * (1.0f + erff(gt * 0.70710678118654752f));
-                    ge = __half2float(__float2half_rn(ge));
-                    o[e] = v * ge;
-                  }
-                  w[j] = pack_h2(o[0], o[1]);
+                for (int e = 0; e < 4; ++e) {
+                  v[e] = __uint_as_float(r[g * 4 + e]) * p.scale;
+                  if (bias && n0 + c + g * 4 + e < p.N) v[e] += bias[n0 + c + g * 4 + e];
                 }
-                *reinterpret_cast<uint4*>(out + c + g * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                pc[g] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
               }
-            }
-          }
-        }
-      } else if (p.mode == EPI_ALPHA) {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld32(taddr, r);
-        tmem_ld_wait();
-        if (valid) {
-          // rounding points of the reference fp16 path: conv outputs fp16, channel mean fp16, (clip+1) fp16, /2 exact
-          const float c0 = __half2float(__float2half_rn(__uint_as_float(r[0]) + bias[0]));
-          const float c1 = __half2float(__float2half_rn(__uint_as_float(r[1]) + bias[1]));
-          const float c2 = __half2float(__float2half_rn(__uint_as_float(r[2]) + bias[2]));
-          const __half m = __float2half_rn((c0 + c1 + c2) / 3.0f);
-          const long long o = (long long)b * p.out_bstride + pix;
-          if (p.out2) reinterpret_cast<__half*>(p.out2)[o] = m;
-          const float cl = fminf(fmaxf(__half2float(m), -1.0f), 1.0f);
-          const __half p1 = __float2half_rn(cl + 1.0f);
-          reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(__half2float(p1) * 0.5f);
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          uint32_t r[32];
-          __syncwarp();  // tcgen05.ld is .sync.aligned: re-converge after the (divergent) store code
-          tmem_ld32(taddr + c, r);
-          tmem_ld_wait();
-          if (valid && (n0 + c < p.N)) {
-          float v[32];
+            } else if constexpr (MODE == EPI_GEGLU) {
+              constexpr int HALF = BLOCK_N / 2;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.scale;
-          if (bias) {
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t rv[32], rg[32];
+                __syncwarp();
+                tmem_ld32(taddr + c + hh * 32, rv);
+                tmem_ld32(taddr + HALF + c + hh * 32, rg);
+                tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              if (n0 + c + g * 4 < p.N) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + g * 4));
-                v[g * 4 + 0] += bb.x; v[g * 4 + 1] += bb.y; v[g * 4 + 2] += bb.z; v[g * 4 + 3] += bb.w;
-              }
-            }
-          }
-          if (p.mode == EPI_F32) {
-            float* out = reinterpret_cast<float*>(p.out) + (long long)b * p.out_bstride + pix * p.out_ld + n0 + c;
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              if (n0 + c + g * 4 < p.N)
-                *reinterpret_cast<float4*>(out + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-          } else if (p.mode == EPI_F16_T) {
-            __half* out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + pix;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n0 + c + i < p.N) out[(long long)(n0 + c + i) * p.out_ld] = __float2half_rn(v[i]);
-          } else {
-            if (p.res) {
-              const __half* res = p.res + (long long)b * p.res_bstride + pix * p.res_ld + n0 + c;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (n0 + c + g * 8 < p.N) {
-                  const uint4 rr = *reinterpret_cast<const uint4*>(res + g * 8);
-                  const __half2* h = reinterpret_cast<const __half2*>(&rr);
+                for (int g = 0; g < 4; ++g) {
+                  uint32_t w[4];
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    // reference rounds the producer output to fp16 before the residual add
-                    const float2 f = __half22float2(h[j]);
-                    v[g * 8 + j * 2] = __half2float(__float2half_rn(v[g * 8 + j * 2])) + f.x;
-                    v[g * 8 + j * 2 + 1] = __half2float(__float2half_rn(v[g * 8 + j * 2 + 1])) + f.y;
+                    float o[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                      const int i = g * 8 + j * 2 + e;
+                      float v = __uint_as_float(rv[i]);
+                      float gt = __uint_as_float(rg[i]);
+                      if (bias) {
+                        v += bias[n0 + c + hh * 32 + i];
+                        gt += bias[n0 + HALF + c + hh * 32 + i];
+                      }
+                      // reference rounding points: proj output fp16, gelu(gate) fp16, product fp16
+                      v = __half2float(__float2half_rn(v));
+                      gt = __half2float(__float2half_rn(gt));
+                      float ge = 0.5f * gt * (1.0f + erff(gt * 0.70710678118654752f));
+                      ge = __half2float(__float2half_rn(ge));
+                      o[e] = v * ge;
+                    }
+                    w[j] = pack_h2(o[0], o[1]);
+                  }
+                  pc[hh * 4 + g] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+              }
+            } else {  // EPI_F16
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                if (c + hh * 32 < BLOCK_N) {
+                  uint32_t r[32];
+                  __syncwarp();
+                  tmem_ld32(taddr + c + hh * 32, r);
+                  tmem_ld_wait();
+                  float v[32];
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.scale;
+                  if (bias) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                      if (n0 + c + hh * 32 + g * 4 < p.N) {
+                        const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + hh * 32 + g * 4));
+                        v[g * 4 + 0] += bq.x; v[g * 4 + 1] += bq.y; v[g * 4 + 2] += bq.z; v[g * 4 + 3] += bq.w;
+                      }
+                    }
+                  }
+                  if (p.post_div != 1.0f) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __half2float(__float2half_rn(v[i])) / p.post_div;
+                  }
+#pragma unroll
+                  for (int g = 0; g < 4; ++g)
+                    pc[hh * 4 + g] = make_uint4(pack_h2(v[g * 8], v[g * 8 + 1]), pack_h2(v[g * 8 + 2], v[g * 8 + 3]),
+                                                pack_h2(v[g * 8 + 4], v[g * 8 + 5]), pack_h2(v[g * 8 + 6], v[g * 8 + 7]));
+                } else {
+#pragma unroll
+                  for (int g = 0; g < 4; ++g) pc[hh * 4 + g] = make_uint4(0, 0, 0, 0);
+                }
+              }
+            }
+            // this thread's row -> staging -> row-contiguous global stores
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = pc[q];
+            __syncwarp();
+            const int col = ocol0 + c + t_piece * CPP;
+            float ssum[8], ssq[8];
+            if constexpr (MODE == EPI_F16 && !UPS2) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { ssum[e] = 0.f; ssq[e] = 0.f; }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rl = i * 4 + t_row0;
+              const uint4 v = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((t_piece ^ (rl & 7)) << 4));
+              if (tpix[i] >= 0 && col < o_lim) {
+                if constexpr (MODE == EPI_F16 && !UPS2) {
+                  if (p.stats) {
+                    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 f = __half22float2(h[j]);
+                      ssum[2 * j] += f.x; ssq[2 * j] = fmaf(f.x, f.x, ssq[2 * j]);
+                      ssum[2 * j + 1] += f.y; ssq[2 * j + 1] = fmaf(f.y, f.y, ssq[2 * j + 1]);
+                    }
+                  }
+                }
+                if constexpr (!UPS2) {
+                  *reinterpret_cast<uint4*>(obase + (tpix[i] * p.out_ld + col) * ES) = v;
+                } else {
+                  // nearest-neighbour 2x upsample fused into the store (reference Upsample2D: F.interpolate scale 2
+                  // "nearest" followed by a conv; the conv then reads this tensor)
+#pragma unroll
+                  for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(obase + ((tpix[i] + (q >> 1) * (2 * p.W) + (q & 1)) * p.out_ld + col) * ES) = v;
+                }
+              }
+            }
+            if constexpr (MODE == EPI_F16 && !UPS2) {
+              if (p.stats) {
+                // column sums over this warp's 32 rows: lanes {l, l+8, l+16, l+24} hold the same 8 columns
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  ssum[e] += __shfl_xor_sync(0xffffffffu, ssum[e], 8);
+                  ssq[e] += __shfl_xor_sync(0xffffffffu, ssq[e], 8);
+                  ssum[e] += __shfl_xor_sync(0xffffffffu, ssum[e], 16);
+                  ssq[e] += __shfl_xor_sync(0xffffffffu, ssq[e], 16);
+                }
+                // combine the four epilogue warps in a fixed order through shared memory (one global writer per slot)
+                float* sred = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256 + 4 * 4096);
+                if (lane < 8) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    sred[(quad * 64 + lane * 8 + e) * 2] = ssum[e];
+                    sred[(quad * 64 + lane * 8 + e) * 2 + 1] = ssq[e];
+                  }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (quad == 0) {
+                  const int cc = lane * 2;  // two columns per lane
+                  const int gcol = n0 + c + cc;
+                  if (gcol < o_lim) {
+                    float4 o;
+                    o.x = (sred[(0 * 64 + cc) * 2] + sred[(1 * 64 + cc) * 2]) + (sred[(2 * 64 + cc) * 2] + sred[(3 * 64 + cc) * 2]);
+                    o.y = (sred[(0 * 64 + cc) * 2 + 1] + sred[(1 * 64 + cc) * 2 + 1]) + (sred[(2 * 64 + cc) * 2 + 1] + sred[(3 * 64 + cc) * 2 + 1]);
+                    o.z = (sred[(0 * 64 + cc + 1) * 2] + sred[(1 * 64 + cc + 1) * 2]) + (sred[(2 * 64 + cc + 1) * 2] + sred[(3 * 64 + cc + 1) * 2]);
+                    o.w = (sred[(0 * 64 + cc + 1) * 2 + 1] + sred[(1 * 64 + cc + 1) * 2 + 1]) + (sred[(2 * 64 + cc + 1) * 2 + 1] + sred[(3 * 64 + cc + 1) * 2 + 1]);
+                    const long long slot = (long long)b * (p.tiles_x * p.tiles_y) + (mt % (p.tiles_x * p.tiles_y));
+                    *reinterpret_cast<float4*>(p.stats + (slot * p.N + gcol) * 2) = o;
+                  }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+              }
+            }
+          }
+        } else {
+          // ---- row-per-thread paths (transposed store is already coalesced along pixels; skinny outputs are tiny)
+          const int x = tx * p.tw + (row & (p.tw - 1));
+          const int y = ty * p.th + (row >> ltw);
+          const bool valid = (x < p.W) && (y < p.H);
+          const long long pix = (long long)y * p.W + x;
+          if constexpr (MODE == EPI_F16_T) {
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+              uint32_t r[32];
+              __syncwarp();  // tcgen05.ld is .sync.aligned: re-converge after the (divergent) store code
+              tmem_ld32(taddr + c, r);
+              tmem_ld_wait();
+              if (valid) {
+                __half* out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + pix;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  if (n0 + c + i < p.N) {
+                    float v = __uint_as_float(r[i]) * p.scale;
+                    if (bias) v += bias[n0 + c + i];
+                    out[(long long)(n0 + c + i) * p.out_ld] = __float2half_rn(v);
                   }
                 }
               }
             }
-            if (p.post_div != 1.0f) {
+          } else {
+            uint32_t r[32];
+            __syncwarp();
+            tmem_ld32(taddr, r);
+            tmem_ld_wait();
+            if (valid) {
+              if constexpr (MODE == EPI_ALPHA) {
+                // rounding points of the reference fp16 path: conv outputs fp16, channel mean fp16, (clip+1) fp16, /2 exact
+                const float c0 = __half2float(__float2half_rn(__uint_as_float(r[0]) + bias[0]));
+                const float c1 = __half2float(__float2half_rn(__uint_as_float(r[1]) + bias[1]));
+                const float c2 = __half2float(__float2half_rn(__uint_as_float(r[2]) + bias[2]));
+                const __half m = __float2half_rn((c0 + c1 + c2) / 3.0f);
+                const long long o = (long long)b * p.out_bstride + pix;
+                if (p.out2) reinterpret_cast<__half*>(p.out2)[o] = m;
+                const float cl = fminf(fmaxf(__half2float(m), -1.0f), 1.0f);
+                const __half p1 = __float2half_rn(cl + 1.0f);
+                reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(__half2float(p1) * 0.5f);
+              } else {  // EPI_SKINNY
+                __half* out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + pix * p.out_ld;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __half2float(__float2half_rn(v[i])) / p.post_div;
-            }
-            uint4 w[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              w[g] = make_uint4(pack_h2(v[g * 8], v[g * 8 + 1]), pack_h2(v[g * 8 + 2], v[g * 8 + 3]),
-                                pack_h2(v[g * 8 + 4], v[g * 8 + 5]), pack_h2(v[g * 8 + 6], v[g * 8 + 7]));
-            if (p.n_store < 8) {
-              __half* out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + pix * p.out_ld;
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (i < p.n_store) out[i] = __float2half_rn(v[i]);
-            } else if (!p.ups2) {
-              __half* out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + pix * p.out_ld + n0 + c;
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                if (n0 + c + g * 8 < p.N) *reinterpret_cast<uint4*>(out + g * 8) = w[g];
-            } else {
-              // nearest-neighbour 2x upsample fused into the store (reference Upsample2D: F.interpolate
-              // scale 2 "nearest" followed by a conv; the conv then reads this tensor)
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const long long pix2 = (long long)(2 * y + (q >> 1)) * (2 * p.W) + (2 * x + (q & 1));
-                __half* out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + pix2 * p.out_ld + n0 + c;
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                  if (n0 + c + g * 8 < p.N) *reinterpret_cast<uint4*>(out + g * 8) = w[g];
+                for (int i = 0; i < 8; ++i) {
+                  if (i < p.n_store) {
+                    float v = __uint_as_float(r[i]) * p.scale + (bias ? bias[i] : 0.f);
+                    if (p.post_div != 1.0f) v = __half2float(__float2half_rn(v)) / p.post_div;
+                    out[i] = __float2half_rn(v);
+                  }
+                }
               }
             }
           }
-          }  // valid
         }
-      }
+      }  // M sub-tile
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));

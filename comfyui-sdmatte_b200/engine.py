@@ -31,7 +31,7 @@ class sdm_conv_gemm_args(C.Structure):
         ("out", C.c_void_p), ("out_ld", C.c_int64), ("out_bstride", C.c_int64),
         ("bias", C.c_void_p), ("bias_sel", C.c_void_p),
         ("res", C.c_void_p), ("res_ld", C.c_int64), ("res_bstride", C.c_int64),
-        ("scale", C.c_float), ("force_block_n", C.c_int), ("post_div", C.c_float), ("n_store", C.c_int), ("out2", C.c_void_p),
+        ("scale", C.c_float), ("force_block_n", C.c_int), ("post_div", C.c_float), ("n_store", C.c_int), ("out2", C.c_void_p), ("force_mt", C.c_int), ("stats", C.c_void_p),
     ]
 
 
@@ -51,6 +51,7 @@ class sdm_groupnorm_args(C.Structure):
         ("src1", C.c_void_p), ("c1", C.c_int), ("ld1", C.c_int64),
         ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("silu", C.c_int),
         ("out", C.c_void_p), ("scratch", C.c_void_p), ("scratch_floats", C.c_size_t),
+        ("pre0", C.c_void_p), ("pre1", C.c_void_p), ("pre_slots", C.c_int),
     ]
 
 
@@ -66,7 +67,7 @@ EXPORTS = [
     "sdm_version", "sdm_last_error", "sdm_create", "sdm_destroy", "sdm_load_weights", "sdm_load_report",
     "sdm_workspace_bytes", "sdm_forward", "sdm_forward_host", "sdm_forward_profiled", "sdm_profile_count", "sdm_profile_entry",
     "sdm_last_forward_stats", "sdm_debug_tensor",
-    "sdm_k_conv_gemm", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
+    "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
     "sdm_k_softmax_rows", "sdm_k_direct_conv",
 ]
 
@@ -109,6 +110,7 @@ def load_library():
     lib.sdm_last_forward_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     lib.sdm_debug_tensor.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
     lib.sdm_k_conv_gemm.argtypes = [C.POINTER(sdm_conv_gemm_args), C.c_void_p]
+    lib.sdm_k_conv_tiles_per_image.argtypes = [C.c_int, C.c_int]
     lib.sdm_k_attention.argtypes = [C.POINTER(sdm_attn_args), C.c_void_p]
     lib.sdm_k_groupnorm_scratch_floats.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.sdm_k_groupnorm_scratch_floats.restype = C.c_size_t
@@ -273,7 +275,7 @@ def _p(t):
 
 
 def k_conv_gemm(srcs, w, N, out, *, B, Hin, Win, ksize=1, stride=1, pad=0, mode=0, ups2=0, bias=None, bias_sel=None,
-                res=None, scale=1.0, w_bstride=0, out_ld=None, out_bstride=None, force_block_n=0, post_div=1.0, n_store=0, out2=None):
+                res=None, scale=1.0, w_bstride=0, out_ld=None, out_bstride=None, force_block_n=0, post_div=1.0, n_store=0, out2=None, force_mt=0, stats=None):
     lib = load_library()
     a = sdm_conv_gemm_args()
     a.B, a.Hin, a.Win, a.nsrc = B, Hin, Win, len(srcs)
@@ -288,7 +290,7 @@ def k_conv_gemm(srcs, w, N, out, *, B, Hin, Win, ksize=1, stride=1, pad=0, mode=
     if res is not None:
         a.res, a.res_ld, a.res_bstride = res[0].data_ptr(), res[1], res[2]
     a.scale, a.force_block_n = scale, force_block_n
-    a.post_div, a.n_store, a.out2 = post_div, n_store, _p(out2)
+    a.post_div, a.n_store, a.out2, a.force_mt, a.stats = post_div, n_store, _p(out2), force_mt, _p(stats)
     _check(lib.sdm_k_conv_gemm(C.byref(a), _stream_ptr(out.device)))
 
 
@@ -302,7 +304,11 @@ def k_attention(q, k, vt, out, *, B, heads, Lq, Lk, ldq, ldk, ldvt, ldo, bias=No
     _check(lib.sdm_k_attention(C.byref(a), _stream_ptr(out.device)))
 
 
-def k_groupnorm(srcs, gamma, beta, out, *, B, HW, eps, silu):
+def conv_tiles_per_image(H, W):
+    return load_library().sdm_k_conv_tiles_per_image(H, W)
+
+
+def k_groupnorm(srcs, gamma, beta, out, *, B, HW, eps, silu, pre=None, pre_slots=0):
     lib = load_library()
     a = sdm_groupnorm_args()
     a.B, a.HW, a.nsrc = B, HW, len(srcs)
@@ -315,6 +321,8 @@ def k_groupnorm(srcs, gamma, beta, out, *, B, HW, eps, silu):
     scratch = torch.empty(n, dtype=torch.float32, device=out.device)
     a.gamma, a.beta, a.eps, a.silu = gamma.data_ptr(), beta.data_ptr(), eps, int(silu)
     a.out, a.scratch, a.scratch_floats = out.data_ptr(), scratch.data_ptr(), n
+    if pre is not None:
+        a.pre0, a.pre1, a.pre_slots = _p(pre[0]), _p(pre[1]) if len(pre) > 1 else None, pre_slots
     _check(lib.sdm_k_groupnorm(C.byref(a), _stream_ptr(out.device)))
     return scratch
 

@@ -91,8 +91,11 @@ typedef struct {
   float post_div;               /* mode 0: fp16(result) / post_div, rounded again; 1 = off */
   int n_store;                  /* mode 0: store only the first n_store (< 8) columns; 0 = all */
   void* out2;                   /* mode 4 (alpha head): optional pre-clip mean */
+  int force_mt;                 /* tests: 1 / 2 = force M sub-tiles per CTA tile (BLOCK_N 128 only), 0 = auto */
+  float* stats;                 /* mode 0 without ups2: GroupNorm partials [B][sdm_k_conv_tiles_per_image][N][2] (sum, sumsq), or NULL */
 } sdm_conv_gemm_args;
 int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream);
+int sdm_k_conv_tiles_per_image(int Hout, int Wout);
 
 typedef struct {
   int B, heads, Lq, Lk;
@@ -111,6 +114,7 @@ typedef struct {
   const void* src1; int c1; int64_t ld1;
   const float* gamma; const float* beta; float eps; int silu;
   void* out; float* scratch; size_t scratch_floats;
+  const float* pre0; const float* pre1; int pre_slots;   /* optional partial statistics from the producing convs' epilogues */
 } sdm_groupnorm_args;
 size_t sdm_k_groupnorm_scratch_floats(int B, int HW, int C);
 int sdm_k_groupnorm(const sdm_groupnorm_args* a, uintptr_t stream);

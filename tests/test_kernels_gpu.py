@@ -381,3 +381,61 @@ def test_silu_accuracy_via_groupnorm(eng_mod):
     torch.cuda.synchronize()
     ref = F.silu(F.group_norm(x.float().transpose(1, 2), 32, g, b, 1e-6)).transpose(1, 2)
     _close(out, ref, 1.2e-3, 2e-4, "silu")
+
+
+@pytest.mark.parametrize("B,H,W,Cin", [(3, 16, 8, 128), (2, 32, 32, 128), (1, 128, 128, 64), (5, 8, 16, 192)])
+def test_conv3x3_two_m_subtiles(eng_mod, B, H, W, Cin):
+    """256x128 CTA tile (two M sub-tiles share one weight tile), incl. an odd number of M tiles and a residual."""
+    Cout = 128
+    x = _rand(B, H, W, Cin, seed=1).half()
+    r = _rand(B, H, W, Cout, seed=5).half()
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2).half()
+    b = _rand(Cout, seed=3).float()
+    out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    eng_mod.k_conv_gemm([(x, Cin, Cin)], _pack_conv_w(w), Cout, out, B=B, Hin=H, Win=W, ksize=3, bias=b, out_ld=Cout,
+                        out_bstride=H * W * Cout, res=(r, Cout, H * W * Cout), force_mt=2)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).half().float().permute(0, 2, 3, 1) + r.float()
+    _close(out, ref, 2e-3, 2e-3, "conv3x3 MT=2")
+
+
+def test_linear_two_m_subtiles(eng_mod):
+    B, M, N, K = 2, 700, 640, 320
+    x = _rand(B, M, K, seed=1).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).half()
+    b = _rand(N, seed=3).float()
+    out = torch.zeros(B, M, N, dtype=torch.float16, device=DEV)
+    eng_mod.k_conv_gemm([(x, K, K)], w, N, out, B=B, Hin=1, Win=M, bias=b, out_ld=N, out_bstride=M * N, force_block_n=128, force_mt=2)
+    torch.cuda.synchronize()
+    _close(out, x.float() @ w.float().t() + b, 2e-3, 2e-3, "linear MT=2")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,mt", [(2, 32, 32, 128, 128, 2), (1, 40, 40, 320, 320, 0), (2, 16, 16, 256, 256, 0), (3, 8, 8, 64, 64, 0)])
+def test_conv_epilogue_groupnorm_partials(eng_mod, B, H, W, Cin, Cout, mt):
+    """The conv epilogue's per-(tile, channel) sums of the STORED fp16 outputs reproduce the tensor's channel statistics,
+    and GroupNorm fed with them equals GroupNorm computing its own statistics (bit for bit run to run)."""
+    x = _rand(B, H, W, Cin, seed=1).half()
+    r = _rand(B, H, W, Cout, seed=5).half()
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2).half()
+    b = _rand(Cout, seed=3).float()
+    out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    slots = eng_mod.conv_tiles_per_image(H, W)
+    stats = torch.full((B, slots, Cout, 2), float("nan"), device=DEV)
+    eng_mod.k_conv_gemm([(x, Cin, Cin)], _pack_conv_w(w), Cout, out, B=B, Hin=H, Win=W, ksize=3, bias=b, out_ld=Cout, out_bstride=H * W * Cout,
+                        res=(r, Cout, H * W * Cout), force_mt=mt, stats=stats)
+    torch.cuda.synchronize()
+    assert torch.isfinite(stats).all()
+    tot = stats.double().sum(1)  # (B, C, 2)
+    o = out.double().view(B, H * W, Cout)
+    assert torch.allclose(tot[..., 0], o.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(tot[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)
+    g = _rand(Cout, seed=7).float() * 0.2 + 1.0
+    bt = _rand(Cout, seed=8).float() * 0.2
+    y1 = torch.zeros_like(out).view(B, H * W, Cout)
+    y2 = torch.zeros_like(y1)
+    eng_mod.k_groupnorm([(out, Cout, Cout)], g, bt, y1, B=B, HW=H * W, eps=1e-5, silu=1)
+    eng_mod.k_groupnorm([(out, Cout, Cout)], g, bt, y2, B=B, HW=H * W, eps=1e-5, silu=1, pre=[stats], pre_slots=slots)
+    torch.cuda.synchronize()
+    ref = F.silu(F.group_norm(out.float().view(B, H * W, Cout).transpose(1, 2), 32, g, bt, 1e-5)).transpose(1, 2)
+    _close(y2, ref, 2e-3, 2e-3, "groupnorm from epilogue partials")
+    assert (y1.float() - y2.float()).abs().max().item() <= 2e-3
