@@ -116,6 +116,18 @@ struct Weights {
         for (int t = 0; t < k * k; ++t) pk[((size_t)o * k * k + t) * Ip + i] = __float2half_rn(w[((size_t)o * I + i) * k * k + t]);
     return (const __half*)upload(key, pk.data(), pk.size() * 2);
   }
+  // 3x3 conv with I <= 4 input channels as a GEMM over im2col rows: [O][64], k = tap*4 + ci
+  const __half* conv_im2col(const std::string& name, int O, int I) {
+    const std::string key = "i:" + name;
+    if (void* p = get(key)) return (const __half*)p;
+    require_loading(key);
+    std::vector<float> w = fetch(name + ".weight", (int64_t)O * I * 9);
+    std::vector<__half> pk((size_t)O * 64, __float2half_rn(0.f));
+    for (int o = 0; o < O; ++o)
+      for (int i = 0; i < I; ++i)
+        for (int t = 0; t < 9; ++t) pk[(size_t)o * 64 + t * 4 + i] = __float2half_rn(w[((size_t)o * I + i) * 9 + t]);
+    return (const __half*)upload(key, pk.data(), pk.size() * 2);
+  }
   const __half* linear(const std::string& name, int N, int K) {
     const std::string key = "l:" + name;
     if (void* p = get(key)) return (const __half*)p;
@@ -671,10 +683,10 @@ struct Builder {
     Plan::Slots* slots = plan ? &plan->slots : nullptr;
 
     // ---- a1: input preparation (sdmatte_nodes.py:343,351; meta_arch.py:141)
-    T x0 = alloc(B2, R, R, 4);
+    T x0 = alloc(B2, R, R, 64);  // im2col rows of the VAE conv_in
     if (!dry) {
       __half* xp = x0.p; const int Bc = B, Rc = R;
-      push([=](cudaStream_t st) { prep_inputs_run(slots->image, slots->trimap, xp, 4, Bc, Rc, st); }, 1, "prep_inputs", 0, (double)Bc * Rc * Rc * (16 + 16));
+      push([=](cudaStream_t st) { prep_inputs_run(slots->image, slots->trimap, xp, 64, Bc, Rc, st); }, 1, "prep_inputs", 0, (double)Bc * Rc * Rc * (16 + 256));
     } else n_launches++;
     // ---- a4/a6: additive key bias per level
     int lpad[4];
@@ -696,8 +708,8 @@ struct Builder {
     {
       const std::string e = "vae.encoder";
       T h = alloc(B2, R, R, 128);
-      { DirectConvDesc d; d.B = B2; d.H = R; d.W = R; d.Cin = 4; d.Cout = 128; d.ksize = 3; d.x = x0.p; d.x_ld = 4;
-        d.w = W.conv(e + ".conv_in", 128, 3, 3, 4); d.bias = W.vec(e + ".conv_in.bias", 128); d.out = h.p; d.out_ld = 128; direct(d); }
+      { GemmOpt o; o.bias = W.vec(e + ".conv_in.bias", 128); o.stats_for = &h; o.label = "conv_in_im2col";
+        conv_tc(x0, nullptr, W.conv_im2col(e + ".conv_in", 128, 3), 128, 1, h, o); }
       free(x0);
       const int ch[4] = {128, 256, 512, 512};
       for (int i = 0; i < 4; ++i) {

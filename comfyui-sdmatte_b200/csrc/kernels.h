@@ -43,6 +43,7 @@ struct ConvGemmDesc {
   float* stats = nullptr;  // EPI_F16 without ups2: GroupNorm partials [B][tiles_per_image][N][2] (see conv_gemm_tiles_per_image)
   int force_block_n = 0;  // tests only
   int force_mt = 0;       // tests only: 1 / 2 = force the number of M sub-tiles per CTA tile
+  int force_light = 0;    // tests only: 1 = force the two-CTAs-per-SM config, -1 = forbid it
 };
 
 struct ConvGemmLaunch;  // opaque: prebuilt tensor maps + params
@@ -119,9 +120,9 @@ void alpha_head_run(const __half* x, long long x_ld, int B, int H, int W, int Ci
                     __half* alpha, __half* premean /*nullable: pre-clip mean, fp16*/, cudaStream_t st);
 
 // ------------------------------------------------------------------ elementwise
-// image [B][R][R][3] fp32 in [0,1] -> (x-0.5)/0.5 fp16 NHWC with 3 channels padded to ldc
-// trimap [B][R][R] fp32 in [0,1] -> t*2-1 replicated to 3 channels
-void prep_inputs_run(const float* image, const float* trimap, __half* out /*[2B][R][R][ldc]*/, int ldc, int B, int R,
+// im2col of the VAE conv_in input: out[2B*R*R][64], k = tap*4 + channel (zero beyond 36); first B images = (x-0.5)/0.5 of the
+// fp32 [B][R][R][3] image, last B = trimap*2-1 replicated to 3 channels (sdmatte_nodes.py:343,351, meta_arch.py:141)
+void prep_inputs_run(const float* image, const float* trimap, __half* out /*[2B][R][R][64]*/, int ldc, int B, int R,
                      cudaStream_t st);
 // key-bias vectors for the 4 UNet levels: bias_k[b][i*s+j] = (1 - trimap[b][8*2^k*i][8*2^k*j]) * -10000,
 // padded to lpad[k] (multiple of 128) with -inf.   (reference meta_arch.py:200-204, replace.py:56-63,401-403)

@@ -13,6 +13,7 @@ struct ConvGemmLaunch {
   ConvGemmParams p;
   int block_n = 0;
   int mt = 1;
+  bool light = false;
   int grid = 0;
   double flops = 0;
 };
@@ -94,12 +95,17 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   p.tiles_y = (Hout + p.th - 1) / p.th;
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * d.B;
   p.N = d.N;
-  const int bn = d.force_block_n ? d.force_block_n : pick_block_n(d.N, d.mode, m_tiles, num_sms);
+  // short-K GEMMs (<= 16 K steps, no taps): epilogue-latency bound -> 128-wide tiles, two CTAs per SM ("light" config)
+  const bool light_ok = d.ksize == 1 && (cin_total + (d.res ? d.N : 0)) <= 1024 && !d.ups2 && d.N >= 64 &&
+                        (d.mode == EPI_F16 || d.mode == EPI_F16_T || d.mode == EPI_F32) && d.n_store == 0;
+  const bool light = d.force_light == 1 || (d.force_light == 0 && d.force_block_n == 0 && light_ok);
+  L->light = light;
+  const int bn = light ? 128 : (d.force_block_n ? d.force_block_n : pick_block_n(d.N, d.mode, m_tiles, num_sms));
   if (d.mode == EPI_GEGLU) SDM_CHECK(bn == 256 && d.N % 256 == 0, "GEGLU needs N % 256 == 0");
   L->block_n = bn;
   p.n_tiles = (d.N + bn - 1) / bn;
   // 256 x 128 CTA tiles (two M sub-tiles per B tile) when there is enough work to keep every SM busy
-  L->mt = (bn == 128 && d.mode == EPI_F16 && d.force_mt != 1 && (d.force_mt == 2 || (m_tiles / 2) * p.n_tiles >= 2 * num_sms)) ? 2 : 1;
+  L->mt = (bn == 128 && !light && d.mode == EPI_F16 && d.force_mt != 1 && (d.force_mt == 2 || (m_tiles / 2) * p.n_tiles >= 2 * num_sms)) ? 2 : 1;
   p.m_tiles = (int)m_tiles;
   const long long total = ((m_tiles + L->mt - 1) / L->mt) * p.n_tiles;
   SDM_CHECK(total < (1ll << 31), "too many tiles");
@@ -198,7 +204,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   p.out2 = d.out2;
   p.stats = (d.mode == EPI_F16 && !d.ups2) ? d.stats : nullptr;
   if (d.mode == EPI_ALPHA) SDM_CHECK(d.N >= 3 && d.N <= 16 && d.bias != nullptr, "EPI_ALPHA needs 3..16 columns and a bias");
-  L->grid = (int)std::min<long long>(total, num_sms);
+  L->grid = (int)std::min<long long>(total, light ? 2 * num_sms : num_sms);
   L->flops = 2.0 * (double)d.B * Hout * Wout * (double)d.N * (double)ktot;
   return L;
 }
@@ -207,6 +213,12 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
   const ConvGemmParams& p = l.p;
   const int bn = l.block_n, mt = l.mt, g = l.grid;
 #define SDM_GO(BN, MT, MODE, UPS2) return conv_gemm_launch<BN, MT, MODE, UPS2>(p, g, st)
+  if (l.light) {
+    if (p.mode == EPI_F16 && !p.ups2) return conv_gemm_launch<128, 1, EPI_F16, false, true>(p, g, st);
+    if (p.mode == EPI_F16_T) return conv_gemm_launch<128, 1, EPI_F16_T, false, true>(p, g, st);
+    if (p.mode == EPI_F32) return conv_gemm_launch<128, 1, EPI_F32, false, true>(p, g, st);
+    throw Error{"conv_gemm: no light instantiation for this mode"};
+  }
   switch (p.mode) {
     case EPI_F16:
       if (!p.ups2) {

@@ -70,12 +70,14 @@ struct alignas(64) ConvGemmParams {
 
 // MT = number of 128-row M sub-tiles a CTA processes against ONE B tile (MT=2 halves the weight traffic per FLOP:
 // the N=128 VAE convs were L2->SM bandwidth bound at 128 B/clk/SM with MT=1, r1c: 545-885 TFLOP/s vs 1300-1440 for N=256)
-template <int BLOCK_N, int MT = 1>
+// LIGHT: 2 pipeline stages and <= 256 TMEM columns so that TWO CTAs share an SM: short-K GEMMs (linears, 1x1 convs, im2col
+// conv_in) are bound by the per-tile epilogue latency, and a second resident CTA doubles the epilogues in flight.
+template <int BLOCK_N, int MT = 1, bool LIGHT = false>
 struct ConvGemmCfg {
   static constexpr int kABytes = 128 * 128;          // 128 rows x 64 fp16 (per M sub-tile)
   static constexpr int kBBytes = BLOCK_N * 128;      // BLOCK_N rows x 64 fp16
   static constexpr int kStageBytes = MT * kABytes + kBBytes;
-  static constexpr int kStages = (206 * 1024 / kStageBytes) > 8 ? 8 : (206 * 1024 / kStageBytes);
+  static constexpr int kStages = LIGHT ? 2 : ((206 * 1024 / kStageBytes) > 8 ? 8 : (206 * 1024 / kStageBytes));
   static constexpr int kSubStride = BLOCK_N < 32 ? 32 : BLOCK_N;  // TMEM columns per M sub-tile accumulator
   static constexpr int kAccStride = MT * kSubStride;              // TMEM columns between the two accumulator stages
   static constexpr int kTmemCols = (2 * kAccStride <= 64) ? 64 : (2 * kAccStride <= 128) ? 128 : (2 * kAccStride <= 256) ? 256 : 512;
@@ -90,9 +92,10 @@ __device__ __forceinline__ void residual_chunks(int n0, int N, int& c_begin, int
   c_end = min(n0 + BLOCK_N, N);
 }
 
-template <int BLOCK_N, int MT, int MODE, bool UPS2>
-__global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BLOCK_N, MT>;
+template <int BLOCK_N, int MT, int MODE, bool UPS2, bool LIGHT = false>
+__global__ void __launch_bounds__(192, LIGHT ? 2 : 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using Cfg = ConvGemmCfg<BLOCK_N, MT, LIGHT>;
+  static_assert(!LIGHT || Cfg::kTmemCols <= 256, "two CTAs per SM need <= 256 TMEM columns each");
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;

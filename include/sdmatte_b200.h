@@ -92,6 +92,7 @@ typedef struct {
   int n_store;                  /* mode 0: store only the first n_store (< 8) columns; 0 = all */
   void* out2;                   /* mode 4 (alpha head): optional pre-clip mean */
   int force_mt;                 /* tests: 1 / 2 = force M sub-tiles per CTA tile (BLOCK_N 128 only), 0 = auto */
+  int force_light;              /* tests: 1 = force the 2-CTAs-per-SM short-K config, -1 = forbid it, 0 = auto */
   float* stats;                 /* mode 0 without ups2: GroupNorm partials [B][sdm_k_conv_tiles_per_image][N][2] (sum, sumsq), or NULL */
 } sdm_conv_gemm_args;
 int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream);

@@ -1,0 +1,93 @@
+"""Kernel micro-benchmarks (GPU): CUDA-event timings of the hot kernels at their real shapes (B=2, 1024^2 path).
+Not a test; used to compare kernel variants on the same box:  python tests/bench_kernels.py [filter]"""
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+E = ge.load_package().engine
+DEV = "cuda:0"
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def attn(B, heads, Lq, Lk, bias):
+    C = heads * 64
+    q = torch.randn(B, Lq, C, device=DEV).half()
+    k = torch.randn(B, Lk, C, device=DEV).half()
+    vt = torch.randn(B, C, Lk, device=DEV).half()
+    out = torch.empty(B, Lq, C, dtype=torch.float16, device=DEV)
+    bz = None
+    if bias:
+        lv = torch.randint(0, 3, (B, Lk), device=DEV).float()
+        bz = (lv * -5000.0 * math.log2(math.e)).contiguous()
+    ms = timeit(lambda: E.k_attention(q, k, vt, out, B=B, heads=heads, Lq=Lq, Lk=Lk, ldq=C, ldk=C, ldvt=Lk, ldo=C, bias=bz, bias_bstride=Lk))
+    fl = 4.0 * B * heads * Lq * Lk * 64
+    return ms, fl / ms / 1e9
+
+
+def conv(B, H, W, Cin, Cout, k=3, res=False, stats=False):
+    x = torch.randn(B, H, W, Cin, device=DEV).half()
+    w = (torch.randn(Cout, k * k * Cin, device=DEV) * (k * k * Cin) ** -0.5).half()
+    b = torch.randn(Cout, device=DEV)
+    out = torch.empty(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    r = torch.randn(B, H, W, Cout, device=DEV).half() if res else None
+    st = torch.empty(B, E.conv_tiles_per_image(H, W), Cout, 2, device=DEV) if stats else None
+    ms = timeit(lambda: E.k_conv_gemm([(x, Cin, Cin)], w, Cout, out, B=B, Hin=H, Win=W, ksize=k, bias=b, out_ld=Cout, out_bstride=H * W * Cout,
+                                      res=(r, Cout, H * W * Cout) if res else None, stats=st))
+    fl = 2.0 * B * H * W * Cout * k * k * Cin
+    return ms, fl / ms / 1e9
+
+
+def linear(B, M, N, K, res=False):
+    x = torch.randn(B, M, K, device=DEV).half()
+    w = (torch.randn(N, K, device=DEV) * K ** -0.5).half()
+    b = torch.randn(N, device=DEV)
+    out = torch.randn(B, M, N, device=DEV).half()
+    ms = timeit(lambda: E.k_conv_gemm([(x, K, K)], w, N, out, B=B, Hin=1, Win=M, bias=b, out_ld=N, out_bstride=M * N,
+                                      res=(out, N, M * N) if res else None))
+    return ms, 2.0 * B * M * N * K / ms / 1e9
+
+
+CASES = {
+    "attn_self_L0 (B2 h5 16384x16384 bias)": lambda: attn(2, 5, 16384, 16384, True),
+    "attn_cross_L0 (B2 h5 16384x16384)": lambda: attn(2, 5, 16384, 16384, False),
+    "attn_cross_L1 (B2 h10 4096x16384)": lambda: attn(2, 10, 4096, 16384, False),
+    "attn_self_L2 (B2 h20 1024x1024 bias)": lambda: attn(2, 20, 1024, 1024, True),
+    "conv3x3 128->128 @1024^2 B2": lambda: conv(2, 1024, 1024, 128, 128),
+    "conv3x3 128->128 @1024^2 B2 +res+stats": lambda: conv(2, 1024, 1024, 128, 128, res=True, stats=True),
+    "conv3x3 256->256 @512^2 B4": lambda: conv(4, 512, 512, 256, 256),
+    "conv3x3 256->256 @512^2 B4 +res+stats": lambda: conv(4, 512, 512, 256, 256, res=True, stats=True),
+    "conv3x3 512->512 @256^2 B4": lambda: conv(4, 256, 256, 512, 512),
+    "conv3x3 320->320 @128^2 B8 +stats": lambda: conv(8, 128, 128, 320, 320, stats=True),
+    "conv1x1 128->256 @512^2 B4": lambda: conv(4, 512, 512, 128, 256, k=1),
+    "linear 16384x320x320 B8 +res": lambda: linear(8, 16384, 320, 320, res=True),
+    "linear 16384x320x1024 B8 (cross K)": lambda: linear(8, 16384, 320, 1024),
+    "linear 4096x640x640 B8": lambda: linear(8, 4096, 640, 640),
+    "linear 16384x320x1280 B8 +res (ff out)": lambda: linear(8, 16384, 320, 1280, res=True),
+}
+
+if __name__ == "__main__":
+    flt = sys.argv[1] if len(sys.argv) > 1 else ""
+    print(f"{'case':48s} {'ms':>9s} {'TFLOP/s':>9s}")
+    for name, fn in CASES.items():
+        if flt and flt not in name:
+            continue
+        ms, tf = fn()
+        print(f"{name:48s} {ms:9.3f} {tf:9.1f}")

@@ -439,3 +439,30 @@ def test_conv_epilogue_groupnorm_partials(eng_mod, B, H, W, Cin, Cout, mt):
     ref = F.silu(F.group_norm(out.float().view(B, H * W, Cout).transpose(1, 2), 32, g, bt, 1e-5)).transpose(1, 2)
     _close(y2, ref, 2e-3, 2e-3, "groupnorm from epilogue partials")
     assert (y1.float() - y2.float()).abs().max().item() <= 2e-3
+
+
+@pytest.mark.parametrize("mode", ["f16", "f16_res", "vT", "f32"])
+def test_light_config_two_ctas_per_sm(eng_mod, mode):
+    """Short-K GEMMs run as 128-wide tiles with two CTAs per SM ("light" config)."""
+    B, M, N, K = 2, 1000, 320, 320
+    x = _rand(B, M, K, seed=1).half()
+    w = _rand(N, K, scale=K ** -0.5, seed=2).half()
+    b = _rand(N, seed=3).float()
+    if mode == "f16":
+        out = torch.zeros(B, M, N, dtype=torch.float16, device=DEV)
+        eng_mod.k_conv_gemm([(x, K, K)], w, N, out, B=B, Hin=1, Win=M, bias=b, out_ld=N, out_bstride=M * N, force_light=1)
+        ref = x.float() @ w.float().t() + b
+    elif mode == "f16_res":
+        out = _rand(B, M, N, seed=4).half()
+        ref = x.float() @ w.float().t() + b + out.float()
+        eng_mod.k_conv_gemm([(x, K, K)], w, N, out, B=B, Hin=1, Win=M, bias=b, out_ld=N, out_bstride=M * N, res=(out, N, M * N), force_light=1)
+    elif mode == "vT":
+        out = torch.zeros(B, N, M, dtype=torch.float16, device=DEV)
+        eng_mod.k_conv_gemm([(x, K, K)], w, N, out, B=B, Hin=1, Win=M, mode=1, out_ld=M, out_bstride=N * M, force_light=1)
+        ref = (x.float() @ w.float().t()).transpose(1, 2)
+    else:
+        out = torch.zeros(B, M, N, dtype=torch.float32, device=DEV)
+        eng_mod.k_conv_gemm([(x, K, K)], w, N, out, B=B, Hin=1, Win=M, mode=3, scale=0.5, out_ld=N, out_bstride=M * N, force_light=1)
+        ref = (x.float() @ w.float().t()) * 0.5
+    torch.cuda.synchronize()
+    _close(out, ref, 2e-3, 2e-3, f"light {mode}")
