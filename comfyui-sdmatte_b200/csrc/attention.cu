@@ -24,6 +24,7 @@
 #include "kernels.h"
 #include "tmap.h"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace sdm {
@@ -286,14 +287,31 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   }
 }
 
+struct Attn5Launch;
+std::shared_ptr<Attn5Launch> attn5_build(const AttnDesc& d);
+void attn5_run(const Attn5Launch& l, cudaStream_t st);
+
 struct AttnLaunch {
   AttnParams p;
   dim3 grid;
   bool has_bias;
+  std::shared_ptr<Attn5Launch> v5;  // 128-key-tile variant (attention5.cu), selected with SDM_ATTN_VARIANT
 };
+
+static int attn_variant() {
+  static int v = [] {
+    const char* e = getenv("SDM_ATTN_VARIANT");
+    return e ? atoi(e) : 5;
+  }();
+  return v;
+}
 
 std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d) {
   auto L = std::make_shared<AttnLaunch>();
+  if (attn_variant() == 5) {
+    L->v5 = attn5_build(d);
+    return L;
+  }
   AttnParams& p = L->p;
   memset(&p, 0, sizeof(p));
   SDM_CHECK(d.Lq > 0 && d.Lk > 0 && d.heads > 0, "attention dims");
@@ -330,6 +348,7 @@ std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d) {
 }
 
 void attn_run(const AttnLaunch& l, cudaStream_t st) {
+  if (l.v5) return attn5_run(*l.v5, st);
   static std::once_flag once;
   std::call_once(once, [] {
     SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));

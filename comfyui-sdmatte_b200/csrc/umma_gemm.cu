@@ -3,6 +3,7 @@
 #include "umma_launch.h"
 #include "tmap.h"
 
+#include <cstdlib>
 #include <map>
 
 #include <mutex>
@@ -14,6 +15,7 @@ struct ConvGemmLaunch {
   int block_n = 0;
   int mt = 1;
   bool light = false;
+  int ewg = 1;
   int grid = 0;
   double flops = 0;
 };
@@ -96,9 +98,10 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * d.B;
   p.N = d.N;
   // short-K GEMMs (<= 16 K steps, no taps): epilogue-latency bound -> 128-wide tiles, two CTAs per SM ("light" config)
-  const bool light_ok = d.ksize == 1 && (cin_total + (d.res ? d.N : 0)) <= 1024 && !d.ups2 && d.N >= 64 &&
+  const bool light_ok = d.ksize == 1 && cin_total <= 1024 && !d.ups2 && d.N >= 64 &&
                         (d.mode == EPI_F16 || d.mode == EPI_F16_T || d.mode == EPI_F32) && d.n_store == 0;
-  const bool light = d.force_light == 1 || (d.force_light == 0 && d.force_block_n == 0 && light_ok);
+  (void)light_ok;  // measured (r1i): the two-CTAs-per-SM config is slower than 160/256-wide tiles -> only on request
+  const bool light = d.force_light == 1;
   L->light = light;
   const int bn = light ? 128 : (d.force_block_n ? d.force_block_n : pick_block_n(d.N, d.mode, m_tiles, num_sms));
   if (d.mode == EPI_GEGLU) SDM_CHECK(bn == 256 && d.N % 256 == 0, "GEGLU needs N % 256 == 0");
@@ -180,7 +183,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
     make_tmap(&p.r_map, d.res, 4, dims, strides, box);
     const uint64_t idims[2] = {(uint64_t)kIdentityN, (uint64_t)kIdentityN};
     const uint64_t istr[1] = {(uint64_t)kIdentityN * 2};
-    const uint32_t ibox[2] = {64u, (uint32_t)bn};
+    const uint32_t ibox[2] = {64u, 64u};
     make_tmap(&p.i_map, identity_matrix(), 2, idims, istr, ibox);
     p.has_res = 1;
   } else {
@@ -204,6 +207,22 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   p.out2 = d.out2;
   p.stats = (d.mode == EPI_F16 && !d.ups2) ? d.stats : nullptr;
   if (d.mode == EPI_ALPHA) SDM_CHECK(d.N >= 3 && d.N <= 16 && d.bias != nullptr, "EPI_ALPHA needs 3..16 columns and a bias");
+  {
+    // epilogue warpgroups: two for the GEMMs whose K loop is too short to hide one epilogue (SDM_EWG=1|2 overrides, for A/B runs)
+    static const int env_ewg = [] { const char* e = getenv("SDM_EWG"); return e ? atoi(e) : 0; }();
+    // measured (A/B on one box): 2 warpgroups help short-K tiles (1x1 conv K=128: 170 -> 294 TFLOP/s), cost a pipeline stage on the
+    // 256-wide and 256x128 tiles (1337 -> 1299) -> only where the tile is <= 160 wide and single
+    const long long ksteps = (long long)p.ntaps * (cin_total / 64);
+    int ewg = (p.mode == EPI_GEGLU || p.mode == EPI_F32 || p.mode == EPI_F16_T ||
+               (p.mode == EPI_F16 && L->mt == 1 && (bn <= 160 || ksteps <= 16))) ? 2 : 1;
+    if (env_ewg == 1 || env_ewg == 2) ewg = env_ewg;
+    if (bn == 16 || light || p.mode == EPI_ALPHA || p.mode == EPI_SKINNY) ewg = 1;
+    L->ewg = ewg;
+  }
+  {
+    static const int env_pf = [] { const char* e = getenv("SDM_PREFETCH"); return e ? atoi(e) : 0; }();
+    p.prefetch = env_pf;  // measured (A/B, one box): L2 prefetch of the next tile slows the large convs by 3-9 % -> off by default
+  }
   L->grid = (int)std::min<long long>(total, light ? 2 * num_sms : num_sms);
   L->flops = 2.0 * (double)d.B * Hout * Wout * (double)d.N * (double)ktot;
   return L;
@@ -212,7 +231,11 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
 void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
   const ConvGemmParams& p = l.p;
   const int bn = l.block_n, mt = l.mt, g = l.grid;
-#define SDM_GO(BN, MT, MODE, UPS2) return conv_gemm_launch<BN, MT, MODE, UPS2>(p, g, st)
+#define SDM_GO(BN, MT, MODE, UPS2)                                                  \
+  do {                                                                              \
+    if (l.ewg == 2) return conv_gemm_launch<BN, MT, MODE, UPS2, false, 2>(p, g, st); \
+    return conv_gemm_launch<BN, MT, MODE, UPS2, false, 1>(p, g, st);                 \
+  } while (0)
   if (l.light) {
     if (p.mode == EPI_F16 && !p.ups2) return conv_gemm_launch<128, 1, EPI_F16, false, true>(p, g, st);
     if (p.mode == EPI_F16_T) return conv_gemm_launch<128, 1, EPI_F16_T, false, true>(p, g, st);
@@ -227,7 +250,7 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
         if (bn == 128 && mt == 2) SDM_GO(128, 2, EPI_F16, false);
         if (bn == 128) SDM_GO(128, 1, EPI_F16, false);
         if (bn == 64) SDM_GO(64, 1, EPI_F16, false);
-        if (bn == 16) SDM_GO(16, 1, EPI_F16, false);
+        if (bn == 16) return conv_gemm_launch<16, 1, EPI_F16, false, false, 1>(p, g, st);
       } else {
         if (bn == 256) SDM_GO(256, 1, EPI_F16, true);
         if (bn == 160) SDM_GO(160, 1, EPI_F16, true);
@@ -251,10 +274,10 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
       if (bn == 64) SDM_GO(64, 1, EPI_F32, false);
       break;
     case EPI_ALPHA:
-      if (bn == 16) SDM_GO(16, 1, EPI_ALPHA, false);
+      if (bn == 16) return conv_gemm_launch<16, 1, EPI_ALPHA, false, false, 1>(p, g, st);
       break;
     case EPI_SKINNY:
-      if (bn == 16) SDM_GO(16, 1, EPI_SKINNY, false);
+      if (bn == 16) return conv_gemm_launch<16, 1, EPI_SKINNY, false, false, 1>(p, g, st);
       break;
   }
 #undef SDM_GO

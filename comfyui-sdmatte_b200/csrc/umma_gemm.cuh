@@ -14,8 +14,9 @@
 //   128 rows x 128 B with the 128-byte swizzle, exactly the K-major layout tcgen05.mma expects.
 // B operand ("weight"): [N][Ktot] fp16, K contiguous, Ktot ordered (tap, cin); 2-D map (or 3-D batched).
 // Residual: "+ x" of ResnetBlock2D / Attention / FeedForward / Transformer2DModel is folded into the contraction as
-//   extra K steps  A = residual tile (TMA, 64 channels),  B = the matching 64 columns of an identity matrix:
-//   the add costs N/64 MMA steps and no epilogue work or uncoalesced loads (fp32 accumulate of fp16 * 1.0 is exact).
+//   extra K steps  A = residual tile (TMA, 64 channels),  B = a 64x64 identity block, issued as N=64 MMAs into the matching
+//   64 accumulator columns: the add costs about one K step per tile and no epilogue work or uncoalesced loads
+//   (fp32 accumulate of fp16 * 1.0 is exact).
 // D: MT x (128 x BLOCK_N) fp32 accumulators in TMEM, double buffered so the epilogue of tile i overlaps
 //   the main loop of tile i+1.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
 //   alloc), warps 2..5 = epilogue (TMEM -> registers -> bias/activation -> smem staging -> row-contiguous stores).
@@ -53,6 +54,7 @@ struct alignas(64) ConvGemmParams {
   signed char tap_map[9], tap_dx[9], tap_dy[9];
   int b_batched;      // weight map has a batch coordinate
   int has_res;        // residual K steps present
+  int prefetch;       // L2-prefetch the next tile's activation rows
   int mode;
   int ups2;           // EPI_F16 only: write each pixel to the 2x2 block of a (2H,2W) output
   void* out;
@@ -72,29 +74,37 @@ struct alignas(64) ConvGemmParams {
 // the N=128 VAE convs were L2->SM bandwidth bound at 128 B/clk/SM with MT=1, r1c: 545-885 TFLOP/s vs 1300-1440 for N=256)
 // LIGHT: 2 pipeline stages and <= 256 TMEM columns so that TWO CTAs share an SM: short-K GEMMs (linears, 1x1 convs, im2col
 // conv_in) are bound by the per-tile epilogue latency, and a second resident CTA doubles the epilogues in flight.
-template <int BLOCK_N, int MT = 1, bool LIGHT = false>
+// EWG: number of epilogue warpgroups.  With 2, tile i of a CTA is drained by warpgroup i%2 (MT=1) or the two M sub-tiles
+// of a tile are drained concurrently (MT=2): twice the epilogues in flight for the GEMMs whose short K loop cannot hide
+// one (r1i: linears 350-600 TFLOP/s, the N=128 VAE convs ~1000 vs ~1400 for long-K layers).
+template <int BLOCK_N, int MT = 1, bool LIGHT = false, int EWG = 1>
 struct ConvGemmCfg {
   static constexpr int kABytes = 128 * 128;          // 128 rows x 64 fp16 (per M sub-tile)
   static constexpr int kBBytes = BLOCK_N * 128;      // BLOCK_N rows x 64 fp16
   static constexpr int kStageBytes = MT * kABytes + kBBytes;
-  static constexpr int kStages = LIGHT ? 2 : ((206 * 1024 / kStageBytes) > 8 ? 8 : (206 * 1024 / kStageBytes));
+  static constexpr int kEpiBytes = EWG * (4 * 4096 /*staging*/ + 2048 /*GroupNorm partials*/);
+  static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes - 512;
+  static constexpr int kStages = LIGHT ? 2 : ((kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes));
   static constexpr int kSubStride = BLOCK_N < 32 ? 32 : BLOCK_N;  // TMEM columns per M sub-tile accumulator
   static constexpr int kAccStride = MT * kSubStride;              // TMEM columns between the two accumulator stages
   static constexpr int kTmemCols = (2 * kAccStride <= 64) ? 64 : (2 * kAccStride <= 128) ? 128 : (2 * kAccStride <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 4096 /*epilogue staging*/ + 2048 /*GroupNorm partials*/;
-  static constexpr int kThreads = 192;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
+  static constexpr int kThreads = 64 + 128 * EWG;
 };
 
-// number of residual K steps of the tile starting at output column n0 (64-channel chunks overlapping [n0, n0+BLOCK_N))
+// residual K steps of the tile starting at output column n0: one per 64-channel slice of the tile's own columns.
+// Step i multiplies the residual slice [n0+64i, n0+64i+64) with the 64x64 identity block and accumulates into the
+// accumulator columns [64i, 64i+64) only (an N=64 — or N=32 for the ragged end of a 160-wide tile — MMA), so the whole
+// residual costs about ONE full K step per tile regardless of BLOCK_N.
 template <int BLOCK_N>
-__device__ __forceinline__ void residual_chunks(int n0, int N, int& c_begin, int& c_end) {
-  c_begin = (n0 >> 6) << 6;
-  c_end = min(n0 + BLOCK_N, N);
+__device__ __forceinline__ int residual_steps(int n0, int N) {
+  return (min(BLOCK_N, N - n0) + 63) >> 6;
 }
 
-template <int BLOCK_N, int MT, int MODE, bool UPS2, bool LIGHT = false>
-__global__ void __launch_bounds__(192, LIGHT ? 2 : 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BLOCK_N, MT, LIGHT>;
+template <int BLOCK_N, int MT, int MODE, bool UPS2, bool LIGHT = false, int EWG = 1>
+__global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using Cfg = ConvGemmCfg<BLOCK_N, MT, LIGHT, EWG>;
+  static_assert(EWG == 1 || EWG == 2, "one or two epilogue warpgroups");
   static_assert(!LIGHT || Cfg::kTmemCols <= 256, "two CTAs per SM need <= 256 TMEM columns each");
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -119,7 +129,7 @@ __global__ void __launch_bounds__(192, LIGHT ? 2 : 1) conv_gemm_kernel(const __g
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), (EWG == 2 && MT == 2) ? 8 : 4);
     }
     fence_barrier_init();
     fence_proxy_async_smem();
@@ -153,6 +163,27 @@ __global__ void __launch_bounds__(192, LIGHT ? 2 : 1) conv_gemm_kernel(const __g
           x0[u] = tx * p.tw; y0[u] = ty * p.th;
           bb[u] = mt < p.m_tiles ? mt / (p.tiles_x * p.tiles_y) : p.B;  // past-the-end sub-tile: batch index out of range -> zero fill
         }
+        // L2 prefetch of the NEXT tile's activation rows (centre column of every tap row): its cold misses then overlap this
+        // tile's main loop instead of stalling the 4-stage ring (ncu r1i, 128->128 conv: 20 % of the A sectors missed L2,
+        // tensor pipe 64 % busy with L2 at 52 % and DRAM at 22 %: latency, not bandwidth)
+        {
+          const int nxt = tile + (int)gridDim.x;
+          if (p.prefetch && nxt < p.total_tiles && (nxt % p.n_tiles) == 0) {
+#pragma unroll
+            for (int u = 0; u < MT; ++u) {
+              const int mt = (nxt / p.n_tiles) * MT + u;
+              if (mt < p.m_tiles) {
+                const int ptx = mt % p.tiles_x, pty = (mt / p.tiles_x) % p.tiles_y, pb = mt / (p.tiles_x * p.tiles_y);
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                  if (p.tap_dx[tap] != 0) continue;
+                  for (int s = 0; s < p.nsrc; ++s)
+                    for (int c0 = 0; c0 < p.src_c[s]; c0 += 64)
+                      tma_prefetch_4d(&p.a_map[p.tap_map[tap] + s], c0, ptx * p.tw, pty * p.th + p.tap_dy[tap], pb);
+                }
+              }
+            }
+          }
+        }
         for (int tap = 0; tap < p.ntaps; ++tap) {
           int koff = tap * p.cin_total;
           for (int s = 0; s < p.nsrc; ++s) {
@@ -174,17 +205,16 @@ __global__ void __launch_bounds__(192, LIGHT ? 2 : 1) conv_gemm_kernel(const __g
             koff += p.src_c[s];
           }
         }
-        if (p.has_res) {  // residual as K steps against the identity
-          int cb, ce;
-          residual_chunks<BLOCK_N>(n0, p.N, cb, ce);
-          for (int c0 = cb; c0 < ce; c0 += 64) {
+        if (p.has_res) {  // residual as K steps against the 64x64 identity block
+          const int nres = residual_steps<BLOCK_N>(n0, p.N);
+          for (int i = 0; i < nres; ++i) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
             const uint32_t b_dst = a_dst + MT * Cfg::kABytes;
-            mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            mbar_expect_tx(full_bar(stage), MT * Cfg::kABytes + 64 * 128);
 #pragma unroll
-            for (int u = 0; u < MT; ++u) tma_load_4d(a_dst + u * Cfg::kABytes, &p.r_map, full_bar(stage), c0, x0[u], y0[u], bb[u]);
-            tma_load_2d(b_dst, &p.i_map, full_bar(stage), c0, n0);
+            for (int u = 0; u < MT; ++u) tma_load_4d(a_dst + u * Cfg::kABytes, &p.r_map, full_bar(stage), n0 + i * 64, x0[u], y0[u], bb[u]);
+            tma_load_2d(b_dst, &p.i_map, full_bar(stage), 0, 0);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -199,27 +229,26 @@ __global__ void __launch_bounds__(192, LIGHT ? 2 : 1) conv_gemm_kernel(const __g
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int nks = num_ksteps;
-        if (p.has_res) {
-          int cb, ce;
-          residual_chunks<BLOCK_N>((tile % p.n_tiles) * BLOCK_N, p.N, cb, ce);
-          nks += (ce - cb + 63) >> 6;
-        }
+        const int n0 = (tile % p.n_tiles) * BLOCK_N;
+        const int nres = p.has_res ? residual_steps<BLOCK_N>(n0, p.N) : 0;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
-        for (int ks = 0; ks < nks; ++ks) {
+        for (int ks = 0; ks < num_ksteps + nres; ++ks) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
           const uint64_t bdesc = umma_desc_k128(a_addr + MT * Cfg::kABytes);
+          const int ri = ks - num_ksteps;  // >= 0: residual slice index
+          const uint32_t id = ri < 0 ? idesc : umma_idesc_f16(min(64, BLOCK_N - ri * 64));
+          const uint32_t dcol = ri < 0 ? 0u : (uint32_t)(ri * 64);
 #pragma unroll
           for (int u = 0; u < MT; ++u) {
             const uint64_t adesc = umma_desc_k128(a_addr + u * Cfg::kABytes);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // +32 B per 16-element K step (start-address field is in 16-byte units)
-              umma_f16(d_tmem + u * Cfg::kSubStride, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+              umma_f16(d_tmem + u * Cfg::kSubStride + dcol, adesc + 2 * k, bdesc + 2 * k, id, (ks | k) != 0);
             }
           }
           umma_commit(empty_bar(stage));
@@ -235,20 +264,27 @@ __global__ void __launch_bounds__(192, LIGHT ? 2 : 1) conv_gemm_kernel(const __g
     // row-contiguous through a per-warp 32 x 128 B staging tile in shared memory (XOR-swizzled 16-byte pieces):
     // a warp-wide 16-byte store then covers 4 rows x 128 contiguous bytes (4 L2 lines) instead of 32 rows x 16 bytes.
     const int quad = warp & 3;
+    const int ewg = (warp - 2) >> 2;   // epilogue warpgroup of this warp (0 or 1)
     const int row = quad * 32 + lane;  // row of the 128-row tile == TMEM lane
-    uint8_t* stg = smem_raw + (bar_base - smem_u32(smem_raw)) + 256 + (warp - 2) * 4096;
+    uint8_t* epi_base = smem_raw + (bar_base - smem_u32(smem_raw)) + 256;
+    uint8_t* stg = epi_base + (warp - 2) * 4096;
+    float* sred = reinterpret_cast<float*>(epi_base + EWG * 4 * 4096 + ewg * 2048);
     const int t_row0 = lane >> 3, t_piece = lane & 7;
     int ltw = 0;
     while ((1 << ltw) < p.tw) ++ltw;
-    int acc = 0;
+    // tile -> warpgroup assignment: MT=1 with two warpgroups alternates tiles (warpgroup e drains accumulator stage e);
+    // otherwise every warpgroup sees every tile (and, for MT=2, owns M sub-tile `ewg`)
+    constexpr bool kAlternate = (EWG == 2 && MT == 1);
+    int acc = kAlternate ? ewg : 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + (kAlternate ? ewg * (int)gridDim.x : 0); tile < p.total_tiles;
+         tile += (kAlternate ? 2 : 1) * (int)gridDim.x) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int nt = tile % p.n_tiles;
       const int n0 = nt * BLOCK_N;
 #pragma unroll 1
-      for (int u = 0; u < MT; ++u) {
+      for (int u = (EWG == 2 && MT == 2) ? ewg : 0; u < ((EWG == 2 && MT == 2) ? ewg + 1 : MT); ++u) {
         const int mt = (tile / p.n_tiles) * MT + u;
         if (mt >= p.m_tiles) break;  // warp-uniform
         const int tx = mt % p.tiles_x;
@@ -411,7 +447,6 @@ __global__ void __launch_bounds__(192, LIGHT ? 2 : 1) conv_gemm_kernel(const __g
                   ssq[e] += __shfl_xor_sync(0xffffffffu, ssq[e], 16);
                 }
                 // combine the four epilogue warps in a fixed order through shared memory (one global writer per slot)
-                float* sred = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256 + 4 * 4096);
                 if (lane < 8) {
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
@@ -419,7 +454,7 @@ __global__ void __launch_bounds__(192, LIGHT ? 2 : 1) conv_gemm_kernel(const __g
                     sred[(quad * 64 + lane * 8 + e) * 2 + 1] = ssq[e];
                   }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + ewg) : "memory");
                 if (quad == 0) {
                   const int cc = lane * 2;  // two columns per lane
                   const int gcol = n0 + c + cc;
@@ -433,7 +468,7 @@ __global__ void __launch_bounds__(192, LIGHT ? 2 : 1) conv_gemm_kernel(const __g
                     *reinterpret_cast<float4*>(p.stats + (slot * p.N + gcol) * 2) = o;
                   }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + ewg) : "memory");
               }
             }
           }
@@ -497,7 +532,8 @@ __global__ void __launch_bounds__(192, LIGHT ? 2 : 1) conv_gemm_kernel(const __g
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (kAlternate) acc_phase ^= 1u;
+      else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 

@@ -1,0 +1,9 @@
+#include "umma_launch.h"
+namespace sdm {
+SDM_DEFINE_CONV_GEMM_LAUNCH_E(256, 1, EPI_F16_T, false, false, 2)
+SDM_DEFINE_CONV_GEMM_LAUNCH_E(160, 1, EPI_F16_T, false, false, 2)
+SDM_DEFINE_CONV_GEMM_LAUNCH_E(128, 1, EPI_F16_T, false, false, 2)
+SDM_DEFINE_CONV_GEMM_LAUNCH_E(64, 1, EPI_F16_T, false, false, 2)
+SDM_DEFINE_CONV_GEMM_LAUNCH_E(128, 1, EPI_F32, false, false, 2)
+SDM_DEFINE_CONV_GEMM_LAUNCH_E(64, 1, EPI_F32, false, false, 2)
+}  // namespace sdm
