@@ -245,18 +245,21 @@ __global__ void __launch_bounds__(a5::kThreads, 1) attention_kernel(const __grid
           m2 = m_new;
         }
         const float neg_m = -m2;
+        // all 32 exponentials first (32 independent FFMA -> MUFU chains keep the XU pipe fed), then the sums / packing
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          e[i] = HAS_BIAS ? ex2f(xs[i] + neg_m) : ex2f(fmaf(__uint_as_float(rr[i]), sc, neg_m));
+        float part[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float e[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            e[i] = HAS_BIAS ? ex2f(xs[q * 8 + i] + neg_m) : ex2f(fmaf(__uint_as_float(rr[q * 8 + i]), sc, neg_m));
-          rowsum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-          P[(c * 4 + q) * 4 + 0] = pack_h2(e[0], e[1]);
-          P[(c * 4 + q) * 4 + 1] = pack_h2(e[2], e[3]);
-          P[(c * 4 + q) * 4 + 2] = pack_h2(e[4], e[5]);
-          P[(c * 4 + q) * 4 + 3] = pack_h2(e[6], e[7]);
+          part[q] = ((e[q * 8 + 0] + e[q * 8 + 1]) + (e[q * 8 + 2] + e[q * 8 + 3])) + ((e[q * 8 + 4] + e[q * 8 + 5]) + (e[q * 8 + 6] + e[q * 8 + 7]));
+          P[(c * 4 + q) * 4 + 0] = pack_h2(e[q * 8 + 0], e[q * 8 + 1]);
+          P[(c * 4 + q) * 4 + 1] = pack_h2(e[q * 8 + 2], e[q * 8 + 3]);
+          P[(c * 4 + q) * 4 + 2] = pack_h2(e[q * 8 + 4], e[q * 8 + 5]);
+          P[(c * 4 + q) * 4 + 3] = pack_h2(e[q * 8 + 6], e[q * 8 + 7]);
         }
+        rowsum += (part[0] + part[1]) + (part[2] + part[3]);
       };
 
       tmem_ld_wait();

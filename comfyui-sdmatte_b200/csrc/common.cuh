@@ -173,6 +173,19 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// erf(z) by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 7 FMA-pipe ops.
+// Used by the GEGLU epilogue (exact-erf GELU of the reference, rounded to fp16 right after).
+__device__ __forceinline__ float erf_fast(float z) {
+  const float a = fabsf(z);
+  const float t = __frcp_rn(fmaf(0.3275911f, a, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float r = 1.0f - p * ex2f(-a * a * 1.4426950408889634f);
+  return copysignf(r, z);
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

@@ -70,17 +70,18 @@ __global__ void gn_stats_kernel(const __half* __restrict__ s0, const __half* __r
 
 // one 128-thread CTA per (b, group): reduce the slab partials in fp64 (fixed order => deterministic), emit per-channel
 // scale/shift
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ part0, const float* __restrict__ part1, int C0,
+template <int NT>
+__global__ void __launch_bounds__(NT) gn_finalize_kernel(const float* __restrict__ part0, const float* __restrict__ part1, int C0,
                                                           int nslab, int Ctot, int HW, float eps, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float* __restrict__ ab) {
-  __shared__ double red[2][4];
+  __shared__ double red[2][NT / 32];
   const int b = blockIdx.x >> 5, g = blockIdx.x & 31;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gs = Ctot >> 5;
   const int C1 = Ctot - C0;
   double s = 0.0, q = 0.0;
   const int n = nslab * gs;
-  for (int i = threadIdx.x; i < n; i += 128) {
+  for (int i = threadIdx.x; i < n; i += NT) {
     const int slab = i / gs, c = g * gs + i % gs;
     const float* src = (c < C0) ? part0 + (((size_t)b * nslab + slab) * C0 + c) * 2
                                 : part1 + (((size_t)b * nslab + slab) * C1 + (c - C0)) * 2;
@@ -95,15 +96,17 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
   }
   if (lane == 0) { red[0][warp] = s; red[1][warp] = q; }
   __syncthreads();
-  s = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
-  q = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+  s = 0.0;
+  q = 0.0;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) { s += red[0][w]; q += red[1][w]; }  // fixed order: deterministic
   const double cnt = (double)HW * gs;
   const double mean = s / cnt;
   double var = q / cnt - mean * mean;
   if (var < 0.0) var = 0.0;
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
   const float fmean = (float)mean;
-  for (int cc = threadIdx.x; cc < gs; cc += 128) {
+  for (int cc = threadIdx.x; cc < gs; cc += NT) {
     const int c = g * gs + cc;
     const float a = rstd * gamma[c];
     ab[((size_t)b * Ctot + c) * 2] = a;
@@ -181,12 +184,17 @@ void groupnorm_run(const GroupNormDesc& d, cudaStream_t st) {
   }
   if (d.pre_partial[0] && (d.nsrc == 1 || d.pre_partial[1])) {
     // statistics were produced by the epilogue of the conv(s) that wrote the input: only reduce them
-    gn_finalize_kernel<<<d.B * 32, 128, 0, st>>>(d.pre_partial[0], d.nsrc > 1 ? d.pre_partial[1] : d.pre_partial[0], C0, d.pre_slots, Ctot,
-                                                 d.HW, d.eps, d.gamma, d.beta, ab);
+    // the thread count only depends on the per-sample slot count, never on B (batch-invariant reduction order)
+    if ((long long)d.pre_slots * (Ctot / 32) > 4096)
+      gn_finalize_kernel<512><<<d.B * 32, 512, 0, st>>>(d.pre_partial[0], d.nsrc > 1 ? d.pre_partial[1] : d.pre_partial[0], C0, d.pre_slots,
+                                                        Ctot, d.HW, d.eps, d.gamma, d.beta, ab);
+    else
+      gn_finalize_kernel<128><<<d.B * 32, 128, 0, st>>>(d.pre_partial[0], d.nsrc > 1 ? d.pre_partial[1] : d.pre_partial[0], C0, d.pre_slots,
+                                                        Ctot, d.HW, d.eps, d.gamma, d.beta, ab);
   } else {
     gn_stats_kernel<<<dim3(nslab, d.B), dim3(nvec, ny), smem, st>>>(d.src[0], s1, C0, Ctot, d.ld[0], ld1, d.HW, pps, partial);
     SDM_CUDA_OK(cudaGetLastError());
-    gn_finalize_kernel<<<d.B * 32, 128, 0, st>>>(partial, partial, Ctot, nslab, Ctot, d.HW, d.eps, d.gamma, d.beta, ab);
+    gn_finalize_kernel<128><<<d.B * 32, 128, 0, st>>>(partial, partial, Ctot, nslab, Ctot, d.HW, d.eps, d.gamma, d.beta, ab);
   }
   SDM_CUDA_OK(cudaGetLastError());
   const int app_pps = ny * 16;  // 16 pixels per thread

@@ -337,6 +337,19 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
                 tmem_ld32(taddr + c + hh * 32, rv);
                 tmem_ld32(taddr + HALF + c + hh * 32, rg);
                 tmem_ld_wait();
+                float bv[32], bg[32];
+                if (bias) {
+#pragma unroll
+                  for (int g4 = 0; g4 < 8; ++g4) {
+                    const float4 x4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + hh * 32 + g4 * 4));
+                    const float4 y4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + HALF + c + hh * 32 + g4 * 4));
+                    bv[g4 * 4] = x4.x; bv[g4 * 4 + 1] = x4.y; bv[g4 * 4 + 2] = x4.z; bv[g4 * 4 + 3] = x4.w;
+                    bg[g4 * 4] = y4.x; bg[g4 * 4 + 1] = y4.y; bg[g4 * 4 + 2] = y4.z; bg[g4 * 4 + 3] = y4.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) { bv[i] = 0.f; bg[i] = 0.f; }
+                }
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                   uint32_t w[4];
@@ -346,16 +359,10 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                       const int i = g * 8 + j * 2 + e;
-                      float v = __uint_as_float(rv[i]);
-                      float gt = __uint_as_float(rg[i]);
-                      if (bias) {
-                        v += bias[n0 + c + hh * 32 + i];
-                        gt += bias[n0 + HALF + c + hh * 32 + i];
-                      }
                       // reference rounding points: proj output fp16, gelu(gate) fp16, product fp16
-                      v = __half2float(__float2half_rn(v));
-                      gt = __half2float(__float2half_rn(gt));
-                      float ge = 0.5f * gt * (1.0f + erff(gt * 0.70710678118654752f));
+                      const float v = __half2float(__float2half_rn(__uint_as_float(rv[i]) + bv[i]));
+                      const float gt = __half2float(__float2half_rn(__uint_as_float(rg[i]) + bg[i]));
+                      float ge = 0.5f * gt * (1.0f + erf_fast(gt * 0.70710678118654752f));
                       ge = __half2float(__float2half_rn(ge));
                       o[e] = v * ge;
                     }

@@ -9,7 +9,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     python bench.py --quick --steps 1 --warmup 0 --batch 2 > gpurun_out/ncu_list_$TAG.log 2>&1
 echo "ncu list exit $?"; wc -l gpurun_out/launches_$TAG.csv
 # full-set captures of the top kernels (1 GPU, few launches)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_kernel -s 30 -c 3 -o gpurun_out/prof_convgemm_$TAG -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_kernel -s 4 -c 4 -o gpurun_out/prof_convgemm_$TAG -f \
     python bench.py --quick --steps 1 --warmup 0 --batch 2 > gpurun_out/ncu_conv_$TAG.log 2>&1
 echo "ncu conv exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 2 -c 2 -o gpurun_out/prof_attn_$TAG -f \
