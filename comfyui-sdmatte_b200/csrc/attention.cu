@@ -12,6 +12,7 @@
 //   warps 4-7  : softmax warpgroup for tile B
 //   warp  8    : TMA producer (Q once; K, V^T and the per-key bias per tile; 3-stage ring)
 //   warp  9    : tcgen05.mma issuer (S_X = Q_X K^T : M128 N128 K64 ; O_X += P_X V : M128 N64 K128) + TMEM alloc
+//   warps 10-11: idle (they complete the third warpgroup so that setmaxnreg can move its registers to the softmax warps)
 // Per key tile a warpgroup pulls S(j) out of TMEM in four 32-column chunks with the next chunk's tcgen05.ld in flight
 // while the current one is exponentiated, and signals `s_free` as soon as the LAST chunk has landed in registers — the
 // tensor core then computes S(j+1) while chunk 3 is still being processed and P(j) written.  O_X accumulates in TMEM over
@@ -46,7 +47,7 @@ struct alignas(64) AttnParams {
 
 namespace a5 {
 constexpr int kStages = 3;
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;   // 8 softmax warps + TMA warp + MMA warp + 2 idle warps (a full third warpgroup for setmaxnreg)
 constexpr uint32_t kQBytes = 128 * 128;        // one 128x64 fp16 tile
 constexpr uint32_t kPBytes = 2 * 128 * 128;    // 128 x 128 fp16 as two 64-key blocks
 constexpr uint32_t kKBytes = 128 * 128;        // 128 keys x 64 d
@@ -66,7 +67,8 @@ __device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, __half2 s) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <bool HAS_BIAS>
+// OPT = false: "v5" chunk (max -> vote -> exp);  OPT = true: "v6" optimistic chunk (exp -> vote -> rare redo), see below.
+template <bool HAS_BIAS, bool OPT>
 __global__ void __launch_bounds__(a5::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   using namespace a5;
   extern __shared__ uint8_t smem_raw[];
@@ -101,6 +103,11 @@ __global__ void __launch_bounds__(a5::kThreads, 1) attention_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
 
+  // Register budget: ptxas caps the kernel at 168 registers (3 warps per scheduler); the softmax warps need ~200 for
+  // P[64] + two S chunks + the exponentials, and spilled inside the MUFU loop.  The data-movement warpgroup hands its
+  // registers over: 2 x 232 + 40 = 3 x 168 per scheduler.
+  if (warp >= 8) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
   if (warp == 8) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
@@ -164,8 +171,10 @@ __global__ void __launch_bounds__(a5::kThreads, 1) attention_kernel(const __grid
         umma_commit(kv_empty(s));
       }
     }
-  } else if (warp < 8) {
+  }
+  } else {
     // ======================================= softmax warpgroups =================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     const int x = warp >> 2;                 // 0: tile A, 1: tile B
     const int r = (warp & 3) * 32 + lane;    // row within the tile == TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -262,18 +271,110 @@ __global__ void __launch_bounds__(a5::kThreads, 1) attention_kernel(const __grid
         rowsum += (part[0] + part[1]) + (part[2] + part[3]);
       };
 
+      // v6 chunk: exponentiate OPTIMISTICALLY against the current reference m2 and look at the result afterwards.  The
+      // v5 order (row max -> vote -> exp) puts a 16-deep FMNMX chain and a branch in front of every 32 MUFU ops, and with
+      // only two softmax warps per scheduler running in lockstep the XU pipe idled half of the time (ncu r1k: XU 50 %,
+      // ~3800 clk per key tile against 2048 clk of MUFU work).  Here the steady-state chunk is ONE basic block of
+      // 32 FFMA -> 32 MUFU -> sums/packing; the chunk's sum doubles as the overflow test: csum <= 2^10 proves every
+      // e <= 2^10 (fp16-safe, fp32 sums safe), anything else (a large score, +inf from m2 = -inf on the very first chunk,
+      // NaN from -inf - -inf) takes the rare redo path, which raises the reference exactly like v5 and recomputes the chunk
+      // from the S registers that are still live.
+      auto chunk_opt = [&](uint32_t (&rr)[32], auto c_tag) {
+        constexpr int c = decltype(c_tag)::value;
+        constexpr float kLimit = 1024.0f;
+        if (!HAS_BIAS && tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kbase + c * 32 + i >= p.Lk) rr[i] = 0xff800000u;  // -inf
+        }
+        float csum;
+        auto exp_pack = [&]() {
+          const float neg_m = -m2;
+          float e[32];
+          if (HAS_BIAS) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 bq = bias4[c * 8 + g];
+              e[g * 4 + 0] = ex2f(fmaf(__uint_as_float(rr[g * 4 + 0]), sc, bq.x) + neg_m);
+              e[g * 4 + 1] = ex2f(fmaf(__uint_as_float(rr[g * 4 + 1]), sc, bq.y) + neg_m);
+              e[g * 4 + 2] = ex2f(fmaf(__uint_as_float(rr[g * 4 + 2]), sc, bq.z) + neg_m);
+              e[g * 4 + 3] = ex2f(fmaf(__uint_as_float(rr[g * 4 + 3]), sc, bq.w) + neg_m);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) e[i] = ex2f(fmaf(__uint_as_float(rr[i]), sc, neg_m));
+          }
+          float part[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            part[q] = ((e[q * 8 + 0] + e[q * 8 + 1]) + (e[q * 8 + 2] + e[q * 8 + 3])) + ((e[q * 8 + 4] + e[q * 8 + 5]) + (e[q * 8 + 6] + e[q * 8 + 7]));
+            P[(c * 4 + q) * 4 + 0] = pack_h2(e[q * 8 + 0], e[q * 8 + 1]);
+            P[(c * 4 + q) * 4 + 1] = pack_h2(e[q * 8 + 2], e[q * 8 + 3]);
+            P[(c * 4 + q) * 4 + 2] = pack_h2(e[q * 8 + 4], e[q * 8 + 5]);
+            P[(c * 4 + q) * 4 + 3] = pack_h2(e[q * 8 + 6], e[q * 8 + 7]);
+          }
+          csum = (part[0] + part[1]) + (part[2] + part[3]);
+        };
+        exp_pack();
+        if (__any_sync(0xffffffffu, !(csum <= kLimit))) {
+          // rare: raise the reference to this chunk's true maximum, rescale what was accumulated, redo the chunk
+          float cm = -INFINITY;
+          if (HAS_BIAS) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float4 bq = bias4[c * 8 + g];
+              cm = fmaxf(cm, fmaxf(fmaxf(fmaf(__uint_as_float(rr[g * 4 + 0]), sc, bq.x), fmaf(__uint_as_float(rr[g * 4 + 1]), sc, bq.y)),
+                                   fmaxf(fmaf(__uint_as_float(rr[g * 4 + 2]), sc, bq.z), fmaf(__uint_as_float(rr[g * 4 + 3]), sc, bq.w))));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(rr[i]));
+            cm *= sc;
+          }
+          const float m_new = fmaxf(m2, cm);
+          const float alpha = (m_new == m2) ? 1.0f : ex2f(m2 - m_new);  // 0 when m2 = -inf
+          if (j > 0) {
+            mbar_wait(o_full(x), (uint32_t)(j - 1) & 1u);  // every P·V issued so far has landed in O
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              uint32_t oo[32];
+              tmem_ld32(t_o + cc * 32, oo);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) oo[i] = __float_as_uint(__uint_as_float(oo[i]) * alpha);
+              tmem_st32(t_o + cc * 32, oo);
+            }
+            tmem_st_wait();
+          }
+          const __half2 a2 = __float2half2_rn(alpha);
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i < c * 16) P[i] = hmul2_u32(P[i], a2);
+          rowsum *= alpha;
+          l *= alpha;
+          m2 = m_new;
+          exp_pack();
+        }
+        rowsum += csum;
+      };
+      auto run_chunk = [&](uint32_t (&rr)[32], auto c_tag) {
+        if constexpr (OPT) chunk_opt(rr, c_tag);
+        else chunk(rr, c_tag);
+      };
+
       tmem_ld_wait();
-      chunk(r0, std::integral_constant<int, 0>{});
+      run_chunk(r0, std::integral_constant<int, 0>{});
       tmem_ld32(t_s + 64, r0);   // chunk 2 in flight while chunk 1 is processed
-      chunk(r1, std::integral_constant<int, 1>{});
+      run_chunk(r1, std::integral_constant<int, 1>{});
       tmem_ld_wait();
       tmem_ld32(t_s + 96, r1);   // chunk 3 in flight while chunk 2 is processed
-      chunk(r0, std::integral_constant<int, 2>{});
+      run_chunk(r0, std::integral_constant<int, 2>{});
       tmem_ld_wait();
       // all of S(j) is in registers: let the tensor core start S(j+1)
       tc_fence_before();
       mbar_arrive(s_free(x));
-      chunk(r1, std::integral_constant<int, 3>{});
+      run_chunk(r1, std::integral_constant<int, 3>{});
       l += rowsum;
       // P(j) overwrites the smem buffer P·V(j-1) reads
       if (j > 0) mbar_wait(o_full(x), (uint32_t)(j - 1) & 1u);
@@ -362,11 +463,19 @@ std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d) {
 void attn_run(const AttnLaunch& l, cudaStream_t st) {
   static std::once_flag once;
   std::call_once(once, [] {
-    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a5::kSmem));
-    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a5::kSmem));
+    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a5::kSmem));
+    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a5::kSmem));
+    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a5::kSmem));
+    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a5::kSmem));
   });
-  if (l.has_bias) attention_kernel<true><<<l.grid, a5::kThreads, a5::kSmem, st>>>(l.p);
-  else attention_kernel<false><<<l.grid, a5::kThreads, a5::kSmem, st>>>(l.p);
+  static const int variant = [] { const char* e = getenv("SDM_ATTN"); return e ? atoi(e) : 6; }();  // 5 = v5 chunk (A/B)
+  if (variant == 5) {
+    if (l.has_bias) attention_kernel<true, false><<<l.grid, a5::kThreads, a5::kSmem, st>>>(l.p);
+    else attention_kernel<false, false><<<l.grid, a5::kThreads, a5::kSmem, st>>>(l.p);
+  } else {
+    if (l.has_bias) attention_kernel<true, true><<<l.grid, a5::kThreads, a5::kSmem, st>>>(l.p);
+    else attention_kernel<false, true><<<l.grid, a5::kThreads, a5::kSmem, st>>>(l.p);
+  }
   SDM_CUDA_OK(cudaGetLastError());
 }
 

@@ -77,6 +77,9 @@ CASES = {
     "conv3x3 512->512 @256^2 B4": lambda: conv(4, 256, 256, 512, 512),
     "conv3x3 320->320 @128^2 B8 +stats": lambda: conv(8, 128, 128, 320, 320, stats=True),
     "conv1x1 128->256 @512^2 B4": lambda: conv(4, 512, 512, 128, 256, k=1),
+    "conv1x1 64->128 @1024^2 B4 +stats (im2col conv_in)": lambda: conv(4, 1024, 1024, 64, 128, k=1, stats=True),
+    "conv1x1 64->128 @1024^2 B4": lambda: conv(4, 1024, 1024, 64, 128, k=1),
+    "conv1x1 256->128 @1024^2 B2 (vae shortcut)": lambda: conv(2, 1024, 1024, 256, 128, k=1),
     "linear 16384x320x320 B8 +res": lambda: linear(8, 16384, 320, 320, res=True),
     "linear 16384x320x1024 B8 (cross K)": lambda: linear(8, 16384, 320, 1024),
     "linear 4096x640x640 B8": lambda: linear(8, 4096, 640, 640),
