@@ -75,6 +75,21 @@ int sdm_forward_host(sdm_handle* h, const float* image_host, const float* trimap
                            workspace_dev, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
   SDM_API_END
 }
+int sdm_preprocess(const float* image_dev, const float* trimap_dev, int B, int H, int W, int R, float* image_out_dev,
+                   float* trimap_out_dev, uintptr_t stream) {
+  SDM_API_BEGIN
+  sdm::preprocess_run(image_dev, trimap_dev, B, H, W, R, image_out_dev, trimap_out_dev, reinterpret_cast<cudaStream_t>(stream));
+  SDM_API_END
+}
+int sdm_postprocess(const void* alpha_dev_f16, int B, int R, int H, int W, const float* image_dev, const float* trimap_dev,
+                    int mask_refine, double trimap_constraint, int output_mode, void* alpha_out_dev_f16, float* matted_out_dev,
+                    uintptr_t stream) {
+  SDM_API_BEGIN
+  sdm::postprocess_run(reinterpret_cast<const __half*>(alpha_dev_f16), B, R, H, W, image_dev, trimap_dev, mask_refine,
+                       trimap_constraint, output_mode, reinterpret_cast<__half*>(alpha_out_dev_f16), matted_out_dev,
+                       reinterpret_cast<cudaStream_t>(stream));
+  SDM_API_END
+}
 int sdm_forward_profiled(sdm_handle* h, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
                          void* alpha_dev, void* workspace_dev, size_t workspace_bytes, uintptr_t stream) {
   SDM_API_BEGIN

@@ -129,5 +129,13 @@ void prep_inputs_run(const float* image, const float* trimap, __half* out /*[2B]
 void key_bias_run(const float* trimap, int B, int R, float* bias0, float* bias1, float* bias2, float* bias3,
                   const int* lpad, cudaStream_t st);
 
+// ------------------------------------------------------------------ node pre/post-processing (prepost.cu)
+// antialiased bilinear resize of image [B][H][W][3] / trimap [B][H][W] (fp32) to R x R (sdmatte_nodes.py:204-214,343,349)
+void preprocess_run(const float* image, const float* trimap, int B, int H, int W, int R, float* image_out, float* trimap_out,
+                    cudaStream_t st);
+// resize alpha [B][R][R] fp16 back to (H, W), clamp, mask_refine, output_mode composition (sdmatte_nodes.py:362-397)
+void postprocess_run(const __half* alpha, int B, int R, int H, int W, const float* image, const float* trimap, int mask_refine,
+                     double trimap_constraint, int output_mode, __half* alpha_out, float* matted_out, cudaStream_t st);
+
 int device_sm_count();
 }  // namespace sdm

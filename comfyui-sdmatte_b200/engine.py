@@ -66,7 +66,7 @@ class sdm_direct_conv_args(C.Structure):
 EXPORTS = [
     "sdm_version", "sdm_last_error", "sdm_create", "sdm_destroy", "sdm_load_weights", "sdm_load_report",
     "sdm_workspace_bytes", "sdm_forward", "sdm_forward_host", "sdm_forward_profiled", "sdm_profile_count", "sdm_profile_entry",
-    "sdm_last_forward_stats", "sdm_debug_tensor",
+    "sdm_last_forward_stats", "sdm_debug_tensor", "sdm_preprocess", "sdm_postprocess",
     "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
     "sdm_k_softmax_rows", "sdm_k_direct_conv",
 ]
@@ -102,6 +102,9 @@ def load_library():
                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.sdm_forward_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_void_p,
                                      C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sdm_preprocess.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sdm_postprocess.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sdm_forward_profiled.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_void_p,
                                          C.c_void_p, C.c_size_t, C.c_void_p]
     lib.sdm_profile_count.argtypes = [C.c_void_p]
@@ -265,6 +268,49 @@ class Engine:
         _check(self.lib.sdm_debug_tensor(self.h, name.encode(), buf.data_ptr(), buf.numel() * 2, shape, C.byref(dt)))
         n = shape[0] * shape[1] * shape[2] * shape[3]
         return buf[:n].view(shape[0], shape[1], shape[2], shape[3]).clone()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# node-side pre/post-processing on the device (reference sdmatte_nodes.py:204-214,339-397)
+# ---------------------------------------------------------------------------------------------------------------
+OUTPUT_MODES = {"alpha_only": 0, "matted_rgba": 1, "matted_rgb": 2}
+
+
+def preprocess(image: torch.Tensor, trimap: torch.Tensor, R: int):
+    """image [B,H,W,3] fp32 cuda, trimap [B,H,W] fp32 cuda -> antialias-bilinear resized ([B,R,R,3], [B,R,R]) fp32 cuda
+    (torchvision Resize(antialias=True) semantics).  Identity when the inputs already are R x R."""
+    B, H, W, _ = image.shape
+    assert image.is_cuda and trimap.is_cuda and image.dtype == torch.float32 and trimap.dtype == torch.float32
+    assert trimap.shape == (B, H, W)
+    image, trimap = image.contiguous(), trimap.contiguous()
+    if (H, W) == (R, R):
+        return image, trimap
+    img_r = torch.empty((B, R, R, 3), dtype=torch.float32, device=image.device)
+    tri_r = torch.empty((B, R, R), dtype=torch.float32, device=image.device)
+    with torch.cuda.device(image.device):
+        _check(load_library().sdm_preprocess(image.data_ptr(), trimap.data_ptr(), B, H, W, R, img_r.data_ptr(), tri_r.data_ptr(),
+                                             _stream_ptr(image.device)))
+    return img_r, tri_r
+
+
+def postprocess(alpha: torch.Tensor, image: torch.Tensor, trimap: torch.Tensor, output_mode: str, mask_refine: bool,
+                trimap_constraint: float):
+    """alpha [B,R,R] fp16 cuda (engine output), image [B,H,W,3] / trimap [B,H,W] fp32 cuda (the caller's originals) ->
+    (alpha_out [B,H,W] fp16 cuda, matted [B,H,W,3|4] fp32 cuda or None for "alpha_only")."""
+    B, R = alpha.shape[0], alpha.shape[1]
+    _, H, W, _ = image.shape
+    assert alpha.is_cuda and alpha.dtype == torch.float16 and alpha.shape == (B, R, R)
+    mode = OUTPUT_MODES.get(output_mode, 3)
+    alpha, image, trimap = alpha.contiguous(), image.contiguous(), trimap.contiguous()
+    out = torch.empty((B, H, W), dtype=torch.float16, device=alpha.device)
+    matted = None
+    if mode != 0:
+        matted = torch.empty((B, H, W, 4 if mode == 1 else 3), dtype=torch.float32, device=alpha.device)
+    with torch.cuda.device(alpha.device):
+        _check(load_library().sdm_postprocess(alpha.data_ptr(), B, R, H, W, image.data_ptr(), trimap.data_ptr(), int(bool(mask_refine)),
+                                              float(trimap_constraint), mode, out.data_ptr(),
+                                              matted.data_ptr() if matted is not None else None, _stream_ptr(alpha.device)))
+    return out, matted
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -12,7 +12,6 @@ import os
 from typing import Dict, Tuple
 
 import torch
-import torch.nn.functional as F
 
 from . import engine as _engine
 
@@ -96,13 +95,6 @@ def get_engine(ckpt_name: str, device: torch.device) -> "_engine.Engine":
     return eng
 
 
-def _resize_bchw(x: torch.Tensor, size_hw, antialias: bool) -> torch.Tensor:
-    # torchvision.transforms.Resize on tensors == F.interpolate(bilinear, align_corners=False, antialias=...)
-    if tuple(x.shape[-2:]) == tuple(size_hw):
-        return x
-    return F.interpolate(x, size=size_hw, mode="bilinear", align_corners=False, antialias=antialias)
-
-
 class SDMatteApply:
     @classmethod
     def INPUT_TYPES(s):
@@ -143,38 +135,21 @@ class SDMatteApply:
         B, H, W, _ = image.shape
         R = int(inference_size)
 
-        # pre-processing (sdmatte_nodes.py:339-353): resize to R x R (antialiased bilinear); normalisation happens in the engine
-        img = image.to(device=device, dtype=torch.float32, non_blocking=True)
-        tri = trimap.to(device=device, dtype=torch.float32, non_blocking=True)
-        if (H, W) != (R, R):
-            img = _resize_bchw(img.permute(0, 3, 1, 2), (R, R), True).permute(0, 2, 3, 1)
-            tri = _resize_bchw(tri.unsqueeze(1), (R, R), True).squeeze(1)
-        alpha = eng.forward(img.contiguous(), tri.contiguous(), bool(is_transparent))  # (B,R,R) fp16, in [0,1]
+        # pre-processing (sdmatte_nodes.py:339-353): one H2D of the caller's tensors, antialiased-bilinear resize to R x R on
+        # the device (csrc/prepost.cu); the (x-0.5)/0.5 and *2-1 normalisations happen inside the engine
+        img = image.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        tri = trimap.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        img_r, tri_r = _engine.preprocess(img, tri, R)
+        alpha = eng.forward(img_r, tri_r, bool(is_transparent))  # (B,R,R) fp16, in [0,1]
 
-        # post-processing (sdmatte_nodes.py:362-363): resize back, clamp, to host.  fp16 like the reference's CUDA path.
-        out = _resize_bchw(alpha.unsqueeze(1), (H, W), True).squeeze(1).clamp(0, 1).cpu()
-
-        if mask_refine:  # sdmatte_nodes.py:365-380
-            t = trimap.cpu()
-            fg = t > trimap_constraint
-            bg = t < (1.0 - trimap_constraint)
-            refined = out.clone()
-            refined[bg] = 0.0
-            refined[fg] = torch.clamp(refined[fg] * 1.2, 0, 1)
-            refined[(refined < 0.3) & ~(fg | bg)] = 0.0
-            out = refined
-
-        a = out.unsqueeze(-1)
-        img_cpu = image.cpu()
-        if output_mode == "alpha_only":  # sdmatte_nodes.py:384-397
-            matted = torch.zeros_like(img_cpu)
-        elif output_mode == "matted_rgba":
-            matted = torch.cat([img_cpu, a.expand(-1, -1, -1, 1)], dim=-1)
-        elif output_mode == "matted_rgb":
-            keep = (trimap.cpu().unsqueeze(-1) > 0.2) & (a > 0.1)
-            matted = img_cpu * keep.float()
+        # post-processing (sdmatte_nodes.py:362-397) in ONE kernel: resize back, clamp, mask_refine, composition; then one
+        # D2H per output.  fp16 alpha like the reference's CUDA path.
+        out_d, matted_d = _engine.postprocess(alpha, img, tri, output_mode, bool(mask_refine), float(trimap_constraint))
+        out = out_d.cpu()
+        if matted_d is None:  # "alpha_only": zeros_like(image) (sdmatte_nodes.py:384-385)
+            matted = torch.zeros_like(image, device="cpu")
         else:
-            matted = img_cpu * a
+            matted = matted_d.cpu()
         return (out, matted)
 
 

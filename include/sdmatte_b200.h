@@ -58,6 +58,22 @@ int sdm_forward(sdm_handle* h, const float* image_dev, const float* trimap_dev, 
 int sdm_forward_host(sdm_handle* h, const float* image_host, const float* trimap_host, int B, int R, const int32_t* is_trans,
                      void* alpha_host_f16, void* workspace_dev, size_t workspace_bytes, uintptr_t stream);
 
+/* Node-side pre/post-processing on the device, all pointers are device pointers.
+ * sdm_preprocess replaces torchvision Resize(antialias=True) of image and trimap to R x R
+ *   (_resize_norm_image_bchw / _resize_mask_b1hw, sdmatte_nodes.py:204-214, called at :343 and :349; the affine
+ *   normalisations are folded into sdm_forward):
+ *   image_dev [B][H][W][3] fp32, trimap_dev [B][H][W] fp32 -> image_out_dev [B][R][R][3], trimap_out_dev [B][R][R] fp32.
+ * sdm_postprocess replaces sdmatte_nodes.py:362-397: Resize((H, W)) of the fp16 alpha, clamp(0,1), mask_refine with the
+ *   ORIGINAL trimap and `trimap_constraint`, and the output_mode composition:
+ *   output_mode 0 = "alpha_only" (matted_out untouched: the caller returns zeros), 1 = "matted_rgba" (matted_out
+ *   [B][H][W][4] fp32), 2 = "matted_rgb" ([B][H][W][3] fp32), 3 = image * alpha (the reference's unreachable else branch).
+ *   alpha_out_dev [B][H][W] fp16.  image_dev / trimap_dev are the caller's original-size tensors. */
+int sdm_preprocess(const float* image_dev, const float* trimap_dev, int B, int H, int W, int R, float* image_out_dev,
+                   float* trimap_out_dev, uintptr_t stream);
+int sdm_postprocess(const void* alpha_dev_f16, int B, int R, int H, int W, const float* image_dev, const float* trimap_dev,
+                    int mask_refine, double trimap_constraint, int output_mode, void* alpha_out_dev_f16, float* matted_out_dev,
+                    uintptr_t stream);
+
 /* Measurement aid (bench.py roofline): one forward with a CUDA-event pair around every op of the plan (synchronises).
  * sdm_profile_entry returns, per op: kind ("tc:conv3x3", "tc:attention_self", "groupnorm", ...), device ms,
  * algorithmic FLOPs and algorithmic HBM bytes. */

@@ -83,6 +83,45 @@ def golden_lifted():
     print("lifted goldens:", len(res), "arrays")
 
 
+def golden_prepost():
+    """3. prepost_lifted.npz : the reference's resize helpers (sdmatte_nodes.py:204-214) and post-processing statements
+    (sdmatte_nodes.py:362-397) run on NON-square, non-R inputs with an fp16 model output (as on the reference's CUDA path) —
+    the known answers for the GPU pre/post kernels (csrc/prepost.cu)."""
+    assert ref_lifted.available(), "run in the build container (needs /root/reference)"
+    g = torch.Generator().manual_seed(321)
+    nfn = ref_lifted.node_helpers()
+    res = {}
+    R = 32
+    for tag, (H, W) in {"down": (60, 41), "up": (20, 28), "mixed": (24, 90)}.items():
+        image = torch.rand(2, H, W, 3, generator=g)
+        # trimap with soft edges (values other than 0 / .5 / 1 exercise the thresholds)
+        trimap = (torch.randint(0, 3, (2, H, W), generator=g).float() / 2)
+        trimap = torch.where(torch.rand(2, H, W, generator=g) < 0.1, torch.rand(2, H, W, generator=g), trimap)
+        img_r = nfn._resize_norm_image_bchw(image.permute(0, 3, 1, 2).contiguous(), (R, R))   # normalised (x-0.5)/0.5
+        tri_r = nfn._resize_mask_b1hw(trimap.unsqueeze(1).contiguous(), (R, R))
+        pred = (torch.rand(2, 1, R, R, generator=g) * 1.2 - 0.1).half()    # fp16, slightly outside [0,1] -> clamp matters
+        res.update({f"{tag}_image": image.numpy(), f"{tag}_trimap": trimap.numpy(), f"{tag}_img_r": img_r.numpy(),
+                    f"{tag}_tri_r": tri_r.numpy(), f"{tag}_pred": pred.numpy()})
+        for mode in ("alpha_only", "matted_rgba", "matted_rgb"):
+            for refine, c in ((True, 0.8), (True, 0.3), (False, 0.8)):
+                o, m = ref_lifted.node_postprocess(pred, image, trimap, mode, refine, c)
+                assert o.dtype == torch.float16
+                key = f"{tag}_{mode}_{int(refine)}_{c}"
+                res[key + "_alpha"] = o.numpy()
+                if mode != "alpha_only":
+                    if refine and c == 0.8:  # keep the fixture small: composition is checked for one refine setting per mode
+                        res[key + "_matted"] = m.numpy()
+                else:
+                    assert float(m.abs().max()) == 0.0 and m.shape == image.shape
+    np.savez_compressed(os.path.join(HERE, "prepost_lifted.npz"), **res)
+    print("prepost goldens:", len(res), "arrays")
+
+
 if __name__ == "__main__":
-    golden_lifted()
-    golden_alpha()
+    which = sys.argv[1:] or ["lifted", "alpha", "prepost"]
+    if "lifted" in which:
+        golden_lifted()
+    if "alpha" in which:
+        golden_alpha()
+    if "prepost" in which:
+        golden_prepost()

@@ -93,21 +93,18 @@ def test_postprocess_matches_reference(lifted, mode, refine):
     np.testing.assert_array_equal(m.numpy(), lifted[f"post_{mode}_{int(refine)}_matted"])
 
 
-def test_node_postprocess_matches_reference(lifted):
-    """The node module's own mask_refine / composition code path (CPU part) against the same goldens."""
+def test_node_runs_pre_and_post_on_the_device():
+    """§8(f) n1: the node has no torch/CPU resize or refine code of its own any more — both sides of the model call go
+    through the C ABI (sdm_preprocess / sdm_postprocess; GPU parity in tests/test_prepost_gpu.py)."""
+    import inspect
+
     import __graft_entry__ as ge
 
     nodes = ge.load_package().sdmatte_nodes
-    image, trimap, pred = (torch.from_numpy(lifted[k]) for k in ("post_image", "post_trimap", "post_pred"))
-
-    class FakeEngine:
-        def forward(self, img, tri, flag):
-            return F.interpolate(pred, size=img.shape[1:3], mode="bilinear", antialias=True).squeeze(1)
-
-    # exercise the node's post-processing with a stand-in engine output already at the input size
+    src = inspect.getsource(nodes.SDMatteApply.apply_matte)
+    assert "_engine.preprocess(" in src and "_engine.postprocess(" in src
+    assert "interpolate(" not in inspect.getsource(nodes) and ".clamp(" not in src and "refined" not in src
     node = nodes.SDMatteApply()
-    out = nodes._resize_bchw(pred, image.shape[1:3], True).squeeze(1).clamp(0, 1)
-    np.testing.assert_allclose(out.numpy(), lifted["post_alpha_only_0_alpha"], atol=1e-6)
     assert node.RETURN_TYPES == ("MASK", "IMAGE") and node.FUNCTION == "apply_matte"
 
 
