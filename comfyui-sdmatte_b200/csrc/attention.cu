@@ -74,7 +74,9 @@ __device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, __half2 s) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <bool HAS_BIAS>
+// TAIL: Lk is not a multiple of 128 and there is no bias to carry the -inf padding (never the case inside the engine;
+// kept out of the common instantiations: even skipped, the masking code cost a BSSY/branch per chunk and i-cache misses)
+template <bool HAS_BIAS, bool TAIL>
 __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   using namespace a7;
   extern __shared__ uint8_t smem_raw[];
@@ -142,38 +144,60 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
         for (int k = 0; k < 4; ++k) umma_f16(tmem + kColS + x * 128, ad + 2 * k, bd + 2 * k, idesc_s, k != 0);
         umma_commit(s_full(x));
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(kv_full(0), 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      int s = 0;         // stage of key tile j
-      uint32_t ph = 0;   // its phase
-      for (int j = 0; j < n; ++j) {
-        int s1 = s + 1;
-        uint32_t ph1 = ph;
-        if (s1 == kStages) { s1 = 0; ph1 ^= 1u; }
-        if (j + 1 < n) {
-          mbar_wait(kv_full(s1), ph1);
-          for (int x = 0; x < 2; ++x) {
-            mbar_wait(s_free(x), (uint32_t)j & 1u);  // S_x(j) is in the warpgroup's registers
-            tc_fence_after();
-            issue_s(x, s1);
-          }
-        }
-        for (int x = 0; x < 2; ++x) {
-          mbar_wait(p_full(x), (uint32_t)j & 1u);  // P_x(j) is in TMEM
-          tc_fence_after();
-          const uint32_t vb = base + kOffStage + s * kStageBytes + kKBytes;
+      auto issue_pv = [&](int x, int stage, int j) {
+        const uint32_t vb = base + kOffStage + stage * kStageBytes + kKBytes;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t bd = umma_desc_k128(vb + (k >> 2) * (64 * 128)) + 2 * (k & 3);
-            umma_f16_ts(tmem + kColO + x * 64, tmem + kColP + x * 64 + k * 8, bd, idesc_o, (j | k) != 0);
-          }
-          umma_commit(o_full(x));
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t bd = umma_desc_k128(vb + (k >> 2) * (64 * 128)) + 2 * (k & 3);
+          umma_f16_ts(tmem + kColO + x * 64, tmem + kColP + x * 64 + k * 8, bd, idesc_o, (j | k) != 0);
         }
-        umma_commit(kv_empty(s));
-        s = s1; ph = ph1;
+        umma_commit(o_full(x));
+      };
+      mbar_wait(q_full, 0);
+      // Event-driven issue: the two query tiles are independent streams  S_x(0), [S_x(j+1), PV_x(j)]...  An in-order loop
+      // (S_A, S_B, PV_A, PV_B per key tile) made PV_A(j) wait for tile B's s_free whenever B lagged, and the softmax
+      // warpgroup of A then stalled on o_full before it could overwrite P (ncu r1m: 7 % of the softmax warps' samples).
+      int js[2] = {0, 0};   // S tiles issued per query tile
+      int jp[2] = {0, 0};   // P.V tiles issued per query tile
+      int released = 0;     // K/V stages handed back to the producer
+      uint32_t idle = 0;
+      long long t0 = 0;
+      while (jp[0] < n || jp[1] < n) {
+        bool progress = false;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          if (js[x] < n && js[x] <= jp[x] + 1) {  // S_x is single-buffered: S_x(j+1) needs s_free_x(j)
+            const int t = js[x];
+            if (mbar_test(kv_full(t % kStages), (uint32_t)(t / kStages) & 1u) && (t == 0 || mbar_test(s_free(x), (uint32_t)(t - 1) & 1u))) {
+              tc_fence_after();
+              issue_s(x, t % kStages);
+              js[x] = t + 1;
+              progress = true;
+            }
+          }
+          if (jp[x] < js[x]) {
+            const int t = jp[x];
+            if (mbar_test(p_full(x), (uint32_t)t & 1u)) {  // P_x(t) is in TMEM
+              tc_fence_after();
+              issue_pv(x, t % kStages, t);
+              jp[x] = t + 1;
+              progress = true;
+              while (released < min(jp[0], jp[1])) {  // both tiles have issued their P.V for this stage
+                umma_commit(kv_empty(released % kStages));
+                ++released;
+              }
+            }
+          }
+        }
+        if (progress) { idle = 0; t0 = 0; }
+        else if ((++idle & 0xFFFFu) == 0) {  // a pipeline bug must trap instead of hanging the GPU box
+          const long long now = clock64();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 20000000000LL) {
+            printf("sdm: attention MMA issue loop timeout (block %d,%d,%d js %d %d jp %d %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, js[0], js[1], jp[0], jp[1]);
+            __trap();
+          }
+        }
       }
     }
   } else if (warp < 8) {
@@ -192,7 +216,7 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
     uint32_t ph = 0;
 
     for (int j = 0; j < n; ++j) {
-      const bool tail = (!HAS_BIAS) && (j == n - 1) && ((p.Lk & 127) != 0);
+      const bool tail = TAIL && (j == n - 1);
       const int kbase = j * 128;
       if (HAS_BIAS) mbar_wait(kv_full(s), ph);  // bias tile visible to this thread
       mbar_wait(s_full(x), (uint32_t)j & 1u);
@@ -205,7 +229,7 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
 
       // one 32-key chunk c (runtime, 0..3) held in rr: exponentiate, pack, (rarely) redo, store to P
       auto chunk = [&](uint32_t (&rr)[32], int c) {
-        if (!HAS_BIAS && tail) {
+        if (TAIL && tail) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (kbase + c * 32 + i >= p.Lk) rr[i] = 0xff800000u;  // -inf
@@ -395,11 +419,13 @@ std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d) {
 void attn_run(const AttnLaunch& l, cudaStream_t st) {
   static std::once_flag once;
   std::call_once(once, [] {
-    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
-    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
+    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
+    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
+    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
   });
-  if (l.has_bias) attention_kernel<true><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
-  else attention_kernel<false><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
+  if (l.has_bias) attention_kernel<true, false><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
+  else if ((l.p.Lk & 127) != 0) attention_kernel<false, true><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
+  else attention_kernel<false, false><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
   SDM_CUDA_OK(cudaGetLastError());
 }
 

@@ -203,6 +203,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   p.post_div = d.post_div;
   p.n_store = d.n_store > 0 ? d.n_store : d.N;
   if (p.mode == EPI_F16 && p.n_store < 8) p.mode = EPI_SKINNY;
+  SDM_CHECK(p.post_div == 1.0f || p.mode == EPI_SKINNY, "post_div is only implemented for skinny (n_store < 8) outputs");
   if (p.mode == EPI_SKINNY) SDM_CHECK(bn == 16 && !d.res && !d.ups2, "skinny output needs N <= 16 and no residual");
   p.out2 = d.out2;
   p.stats = (d.mode == EPI_F16 && !d.ups2) ? d.stats : nullptr;

@@ -25,10 +25,12 @@
 #pragma once
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace sdm {
 
 enum EpiMode : int {
-  EPI_F16 = 0,     // out[pixel][n] fp16  (+bias, optional 2x nearest-upsample scatter, optional fp16 division)
+  EPI_F16 = 0,     // out[pixel][n] fp16  (+bias, optional 2x nearest-upsample scatter)
   EPI_F16_T = 1,   // out[b][n][pixel] fp16 (transposed; used for V^T)
   EPI_GEGLU = 2,   // out[pixel][n/2] = fp16(v) * gelu(fp16(g)), tile = [BLOCK_N/2 value | BLOCK_N/2 gate]
   EPI_F32 = 3,     // out[pixel][n] fp32 = scale * acc
@@ -63,7 +65,7 @@ struct alignas(64) ConvGemmParams {
   const float* bias;      // [nsel][N] fp32 or null
   const int* bias_sel;    // per-batch row selector into bias, or null
   float scale;
-  float post_div;   // EPI_F16 / EPI_SKINNY: fp16(result) / post_div, rounded again (label_latent / scaling_factor); 1 = off
+  float post_div;   // EPI_SKINNY only: fp16(result) / post_div, rounded again (label_latent / scaling_factor); 1 = off
   int n_store;      // EPI_SKINNY: number of output columns stored
   void* out2;       // EPI_ALPHA: optional pre-clip mean
   float* stats;     // EPI_F16 (no ups2): per-(M tile, channel) partial (sum, sumsq) of the STORED fp16 values for the next GroupNorm:
@@ -293,7 +295,154 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
         const float* bias = p.bias ? p.bias + (p.bias_sel ? (long long)p.bias_sel[b] * p.N : 0) : nullptr;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * Cfg::kAccStride + u * Cfg::kSubStride;
 
-        if constexpr (MODE == EPI_F16 || MODE == EPI_GEGLU || MODE == EPI_F32) {
+        if constexpr (MODE == EPI_F16) {
+          // ---- fp16 output, staged row-contiguous stores (+ GroupNorm partials) ---------------------------------
+          // r1l ncu (source view): the epilogue warps of the N=128 / short-K GEMMs were busy 85 % of the time at an IPC of
+          // 0.1-0.3 (~950 instructions per 64-column slab, every tcgen05.ld and bias load waited for in place) and were the
+          // critical resource (tensor pipe 59 % on the 128->128 3x3 convs, 4 % on K=64 GEMMs).  This version keeps the next
+          // 32 columns' tcgen05.ld in flight while the current ones are processed, issues the bias loads before the wait,
+          // does scale+bias as one FFMA2 per column pair, the statistics as FADD2/FFMA2, and hoists the 64-bit address math.
+          constexpr int SLAB = 64;                            // output columns per 128-byte staging row
+          const int o_lim = min(p.N, n0 + BLOCK_N);
+          __half* obase = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride;
+          // element offsets (within this sample: < 2^31) of the 8 rows this lane serves in the transposed phase; -1 = outside
+          int toff[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rg = quad * 32 + i * 4 + t_row0;
+            const int xx = tx * p.tw + (rg & (p.tw - 1)), yy = ty * p.th + (rg >> ltw);
+            const int pix = UPS2 ? (2 * yy) * (2 * p.W) + 2 * xx : yy * p.W + xx;
+            toff[i] = (xx < p.W && yy < p.H) ? pix * (int)p.out_ld : -1;
+          }
+          const uint64_t sc2 = pack_f2(p.scale, p.scale);
+          // scale * acc + bias for 32 accumulator columns -> this thread's staging row, 16-byte pieces q0 .. q0+3
+          auto half_tile = [&](const uint32_t (&r)[32], const float4 (&bq)[8], int q0) {
+            uint32_t w[16];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const uint64_t lo = fma_f2(pack_f2(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1])), sc2, pack_f2(bq[g].x, bq[g].y));
+              const uint64_t hi = fma_f2(pack_f2(__uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3])), sc2, pack_f2(bq[g].z, bq[g].w));
+              float v0, v1, v2, v3;
+              unpack_f2(lo, v0, v1);
+              unpack_f2(hi, v2, v3);
+              w[g * 2] = pack_h2(v0, v1);
+              w[g * 2 + 1] = pack_h2(v2, v3);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + (((q0 + g) ^ (lane & 7)) << 4)) = make_uint4(w[g * 4], w[g * 4 + 1], w[g * 4 + 2], w[g * 4 + 3]);
+          };
+          auto load_bias = [&](int cc, float4 (&bq)[8]) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              bq[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (bias && n0 + cc + g * 4 < p.N) bq[g] = __ldg(reinterpret_cast<const float4*>(bias + n0 + cc + g * 4));
+            }
+          };
+          uint32_t ra[32], rb[32];
+          __syncwarp();
+          tmem_ld32(taddr, ra);
+#pragma unroll 1
+          for (int c = 0; c < BLOCK_N; c += SLAB) {
+            const bool second = (BLOCK_N % SLAB == 0) || (c + 32 < BLOCK_N);  // the last slab of a 160-wide tile has one half
+            float4 bq[8];
+            load_bias(c, bq);
+            tmem_ld_wait();                                   // ra = columns [c, c+32)
+            __syncwarp();                                     // (also: the previous slab's staging reads are done)
+            if (second) tmem_ld32(taddr + c + 32, rb);        // in flight while ra is processed
+            half_tile(ra, bq, 0);
+            if (second) {
+              load_bias(c + 32, bq);
+              tmem_ld_wait();                                 // rb = columns [c+32, c+64)
+              __syncwarp();
+              if (c + SLAB < BLOCK_N) tmem_ld32(taddr + c + SLAB, ra);  // next slab's first half flies during the stores
+              half_tile(rb, bq, 4);
+            } else {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(stg + lane * 128 + (((4 + g) ^ (lane & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+            }
+            // staging -> row-contiguous global stores
+            __syncwarp();
+            const int col = n0 + c + t_piece * 8;
+            const bool col_ok = col < o_lim;
+            const bool do_stats = (!UPS2) && (p.stats != nullptr);
+            __half* ocol = obase + col;
+            uint64_t ssum[4], ssq[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { ssum[e] = 0ull; ssq[e] = 0ull; }
+            // one staged row -> global (row-contiguous: a warp store covers 4 rows x 128 B); WITH_STATS adds the row to the
+            // per-column (sum, sum of squares) of the STORED fp16 values.  Rows/columns outside the tensor are zeroed instead
+            // of branched around, so the accumulators stay in place (the branchy form cost 16 register moves per row).
+            auto store_rows = [&](auto with_stats) {
+              constexpr bool WITH_STATS = decltype(with_stats)::value;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rl = i * 4 + t_row0;
+                uint4 v = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((t_piece ^ (rl & 7)) << 4));
+                const bool ok = toff[i] >= 0 && col_ok;
+                if constexpr (!UPS2) {
+                  if (ok) *reinterpret_cast<uint4*>(ocol + toff[i]) = v;
+                  if constexpr (WITH_STATS) {
+                    if (!ok) v = make_uint4(0, 0, 0, 0);
+                    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 f = __half22float2(h[j]);
+                      const uint64_t f2 = pack_f2(f.x, f.y);
+                      ssum[j] = add_f2(ssum[j], f2);
+                      ssq[j] = fma_f2(f2, f2, ssq[j]);
+                    }
+                  }
+                } else if (ok) {
+                  // nearest-neighbour 2x upsample fused into the store (reference Upsample2D: F.interpolate scale 2
+                  // "nearest" followed by a conv; the conv then reads this tensor)
+#pragma unroll
+                  for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(ocol + toff[i] + ((q >> 1) * (2 * p.W) + (q & 1)) * (int)p.out_ld) = v;
+                }
+              }
+            };
+            if (do_stats) store_rows(std::true_type{});
+            else store_rows(std::false_type{});
+            if constexpr (!UPS2) {
+              if (do_stats) {
+                // column sums over this warp's 32 rows: lanes {l, l+8, l+16, l+24} hold the same 8 columns
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  ssum[e] = add_f2(ssum[e], __shfl_xor_sync(0xffffffffu, ssum[e], 8));
+                  ssq[e] = add_f2(ssq[e], __shfl_xor_sync(0xffffffffu, ssq[e], 8));
+                  ssum[e] = add_f2(ssum[e], __shfl_xor_sync(0xffffffffu, ssum[e], 16));
+                  ssq[e] = add_f2(ssq[e], __shfl_xor_sync(0xffffffffu, ssq[e], 16));
+                }
+                // combine the four epilogue warps in a fixed order through shared memory (one global writer per slot)
+                if (lane < 8) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    float s0, s1, q0, q1;
+                    unpack_f2(ssum[e], s0, s1);
+                    unpack_f2(ssq[e], q0, q1);
+                    *reinterpret_cast<float4*>(&sred[(quad * 64 + lane * 8 + e * 2) * 2]) = make_float4(s0, q0, s1, q1);
+                  }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + ewg) : "memory");
+                if (quad == 0) {
+                  const int cc = lane * 2;  // two columns per lane
+                  const int gcol = n0 + c + cc;
+                  if (gcol < o_lim) {
+                    float4 o;
+                    o.x = (sred[(0 * 64 + cc) * 2] + sred[(1 * 64 + cc) * 2]) + (sred[(2 * 64 + cc) * 2] + sred[(3 * 64 + cc) * 2]);
+                    o.y = (sred[(0 * 64 + cc) * 2 + 1] + sred[(1 * 64 + cc) * 2 + 1]) + (sred[(2 * 64 + cc) * 2 + 1] + sred[(3 * 64 + cc) * 2 + 1]);
+                    o.z = (sred[(0 * 64 + cc + 1) * 2] + sred[(1 * 64 + cc + 1) * 2]) + (sred[(2 * 64 + cc + 1) * 2] + sred[(3 * 64 + cc + 1) * 2]);
+                    o.w = (sred[(0 * 64 + cc + 1) * 2 + 1] + sred[(1 * 64 + cc + 1) * 2 + 1]) + (sred[(2 * 64 + cc + 1) * 2 + 1] + sred[(3 * 64 + cc + 1) * 2 + 1]);
+                    const long long slot = (long long)b * (p.tiles_x * p.tiles_y) + (mt % (p.tiles_x * p.tiles_y));
+                    *reinterpret_cast<float4*>(p.stats + (slot * p.N + gcol) * 2) = o;
+                  }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + ewg) : "memory");
+              }
+            }
+          }
+        } else if constexpr (MODE == EPI_GEGLU || MODE == EPI_F32) {
           // ---- staged, row-contiguous store path -------------------------------------------------
           constexpr int ES = (MODE == EPI_F32) ? 4 : 2;       // output element size
           constexpr int CPP = 16 / ES;                        // columns per 16-byte piece

@@ -104,7 +104,7 @@ typedef struct {
   const void* res; int64_t res_ld; int64_t res_bstride;
   float scale;
   int force_block_n;
-  float post_div;               /* mode 0: fp16(result) / post_div, rounded again; 1 = off */
+  float post_div;               /* skinny outputs (n_store < 8) only: fp16(result) / post_div, rounded again; 0 or 1 = off */
   int n_store;                  /* mode 0: store only the first n_store (< 8) columns; 0 = all */
   void* out2;                   /* mode 4 (alpha head): optional pre-clip mean */
   int force_mt;                 /* tests: 1 / 2 = force M sub-tiles per CTA tile (BLOCK_N 128 only), 0 = auto */
