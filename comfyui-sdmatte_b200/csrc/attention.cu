@@ -12,7 +12,7 @@
 //   warps 4-7  : softmax warpgroup for tile B
 //   warp  8    : TMA producer (Q once; K, V^T and the per-key bias per tile; 5-stage ring)
 //   warp  9    : tcgen05.mma issuer + TMEM alloc
-//                S_X  = Q_X K^T : M128 N128 K64, both operands from shared memory
+//                S_X  = Q_X K^T : two M128 N64 K64 halves (keys 0-63 / 64-127), both operands from shared memory
 //                O_X += P_X V   : M128 N64 K128, A = P_X read from TENSOR MEMORY ("TS" MMA), B = V^T from shared memory
 // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)   (P = packed fp16x2).
 //
@@ -23,8 +23,9 @@
 // exponentials) the shared-memory traffic halves, the 64-register P array disappears (no setmaxnreg, no spills) and the
 // per-tile publication tail is a tcgen05.wait::st.
 // Per key tile a warpgroup pulls S(j) out of TMEM in four 32-column chunks, the next chunk's tcgen05.ld in flight while the
-// current one is exponentiated, and signals `s_free` as soon as the LAST chunk has landed in registers — the tensor core
-// then computes S(j+1) while chunk 3 is still being processed.  O_X accumulates in TMEM over all key tiles.
+// current one is exponentiated.  S is produced and released in two 64-key halves: the low half is handed back to the tensor
+// core as soon as chunks 0-1 sit in registers (the very start of the tile), the high half once chunks 2-3 do, so S(j+1) is
+// complete long before the warpgroup needs it.  O_X accumulates in TMEM over all key tiles.
 // Softmax reference (lazy, optimistic): a chunk is exponentiated against the current reference m2 FIRST; its sum doubles as
 // the overflow test (csum <= 2^10 proves every e <= 2^10: fp16-safe).  Anything else (a score far above the reference,
 // +inf from m2 = -inf on the very first chunk, NaN) takes the rare redo path: raise m2 to the chunk's true maximum, rescale
@@ -76,7 +77,11 @@ __device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, __half2 s) {
 
 // TAIL: Lk is not a multiple of 128 and there is no bias to carry the -inf padding (never the case inside the engine;
 // kept out of the common instantiations: even skipped, the masking code cost a BSSY/branch per chunk and i-cache misses)
-template <bool HAS_BIAS, bool TAIL>
+// PP: pairs (of the 16 column pairs of a 32-key chunk) whose exponentials are computed on the FMA pipe instead of the
+// MUFU: 2^x = 2^n * p(f), n = round(x), f = x - n in [-0.5, 0.5], p = degree-4 minimax polynomial (relative error 2.7e-6,
+// two orders below the fp16 rounding of P), all as packed fp32x2 arithmetic; 2^n is added into the exponent field.
+// At d = 64 the kernel is bound by the 16 ex2/clk/SM of the MUFU, the FMA pipe is mostly idle.
+template <bool HAS_BIAS, bool TAIL, int PP>
 __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   using namespace a7;
   extern __shared__ uint8_t smem_raw[];
@@ -86,13 +91,14 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
   const uint32_t q_full = bar;
   auto kv_full = [&](int s) { return bar + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bar + 8u * (1 + kStages + s); };
-  auto s_full = [&](int x) { return bar + 8u * (1 + 2 * kStages + x); };
-  auto s_free = [&](int x) { return bar + 8u * (3 + 2 * kStages + x); };
-  auto p_full = [&](int x) { return bar + 8u * (5 + 2 * kStages + x); };
-  auto o_full = [&](int x) { return bar + 8u * (7 + 2 * kStages + x); };
-  const uint32_t tmem_slot = bar + 8u * (9 + 2 * kStages);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kOffBar + 8 * (9 + 2 * kStages));
-  static_assert(8 * (9 + 2 * kStages) + 4 <= 256, "barrier area");
+  // S is produced and released in two 64-key halves (hf = 0: keys 0-63, 1: keys 64-127)
+  auto s_full = [&](int x, int hf) { return bar + 8u * (1 + 2 * kStages + x * 2 + hf); };
+  auto s_free = [&](int x, int hf) { return bar + 8u * (5 + 2 * kStages + x * 2 + hf); };
+  auto p_full = [&](int x) { return bar + 8u * (9 + 2 * kStages + x); };
+  auto o_full = [&](int x) { return bar + 8u * (11 + 2 * kStages + x); };
+  const uint32_t tmem_slot = bar + 8u * (13 + 2 * kStages);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kOffBar + 8 * (13 + 2 * kStages));
+  static_assert(8 * (13 + 2 * kStages) + 4 <= 256, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256;
@@ -102,7 +108,11 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < kStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int x = 0; x < 2; ++x) { mbar_init(s_full(x), 1); mbar_init(s_free(x), 128); mbar_init(p_full(x), 128); mbar_init(o_full(x), 1); }
+    for (int x = 0; x < 2; ++x) {
+      for (int hf = 0; hf < 2; ++hf) { mbar_init(s_full(x, hf), 1); mbar_init(s_free(x, hf), 128); }
+      mbar_init(p_full(x), 128);
+      mbar_init(o_full(x), 1);
+    }
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -135,14 +145,15 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
   } else if (warp == 9) {
     // ======================================= MMA issuer =========================================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(128);
+      constexpr uint32_t idesc_s = umma_idesc_f16(64);
       constexpr uint32_t idesc_o = umma_idesc_f16(64);
-      auto issue_s = [&](int x, int stage) {
+      // S_x half hf = Q_x (128 x 64) . K[hf*64 .. hf*64+63]^T  -> S columns [hf*64, hf*64+64)
+      auto issue_s = [&](int x, int hf, int stage) {
         const uint64_t ad = umma_desc_k128(base + kOffQ + x * kQBytes);
-        const uint64_t bd = umma_desc_k128(base + kOffStage + stage * kStageBytes);
+        const uint64_t bd = umma_desc_k128(base + kOffStage + stage * kStageBytes + hf * (64 * 128));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tmem + kColS + x * 128, ad + 2 * k, bd + 2 * k, idesc_s, k != 0);
-        umma_commit(s_full(x));
+        for (int k = 0; k < 4; ++k) umma_f16(tmem + kColS + x * 128 + hf * 64, ad + 2 * k, bd + 2 * k, idesc_s, k != 0);
+        umma_commit(s_full(x, hf));
       };
       auto issue_pv = [&](int x, int stage, int j) {
         const uint32_t vb = base + kOffStage + stage * kStageBytes + kKBytes;
@@ -154,38 +165,43 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
         umma_commit(o_full(x));
       };
       mbar_wait(q_full, 0);
-      // Event-driven issue: the two query tiles are independent streams  S_x(0), [S_x(j+1), PV_x(j)]...  An in-order loop
-      // (S_A, S_B, PV_A, PV_B per key tile) made PV_A(j) wait for tile B's s_free whenever B lagged, and the softmax
-      // warpgroup of A then stalled on o_full before it could overwrite P (ncu r1m: 7 % of the softmax warps' samples).
-      int js[2] = {0, 0};   // S tiles issued per query tile
-      int jp[2] = {0, 0};   // P.V tiles issued per query tile
-      int released = 0;     // K/V stages handed back to the producer
+      // Event-driven issue.  Per query tile x the streams are  S_lo(t), S_hi(t), P.V(t)  with
+      //   S_lo_x(t+1) as soon as the warpgroup holds chunks 0-1 of S_x(t) in registers (right at the start of its tile t),
+      //   S_hi_x(t+1) once chunks 2-3 are in registers, P.V_x(t) once P_x(t) is in TMEM.
+      // S is issued with priority: it sits on the softmax warps' critical path (ncu r1n: with whole-tile S and in-order /
+      // round-robin issue the warpgroups waited 12 % of their time for S(j+1)); P.V is only needed one tile later.
+      int js[2][2] = {{0, 0}, {0, 0}};   // S halves issued per query tile
+      int jp[2] = {0, 0};                // P.V tiles issued per query tile
+      int released = 0;                  // K/V stages handed back to the producer
       uint32_t idle = 0;
       long long t0 = 0;
       while (jp[0] < n || jp[1] < n) {
         bool progress = false;
 #pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          if (js[x] < n && js[x] <= jp[x] + 1) {  // S_x is single-buffered: S_x(j+1) needs s_free_x(j)
-            const int t = js[x];
-            if (mbar_test(kv_full(t % kStages), (uint32_t)(t / kStages) & 1u) && (t == 0 || mbar_test(s_free(x), (uint32_t)(t - 1) & 1u))) {
+        for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            const int t = js[x][hf];
+            if (t < n && mbar_test(kv_full(t % kStages), (uint32_t)(t / kStages) & 1u) &&
+                (t == 0 || mbar_test(s_free(x, hf), (uint32_t)(t - 1) & 1u))) {
               tc_fence_after();
-              issue_s(x, t % kStages);
-              js[x] = t + 1;
+              issue_s(x, hf, t % kStages);
+              js[x][hf] = t + 1;
               progress = true;
             }
           }
-          if (jp[x] < js[x]) {
-            const int t = jp[x];
-            if (mbar_test(p_full(x), (uint32_t)t & 1u)) {  // P_x(t) is in TMEM
-              tc_fence_after();
-              issue_pv(x, t % kStages, t);
-              jp[x] = t + 1;
-              progress = true;
-              while (released < min(jp[0], jp[1])) {  // both tiles have issued their P.V for this stage
-                umma_commit(kv_empty(released % kStages));
-                ++released;
-              }
+        }
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          const int t = jp[x];
+          if (t < js[x][1] && mbar_test(p_full(x), (uint32_t)t & 1u)) {  // P_x(t) is in TMEM
+            tc_fence_after();
+            issue_pv(x, t % kStages, t);
+            jp[x] = t + 1;
+            progress = true;
+            while (released < min(jp[0], jp[1])) {  // both tiles have issued their P.V for this stage
+              umma_commit(kv_empty(released % kStages));
+              ++released;
             }
           }
         }
@@ -194,7 +210,8 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           const long long now = clock64();
           if (t0 == 0) t0 = now;
           else if (now - t0 > 20000000000LL) {
-            printf("sdm: attention MMA issue loop timeout (block %d,%d,%d js %d %d jp %d %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, js[0], js[1], jp[0], jp[1]);
+            printf("sdm: attention MMA issue loop timeout (block %d,%d,%d js %d %d %d %d jp %d %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+                   js[0][0], js[0][1], js[1][0], js[1][1], jp[0], jp[1]);
             __trap();
           }
         }
@@ -219,7 +236,7 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
       const bool tail = TAIL && (j == n - 1);
       const int kbase = j * 128;
       if (HAS_BIAS) mbar_wait(kv_full(s), ph);  // bias tile visible to this thread
-      mbar_wait(s_full(x), (uint32_t)j & 1u);
+      mbar_wait(s_full(x, 0), (uint32_t)j & 1u);
       tc_fence_after();
       const uint2* bias2 = reinterpret_cast<const uint2*>(base_ptr + kOffBias + s * 512);
       float rowsum = 0.f;
@@ -236,9 +253,11 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
         }
         uint32_t pk[16];
         float csum;
+        float pmax;  // largest log2-domain argument that went through the polynomial (it has no overflow behaviour of its own)
         auto exp_pack = [&]() {
           const uint64_t nm2 = pack_f2(-m2, -m2);
           float e[32];
+          pmax = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             uint64_t v = pack_f2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
@@ -250,8 +269,26 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
             }
             float x0, x1;
             unpack_f2(v, x0, x1);
-            e[2 * i] = ex2f(x0);
-            e[2 * i + 1] = ex2f(x1);
+            const bool kPoly = (PP == 8) ? (i % 2 == 1) : (PP == 6) ? (i % 4 == 3 || i % 8 == 1) : (PP == 4) ? (i % 4 == 3) : false;
+            if (kPoly) {
+              pmax = fmaxf(pmax, fmaxf(x0, x1));
+              const uint64_t vc = pack_f2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+              const uint64_t t = add_f2(vc, pack_f2(12582912.0f, 12582912.0f));       // integer part lands in the low mantissa bits
+              const uint64_t nn = add_f2(t, pack_f2(-12582912.0f, -12582912.0f));
+              const uint64_t f = fma_f2(nn, pack_f2(-1.0f, -1.0f), vc);
+              uint64_t pl = fma_f2(pack_f2(0.009570102207362652f, 0.009570102207362652f), f, pack_f2(0.05591785907745361f, 0.05591785907745361f));
+              pl = fma_f2(pl, f, pack_f2(0.240247443318367f, 0.240247443318367f));
+              pl = fma_f2(pl, f, pack_f2(0.6931217908859253f, 0.6931217908859253f));
+              pl = fma_f2(pl, f, pack_f2(0.9999992847442627f, 0.9999992847442627f));
+              float p0, p1, t0, t1;
+              unpack_f2(pl, p0, p1);
+              unpack_f2(t, t0, t1);
+              e[2 * i] = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+              e[2 * i + 1] = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+            } else {
+              e[2 * i] = ex2f(x0);
+              e[2 * i + 1] = ex2f(x1);
+            }
           }
           // pairwise tree on packed lanes: 8 + 4 + 2 + 1 FADD2, then one FADD
           uint64_t t8[8];
@@ -267,7 +304,7 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           for (int i = 0; i < 16; ++i) pk[i] = pack_h2(e[2 * i], e[2 * i + 1]);
         };
         exp_pack();
-        if (__any_sync(0xffffffffu, !(csum <= kLimit))) {
+        if (__any_sync(0xffffffffu, !(csum <= kLimit) || (PP > 0 && pmax > 12.0f))) {
           // rare: raise the reference to this chunk's true maximum, rescale what was accumulated, redo the chunk
           float cm = -INFINITY;
 #pragma unroll
@@ -320,15 +357,20 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
       };
 
       tmem_ld_wait();
+      // chunks 0-1 are in registers: the tensor core may overwrite the low half with S_lo(j+1) already
+      tc_fence_before();
+      mbar_arrive(s_free(x, 0));
 #pragma unroll 1
       for (int cp = 0; cp < 2; ++cp) {
         chunk(r0, 2 * cp);
         if (cp == 0) {
+          mbar_wait(s_full(x, 1), (uint32_t)j & 1u);  // high half of S(j) (issued long ago)
+          tc_fence_after();
           tmem_ld32(t_s + 64, r0);   // chunk 2 in flight while chunk 1 is processed
         } else {
-          tmem_ld_wait();            // chunk 3 has landed: all of S(j) is in registers, the tensor core may start S(j+1)
+          tmem_ld_wait();            // chunk 3 has landed: the high half may be overwritten with S_hi(j+1)
           tc_fence_before();
-          mbar_arrive(s_free(x));
+          mbar_arrive(s_free(x, 1));
         }
         chunk(r1, 2 * cp + 1);
         if (cp == 0) {
@@ -416,16 +458,31 @@ std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d) {
   return L;
 }
 
+template <bool HB, bool TL, int PP>
+static void attn_launch(const AttnLaunch& l, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<HB, TL, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
+    attr = true;
+  }
+  attention_kernel<HB, TL, PP><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
+}
+
 void attn_run(const AttnLaunch& l, cudaStream_t st) {
-  static std::once_flag once;
-  std::call_once(once, [] {
-    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
-    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
-    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
-  });
-  if (l.has_bias) attention_kernel<true, false><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
-  else if ((l.p.Lk & 127) != 0) attention_kernel<false, true><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
-  else attention_kernel<false, false><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
+  // SDM_ATTN_POLY = 0 | 4 | 6 | 8 column pairs per 32-key chunk on the FMA pipe (A/B switch; default below)
+  static const int poly = [] { const char* e = getenv("SDM_ATTN_POLY"); return e ? atoi(e) : 0; }();
+  if (!l.has_bias && (l.p.Lk & 127) != 0) attn_launch<false, true, 0>(l, st);
+  else if (l.has_bias) {
+    if (poly == 8) attn_launch<true, false, 8>(l, st);
+    else if (poly == 6) attn_launch<true, false, 6>(l, st);
+    else if (poly == 4) attn_launch<true, false, 4>(l, st);
+    else attn_launch<true, false, 0>(l, st);
+  } else {
+    if (poly == 8) attn_launch<false, false, 8>(l, st);
+    else if (poly == 6) attn_launch<false, false, 6>(l, st);
+    else if (poly == 4) attn_launch<false, false, 4>(l, st);
+    else attn_launch<false, false, 0>(l, st);
+  }
   SDM_CUDA_OK(cudaGetLastError());
 }
 

@@ -423,7 +423,7 @@ struct Builder {
         d.pre_partial[1] = a2 ? a2->stats : nullptr;
         d.pre_slots = a.stat_slots;
       }
-      push([d](cudaStream_t st) { groupnorm_run(d, st); }, 3, "groupnorm", 0, 4.0 * a.B * (double)a.HW() * Ctot);
+      push([d](cudaStream_t st) { groupnorm_run(d, st); }, groupnorm_num_launches(d), "groupnorm", 0, 4.0 * a.B * (double)a.HW() * Ctot);
     } else n_launches += 3;
     arena.release(soff, sbytes);
     return out;

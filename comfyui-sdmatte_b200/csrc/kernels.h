@@ -93,6 +93,7 @@ struct GroupNormDesc {
 };
 size_t groupnorm_scratch_floats(int B, int HW, int Ctot);
 void groupnorm_run(const GroupNormDesc& d, cudaStream_t st);
+int groupnorm_num_launches(const GroupNormDesc& d);  // kernels groupnorm_run will launch for this descriptor (2..4)
 
 void layernorm_run(const __half* x, __half* y, const float* gamma, const float* beta, long long rows, int C, float eps,
                    cudaStream_t st);

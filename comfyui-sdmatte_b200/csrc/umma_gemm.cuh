@@ -84,7 +84,7 @@ struct ConvGemmCfg {
   static constexpr int kABytes = 128 * 128;          // 128 rows x 64 fp16 (per M sub-tile)
   static constexpr int kBBytes = BLOCK_N * 128;      // BLOCK_N rows x 64 fp16
   static constexpr int kStageBytes = MT * kABytes + kBBytes;
-  static constexpr int kEpiBytes = EWG * (4 * 4096 /*staging*/ + 2048 /*GroupNorm partials*/);
+  static constexpr int kEpiBytes = EWG * (4 * 4096 /*staging*/ + 2 * 2048 /*GroupNorm partials, double buffered*/);
   static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes - 512;
   static constexpr int kStages = LIGHT ? 2 : ((kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes));
   static constexpr int kSubStride = BLOCK_N < 32 ? 32 : BLOCK_N;  // TMEM columns per M sub-tile accumulator
@@ -270,7 +270,8 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
     const int row = quad * 32 + lane;  // row of the 128-row tile == TMEM lane
     uint8_t* epi_base = smem_raw + (bar_base - smem_u32(smem_raw)) + 256;
     uint8_t* stg = epi_base + (warp - 2) * 4096;
-    float* sred = reinterpret_cast<float*>(epi_base + EWG * 4 * 4096 + ewg * 2048);
+    float* sred_base = reinterpret_cast<float*>(epi_base + EWG * 4 * 4096 + ewg * 4096);
+    int sred_sel = 0;  // the partials buffer alternates per slab: one named barrier per slab instead of two
     const int t_row0 = lane >> 3, t_piece = lane & 7;
     int ltw = 0;
     while ((1 << ltw) < p.tw) ++ltw;
@@ -414,7 +415,11 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
                   ssum[e] = add_f2(ssum[e], __shfl_xor_sync(0xffffffffu, ssum[e], 16));
                   ssq[e] = add_f2(ssq[e], __shfl_xor_sync(0xffffffffu, ssq[e], 16));
                 }
-                // combine the four epilogue warps in a fixed order through shared memory (one global writer per slot)
+                // combine the four epilogue warps in a fixed order through shared memory (one global writer per slot).
+                // Two buffers: warp 0 of the warpgroup reads buffer k while the others may already fill buffer k^1 for the
+                // next slab; nobody can reach buffer k again before passing the next slab's barrier, i.e. after warp 0 left it.
+                float* sred = sred_base + sred_sel * 512;
+                sred_sel ^= 1;
                 if (lane < 8) {
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
@@ -438,54 +443,54 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
                     *reinterpret_cast<float4*>(p.stats + (slot * p.N + gcol) * 2) = o;
                   }
                 }
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + ewg) : "memory");
               }
             }
           }
         } else if constexpr (MODE == EPI_GEGLU || MODE == EPI_F32) {
-          // ---- staged, row-contiguous store path -------------------------------------------------
+          // ---- staged, row-contiguous store path for the fp32 scores (VAE attention) and the GEGLU projection ------------
           constexpr int ES = (MODE == EPI_F32) ? 4 : 2;       // output element size
           constexpr int CPP = 16 / ES;                        // columns per 16-byte piece
           constexpr int SLAB = 128 / ES;                      // output columns per 128-byte staging row
           constexpr int OUT_COLS = (MODE == EPI_GEGLU) ? BLOCK_N / 2 : BLOCK_N;
+          constexpr int HALF = BLOCK_N / 2;                   // GEGLU: tile = [HALF value columns | HALF gate columns]
           const int ocol0 = (MODE == EPI_GEGLU) ? (n0 >> 1) : n0;
           const int o_lim = (MODE == EPI_GEGLU) ? min(p.N >> 1, ocol0 + OUT_COLS) : min(p.N, n0 + BLOCK_N);
           uint8_t* obase = reinterpret_cast<uint8_t*>(p.out) + (long long)b * p.out_bstride * ES;
-          // pixel offsets of the 8 rows this lane serves in the transposed phase; -1 = outside the image
-          long long tpix[8];
+          // element offsets (within this sample) of the 8 rows this lane serves in the transposed phase; -1 = outside
+          long long toff[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rg = quad * 32 + i * 4 + t_row0;
             const int xx = tx * p.tw + (rg & (p.tw - 1)), yy = ty * p.th + (rg >> ltw);
-            tpix[i] = (xx < p.W && yy < p.H) ? (UPS2 ? (long long)(2 * yy) * (2 * p.W) + 2 * xx : (long long)yy * p.W + xx) : -1;
+            toff[i] = (xx < p.W && yy < p.H) ? ((long long)yy * p.W + xx) * p.out_ld : -1;
           }
+          // the first tcgen05.ld of the next slab is issued before this slab's stores (ra / rg hold 32 accumulator columns)
+          uint32_t ra[32], rg[32];
+          __syncwarp();
+          tmem_ld32(taddr, ra);
+          if constexpr (MODE == EPI_GEGLU) tmem_ld32(taddr + HALF, rg);
 #pragma unroll 1
           for (int c = 0; c < OUT_COLS; c += SLAB) {
-            uint4 pc[8];
             if constexpr (MODE == EPI_F32) {
-              uint32_t r[32];
-              __syncwarp();
-              tmem_ld32(taddr + c, r);
+              // 32 fp32 columns per slab
+              float bv[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) bv[i] = (bias && n0 + c + i < p.N) ? __ldg(bias + n0 + c + i) : 0.f;
               tmem_ld_wait();
+              __syncwarp();
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
                 float v[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  v[e] = __uint_as_float(r[g * 4 + e]) * p.scale;
-                  if (bias && n0 + c + g * 4 + e < p.N) v[e] += bias[n0 + c + g * 4 + e];
-                }
-                pc[g] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                for (int e = 0; e < 4; ++e) v[e] = fmaf(__uint_as_float(ra[g * 4 + e]), p.scale, bv[g * 4 + e]);
+                *reinterpret_cast<uint4*>(stg + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+                    make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
               }
-            } else if constexpr (MODE == EPI_GEGLU) {
-              constexpr int HALF = BLOCK_N / 2;
+              if (c + SLAB < OUT_COLS) tmem_ld32(taddr + c + SLAB, ra);
+            } else {
+              // 64 output columns per slab = two 32-column halves of value and gate
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
-                uint32_t rv[32], rg[32];
-                __syncwarp();
-                tmem_ld32(taddr + c + hh * 32, rv);
-                tmem_ld32(taddr + HALF + c + hh * 32, rg);
-                tmem_ld_wait();
                 float bv[32], bg[32];
                 if (bias) {
 #pragma unroll
@@ -499,134 +504,44 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
 #pragma unroll
                   for (int i = 0; i < 32; ++i) { bv[i] = 0.f; bg[i] = 0.f; }
                 }
+                tmem_ld_wait();
+                __syncwarp();
+                uint32_t w[16];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  uint32_t w[4];
+                for (int i = 0; i < 16; ++i) {
+                  float o[2];
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    float o[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                      const int i = g * 8 + j * 2 + e;
-                      // reference rounding points: proj output fp16, gelu(gate) fp16, product fp16
-                      const float v = __half2float(__float2half_rn(__uint_as_float(rv[i]) + bv[i]));
-                      const float gt = __half2float(__float2half_rn(__uint_as_float(rg[i]) + bg[i]));
-                      float ge = 0.5f * gt * (1.0f + erf_fast(gt * 0.70710678118654752f));
-                      ge = __half2float(__float2half_rn(ge));
-                      o[e] = v * ge;
-                    }
-                    w[j] = pack_h2(o[0], o[1]);
+                  for (int e = 0; e < 2; ++e) {
+                    // reference rounding points: proj output fp16, gelu(gate) fp16, product fp16
+                    const float v = __half2float(__float2half_rn(__uint_as_float(ra[2 * i + e]) + bv[2 * i + e]));
+                    const float gt = __half2float(__float2half_rn(__uint_as_float(rg[2 * i + e]) + bg[2 * i + e]));
+                    float ge = 0.5f * gt * (1.0f + erf_fast(gt * 0.70710678118654752f));
+                    ge = __half2float(__float2half_rn(ge));
+                    o[e] = v * ge;
                   }
-                  pc[hh * 4 + g] = make_uint4(w[0], w[1], w[2], w[3]);
+                  w[i] = pack_h2(o[0], o[1]);
                 }
-              }
-            } else {  // EPI_F16
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                if (c + hh * 32 < BLOCK_N) {
-                  uint32_t r[32];
-                  __syncwarp();
-                  tmem_ld32(taddr + c + hh * 32, r);
-                  tmem_ld_wait();
-                  float v[32];
-#pragma unroll
-                  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.scale;
-                  if (bias) {
-#pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                      if (n0 + c + hh * 32 + g * 4 < p.N) {
-                        const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + hh * 32 + g * 4));
-                        v[g * 4 + 0] += bq.x; v[g * 4 + 1] += bq.y; v[g * 4 + 2] += bq.z; v[g * 4 + 3] += bq.w;
-                      }
-                    }
-                  }
-                  if (p.post_div != 1.0f) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __half2float(__float2half_rn(v[i])) / p.post_div;
-                  }
-#pragma unroll
-                  for (int g = 0; g < 4; ++g)
-                    pc[hh * 4 + g] = make_uint4(pack_h2(v[g * 8], v[g * 8 + 1]), pack_h2(v[g * 8 + 2], v[g * 8 + 3]),
-                                                pack_h2(v[g * 8 + 4], v[g * 8 + 5]), pack_h2(v[g * 8 + 6], v[g * 8 + 7]));
-                } else {
-#pragma unroll
-                  for (int g = 0; g < 4; ++g) pc[hh * 4 + g] = make_uint4(0, 0, 0, 0);
+                // the next 32 value / gate columns fly while this half is staged and (after the second half) stored
+                const int nc = c + hh * 32 + 32;
+                if (nc < OUT_COLS) {
+                  tmem_ld32(taddr + nc, ra);
+                  tmem_ld32(taddr + HALF + nc, rg);
                 }
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  *reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + g) ^ (lane & 7)) << 4)) = make_uint4(w[g * 4], w[g * 4 + 1], w[g * 4 + 2], w[g * 4 + 3]);
               }
             }
-            // this thread's row -> staging -> row-contiguous global stores
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = pc[q];
+            // staging -> row-contiguous global stores
             __syncwarp();
             const int col = ocol0 + c + t_piece * CPP;
-            float ssum[8], ssq[8];
-            if constexpr (MODE == EPI_F16 && !UPS2) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) { ssum[e] = 0.f; ssq[e] = 0.f; }
-            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rl = i * 4 + t_row0;
               const uint4 v = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((t_piece ^ (rl & 7)) << 4));
-              if (tpix[i] >= 0 && col < o_lim) {
-                if constexpr (MODE == EPI_F16 && !UPS2) {
-                  if (p.stats) {
-                    const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const float2 f = __half22float2(h[j]);
-                      ssum[2 * j] += f.x; ssq[2 * j] = fmaf(f.x, f.x, ssq[2 * j]);
-                      ssum[2 * j + 1] += f.y; ssq[2 * j + 1] = fmaf(f.y, f.y, ssq[2 * j + 1]);
-                    }
-                  }
-                }
-                if constexpr (!UPS2) {
-                  *reinterpret_cast<uint4*>(obase + (tpix[i] * p.out_ld + col) * ES) = v;
-                } else {
-                  // nearest-neighbour 2x upsample fused into the store (reference Upsample2D: F.interpolate scale 2
-                  // "nearest" followed by a conv; the conv then reads this tensor)
-#pragma unroll
-                  for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<uint4*>(obase + ((tpix[i] + (q >> 1) * (2 * p.W) + (q & 1)) * p.out_ld + col) * ES) = v;
-                }
-              }
+              if (toff[i] >= 0 && col < o_lim) *reinterpret_cast<uint4*>(obase + (toff[i] + col) * ES) = v;
             }
-            if constexpr (MODE == EPI_F16 && !UPS2) {
-              if (p.stats) {
-                // column sums over this warp's 32 rows: lanes {l, l+8, l+16, l+24} hold the same 8 columns
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  ssum[e] += __shfl_xor_sync(0xffffffffu, ssum[e], 8);
-                  ssq[e] += __shfl_xor_sync(0xffffffffu, ssq[e], 8);
-                  ssum[e] += __shfl_xor_sync(0xffffffffu, ssum[e], 16);
-                  ssq[e] += __shfl_xor_sync(0xffffffffu, ssq[e], 16);
-                }
-                // combine the four epilogue warps in a fixed order through shared memory (one global writer per slot)
-                if (lane < 8) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    sred[(quad * 64 + lane * 8 + e) * 2] = ssum[e];
-                    sred[(quad * 64 + lane * 8 + e) * 2 + 1] = ssq[e];
-                  }
-                }
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + ewg) : "memory");
-                if (quad == 0) {
-                  const int cc = lane * 2;  // two columns per lane
-                  const int gcol = n0 + c + cc;
-                  if (gcol < o_lim) {
-                    float4 o;
-                    o.x = (sred[(0 * 64 + cc) * 2] + sred[(1 * 64 + cc) * 2]) + (sred[(2 * 64 + cc) * 2] + sred[(3 * 64 + cc) * 2]);
-                    o.y = (sred[(0 * 64 + cc) * 2 + 1] + sred[(1 * 64 + cc) * 2 + 1]) + (sred[(2 * 64 + cc) * 2 + 1] + sred[(3 * 64 + cc) * 2 + 1]);
-                    o.z = (sred[(0 * 64 + cc + 1) * 2] + sred[(1 * 64 + cc + 1) * 2]) + (sred[(2 * 64 + cc + 1) * 2] + sred[(3 * 64 + cc + 1) * 2]);
-                    o.w = (sred[(0 * 64 + cc + 1) * 2 + 1] + sred[(1 * 64 + cc + 1) * 2 + 1]) + (sred[(2 * 64 + cc + 1) * 2 + 1] + sred[(3 * 64 + cc + 1) * 2 + 1]);
-                    const long long slot = (long long)b * (p.tiles_x * p.tiles_y) + (mt % (p.tiles_x * p.tiles_y));
-                    *reinterpret_cast<float4*>(p.stats + (slot * p.N + gcol) * 2) = o;
-                  }
-                }
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + ewg) : "memory");
-              }
-            }
+            __syncwarp();  // staging is rewritten by the next slab
           }
         } else {
           // ---- row-per-thread paths (transposed store is already coalesced along pixels; skinny outputs are tiny)

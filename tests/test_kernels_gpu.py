@@ -410,7 +410,8 @@ def test_linear_two_m_subtiles(eng_mod):
     _close(out, x.float() @ w.float().t() + b, 2e-3, 2e-3, "linear MT=2")
 
 
-@pytest.mark.parametrize("B,H,W,Cin,Cout,mt", [(2, 32, 32, 128, 128, 2), (1, 40, 40, 320, 320, 0), (2, 16, 16, 256, 256, 0), (3, 8, 8, 64, 64, 0)])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,mt", [(2, 32, 32, 128, 128, 2), (1, 40, 40, 320, 320, 0), (2, 16, 16, 256, 256, 0), (3, 8, 8, 64, 64, 0),
+                                               (2, 256, 256, 64, 128, 2)])  # last: 512 slots -> coalesced two-stage reduction of the partials
 def test_conv_epilogue_groupnorm_partials(eng_mod, B, H, W, Cin, Cout, mt):
     """The conv epilogue's per-(tile, channel) sums of the STORED fp16 outputs reproduce the tensor's channel statistics,
     and GroupNorm fed with them equals GroupNorm computing its own statistics (bit for bit run to run)."""
@@ -439,6 +440,34 @@ def test_conv_epilogue_groupnorm_partials(eng_mod, B, H, W, Cin, Cout, mt):
     ref = F.silu(F.group_norm(out.float().view(B, H * W, Cout).transpose(1, 2), 32, g, bt, 1e-5)).transpose(1, 2)
     _close(y2, ref, 2e-3, 2e-3, "groupnorm from epilogue partials")
     assert (y1.float() - y2.float()).abs().max().item() <= 2e-3
+
+
+def test_groupnorm_two_sources_many_partial_slots(eng_mod):
+    """concat GroupNorm fed with per-slot partials of BOTH sources (1024 slots each -> the pre-reduction kernel runs per
+    source); must equal the GroupNorm that computes its own statistics, and be bit-identical for a sample alone vs in a batch."""
+    B, HW, C0, C1, slots = 2, 65536, 128, 64, 1024
+    a = (_rand(B, HW, C0, seed=1) + 0.3).half()
+    s2 = (_rand(B, HW, C1, seed=2) * 2).half()
+    g = _rand(C0 + C1, seed=3).float() * 0.2 + 1.0
+    bt = _rand(C0 + C1, seed=4).float() * 0.2
+
+    def partials(t, C):
+        v = t.float().view(B, slots, HW // slots, C)
+        return torch.stack([v.sum(2), (v * v).sum(2)], dim=-1).contiguous()  # (B, slots, C, 2)
+
+    pa, ps = partials(a, C0), partials(s2, C1)
+    y1 = torch.zeros(B, HW, C0 + C1, dtype=torch.float16, device=DEV)
+    y2 = torch.zeros_like(y1)
+    eng_mod.k_groupnorm([(a, C0, C0), (s2, C1, C1)], g, bt, y1, B=B, HW=HW, eps=1e-5, silu=1)
+    eng_mod.k_groupnorm([(a, C0, C0), (s2, C1, C1)], g, bt, y2, B=B, HW=HW, eps=1e-5, silu=1, pre=[pa, ps], pre_slots=slots)
+    torch.cuda.synchronize()
+    ref = F.silu(F.group_norm(torch.cat([a, s2], -1).float().transpose(1, 2), 32, g, bt, 1e-5)).transpose(1, 2)
+    _close(y2, ref, 2e-3, 2e-3, "groupnorm two-source partials")
+    assert (y1.float() - y2.float()).abs().max().item() <= 2e-3
+    y3 = torch.zeros(1, HW, C0 + C1, dtype=torch.float16, device=DEV)
+    eng_mod.k_groupnorm([(a[1:], C0, C0), (s2[1:], C1, C1)], g, bt, y3, B=1, HW=HW, eps=1e-5, silu=1, pre=[pa[1:].contiguous(), ps[1:].contiguous()], pre_slots=slots)
+    torch.cuda.synchronize()
+    assert torch.equal(y3[0], y2[1])
 
 
 @pytest.mark.parametrize("mode", ["f16", "f16_res", "vT", "f32"])
