@@ -145,8 +145,23 @@ int sdm_k_attention(const sdm_attn_args* a, uintptr_t stream) {
   d.vt = reinterpret_cast<const __half*>(a->vt); d.ldvt = a->ldvt;
   d.bias = a->bias; d.bias_bstride = a->bias_bstride;
   d.out = reinterpret_cast<__half*>(a->out); d.ldo = a->ldo; d.scale = a->scale;
+  d.ntiles = a->ntiles;
   auto l = sdm::attn_build(d);
   sdm::attn_run(*l, reinterpret_cast<cudaStream_t>(stream));
+  SDM_API_END
+}
+
+int sdm_k_key_compact(const float* bias, float* cbias, int32_t* idx, int32_t* ntiles, int B, int L, int lpad, uintptr_t stream) {
+  SDM_API_BEGIN
+  sdm::key_compact_level_run(bias, cbias, idx, ntiles, B, L, lpad, reinterpret_cast<cudaStream_t>(stream));
+  SDM_API_END
+}
+
+int sdm_k_gather_rows(const void* src, void* dst, const int32_t* idx, const int32_t* ntiles, int B, int L, int C, int idx_bstride,
+                      uintptr_t stream) {
+  SDM_API_BEGIN
+  sdm::gather_rows_run(reinterpret_cast<const __half*>(src), reinterpret_cast<__half*>(dst), idx, ntiles, B, L, C, idx_bstride,
+                       reinterpret_cast<cudaStream_t>(stream));
   SDM_API_END
 }
 

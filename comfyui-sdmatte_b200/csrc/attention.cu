@@ -33,6 +33,12 @@
 // alpha = 2^(m2_old - m2_new), and exponentiate the chunk again from the S registers that are still live.  Steady state is
 // one basic block per chunk: 16 FFMA2 -> 32 MUFU.EX2 -> 16 FADD2 / 16 F2FP -> tcgen05.st (fp32x2 packed arithmetic).
 // Measured (B2 h5 16384x16384, same box): v5 (row max -> vote -> exp, P via smem) 532 TFLOP/s, v6 (optimistic, P via smem) 478.
+// v8 (r1p): P.V is issued in two 64-key halves as well (SPLIT_PV).  ncu source view of v7c (profiles/r1o): 19 % of the
+// softmax warps' samples sat on ONE instruction, the wait for P.V(j-1) before chunk 0 of P(j) may overwrite the P columns
+// it reads (P.V(j-1) is only issued at the very end of tile j-1 and queues behind the other warpgroup's MMAs).  With
+// P_lo = chunks 0-1 published after chunk 1 and P_hi after chunk 3, O += P_lo V_lo runs half a tile earlier, the chunk-0
+// store of tile j waits for an MMA issued two chunks before the end of tile j-1, the chunk-2 store for the one issued at
+// its end: both have >= 2 chunks of exponentials of slack.
 // The per-key bias is expected pre-multiplied by log2(e); scores are handled in the log2 domain, statistics in fp32,
 // and scores are NOT rounded to fp16 before the softmax (the reference does).
 #include "common.cuh"
@@ -48,6 +54,7 @@ struct alignas(64) AttnParams {
   CUtensorMap q_map, k_map, vt_map;
   const float* bias;
   long long bias_bstride;
+  const int* ntiles;  // per-sample key-tile count (compacted keys) or null
   __half* out;
   long long ldo;
   int Lq, Lk, heads, n_ktiles;
@@ -77,11 +84,10 @@ __device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, __half2 s) {
 
 // TAIL: Lk is not a multiple of 128 and there is no bias to carry the -inf padding (never the case inside the engine;
 // kept out of the common instantiations: even skipped, the masking code cost a BSSY/branch per chunk and i-cache misses)
-// PP: pairs (of the 16 column pairs of a 32-key chunk) whose exponentials are computed on the FMA pipe instead of the
-// MUFU: 2^x = 2^n * p(f), n = round(x), f = x - n in [-0.5, 0.5], p = degree-4 minimax polynomial (relative error 2.7e-6,
-// two orders below the fp16 rounding of P), all as packed fp32x2 arithmetic; 2^n is added into the exponent field.
-// At d = 64 the kernel is bound by the 16 ex2/clk/SM of the MUFU, the FMA pipe is mostly idle.
-template <bool HAS_BIAS, bool TAIL, int PP>
+// SPLIT_PV: see the v8 note above (false = v7c behaviour, kept as the A/B baseline: SDM_ATTN_SPLIT=0)
+// (An FMA-pipe polynomial exp2 for 4/6/8 of the 16 column pairs of a chunk was measured on B200 in r1o: 519 -> 494 / 475 /
+// 464 TFLOP/s at L0 — the softmax warps are latency-, not MUFU-throughput-bound — and removed.)
+template <bool HAS_BIAS, bool TAIL, bool SPLIT_PV>
 __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   using namespace a7;
   extern __shared__ uint8_t smem_raw[];
@@ -94,24 +100,26 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
   // S is produced and released in two 64-key halves (hf = 0: keys 0-63, 1: keys 64-127)
   auto s_full = [&](int x, int hf) { return bar + 8u * (1 + 2 * kStages + x * 2 + hf); };
   auto s_free = [&](int x, int hf) { return bar + 8u * (5 + 2 * kStages + x * 2 + hf); };
-  auto p_full = [&](int x) { return bar + 8u * (9 + 2 * kStages + x); };
-  auto o_full = [&](int x) { return bar + 8u * (11 + 2 * kStages + x); };
-  const uint32_t tmem_slot = bar + 8u * (13 + 2 * kStages);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kOffBar + 8 * (13 + 2 * kStages));
-  static_assert(8 * (13 + 2 * kStages) + 4 <= 256, "barrier area");
+  // P is published and P.V committed per 64-key half when SPLIT_PV (otherwise only index hf = 1 is used: whole tile)
+  auto p_full = [&](int x, int hf) { return bar + 8u * (9 + 2 * kStages + x * 2 + hf); };
+  auto o_full = [&](int x, int hf) { return bar + 8u * (13 + 2 * kStages + x * 2 + hf); };
+  const uint32_t tmem_slot = bar + 8u * (17 + 2 * kStages);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kOffBar + 8 * (17 + 2 * kStages));
+  static_assert(8 * (17 + 2 * kStages) + 4 <= 256, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int n = p.n_ktiles;
+  const int n = p.ntiles ? min(__ldg(p.ntiles + b), p.n_ktiles) : p.n_ktiles;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < kStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     for (int x = 0; x < 2; ++x) {
-      for (int hf = 0; hf < 2; ++hf) { mbar_init(s_full(x, hf), 1); mbar_init(s_free(x, hf), 128); }
-      mbar_init(p_full(x), 128);
-      mbar_init(o_full(x), 1);
+      for (int hf = 0; hf < 2; ++hf) {
+        mbar_init(s_full(x, hf), 1); mbar_init(s_free(x, hf), 128);
+        mbar_init(p_full(x, hf), 128); mbar_init(o_full(x, hf), 1);
+      }
     }
     fence_barrier_init();
     fence_proxy_async_smem();
@@ -155,27 +163,27 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
         for (int k = 0; k < 4; ++k) umma_f16(tmem + kColS + x * 128 + hf * 64, ad + 2 * k, bd + 2 * k, idesc_s, k != 0);
         umma_commit(s_full(x, hf));
       };
-      auto issue_pv = [&](int x, int stage, int j) {
+      // O_x += P_x[:, keys k0*16 .. k1*16) . V[those keys]   (K16 steps k0..k1-1 of the 8 in a 128-key tile)
+      auto issue_pv = [&](int x, int stage, int j, int k0, int k1, uint32_t commit_bar) {
         const uint32_t vb = base + kOffStage + stage * kStageBytes + kKBytes;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = k0; k < k1; ++k) {
           const uint64_t bd = umma_desc_k128(vb + (k >> 2) * (64 * 128)) + 2 * (k & 3);
           umma_f16_ts(tmem + kColO + x * 64, tmem + kColP + x * 64 + k * 8, bd, idesc_o, (j | k) != 0);
         }
-        umma_commit(o_full(x));
+        umma_commit(commit_bar);
       };
       mbar_wait(q_full, 0);
-      // Event-driven issue.  Per query tile x the streams are  S_lo(t), S_hi(t), P.V(t)  with
+      // Event-driven issue.  Per query tile x the streams are  S_lo(t), S_hi(t), P.V_lo(t), P.V_hi(t)  with
       //   S_lo_x(t+1) as soon as the warpgroup holds chunks 0-1 of S_x(t) in registers (right at the start of its tile t),
-      //   S_hi_x(t+1) once chunks 2-3 are in registers, P.V_x(t) once P_x(t) is in TMEM.
+      //   S_hi_x(t+1) once chunks 2-3 are in registers, P.V_lo/hi_x(t) once that half of P_x(t) is in TMEM.
       // S is issued with priority: it sits on the softmax warps' critical path (ncu r1n: with whole-tile S and in-order /
-      // round-robin issue the warpgroups waited 12 % of their time for S(j+1)); P.V is only needed one tile later.
+      // round-robin issue the warpgroups waited 12 % of their time for S(j+1)); P.V is only needed later.
       int js[2][2] = {{0, 0}, {0, 0}};   // S halves issued per query tile
-      int jp[2] = {0, 0};                // P.V tiles issued per query tile
+      int jp[2][2] = {{0, 0}, {0, 0}};   // P.V halves issued per query tile ([x][1] = whole tiles when !SPLIT_PV)
       int released = 0;                  // K/V stages handed back to the producer
       uint32_t idle = 0;
       long long t0 = 0;
-      while (jp[0] < n || jp[1] < n) {
+      while (jp[0][1] < n || jp[1][1] < n) {
         bool progress = false;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -193,15 +201,28 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
         }
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
-          const int t = jp[x];
-          if (t < js[x][1] && mbar_test(p_full(x), (uint32_t)t & 1u)) {  // P_x(t) is in TMEM
-            tc_fence_after();
-            issue_pv(x, t % kStages, t);
-            jp[x] = t + 1;
-            progress = true;
-            while (released < min(jp[0], jp[1])) {  // both tiles have issued their P.V for this stage
-              umma_commit(kv_empty(released % kStages));
-              ++released;
+          // older half first: hi(t) is issued after lo(t) and before lo(t+1), so every commit also covers all earlier P.V
+          {
+            const int t = jp[x][1];
+            if (t < js[x][1] && (!SPLIT_PV || t < jp[x][0]) && mbar_test(p_full(x, 1), (uint32_t)t & 1u)) {
+              tc_fence_after();
+              if (SPLIT_PV) issue_pv(x, t % kStages, t, 4, 8, o_full(x, 1));
+              else issue_pv(x, t % kStages, t, 0, 8, o_full(x, 1));
+              jp[x][1] = t + 1;
+              progress = true;
+              while (released < min(jp[0][1], jp[1][1])) {  // both tiles have issued all their P.V for this stage
+                umma_commit(kv_empty(released % kStages));
+                ++released;
+              }
+            }
+          }
+          if (SPLIT_PV) {
+            const int t = jp[x][0];
+            if (t == jp[x][1] && t < js[x][0] && mbar_test(p_full(x, 0), (uint32_t)t & 1u)) {
+              tc_fence_after();
+              issue_pv(x, t % kStages, t, 0, 4, o_full(x, 0));
+              jp[x][0] = t + 1;
+              progress = true;
             }
           }
         }
@@ -210,8 +231,8 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           const long long now = clock64();
           if (t0 == 0) t0 = now;
           else if (now - t0 > 20000000000LL) {
-            printf("sdm: attention MMA issue loop timeout (block %d,%d,%d js %d %d %d %d jp %d %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-                   js[0][0], js[0][1], js[1][0], js[1][1], jp[0], jp[1]);
+            printf("sdm: attention MMA issue loop timeout (block %d,%d,%d js %d %d %d %d jp %d %d %d %d)\n", blockIdx.x, blockIdx.y,
+                   blockIdx.z, js[0][0], js[0][1], js[1][0], js[1][1], jp[0][0], jp[0][1], jp[1][0], jp[1][1]);
             __trap();
           }
         }
@@ -253,11 +274,9 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
         }
         uint32_t pk[16];
         float csum;
-        float pmax;  // largest log2-domain argument that went through the polynomial (it has no overflow behaviour of its own)
         auto exp_pack = [&]() {
           const uint64_t nm2 = pack_f2(-m2, -m2);
           float e[32];
-          pmax = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             uint64_t v = pack_f2(__uint_as_float(rr[2 * i]), __uint_as_float(rr[2 * i + 1]));
@@ -269,26 +288,8 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
             }
             float x0, x1;
             unpack_f2(v, x0, x1);
-            const bool kPoly = (PP == 8) ? (i % 2 == 1) : (PP == 6) ? (i % 4 == 3 || i % 8 == 1) : (PP == 4) ? (i % 4 == 3) : false;
-            if (kPoly) {
-              pmax = fmaxf(pmax, fmaxf(x0, x1));
-              const uint64_t vc = pack_f2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
-              const uint64_t t = add_f2(vc, pack_f2(12582912.0f, 12582912.0f));       // integer part lands in the low mantissa bits
-              const uint64_t nn = add_f2(t, pack_f2(-12582912.0f, -12582912.0f));
-              const uint64_t f = fma_f2(nn, pack_f2(-1.0f, -1.0f), vc);
-              uint64_t pl = fma_f2(pack_f2(0.009570102207362652f, 0.009570102207362652f), f, pack_f2(0.05591785907745361f, 0.05591785907745361f));
-              pl = fma_f2(pl, f, pack_f2(0.240247443318367f, 0.240247443318367f));
-              pl = fma_f2(pl, f, pack_f2(0.6931217908859253f, 0.6931217908859253f));
-              pl = fma_f2(pl, f, pack_f2(0.9999992847442627f, 0.9999992847442627f));
-              float p0, p1, t0, t1;
-              unpack_f2(pl, p0, p1);
-              unpack_f2(t, t0, t1);
-              e[2 * i] = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
-              e[2 * i + 1] = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
-            } else {
-              e[2 * i] = ex2f(x0);
-              e[2 * i + 1] = ex2f(x1);
-            }
+            e[2 * i] = ex2f(x0);
+            e[2 * i + 1] = ex2f(x1);
           }
           // pairwise tree on packed lanes: 8 + 4 + 2 + 1 FADD2, then one FADD
           uint64_t t8[8];
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           for (int i = 0; i < 16; ++i) pk[i] = pack_h2(e[2 * i], e[2 * i + 1]);
         };
         exp_pack();
-        if (__any_sync(0xffffffffu, !(csum <= kLimit) || (PP > 0 && pmax > 12.0f))) {
+        if (__any_sync(0xffffffffu, !(csum <= kLimit))) {
           // rare: raise the reference to this chunk's true maximum, rescale what was accumulated, redo the chunk
           float cm = -INFINITY;
 #pragma unroll
@@ -319,8 +320,12 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           }
           const float m_new = fmaxf(m2, cm);
           const float alpha = (m_new == m2) ? 1.0f : ex2f(m2 - m_new);  // 0 when m2 = -inf
-          if (j > 0) {
-            mbar_wait(o_full(x), (uint32_t)(j - 1) & 1u);  // every P·V issued so far has landed in O
+          // every P.V issued so far must have landed in O before its rows are rescaled: all of tile j-1, and with
+          // SPLIT_PV the low half of this tile once it has been published (c >= 2)
+          const bool lo_consumed = SPLIT_PV && c >= 2;
+          if (j > 0) mbar_wait(o_full(x, 1), (uint32_t)(j - 1) & 1u);
+          if (lo_consumed) mbar_wait(o_full(x, 0), (uint32_t)j & 1u);
+          if (j > 0 || lo_consumed) {
             tc_fence_after();
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
@@ -334,7 +339,8 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           }
           const __half2 a2 = __float2half2_rn(alpha);
           tmem_st_wait();  // this tile's earlier P chunks are in TMEM before they are read back
-          for (int cc = 0; cc < c; ++cc) {
+          // chunks of this tile stored but not yet handed to the tensor core (chunks 0-1 already are when lo_consumed)
+          for (int cc = lo_consumed ? 2 : 0; cc < c; ++cc) {
             uint32_t pp[16];
             tmem_ld16(t_p + cc * 16, pp);
             tmem_ld_wait();
@@ -347,10 +353,17 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           m2 = m_new;
           exp_pack();
         }
-        // P(j) overwrites the columns P·V(j-1) reads
-        if (c == 0 && j > 0) {
-          mbar_wait(o_full(x), (uint32_t)(j - 1) & 1u);
-          tc_fence_after();
+        // P(j) overwrites the columns P.V(j-1) reads: chunks 0-1 the low half's, chunks 2-3 the high half's
+        if (j > 0) {
+          if (SPLIT_PV) {
+            if ((c & 1) == 0) {
+              mbar_wait(o_full(x, c >> 1), (uint32_t)(j - 1) & 1u);
+              tc_fence_after();
+            }
+          } else if (c == 0) {
+            mbar_wait(o_full(x, 1), (uint32_t)(j - 1) & 1u);
+            tc_fence_after();
+          }
         }
         tmem_st16(t_p + c * 16, pk);
         rowsum += csum;
@@ -376,16 +389,21 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
         if (cp == 0) {
           tmem_ld_wait();
           tmem_ld32(t_s + 96, r1);   // chunk 3 in flight while chunk 2 is processed
+          if (SPLIT_PV) {            // chunks 0-1 of P(j) are complete: O += P_lo V_lo may start
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(p_full(x, 0));
+          }
         }
       }
       l += rowsum;
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full(x));
+      mbar_arrive(p_full(x, 1));
       if (++s == kStages) { s = 0; ph ^= 1u; }
     }
-    // ---- normalise and store
-    mbar_wait(o_full(x), (uint32_t)(n - 1) & 1u);
+    // ---- normalise and store (the last commit covers every earlier P.V)
+    mbar_wait(o_full(x, 1), (uint32_t)(n - 1) & 1u);
     tc_fence_after();
     const int q = q0 + x * 128 + r;
     const float inv = 1.0f / l;
@@ -447,6 +465,7 @@ std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d) {
   }
   p.bias = d.bias;
   p.bias_bstride = d.bias_bstride;
+  p.ntiles = d.ntiles;
   if (d.bias) SDM_CHECK(d.bias_bstride % 4 == 0 && d.bias_bstride >= ((d.Lk + 127) / 128) * 128, "bias must be padded to 128 keys");
   p.out = d.out;
   p.ldo = d.ldo;
@@ -458,30 +477,26 @@ std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d) {
   return L;
 }
 
-template <bool HB, bool TL, int PP>
+template <bool HB, bool TL, bool SP>
 static void attn_launch(const AttnLaunch& l, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<HB, TL, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
+    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<HB, TL, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
     attr = true;
   }
-  attention_kernel<HB, TL, PP><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
+  attention_kernel<HB, TL, SP><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
 }
 
 void attn_run(const AttnLaunch& l, cudaStream_t st) {
-  // SDM_ATTN_POLY = 0 | 4 | 6 | 8 column pairs per 32-key chunk on the FMA pipe (A/B switch; default below)
-  static const int poly = [] { const char* e = getenv("SDM_ATTN_POLY"); return e ? atoi(e) : 0; }();
-  if (!l.has_bias && (l.p.Lk & 127) != 0) attn_launch<false, true, 0>(l, st);
+  // SDM_ATTN_SPLIT=0 selects the whole-tile P.V of v7c (A/B switch, read once)
+  static const bool split = [] { const char* e = getenv("SDM_ATTN_SPLIT"); return e ? atoi(e) != 0 : true; }();
+  if (!l.has_bias && (l.p.Lk & 127) != 0) attn_launch<false, true, true>(l, st);
   else if (l.has_bias) {
-    if (poly == 8) attn_launch<true, false, 8>(l, st);
-    else if (poly == 6) attn_launch<true, false, 6>(l, st);
-    else if (poly == 4) attn_launch<true, false, 4>(l, st);
-    else attn_launch<true, false, 0>(l, st);
+    if (split) attn_launch<true, false, true>(l, st);
+    else attn_launch<true, false, false>(l, st);
   } else {
-    if (poly == 8) attn_launch<false, false, 8>(l, st);
-    else if (poly == 6) attn_launch<false, false, 6>(l, st);
-    else if (poly == 4) attn_launch<false, false, 4>(l, st);
-    else attn_launch<false, false, 0>(l, st);
+    if (split) attn_launch<false, false, true>(l, st);
+    else attn_launch<false, false, false>(l, st);
   }
   SDM_CUDA_OK(cudaGetLastError());
 }

@@ -116,6 +116,19 @@ struct Weights {
         for (int t = 0; t < k * k; ++t) pk[((size_t)o * k * k + t) * Ip + i] = __float2half_rn(w[((size_t)o * I + i) * k * k + t]);
     return (const __half*)upload(key, pk.data(), pk.size() * 2);
   }
+  // 3x3 conv with O <= 3 output channels as a 1x1 GEMM producing the 9*O per-tap partial products of every INPUT pixel
+  // (rows tap*O + o, padded to 32 rows); alpha_col2im_kernel then sums the 9 shifted partials per output pixel
+  const __half* conv_taprows(const std::string& name, int O, int I) {
+    const std::string key = "t:" + name;
+    if (void* p = get(key)) return (const __half*)p;
+    require_loading(key);
+    std::vector<float> w = fetch(name + ".weight", (int64_t)O * I * 9);
+    std::vector<__half> pk((size_t)32 * I, __float2half_rn(0.f));
+    for (int o = 0; o < O; ++o)
+      for (int i = 0; i < I; ++i)
+        for (int t = 0; t < 9; ++t) pk[(size_t)(t * O + o) * I + i] = __float2half_rn(w[((size_t)o * I + i) * 9 + t]);
+    return (const __half*)upload(key, pk.data(), pk.size() * 2);
+  }
   // 3x3 conv with I <= 4 input channels as a GEMM over im2col rows: [O][64], k = tap*4 + ci
   const __half* conv_im2col(const std::string& name, int O, int I) {
     const std::string key = "i:" + name;
@@ -444,7 +457,7 @@ struct Builder {
     if (!dry) push([d](cudaStream_t st) { direct_conv_run(d, st); }, 1, "direct_conv", 0, 2.0 * d.B * (double)d.H * d.W * (d.Cin + (d.cout_limit ? d.cout_limit : d.Cout)));
     else n_launches++;
   }
-  void attention(const T& q, const T& k, const T& vt, int heads, const float* bias, long long bias_bs, const T& out) {
+  void attention(const T& q, const T& k, const T& vt, int heads, const float* bias, long long bias_bs, const int* ntiles, const T& out) {
     const int Lq = (int)q.HW(), Lk = (int)k.HW();
     const double fl = 4.0 * q.B * heads * (double)Lq * Lk * 64;
     flops += fl;
@@ -453,7 +466,7 @@ struct Builder {
     d.B = q.B; d.heads = heads; d.Lq = Lq; d.Lk = Lk;
     d.q = q.p; d.ldq = q.C; d.k = k.p; d.ldk = k.C;
     d.vt = vt.p; d.ldvt = vt.W;
-    d.bias = bias; d.bias_bstride = bias_bs;
+    d.bias = bias; d.bias_bstride = bias_bs; d.ntiles = ntiles;
     d.out = out.p; d.ldo = out.C; d.scale = 0.125f;
     auto l = attn_build(d);
     push([l](cudaStream_t st) { attn_run(*l, st); }, 1, bias ? "tc:attention_self" : "tc:attention_cross", fl, 2.0 * q.B * heads * 64.0 * (2.0 * Lq + 2.0 * Lk));
@@ -502,14 +515,16 @@ struct Builder {
   }
 
   // Transformer2DModel with one BasicTransformerBlock; ctx = trimap tokens [B][Lctx][1024]
-  T transformer(const T& x, const std::string& p, int heads, const T& ctx, const float* key_bias, long long key_bias_bs, int ups2) {
+  // per-level key bias of attn1 (+ the compacted form, see key_compact_kernel; idx == null: compaction off)
+  struct KeyBias { const float* bias = nullptr; long long bs = 0; const float* cbias = nullptr; const int* idx = nullptr; const int* ntiles = nullptr; };
+  T transformer(const T& x, const std::string& p, int heads, const T& ctx, const KeyBias& kbias, int ups2) {
     const int C = x.C, L = (int)x.HW(), Bq = x.B;
     const std::string tb = p + ".transformer_blocks.0";
     T n = groupnorm(x, nullptr, p + ".norm", 1e-6f, 0);
     T h = alloc(Bq, x.H, x.W, C);
     { GemmOpt o; o.bias = W.vec(p + ".proj_in.bias", C); linear(n, W.linear(p + ".proj_in", C, C), C, h, o); }
     free(n);
-    auto attn = [&](const std::string& ap, const T& qsrc, const T& kvsrc, int Ckv, const float* bias, long long bias_bs) {
+    auto attn = [&](const std::string& ap, const T& qsrc, const T& kvsrc, int Ckv, const float* bias, long long bias_bs, const int* ntiles) {
       const int Lk = (int)kvsrc.HW();
       const int Lld = (Lk + 7) & ~7;
       T q = alloc(Bq, x.H, x.W, C);
@@ -520,19 +535,31 @@ struct Builder {
       { GemmOpt o; linear(kvsrc, W.linear(ap + ".to_k", C, Ckv), C, k, o); }
       { GemmOpt o; o.mode = EPI_F16_T; linear(kvsrc, W.linear(ap + ".to_v", C, Ckv), C, vt, o); }
       T o_ = alloc(Bq, x.H, x.W, C);
-      attention(q, k, vt, heads, bias, bias_bs, o_);
+      attention(q, k, vt, heads, bias, bias_bs, ntiles, o_);
       free(q); free(k); free(vt);
       { GemmOpt o; o.bias = W.vec(ap + ".to_out.0.bias", C); o.res = &h; linear(o_, W.linear(ap + ".to_out.0", C, C), C, h, o); }
       free(o_);
     };
     {  // attn1: self attention with the trimap key bias (replace.py:20-122)
       T ln = layernorm(h, tb + ".norm1");
-      attn(tb + ".attn1", ln, ln, C, key_bias, key_bias_bs);
+      if (kbias.idx) {
+        // keys/values only for the keys that can have a non-zero probability: gather their LayerNorm rows in front
+        // (rows beyond 128*ntiles[b] of lnc, and so of K / V^T, are never read by the attention kernel)
+        T lnc = alloc(Bq, x.H, x.W, C);
+        if (!dry) {
+          const __half* sp = ln.p; __half* dp = lnc.p; const int* ip = kbias.idx; const int* np = kbias.ntiles; const int bs = (int)kbias.bs;
+          push([=](cudaStream_t st) { gather_rows_run(sp, dp, ip, np, Bq, L, C, bs, st); }, 1, "gather_keys", 0, 0);
+        } else n_launches++;
+        attn(tb + ".attn1", ln, lnc, C, kbias.cbias, kbias.bs, kbias.ntiles);
+        free(lnc);
+      } else {
+        attn(tb + ".attn1", ln, ln, C, kbias.bias, kbias.bs, nullptr);
+      }
       free(ln);
     }
     {  // attn2: cross attention to the trimap tokens, no mask (replace.py:96-98 beta=0)
       T ln = layernorm(h, tb + ".norm2");
-      attn(tb + ".attn2", ln, ctx, 1024, nullptr, 0);
+      attn(tb + ".attn2", ln, ctx, 1024, nullptr, 0, nullptr);
       free(ln);
     }
     {  // feed-forward (GEGLU)
@@ -702,6 +729,28 @@ struct Builder {
       const int l0 = lpad[0], l1 = lpad[1], l2 = lpad[2], l3 = lpad[3];
       push([=](cudaStream_t st) { const int lp[4] = {l0, l1, l2, l3}; key_bias_run(slots->trimap, Bc, Rc, k0, k1, k2, k3, lp, st); }, 1, "key_bias");
     } else n_launches++;
+    // compacted keys for attn1 (SDM_ATTN_COMPACT=0: stream all keys, the A/B baseline)
+    const bool compact = [] { const char* e = getenv("SDM_ATTN_COMPACT"); return e ? atoi(e) != 0 : true; }();  // read per plan build
+    KeyBias kbl[4];
+    {
+      float* cb[4]; int* ix[4]; int* nt[4];
+      for (int k = 0; k < 4; ++k) {
+        kbl[k].bias = kb[k]; kbl[k].bs = lpad[k];
+        if (!compact) continue;
+        cb[k] = (float*)alloc_raw((size_t)B * lpad[k] * 4, &off);
+        ix[k] = (int*)alloc_raw((size_t)B * lpad[k] * 4, &off);
+        nt[k] = (int*)alloc_raw((size_t)B * 4, &off);
+        kbl[k].cbias = cb[k]; kbl[k].idx = ix[k]; kbl[k].ntiles = nt[k];
+      }
+      if (compact) {
+        if (!dry) {
+          const int Bc = B, Sc = S;
+          struct Ptrs { const float* b[4]; float* c[4]; int* i[4]; int* n[4]; int lp[4]; } pp;
+          for (int k = 0; k < 4; ++k) { pp.b[k] = kb[k]; pp.c[k] = cb[k]; pp.i[k] = ix[k]; pp.n[k] = nt[k]; pp.lp[k] = lpad[k]; }
+          push([=](cudaStream_t st) { key_compact_run(pp.b, pp.c, pp.i, pp.n, pp.lp, Bc, Sc, st); }, 1, "key_bias");
+        } else n_launches++;
+      }
+    }
 
     // ---- a2: VAE encoder over [rgb ; trimap x3] as one batch of 2B (meta_arch.py:139-145,209-212)
     T unet_in = alloc(B, S, S, 8);
@@ -764,7 +813,7 @@ struct Builder {
         for (int j = 0; j < 2; ++j) {
           T o = resnet(h, nullptr, bp + ".resnets." + std::to_string(j), ch[i], 1e-5f, true, 0);
           if (i < 3) {
-            T o2 = transformer(o, bp + ".attentions." + std::to_string(j), heads[i], ctx, kb[i], lpad[i], 0);
+            T o2 = transformer(o, bp + ".attentions." + std::to_string(j), heads[i], ctx, kbl[i], 0);
             free(o); o = o2;
           }
           h = o;
@@ -778,7 +827,7 @@ struct Builder {
       // mid (h is the last skip; it stays alive as a skip)
       {
         T o = resnet(h, nullptr, "unet.mid_block.resnets.0", 1280, 1e-5f, true, 0);
-        T o2 = transformer(o, "unet.mid_block.attentions.0", 20, ctx, kb[3], lpad[3], 0);
+        T o2 = transformer(o, "unet.mid_block.attentions.0", 20, ctx, kbl[3], 0);
         free(o);
         T o3 = resnet(o2, nullptr, "unet.mid_block.resnets.1", 1280, 1e-5f, true, 0);
         free(o2);
@@ -797,7 +846,7 @@ struct Builder {
           T o = resnet(h, &skip, bp + ".resnets." + std::to_string(j), rch[i], 1e-5f, true, (last && !has_attn) ? 1 : 0);
           free(h); free(skip);
           if (has_attn) {
-            T o2 = transformer(o, bp + ".attentions." + std::to_string(j), rheads[i], ctx, kb[level], lpad[level], last ? 1 : 0);
+            T o2 = transformer(o, bp + ".attentions." + std::to_string(j), rheads[i], ctx, kbl[level], last ? 1 : 0);
             free(o); o = o2;
           }
           h = o;
@@ -843,9 +892,32 @@ struct Builder {
       T n = groupnorm(h, nullptr, dcd + ".conv_norm_out", 1e-6f, 1);
       free(h);
       // ---- a16: conv_out (128->3) + channel mean + clip + (x+1)/2 (meta_arch.py:258-260)
-      { GemmOpt o; o.bias = W.vec(dcd + ".conv_out.bias", 3, 8); o.mode = EPI_ALPHA; o.alpha_slots = true; o.label = "conv3x3_alpha_head";
+      // r1a-r1o: ONE tcgen05 conv with N = 16 and the alpha math in the epilogue — 3.8 ms at bs=8: the nine shifted TMA boxes
+      // re-read the 2.1 GB input nine times through L2 -> shared memory for 0.15 TFLOP of math.  r1p: the 27 per-tap partial
+      // products of every input pixel as ONE 1x1 GEMM (input read once, fp32 out), then a col2im sum of the nine shifted
+      // partials + the alpha math (SDM_ALPHA_HEAD=0 selects the old path for A/B).
+      const bool taprows = [] { const char* e = getenv("SDM_ALPHA_HEAD"); return e ? atoi(e) != 0 : true; }();
+      const float* cbias = W.vec(dcd + ".conv_out.bias", 3, 8);
+      if (taprows) {
+        const __half* wt = W.conv_taprows(dcd + ".conv_out", 3, 128);
+        size_t yoff;
+        const size_t ybytes = (size_t)B * R * R * 32 * sizeof(float);
+        float* y = (float*)alloc_raw(ybytes, &yoff);
+        { GemmOpt o; o.mode = EPI_F32; o.label = "alpha_head_taps";
+          T yv; yv.B = B; yv.H = R; yv.W = R; yv.C = 32; yv.p = (__half*)y;
+          conv_tc(n, nullptr, wt, 32, 1, yv, o); }
+        if (!dry) {
+          Plan::Slots* slots = &plan->slots;
+          const int Bc = B, Rc = R;
+          push([=](cudaStream_t st) { alpha_col2im_run(y, cbias, Bc, Rc, Rc, slots->alpha, slots->premean, st); }, 1, "alpha_col2im", 0,
+               (double)B * R * R * (128.0 + 2.0));
+        } else n_launches++;
+        arena.release(yoff, ybytes);
+      } else {
+        GemmOpt o; o.bias = cbias; o.mode = EPI_ALPHA; o.alpha_slots = true; o.label = "conv3x3_alpha_head";
         T dummy; dummy.B = B; dummy.H = R; dummy.W = R; dummy.C = 1;
-        conv_tc(n, nullptr, W.conv(dcd + ".conv_out", 3, 128, 3, 0, 8), 8, 3, dummy, o); }
+        conv_tc(n, nullptr, W.conv(dcd + ".conv_out", 3, 128, 3, 0, 8), 8, 3, dummy, o);
+      }
       free(n);
     }
   }

@@ -64,6 +64,7 @@ struct AttnDesc {
   long long ldvt = 0;          // row length (>= Lk, multiple of 8)
   const float* bias = nullptr; // [B][Lk_pad] additive per-key bias * log2(e) (padded with -inf to a multiple of 128) or null
   long long bias_bstride = 0;
+  const int* ntiles = nullptr; // optional [B]: 128-key tiles to stream for sample b (compacted keys); null = ceil(Lk/128)
   __half* out = nullptr;       // [B][Lq][ldo]
   long long ldo = 0;
   float scale = 0.125f;
@@ -120,6 +121,11 @@ void direct_conv_run(const DirectConvDesc& d, cudaStream_t st);
 void alpha_head_run(const __half* x, long long x_ld, int B, int H, int W, int Cin, const __half* w, const float* bias,
                     __half* alpha, __half* premean /*nullable: pre-clip mean, fp16*/, cudaStream_t st);
 
+// alpha head, second half: y [B][H][W][32] fp32 = per-tap partial products (column tap*3 + c) of the decoder conv_out;
+// alpha[b][y][x] = (clip(mean_c fp16(bias_c + sum_tap y[(y+ky-1, x+kx-1)][tap*3+c]), -1, 1) + 1) / 2 with the reference's fp16
+// rounding points (meta_arch.py:256-260); premean (nullable) = the pre-clip mean
+void alpha_col2im_run(const float* y, const float* bias, int B, int H, int W, __half* alpha, __half* premean, cudaStream_t st);
+
 // ------------------------------------------------------------------ elementwise
 // im2col of the VAE conv_in input: out[2B*R*R][64], k = tap*4 + channel (zero beyond 36); first B images = (x-0.5)/0.5 of the
 // fp32 [B][R][R][3] image, last B = trimap*2-1 replicated to 3 channels (sdmatte_nodes.py:343,351, meta_arch.py:141)
@@ -129,6 +135,15 @@ void prep_inputs_run(const float* image, const float* trimap, __half* out /*[2B]
 // padded to lpad[k] (multiple of 128) with -inf.   (reference meta_arch.py:200-204, replace.py:56-63,401-403)
 void key_bias_run(const float* trimap, int B, int R, float* bias0, float* bias1, float* bias2, float* bias3,
                   const int* lpad, cudaStream_t st);
+// self-attention key compaction (small_ops.cu): per sample and level, the keys whose bias is within 2500 of the sample's
+// maximum, gathered in order: idx[b][i] (padded to a multiple of 128 with a valid index), cbias[b][i] (padding = -inf),
+// ntiles[b] = padded count / 128.  All arrays use the batch stride lpad[level].
+void key_compact_run(const float* const* bias, float* const* cbias, int* const* idx, int* const* ntiles, const int* lpad, int B, int S,
+                     cudaStream_t st);
+void key_compact_level_run(const float* bias, float* cbias, int* idx, int* ntiles, int B, int L, int lpad, cudaStream_t st);  // one level
+// dst[b][i][:] = src[b][idx[b][i]][:] for i < 128 * ntiles[b]; src/dst are [B][L][C] fp16
+void gather_rows_run(const __half* src, __half* dst, const int* idx, const int* ntiles, int B, int L, int C, int idx_bstride,
+                     cudaStream_t st);
 
 // ------------------------------------------------------------------ node pre/post-processing (prepost.cu)
 // antialiased bilinear resize of image [B][H][W][3] / trimap [B][H][W] (fp32) to R x R (sdmatte_nodes.py:204-214,343,349)

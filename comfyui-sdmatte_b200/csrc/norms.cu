@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(NT) gn_finalize_kernel(const float* __restrict
 // apply: same (channel-vector, pixel-row) thread layout as the stats kernel, so each thread keeps the scale/shift of its
 // 8 channels in registers and streams pixels with 4 independent 16-byte loads in flight (r1c ncu: the grid-stride version
 // was latency/issue-bound at 3.4 TB/s: one load in flight per thread, 64 B of scale/shift re-fetched per vector).
-__global__ void gn_apply_kernel(const __half* __restrict__ s0, const __half* __restrict__ s1, int C0, int Ctot, long long ld0,
+// v0 (r1c-r1o): scalar fp32 arithmetic; kept as the A/B baseline (SDM_GN_APPLY=0)
+__global__ void gn_apply_kernel_v0(const __half* __restrict__ s0, const __half* __restrict__ s1, int C0, int Ctot, long long ld0,
                                 long long ld1, int HW, int pix_per_slab, const float* __restrict__ ab, int silu,
                                 __half* __restrict__ out) {
   const int v = threadIdx.x, y = threadIdx.y, ny = blockDim.y;
@@ -194,6 +195,89 @@ __global__ void gn_apply_kernel(const __half* __restrict__ s0, const __half* __r
     for (int u = 0; u < 4; ++u) emit(r[u], p + u * ny);
   }
   for (; p < p1; p += ny) emit(__ldg(reinterpret_cast<const uint4*>(base + (long long)p * ld)), p);
+}
+
+// r1p: packed fp32x2 arithmetic (FFMA2/FMUL2/FADD2) and sign-folded constants.  Inside a step the SM clock sits at
+// 1.3-1.4 GHz (power cap) and this kernel was issue-bound there (ncu r1k: 59 % issue-active at 5.4 TB/s unthrottled,
+// 4.0 TB/s in the step): 12.5 -> 8.5 instructions per element.  SiLU(y) = y / (1 + 2^(-y log2 e)) with ONE MUFU op: the
+// reciprocal of d = 1 + e is the bit-trick guess (negated for free through the magic constant) + two Newton steps,
+//   n0 = -r0,  p1 = n0 (2 + d n0) = -r1,  p2 = p1 (2 + d p1) = -r2,  result = (-y) p2,
+// with -y produced directly by the scale/shift FMA (negated per-channel constants).
+// JOIN: make the arithmetic of pixel 0 depend on all four loads of the iteration (a never-taken trap on the xor of their
+// first words): ptxas otherwise sinks loads 2 and 3 below the arithmetic of pixel 0 — two 16-byte loads in flight per
+// thread instead of four (volatile accesses did not help: it then parks them right before the first store).
+template <bool SILU, bool JOIN>
+__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __half* __restrict__ s0, const __half* __restrict__ s1, int C0, int Ctot,
+                                                          long long ld0, long long ld1, int HW, int pix_per_slab,
+                                                          const float* __restrict__ ab, __half* __restrict__ out) {
+  const int v = threadIdx.x, y = threadIdx.y, ny = blockDim.y;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_slab;
+  const int p1 = min(HW, p0 + pix_per_slab);
+  const int c = v * 8;
+  const __half* base;
+  long long ld;
+  if (c < C0) { base = s0 + (long long)b * HW * ld0 + c; ld = ld0; }
+  else { base = s1 + (long long)b * HW * ld1 + (c - C0); ld = ld1; }
+  __half* obase = out + (long long)b * HW * Ctot + c;
+  uint64_t ka[4], ks[4];  // channel pairs (2j, 2j+1); negated when SILU
+  {
+    const float4* abp = reinterpret_cast<const float4*>(ab + ((size_t)b * Ctot + c) * 2);
+    const float sg = SILU ? -1.0f : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 k = __ldg(abp + j);  // (a0, s0, a1, s1)
+      ka[j] = pack_f2(sg * k.x, sg * k.z);
+      ks[j] = pack_f2(sg * k.y, sg * k.w);
+    }
+  }
+  const uint64_t kLog2e = pack_f2(1.4426950408889634f, 1.4426950408889634f);
+  const uint64_t kOne = pack_f2(1.0f, 1.0f), kTwo = pack_f2(2.0f, 2.0f);
+  auto emit = [&](const uint4& raw, __half* dst) {
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      uint64_t r = fma_f2(pack_f2(f.x, f.y), ka[j], ks[j]);  // y, or -y when SILU
+      if (SILU) {
+        float t0, t1;
+        unpack_f2(mul_f2(r, kLog2e), t0, t1);                // -y log2(e)
+        const uint64_t d = add_f2(pack_f2(ex2f(fminf(t0, 80.0f)), ex2f(fminf(t1, 80.0f))), kOne);
+        float d0, d1;
+        unpack_f2(d, d0, d1);
+        uint64_t n = pack_f2(__int_as_float(0xFEF311C7 - __float_as_int(d0)), __int_as_float(0xFEF311C7 - __float_as_int(d1)));
+        n = mul_f2(n, fma_f2(d, n, kTwo));
+        n = mul_f2(n, fma_f2(d, n, kTwo));
+        r = mul_f2(r, n);
+      }
+      float y0, y1;
+      unpack_f2(r, y0, y1);
+      w[j] = pack_h2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  };
+  // pointer-increment addressing: the 64-bit (pixel * ld) products were 7 instructions per 16-byte load
+  int p = p0 + y;
+  const __half* src = base + (long long)p * ld;
+  __half* dst = obase + (long long)p * Ctot;
+  const long long ss = (long long)ny * ld, ds = (long long)ny * Ctot;
+#pragma unroll 1
+  for (; p + 3 * ny < p1; p += 4 * ny) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = __ldg(reinterpret_cast<const uint4*>(src + u * ss));
+    if (JOIN) {
+      // four fp16 NaN payloads that a finite tensor can never hold all at once
+      if (((r[0].x & r[1].x & r[2].x & r[3].x) & 0x7fff7fffu) == 0x7fff7fffu) __trap();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(r[u], dst + u * ds);
+    src += 4 * ss;
+    dst += 4 * ds;
+  }
+#pragma unroll 1
+  for (; p < p1; p += ny, src += ss, dst += ds) emit(__ldg(reinterpret_cast<const uint4*>(src)), dst);
 }
 
 // how the statistics of this GroupNorm are obtained: 0 = own stats pass, 1 = finalize the conv-epilogue partials directly,
@@ -264,7 +348,19 @@ void groupnorm_run(const GroupNormDesc& d, cudaStream_t st) {
   SDM_CUDA_OK(cudaGetLastError());
   const int app_pps = ny * 16;  // 16 pixels per thread
   const int app_slabs = (d.HW + app_pps - 1) / app_pps;
-  gn_apply_kernel<<<dim3(app_slabs, d.B), dim3(nvec, ny), 0, st>>>(d.src[0], s1, C0, Ctot, d.ld[0], ld1, d.HW, app_pps, ab, d.silu, d.out);
+  // SDM_GN_APPLY = 0 (scalar v0) | 1 (packed) | 2 (packed + joined loads); A/B switch read once
+  static const int variant = [] { const char* e = getenv("SDM_GN_APPLY"); return e ? atoi(e) : 1; }();
+  const dim3 ag(app_slabs, d.B), ab_(nvec, ny);
+#define SDM_GN_APPLY_ARGS d.src[0], s1, C0, Ctot, d.ld[0], ld1, d.HW, app_pps, ab
+  if (variant == 0) gn_apply_kernel_v0<<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.silu, d.out);
+  else if (variant == 2) {
+    if (d.silu) gn_apply_kernel<true, true><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);
+    else gn_apply_kernel<false, true><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);
+  } else {
+    if (d.silu) gn_apply_kernel<true, false><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);
+    else gn_apply_kernel<false, false><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);
+  }
+#undef SDM_GN_APPLY_ARGS
   SDM_CUDA_OK(cudaGetLastError());
 }
 

@@ -285,6 +285,53 @@ void alpha_head_run(const __half* x, long long x_ld, int B, int H, int W, int Ci
 }
 
 // ------------------------------------------------------------------------------------------------
+// alpha head as GEMM + col2im (r1p).  The tensor-core GEMM leaves, for every INPUT pixel q, the 27 partial products
+// y[q][tap*3 + c] = sum_ch w[c][tap][ch] * x[q][ch]; the 3x3 conv output at p is sum_tap y[p + off(tap)][tap*3 + c].
+// CTA = 32 x 8 output pixels; the (34 x 10) halo of y rows is staged in shared memory with fully coalesced 128-byte row
+// reads (pixel stride 33 floats: conflict-free column reads), zero outside the image (= the conv's zero padding).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) alpha_col2im_kernel(const float* __restrict__ y, const float* __restrict__ bias, int H, int W,
+                                                           __half* __restrict__ alpha, __half* __restrict__ premean) {
+  __shared__ float sm[10 * 34 * 33];
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+  const float* yb = y + (size_t)b * H * W * 32;
+  for (int i = threadIdx.x; i < 340 * 8; i += 256) {
+    const int px = i >> 3, q = i & 7;
+    const int hy = px / 34, hx = px - hy * 34;
+    const int gy = y0 + hy - 1, gx = x0 + hx - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const float4*>(yb + ((size_t)gy * W + gx) * 32) + q);
+    float* d = sm + px * 33 + q * 4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int gx = x0 + tx, gy = y0 + ty;
+  if (gx >= W || gy >= H) return;
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float* s = sm + ((ty + t / 3) * 34 + tx + t % 3) * 33 + t * 3;
+    acc[0] += s[0]; acc[1] += s[1]; acc[2] += s[2];
+  }
+  // rounding points of the reference fp16 path: conv outputs fp16, channel mean fp16, (clip+1) fp16, /2 exact
+  const float c0 = __half2float(__float2half_rn(acc[0] + bias[0]));
+  const float c1 = __half2float(__float2half_rn(acc[1] + bias[1]));
+  const float c2 = __half2float(__float2half_rn(acc[2] + bias[2]));
+  const __half m = __float2half_rn((c0 + c1 + c2) / 3.0f);
+  const size_t o = ((size_t)b * H + gy) * W + gx;
+  if (premean) premean[o] = m;
+  const float cl = fminf(fmaxf(__half2float(m), -1.0f), 1.0f);
+  const __half p1 = __float2half_rn(cl + 1.0f);
+  alpha[o] = __float2half_rn(__half2float(p1) * 0.5f);
+}
+void alpha_col2im_run(const float* y, const float* bias, int B, int H, int W, __half* alpha, __half* premean, cudaStream_t st) {
+  alpha_col2im_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, B), 256, 0, st>>>(y, bias, H, W, alpha, premean);
+  SDM_CUDA_OK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
 // input preparation (sdmatte_nodes.py:343,351 at native resolution; meta_arch.py:141)
 // ------------------------------------------------------------------------------------------------
 // Writes the im2col matrix of the VAE conv_in (3x3, 3 input channels): out[pixel][k], k = tap*4 + channel (k >= 36 zero),
@@ -366,6 +413,112 @@ void key_bias_run(const float* trimap, int B, int R, float* bias0, float* bias1,
   const long long n = (long long)B * lpad[0];
   const int blocks = (int)std::min<long long>((n + 255) / 256, 1024);
   key_bias_kernel<<<dim3(blocks, 4), 256, 0, st>>>(trimap, B, R, a);
+  SDM_CUDA_OK(cudaGetLastError());
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Self-attention key compaction.
+// The additive key bias of attn1 is (1 - mask) * -10000 (replace.py:401-403): as soon as a sample has ONE key with mask 1
+// (definite foreground), every key with a smaller mask gets exp(-5000) or exp(-10000) = exactly 0 in the reference's fp32
+// softmax.  Those keys contribute nothing to either the row sum or P.V, so the engine drops them: the kept keys
+// {k : bias_k >= max_k(bias) - kDropMargin} are gathered (in order) in front, padded to a multiple of 128 with bias -inf,
+// and the attention kernel streams ntiles[b] = ceil(kept/128) key tiles instead of L/128.
+// Exact whenever |scale * q.k| < 1190 for all pairs (then a dropped key's probability is < exp(2*1190 - 2500) = 2^-173 < the
+// smallest fp32 denormal relative to the kept maximum; LayerNorm-ed activations give |scale q.k| of order 10).
+// One CTA per (sample, level); deterministic ordered compaction (block scan), per-sample only => batch-invariant.
+// ------------------------------------------------------------------------------------------------
+struct KeyCompactArgs {
+  const float* bias[4];
+  float* cbias[4];
+  int* idx[4];
+  int* ntiles[4];
+  int lpad[4];
+  int L[4];
+};
+constexpr float kDropMarginLog2 = 2500.0f * 1.4426950408889634f;
+
+__global__ void __launch_bounds__(1024) key_compact_kernel(KeyCompactArgs a) {
+  __shared__ float redf[32];
+  __shared__ int redi[32];
+  __shared__ int total_s;
+  const int level = blockIdx.y, b = blockIdx.x;
+  const int L = a.L[level], lp = a.lpad[level];
+  const float* bias = a.bias[level] + (size_t)b * lp;
+  float* cb = a.cbias[level] + (size_t)b * lp;
+  int* idx = a.idx[level] + (size_t)b * lp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mx = -INFINITY;
+  for (int k = tid; k < L; k += 1024) mx = fmaxf(mx, bias[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) redf[warp] = mx;
+  __syncthreads();
+  mx = redf[0];
+#pragma unroll
+  for (int w = 1; w < 32; ++w) mx = fmaxf(mx, redf[w]);
+  const float thr = mx - kDropMarginLog2;
+  // thread t owns the contiguous run [t*per, (t+1)*per): ordered compaction = exclusive scan of the per-run counts
+  const int per = (L + 1023) / 1024;
+  const int k0 = tid * per, k1 = min(L, k0 + per);
+  int cnt = 0;
+  for (int k = k0; k < k1; ++k) cnt += (bias[k] >= thr) ? 1 : 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) redi[warp] = incl;
+  __syncthreads();
+  int wbase = 0;
+  for (int w = 0; w < warp; ++w) wbase += redi[w];
+  if (tid == 1023) total_s = wbase + incl;
+  int pos = wbase + incl - cnt;
+  for (int k = k0; k < k1; ++k) {
+    const float v = bias[k];
+    if (v >= thr) { idx[pos] = k; cb[pos] = v; ++pos; }
+  }
+  __syncthreads();
+  const int total = total_s;                 // >= 1: the maximum itself is kept
+  const int padded = (total + 127) & ~127;   // <= lp
+  const int first = idx[0];
+  for (int i = total + tid; i < padded; i += 1024) { idx[i] = first; cb[i] = -INFINITY; }  // valid row, probability 0
+  if (tid == 0) a.ntiles[level][b] = padded >> 7;
+}
+void key_compact_run(const float* const* bias, float* const* cbias, int* const* idx, int* const* ntiles, const int* lpad, int B, int S,
+                     cudaStream_t st) {
+  KeyCompactArgs a;
+  for (int i = 0; i < 4; ++i) {
+    a.bias[i] = bias[i]; a.cbias[i] = cbias[i]; a.idx[i] = idx[i]; a.ntiles[i] = ntiles[i]; a.lpad[i] = lpad[i];
+    a.L[i] = (S >> i) * (S >> i);
+  }
+  key_compact_kernel<<<dim3(B, 4), 1024, 0, st>>>(a);
+  SDM_CUDA_OK(cudaGetLastError());
+}
+void key_compact_level_run(const float* bias, float* cbias, int* idx, int* ntiles, int B, int L, int lpad, cudaStream_t st) {
+  SDM_CHECK(lpad % 128 == 0 && lpad >= L && L > 0, "key_compact: lpad must be a multiple of 128 and >= L");
+  KeyCompactArgs a{};
+  a.bias[0] = bias; a.cbias[0] = cbias; a.idx[0] = idx; a.ntiles[0] = ntiles; a.lpad[0] = lpad; a.L[0] = L;
+  key_compact_kernel<<<dim3(B, 1), 1024, 0, st>>>(a);
+  SDM_CUDA_OK(cudaGetLastError());
+}
+
+// dst[b][i][:] = src[b][idx[b][i]][:] for i < 128 * ntiles[b]   (rows of C fp16, C % 8 == 0); one warp per row
+__global__ void __launch_bounds__(256) gather_rows_kernel(const __half* __restrict__ src, __half* __restrict__ dst, const int* __restrict__ idx,
+                                                          const int* __restrict__ ntiles, int L, int C, int idx_bstride) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= (ntiles[b] << 7) || i >= L) return;
+  const int k = idx[(size_t)b * idx_bstride + i];
+  const uint4* s = reinterpret_cast<const uint4*>(src + ((size_t)b * L + k) * C);
+  uint4* d = reinterpret_cast<uint4*>(dst + ((size_t)b * L + i) * C);
+  for (int v = threadIdx.x & 31; v < (C >> 3); v += 32) d[v] = __ldg(s + v);
+}
+void gather_rows_run(const __half* src, __half* dst, const int* idx, const int* ntiles, int B, int L, int C, int idx_bstride,
+                     cudaStream_t st) {
+  SDM_CHECK(C % 8 == 0, "gather_rows: C must be a multiple of 8");
+  gather_rows_kernel<<<dim3((L + 7) / 8, B), 256, 0, st>>>(src, dst, idx, ntiles, L, C, idx_bstride);
   SDM_CUDA_OK(cudaGetLastError());
 }
 

@@ -214,8 +214,12 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
     // measured (A/B on one box): 2 warpgroups help short-K tiles (1x1 conv K=128: 170 -> 294 TFLOP/s), cost a pipeline stage on the
     // 256-wide and 256x128 tiles (1337 -> 1299) -> only where the tile is <= 160 wide and single
     const long long ksteps = (long long)p.ntaps * (cin_total / 64);
+    // r1p: 256x128 tiles with ONE or a few K steps (im2col conv_in: 1, VAE 1x1 shortcuts: 4) are pure epilogue: drain the two
+    // M sub-tiles concurrently (SDM_EWG_MT2=0 restores the single warpgroup for A/B)
+    static const int env_mt2 = [] { const char* e = getenv("SDM_EWG_MT2"); return e ? atoi(e) : 1; }();
     int ewg = (p.mode == EPI_GEGLU || p.mode == EPI_F32 || p.mode == EPI_F16_T ||
-               (p.mode == EPI_F16 && L->mt == 1 && (bn <= 160 || ksteps <= 16))) ? 2 : 1;
+               (p.mode == EPI_F16 && L->mt == 1 && (bn <= 160 || ksteps <= 16)) ||
+               (p.mode == EPI_F16 && L->mt == 2 && ksteps <= 4 && env_mt2 != 0)) ? 2 : 1;
     if (env_ewg == 1 || env_ewg == 2) ewg = env_ewg;
     if (bn == 16 || light || p.mode == EPI_ALPHA || p.mode == EPI_SKINNY) ewg = 1;
     L->ewg = ewg;

@@ -40,7 +40,7 @@ class sdm_attn_args(C.Structure):
         ("B", C.c_int), ("heads", C.c_int), ("Lq", C.c_int), ("Lk", C.c_int),
         ("q", C.c_void_p), ("ldq", C.c_int64), ("k", C.c_void_p), ("ldk", C.c_int64),
         ("vt", C.c_void_p), ("ldvt", C.c_int64), ("bias", C.c_void_p), ("bias_bstride", C.c_int64),
-        ("out", C.c_void_p), ("ldo", C.c_int64), ("scale", C.c_float),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("scale", C.c_float), ("ntiles", C.c_void_p),
     ]
 
 
@@ -68,7 +68,7 @@ EXPORTS = [
     "sdm_workspace_bytes", "sdm_forward", "sdm_forward_host", "sdm_forward_profiled", "sdm_profile_count", "sdm_profile_entry",
     "sdm_last_forward_stats", "sdm_debug_tensor", "sdm_preprocess", "sdm_postprocess",
     "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
-    "sdm_k_softmax_rows", "sdm_k_direct_conv",
+    "sdm_k_softmax_rows", "sdm_k_direct_conv", "sdm_k_key_compact", "sdm_k_gather_rows",
 ]
 
 
@@ -115,6 +115,8 @@ def load_library():
     lib.sdm_k_conv_gemm.argtypes = [C.POINTER(sdm_conv_gemm_args), C.c_void_p]
     lib.sdm_k_conv_tiles_per_image.argtypes = [C.c_int, C.c_int]
     lib.sdm_k_attention.argtypes = [C.POINTER(sdm_attn_args), C.c_void_p]
+    lib.sdm_k_key_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.sdm_k_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.sdm_k_groupnorm_scratch_floats.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.sdm_k_groupnorm_scratch_floats.restype = C.c_size_t
     lib.sdm_k_groupnorm.argtypes = [C.POINTER(sdm_groupnorm_args), C.c_void_p]
@@ -340,14 +342,26 @@ def k_conv_gemm(srcs, w, N, out, *, B, Hin, Win, ksize=1, stride=1, pad=0, mode=
     _check(lib.sdm_k_conv_gemm(C.byref(a), _stream_ptr(out.device)))
 
 
-def k_attention(q, k, vt, out, *, B, heads, Lq, Lk, ldq, ldk, ldvt, ldo, bias=None, bias_bstride=0, scale=0.125):
+def k_attention(q, k, vt, out, *, B, heads, Lq, Lk, ldq, ldk, ldvt, ldo, bias=None, bias_bstride=0, scale=0.125, ntiles=None):
     lib = load_library()
     a = sdm_attn_args()
     a.B, a.heads, a.Lq, a.Lk = B, heads, Lq, Lk
     a.q, a.ldq, a.k, a.ldk, a.vt, a.ldvt = q.data_ptr(), ldq, k.data_ptr(), ldk, vt.data_ptr(), ldvt
     a.bias, a.bias_bstride = _p(bias), bias_bstride
     a.out, a.ldo, a.scale = out.data_ptr(), ldo, scale
+    a.ntiles = _p(ntiles)
     _check(lib.sdm_k_attention(C.byref(a), _stream_ptr(out.device)))
+
+
+def k_key_compact(bias, cbias, idx, ntiles, *, B, L, lpad):
+    """bias/cbias float32 [B][lpad], idx int32 [B][lpad], ntiles int32 [B] (see include/sdmatte_b200.h)."""
+    _check(load_library().sdm_k_key_compact(bias.data_ptr(), cbias.data_ptr(), idx.data_ptr(), ntiles.data_ptr(), B, L, lpad,
+                                           _stream_ptr(bias.device)))
+
+
+def k_gather_rows(src, dst, idx, ntiles, *, B, L, C_, idx_bstride):
+    _check(load_library().sdm_k_gather_rows(src.data_ptr(), dst.data_ptr(), idx.data_ptr(), ntiles.data_ptr(), B, L, C_, idx_bstride,
+                                           _stream_ptr(src.device)))
 
 
 def conv_tiles_per_image(H, W):

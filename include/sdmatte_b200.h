@@ -122,8 +122,17 @@ typedef struct {
   const float* bias; int64_t bias_bstride;   /* additive per-key bias * log2(e), padded with -inf to 128 keys */
   void* out; int64_t ldo;
   float scale;
+  const int32_t* ntiles;                     /* optional [B]: number of 128-key tiles to stream for sample b (compacted keys) */
 } sdm_attn_args;
 int sdm_k_attention(const sdm_attn_args* a, uintptr_t stream);
+/* Self-attention key compaction for ONE UNet level (replaces nothing in the reference: it removes the keys whose
+   probability is exactly 0 under the -10000 trimap bias of replace.py:401-403 / :100-106).
+   bias [B][lpad] (log2 domain, -inf padded) -> idx [B][lpad] kept key indices in order (padded to a multiple of 128 with a
+   valid index), cbias [B][lpad] their biases (-inf padding), ntiles [B] = padded count / 128.  L = real key count. */
+int sdm_k_key_compact(const float* bias, float* cbias, int32_t* idx, int32_t* ntiles, int B, int L, int lpad, uintptr_t stream);
+/* dst[b][i][:] = src[b][idx[b][i]][:] for i < 128 * ntiles[b]; src/dst [B][L][C] fp16 */
+int sdm_k_gather_rows(const void* src, void* dst, const int32_t* idx, const int32_t* ntiles, int B, int L, int C, int idx_bstride,
+                      uintptr_t stream);
 
 typedef struct {
   int B, HW, nsrc;

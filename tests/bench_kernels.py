@@ -65,7 +65,22 @@ def linear(B, M, N, K, res=False):
     return ms, 2.0 * B * M * N * K / ms / 1e9
 
 
+def gn(B, H, W, C):
+    """GroupNorm(+SiLU) with the statistics arriving as conv-epilogue partials (the in-engine case): reduce + finalize + apply."""
+    x = torch.randn(B, H * W, C, device=DEV).half()
+    g, b = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    out = torch.empty_like(x)
+    slots = E.conv_tiles_per_image(H, W)
+    pre = torch.rand(B, slots, C, 2, device=DEV)
+    pre[..., 1] += 1.0
+    ms = timeit(lambda: E.k_groupnorm([(x, C, C)], g, b, out, B=B, HW=H * W, eps=1e-6, silu=1, pre=(pre, None), pre_slots=slots))
+    return ms, 4.0 * B * H * W * C / ms / 1e9  # "TFLOP/s" column = TB/s here
+
+
 CASES = {
+    "gn+silu 128ch @1024^2 B4 (TB/s)": lambda: gn(4, 1024, 1024, 128),
+    "gn+silu 256ch @512^2 B4 (TB/s)": lambda: gn(4, 512, 512, 256),
+    "gn+silu 320ch @128^2 B8 (TB/s)": lambda: gn(8, 128, 128, 320),
     "attn_self_L0 (B2 h5 16384x16384 bias)": lambda: attn(2, 5, 16384, 16384, True),
     "attn_cross_L0 (B2 h5 16384x16384)": lambda: attn(2, 5, 16384, 16384, False),
     "attn_cross_L1 (B2 h10 4096x16384)": lambda: attn(2, 10, 4096, 16384, False),

@@ -190,3 +190,29 @@ def test_full_size_properties(engine, R):
     assert frac_sat < 0.5
     a_single = engine.forward(img[1:2].contiguous(), tri[1:2].contiguous(), False)
     assert torch.equal(a_single[0], a[1])
+
+
+@pytest.mark.parametrize("R,B", [(128, 2), (512, 1)])
+def test_key_compaction_is_transparent(pkg, ckpt, engine, R, B):
+    """attn1 streams only the keys whose softmax probability can be non-zero (key_compact_kernel).  The dropped keys have
+    probability exactly 0 in the reference, so switching the compaction off must give the same alpha up to the summation
+    order of the kept keys (tile boundaries move): far below the fp16 grid of the output."""
+    from oracle import synth
+
+    image, trimap = synth.make_inputs(B, R, seed=31)
+    img, tri = image.cuda(), trimap.cuda()
+    a_on = engine.forward(img, tri, False).clone()
+    os.environ["SDM_ATTN_COMPACT"] = "0"
+    try:
+        eng2 = pkg.engine.Engine(0)
+        eng2.load_state_dict(ckpt)
+        a_off = eng2.forward(img, tri, False).clone()
+        n_off = eng2.stats()["launches"]
+        eng2.close()
+    finally:
+        del os.environ["SDM_ATTN_COMPACT"]
+    n_on = engine.stats()["launches"]
+    d = (a_on.float() - a_off.float()).abs()
+    print(f"[compact] R={R} launches on/off {n_on}/{n_off} max|da|={d.max():.3e} differing px {(d > 0).float().mean():.4f}")
+    assert n_on == n_off + 17  # 16 gathers + the compaction kernel
+    assert d.max().item() <= 2e-3 and d.mean().item() <= 1e-4

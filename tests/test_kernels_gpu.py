@@ -316,15 +316,17 @@ def test_attention_late_rescale(eng_mod):
     _close(out, _attn_ref(q, k, v, heads, None, 0.125), 4e-3, 2e-3, "attention late rescale")
 
 
-def test_attention_bias_background_first(eng_mod):
+@pytest.mark.parametrize("start", [300, 330, 360, 384])  # first foreground key in chunk 1 / 2 / 3 / 0 of its 128-key tile
+def test_attention_bias_background_first(eng_mod, start):
     """First key tiles are all background (-10000), foreground keys only appear later: the reference max jumps by ~14 000
-    (log2 units) and everything accumulated so far must vanish."""
+    (log2 units) and everything accumulated so far must vanish (redo path of the softmax, before and after the low half
+    of P has been handed to the tensor core)."""
     B, heads, L = 1, 1, 512
     C = 64
     q, k, v = _rand(B, L, C, seed=1).half(), _rand(B, L, C, seed=2).half(), _rand(B, L, C, seed=3).half()
     vt = v.transpose(1, 2).contiguous()
     bias = torch.full((B, L), -10000.0)
-    bias[:, 300:340] = 0.0
+    bias[:, start:start + 40] = 0.0
     bias = bias.to(DEV)
     out = torch.zeros(B, L, C, dtype=torch.float16, device=DEV)
     eng_mod.k_attention(q, k, vt, out, B=B, heads=heads, Lq=L, Lk=L, ldq=C, ldk=C, ldvt=L, ldo=C, bias=(bias * math.log2(math.e)).contiguous(), bias_bstride=L)
@@ -495,3 +497,95 @@ def test_light_config_two_ctas_per_sm(eng_mod, mode):
         ref = (x.float() @ w.float().t()) * 0.5
     torch.cuda.synchronize()
     _close(out, ref, 2e-3, 2e-3, f"light {mode}")
+
+
+# ------------------------------------------------------------------------------------------------ key compaction (attn1)
+def _compact_ref(bias_l2, L):
+    """torch restatement of key_compact_kernel for one sample: (idx, cbias, ntiles)."""
+    b = bias_l2[:L]
+    keep = (b >= b.max() - 2500.0 * math.log2(math.e)).nonzero().flatten()
+    n = keep.numel()
+    padded = (n + 127) // 128 * 128
+    idx = torch.cat([keep, keep[:1].repeat(padded - n)])
+    cb = torch.cat([b[keep], torch.full((padded - n,), float("-inf"), device=b.device)])
+    return idx, cb, padded // 128
+
+
+@pytest.mark.parametrize("B,L", [(3, 1024), (2, 16384), (4, 64), (1, 4096)])
+def test_key_compact_and_gather(eng_mod, B, L):
+    lpad = (L + 127) // 128 * 128
+    g = torch.Generator().manual_seed(L + B)
+    lv = torch.randint(0, 3, (B, L), generator=g).float()
+    if B > 1:
+        lv[1] = lv[1].clamp(min=1)  # sample 1 has no foreground key: unknown keys (-5000) are the maximum
+    if B > 2:
+        lv[2] = 2                   # all background: nothing can be dropped
+    bias = torch.full((B, lpad), float("-inf"))
+    bias[:, :L] = lv * -5000.0 * math.log2(math.e)
+    bias = bias.to(DEV)
+    cb = torch.zeros(B, lpad, device=DEV)
+    idx = torch.full((B, lpad), -1, dtype=torch.int32, device=DEV)
+    nt = torch.zeros(B, dtype=torch.int32, device=DEV)
+    eng_mod.k_key_compact(bias, cb, idx, nt, B=B, L=L, lpad=lpad)
+    C = 192
+    src = _rand(B, L, C, seed=5).half()
+    dst = torch.zeros_like(src)
+    eng_mod.k_gather_rows(src, dst, idx, nt, B=B, L=L, C_=C, idx_bstride=lpad)
+    torch.cuda.synchronize()
+    for b in range(B):
+        ri, rc, rn = _compact_ref(bias[b], L)
+        assert int(nt[b]) == rn, (b, int(nt[b]), rn)
+        n = rn * 128
+        assert torch.equal(idx[b, :n].long(), ri), f"idx sample {b}"
+        assert torch.equal(cb[b, :n], rc), f"cbias sample {b}"
+        assert torch.equal(dst[b, :n], src[b, ri]), f"gather sample {b}"
+        assert torch.count_nonzero(dst[b, n:]) == 0  # rows beyond the padded count are left alone
+
+
+@pytest.mark.parametrize("B,heads,L", [(3, 2, 1024), (2, 5, 4096)])
+def test_attention_compacted_keys_matches_full(eng_mod, B, heads, L):
+    """attn1 with the dropped keys (probability exactly 0 under the -5000/-10000 bias) == the reference softmax over ALL keys;
+    per-sample tile counts differ."""
+    C = heads * 64
+    q, k, v = _rand(B, L, C, seed=1).half(), _rand(B, L, C, seed=2).half(), _rand(B, L, C, seed=3).half()
+    g = torch.Generator().manual_seed(11)
+    lv = torch.randint(0, 3, (B, L), generator=g).float()
+    lv[0, L // 3:] = 2          # sample 0: foreground only in the first third
+    lv[1] = lv[1].clamp(min=1)  # sample 1: no foreground at all
+    bias = (lv * -5000.0).to(DEV)
+    bias_l2 = (bias * math.log2(math.e)).contiguous()
+    cb = torch.zeros(B, L, device=DEV)
+    idx = torch.zeros(B, L, dtype=torch.int32, device=DEV)
+    nt = torch.zeros(B, dtype=torch.int32, device=DEV)
+    eng_mod.k_key_compact(bias_l2, cb, idx, nt, B=B, L=L, lpad=L)
+    kc, vc = torch.full_like(k, float("nan")), torch.full_like(v, float("nan"))  # rows beyond the kept keys must never be read
+    eng_mod.k_gather_rows(k, kc, idx, nt, B=B, L=L, C_=C, idx_bstride=L)
+    eng_mod.k_gather_rows(v, vc, idx, nt, B=B, L=L, C_=C, idx_bstride=L)
+    vt = vc.transpose(1, 2).contiguous()
+    out = torch.zeros(B, L, C, dtype=torch.float16, device=DEV)
+    eng_mod.k_attention(q, kc, vt, out, B=B, heads=heads, Lq=L, Lk=L, ldq=C, ldk=C, ldvt=L, ldo=C, bias=cb, bias_bstride=L, ntiles=nt)
+    torch.cuda.synchronize()
+    assert int(nt[0]) < int(nt[1]) <= L // 128
+    _close(out, _attn_ref(q, k, v, heads, bias, 0.125), 4e-3, 2e-3, "attention over compacted keys")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 64, 128), (3, 32, 48, 256, 128)])
+def test_conv1x1_two_m_subtiles_dual_epilogue(eng_mod, B, H, W, Cin, Cout):
+    """1x1 conv with 1 / 4 K steps on 256x128 tiles: the two M sub-tiles are drained by two epilogue warpgroups (the im2col
+    conv_in and the VAE shortcut convs); output and GroupNorm partials must match, odd number of M tiles included."""
+    x = _rand(B, H, W, Cin, seed=1).half()
+    w = _rand(Cout, Cin, scale=Cin ** -0.5, seed=2).half()
+    b = _rand(Cout, seed=3).float()
+    out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    slots = eng_mod.conv_tiles_per_image(H, W)
+    stats = torch.full((B, slots, Cout, 2), float("nan"), device=DEV)
+    eng_mod.k_conv_gemm([(x, Cin, Cin)], w, Cout, out, B=B, Hin=H, Win=W, ksize=1, bias=b, out_ld=Cout, out_bstride=H * W * Cout,
+                        force_mt=2, stats=stats)
+    torch.cuda.synchronize()
+    ref = (x.float() @ w.float().t() + b)
+    _close(out, ref, 2e-3, 2e-3, "conv1x1 MT=2 EWG=2")
+    assert torch.isfinite(stats).all()
+    tot = stats.double().sum(1)
+    o = out.double().view(B, H * W, Cout)
+    assert torch.allclose(tot[..., 0], o.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(tot[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)
