@@ -63,7 +63,8 @@ struct alignas(64) AttnParams {
 
 namespace a7 {
 constexpr int kStages = 5;
-constexpr int kThreads = 320;
+constexpr int kThreads = 320;      // 8 softmax warps + TMA producer + one MMA issuer
+constexpr int kThreadsDual = 352;  // ... + a second MMA issuer (one per query tile)
 constexpr uint32_t kQBytes = 128 * 128;        // one 128x64 fp16 tile
 constexpr uint32_t kKBytes = 128 * 128;        // 128 keys x 64 d
 constexpr uint32_t kVBytes = 2 * 64 * 128;     // 64 d x 128 keys as two 64-key blocks
@@ -87,8 +88,12 @@ __device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, __half2 s) {
 // SPLIT_PV: see the v8 note above (false = v7c behaviour, kept as the A/B baseline: SDM_ATTN_SPLIT=0)
 // (An FMA-pipe polynomial exp2 for 4/6/8 of the 16 column pairs of a chunk was measured on B200 in r1o: 519 -> 494 / 475 /
 // 464 TFLOP/s at L0 — the softmax warps are latency-, not MUFU-throughput-bound — and removed.)
-template <bool HAS_BIAS, bool TAIL, bool SPLIT_PV>
-__global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+// DUAL (v9, r1q): one MMA issuer warp PER QUERY TILE running the tile's fixed event sequence with blocking mbarrier waits
+//   S_lo(t+1) <- s_free_lo(t),  [P.V_lo(t) <- p_full_lo(t)],  S_hi(t+1) <- s_free_hi(t),  P.V(t) <- p_full(t)
+// instead of one thread polling all ~12 barriers of both tiles round-robin (ncu r1p: with the extra events of SPLIT_PV the
+// single poller became the bottleneck — the softmax warps then waited 25 % of their time for S_hi(j), issued late).
+template <bool HAS_BIAS, bool TAIL, bool SPLIT_PV, bool DUAL>
+__global__ void __launch_bounds__(a7::kThreadsDual, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   using namespace a7;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), DUAL ? 2 : 1); }
     for (int x = 0; x < 2; ++x) {
       for (int hf = 0; hf < 2; ++hf) {
         mbar_init(s_full(x, hf), 1); mbar_init(s_free(x, hf), 128);
@@ -150,8 +155,8 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 9) {
-    // ======================================= MMA issuer =========================================
+  } else if (warp == 9 || warp == 10) {
+    // ======================================= MMA issuer(s) ======================================
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_f16(64);
       constexpr uint32_t idesc_o = umma_idesc_f16(64);
@@ -173,6 +178,39 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
         umma_commit(commit_bar);
       };
       mbar_wait(q_full, 0);
+      if constexpr (DUAL) {
+        const int x = warp - 9;  // this issuer's query tile
+        auto wait_kv = [&](int t) { mbar_wait(kv_full(t % kStages), (uint32_t)(t / kStages) & 1u); };
+        wait_kv(0);
+        tc_fence_after();
+        issue_s(x, 0, 0);
+        issue_s(x, 1, 0);
+        for (int t = 0; t < n; ++t) {
+          const int st = t % kStages;
+          const bool more = t + 1 < n;
+          if (more) {
+            wait_kv(t + 1);
+            mbar_wait(s_free(x, 0), (uint32_t)t & 1u);
+            tc_fence_after();
+            issue_s(x, 0, (t + 1) % kStages);
+          }
+          if (SPLIT_PV) {
+            mbar_wait(p_full(x, 0), (uint32_t)t & 1u);
+            tc_fence_after();
+            issue_pv(x, st, t, 0, 4, o_full(x, 0));
+          }
+          if (more) {
+            mbar_wait(s_free(x, 1), (uint32_t)t & 1u);
+            tc_fence_after();
+            issue_s(x, 1, (t + 1) % kStages);
+          }
+          mbar_wait(p_full(x, 1), (uint32_t)t & 1u);
+          tc_fence_after();
+          if (SPLIT_PV) issue_pv(x, st, t, 4, 8, o_full(x, 1));
+          else issue_pv(x, st, t, 0, 8, o_full(x, 1));
+          umma_commit(kv_empty(st));  // this tile's MMAs on the stage are done (the barrier counts both issuers)
+        }
+      } else {
       // Event-driven issue.  Per query tile x the streams are  S_lo(t), S_hi(t), P.V_lo(t), P.V_hi(t)  with
       //   S_lo_x(t+1) as soon as the warpgroup holds chunks 0-1 of S_x(t) in registers (right at the start of its tile t),
       //   S_hi_x(t+1) once chunks 2-3 are in registers, P.V_lo/hi_x(t) once that half of P_x(t) is in TMEM.
@@ -237,6 +275,7 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           }
         }
       }
+      }  // !DUAL
     }
   } else if (warp < 8) {
     // ======================================= softmax warpgroups =================================
@@ -477,26 +516,31 @@ std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d) {
   return L;
 }
 
-template <bool HB, bool TL, bool SP>
+template <bool HB, bool TL, bool SP, bool DU>
 static void attn_launch(const AttnLaunch& l, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<HB, TL, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
+    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<HB, TL, SP, DU>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
     attr = true;
   }
-  attention_kernel<HB, TL, SP><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
+  attention_kernel<HB, TL, SP, DU><<<l.grid, DU ? a7::kThreadsDual : a7::kThreads, a7::kSmem, st>>>(l.p);
 }
 
 void attn_run(const AttnLaunch& l, cudaStream_t st) {
-  // SDM_ATTN_SPLIT=0 selects the whole-tile P.V of v7c (A/B switch, read once)
-  static const bool split = [] { const char* e = getenv("SDM_ATTN_SPLIT"); return e ? atoi(e) != 0 : true; }();
-  if (!l.has_bias && (l.p.Lk & 127) != 0) attn_launch<false, true, true>(l, st);
+  // SDM_ATTN_VARIANT (A/B switch, read once): 0 = v7c (one polling issuer, whole-tile P.V), 1 = v8 (polling, split P.V),
+  // 2 = v9 (two sequenced issuers, whole-tile P.V), 3 = v9 + split P.V
+  static const int variant = [] { const char* e = getenv("SDM_ATTN_VARIANT"); return e ? atoi(e) : 2; }();
+  if (!l.has_bias && (l.p.Lk & 127) != 0) attn_launch<false, true, false, false>(l, st);
   else if (l.has_bias) {
-    if (split) attn_launch<true, false, true>(l, st);
-    else attn_launch<true, false, false>(l, st);
+    if (variant == 3) attn_launch<true, false, true, true>(l, st);
+    else if (variant == 2) attn_launch<true, false, false, true>(l, st);
+    else if (variant == 1) attn_launch<true, false, true, false>(l, st);
+    else attn_launch<true, false, false, false>(l, st);
   } else {
-    if (split) attn_launch<false, false, true>(l, st);
-    else attn_launch<false, false, false>(l, st);
+    if (variant == 3) attn_launch<false, false, true, true>(l, st);
+    else if (variant == 2) attn_launch<false, false, false, true>(l, st);
+    else if (variant == 1) attn_launch<false, false, true, false>(l, st);
+    else attn_launch<false, false, false, false>(l, st);
   }
   SDM_CUDA_OK(cudaGetLastError());
 }

@@ -44,6 +44,7 @@ struct ConvGemmDesc {
   int force_block_n = 0;  // tests only
   int force_mt = 0;       // tests only: 1 / 2 = force the number of M sub-tiles per CTA tile
   int force_light = 0;    // tests only: 1 = force the two-CTAs-per-SM config, -1 = forbid it
+  int force_pair = 0;     // tests only: 1 = force the CTA-pair (cta_group::2) kernel, -1 = forbid it, 0 = auto
 };
 
 struct ConvGemmLaunch;  // opaque: prebuilt tensor maps + params

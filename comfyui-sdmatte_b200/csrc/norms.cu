@@ -206,8 +206,11 @@ __global__ void gn_apply_kernel_v0(const __half* __restrict__ s0, const __half* 
 // JOIN: make the arithmetic of pixel 0 depend on all four loads of the iteration (a never-taken trap on the xor of their
 // first words): ptxas otherwise sinks loads 2 and 3 below the arithmetic of pixel 0 — two 16-byte loads in flight per
 // thread instead of four (volatile accesses did not help: it then parks them right before the first store).
-template <bool SILU, bool JOIN>
-__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __half* __restrict__ s0, const __half* __restrict__ s1, int C0, int Ctot,
+// PACKED = false: scalar fp32 arithmetic (silu_f) inside the same loop structure (measured r1p: packed math alone was slower
+// than v0, 4.5 vs 5.1 TB/s at 1024^2 x 128 ch; packed + joined loads 5.5)
+// MAXT: launch bound (256 for up to 2048 channels at 8 per thread, 1024 beyond)
+template <bool SILU, bool JOIN, bool PACKED, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 1) gn_apply_kernel(const __half* __restrict__ s0, const __half* __restrict__ s1, int C0, int Ctot,
                                                           long long ld0, long long ld1, int HW, int pix_per_slab,
                                                           const float* __restrict__ ab, __half* __restrict__ out) {
   const int v = threadIdx.x, y = threadIdx.y, ny = blockDim.y;
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __half* __restri
   uint64_t ka[4], ks[4];  // channel pairs (2j, 2j+1); negated when SILU
   {
     const float4* abp = reinterpret_cast<const float4*>(ab + ((size_t)b * Ctot + c) * 2);
-    const float sg = SILU ? -1.0f : 1.0f;
+    const float sg = (SILU && PACKED) ? -1.0f : 1.0f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float4 k = __ldg(abp + j);  // (a0, s0, a1, s1)
@@ -239,6 +242,15 @@ __global__ void __launch_bounds__(256, 3) gn_apply_kernel(const __half* __restri
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = __half22float2(h[j]);
+      if (!PACKED) {
+        float a0, a1, b0, b1;
+        unpack_f2(ka[j], a0, a1);
+        unpack_f2(ks[j], b0, b1);
+        float y0 = fmaf(f.x, a0, b0), y1 = fmaf(f.y, a1, b1);
+        if (SILU) { y0 = silu_f(y0); y1 = silu_f(y1); }
+        w[j] = pack_h2(y0, y1);
+        continue;
+      }
       uint64_t r = fma_f2(pack_f2(f.x, f.y), ka[j], ks[j]);  // y, or -y when SILU
       if (SILU) {
         float t0, t1;
@@ -348,18 +360,25 @@ void groupnorm_run(const GroupNormDesc& d, cudaStream_t st) {
   SDM_CUDA_OK(cudaGetLastError());
   const int app_pps = ny * 16;  // 16 pixels per thread
   const int app_slabs = (d.HW + app_pps - 1) / app_pps;
-  // SDM_GN_APPLY = 0 (scalar v0) | 1 (packed) | 2 (packed + joined loads); A/B switch read once
-  static const int variant = [] { const char* e = getenv("SDM_GN_APPLY"); return e ? atoi(e) : 1; }();
+  // SDM_GN_APPLY = 0 (scalar v0) | 1 (packed) | 2 (packed + joined loads) | 3 (scalar + joined loads); A/B switch read once
+  static const int variant = [] { const char* e = getenv("SDM_GN_APPLY"); return e ? atoi(e) : 2; }();
   const dim3 ag(app_slabs, d.B), ab_(nvec, ny);
 #define SDM_GN_APPLY_ARGS d.src[0], s1, C0, Ctot, d.ld[0], ld1, d.HW, app_pps, ab
+#define SDM_GN_GO(JOIN, PACKED)                                                                                                  \
+  do {                                                                                                                           \
+    if (nvec * ny <= 256) {                                                                                                      \
+      if (d.silu) gn_apply_kernel<true, JOIN, PACKED, 256><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);                         \
+      else gn_apply_kernel<false, JOIN, PACKED, 256><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);                               \
+    } else {                                                                                                                     \
+      if (d.silu) gn_apply_kernel<true, JOIN, PACKED, 1024><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);                        \
+      else gn_apply_kernel<false, JOIN, PACKED, 1024><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);                              \
+    }                                                                                                                            \
+  } while (0)
   if (variant == 0) gn_apply_kernel_v0<<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.silu, d.out);
-  else if (variant == 2) {
-    if (d.silu) gn_apply_kernel<true, true><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);
-    else gn_apply_kernel<false, true><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);
-  } else {
-    if (d.silu) gn_apply_kernel<true, false><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);
-    else gn_apply_kernel<false, false><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);
-  }
+  else if (variant == 1) SDM_GN_GO(false, true);
+  else if (variant == 3) SDM_GN_GO(true, false);
+  else SDM_GN_GO(true, true);
+#undef SDM_GN_GO
 #undef SDM_GN_APPLY_ARGS
   SDM_CUDA_OK(cudaGetLastError());
 }

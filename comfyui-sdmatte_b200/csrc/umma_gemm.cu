@@ -16,6 +16,7 @@ struct ConvGemmLaunch {
   int mt = 1;
   bool light = false;
   int ewg = 1;
+  bool pair = false;  // CTA-pair (cta_group::2) kernel
   int grid = 0;
   double flops = 0;
 };
@@ -109,6 +110,15 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   p.n_tiles = (d.N + bn - 1) / bn;
   // 256 x 128 CTA tiles (two M sub-tiles per B tile) when there is enough work to keep every SM busy
   L->mt = (bn == 128 && !light && d.mode == EPI_F16 && d.force_mt != 1 && (d.force_mt == 2 || (m_tiles / 2) * p.n_tiles >= 2 * num_sms)) ? 2 : 1;
+  // CTA pairs for the 256 x 128 tiles of the long-K convs (SDM_PAIR=0 keeps the single-CTA MT=2 kernel for A/B; force_pair = 1 / -1
+  // from the kernel tests).  Restrictions of the pair kernel: one weight set, N % 128 == 0, fp16 epilogue without the 2x scatter.
+  {
+    static const int env_pair = [] { const char* e = getenv("SDM_PAIR"); return e ? atoi(e) : 1; }();
+    const long long ksteps_all = (long long)d.ksize * d.ksize * (cin_total / 64);
+    const bool can = bn == 128 && L->mt == 2 && d.mode == EPI_F16 && !d.ups2 && !d.w_bstride && d.N % 128 == 0 && (d.n_store == 0 || d.n_store == d.N);
+    L->pair = can && (d.force_pair == 1 || (d.force_pair == 0 && env_pair != 0 && ksteps_all > 4));
+    if (d.force_pair == 1) SDM_CHECK(can, "force_pair: configuration not supported by the CTA-pair kernel");
+  }
   p.m_tiles = (int)m_tiles;
   const long long total = ((m_tiles + L->mt - 1) / L->mt) * p.n_tiles;
   SDM_CHECK(total < (1ll << 31), "too many tiles");
@@ -170,7 +180,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   } else {
     const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d.N};
     const uint64_t strides[1] = {(uint64_t)ktot * 2};
-    const uint32_t bbox[2] = {64u, (uint32_t)bn};
+    const uint32_t bbox[2] = {64u, (uint32_t)(L->pair ? bn / 2 : bn)};  // pair: each CTA loads half of the tile's weight rows
     make_tmap(&p.b_map, d.w, 2, dims, strides, bbox);
   }
   // ---- residual: extra K steps  A = residual tile, B = identity columns
@@ -183,7 +193,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
     make_tmap(&p.r_map, d.res, 4, dims, strides, box);
     const uint64_t idims[2] = {(uint64_t)kIdentityN, (uint64_t)kIdentityN};
     const uint64_t istr[1] = {(uint64_t)kIdentityN * 2};
-    const uint32_t ibox[2] = {64u, 64u};
+    const uint32_t ibox[2] = {64u, L->pair ? 32u : 64u};
     make_tmap(&p.i_map, identity_matrix(), 2, idims, istr, ibox);
     p.has_res = 1;
   } else {
@@ -221,7 +231,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
                (p.mode == EPI_F16 && L->mt == 1 && (bn <= 160 || ksteps <= 16)) ||
                (p.mode == EPI_F16 && L->mt == 2 && ksteps <= 4 && env_mt2 != 0)) ? 2 : 1;
     if (env_ewg == 1 || env_ewg == 2) ewg = env_ewg;
-    if (bn == 16 || light || p.mode == EPI_ALPHA || p.mode == EPI_SKINNY) ewg = 1;
+    if (bn == 16 || light || p.mode == EPI_ALPHA || p.mode == EPI_SKINNY || L->pair) ewg = 1;
     L->ewg = ewg;
   }
   {
@@ -229,6 +239,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
     p.prefetch = env_pf;  // measured (A/B, one box): L2 prefetch of the next tile slows the large convs by 3-9 % -> off by default
   }
   L->grid = (int)std::min<long long>(total, light ? 2 * num_sms : num_sms);
+  if (L->pair) L->grid = (int)std::min<long long>(2 * total, (long long)(num_sms & ~1));  // two CTAs per pair tile
   L->flops = 2.0 * (double)d.B * Hout * Wout * (double)d.N * (double)ktot;
   return L;
 }
@@ -241,6 +252,7 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
     if (l.ewg == 2) return conv_gemm_launch<BN, MT, MODE, UPS2, false, 2>(p, g, st); \
     return conv_gemm_launch<BN, MT, MODE, UPS2, false, 1>(p, g, st);                 \
   } while (0)
+  if (l.pair) return conv_gemm_launch_pair<128, EPI_F16>(p, g, st);
   if (l.light) {
     if (p.mode == EPI_F16 && !p.ups2) return conv_gemm_launch<128, 1, EPI_F16, false, true>(p, g, st);
     if (p.mode == EPI_F16_T) return conv_gemm_launch<128, 1, EPI_F16_T, false, true>(p, g, st);

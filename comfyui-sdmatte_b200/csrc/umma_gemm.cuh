@@ -79,10 +79,14 @@ struct alignas(64) ConvGemmParams {
 // EWG: number of epilogue warpgroups.  With 2, tile i of a CTA is drained by warpgroup i%2 (MT=1) or the two M sub-tiles
 // of a tile are drained concurrently (MT=2): twice the epilogues in flight for the GEMMs whose short K loop cannot hide
 // one (r1i: linears 350-600 TFLOP/s, the N=128 VAE convs ~1000 vs ~1400 for long-K layers).
-template <int BLOCK_N, int MT = 1, bool LIGHT = false, int EWG = 1>
+// PAIR (r1q): the 256 x BLOCK_N tile is computed by a CTA PAIR (cluster of 2, tcgen05 cta_group::2, MMA M = 256): each CTA stages
+// its own 128-row A sub-tile and HALF of the B rows, and owns 128 accumulator lanes.  Per MMA each SM then reads 4 KB (A) +
+// N/2 x 32 B (B) of shared memory instead of 4 KB + N x 32 B: the N=128 convs sat exactly at the 128 B/clk shared-memory limit
+// (tensor pipe 59-62 %, ncu r1k/r1n) while the N=256 tiles (96 B/clk) reach 80 %+.  MT must be 1 (the pair IS the two sub-tiles).
+template <int BLOCK_N, int MT = 1, bool LIGHT = false, int EWG = 1, bool PAIR = false>
 struct ConvGemmCfg {
   static constexpr int kABytes = 128 * 128;          // 128 rows x 64 fp16 (per M sub-tile)
-  static constexpr int kBBytes = BLOCK_N * 128;      // BLOCK_N rows x 64 fp16
+  static constexpr int kBBytes = (PAIR ? BLOCK_N / 2 : BLOCK_N) * 128;  // B rows held by this CTA x 64 fp16
   static constexpr int kStageBytes = MT * kABytes + kBBytes;
   static constexpr int kEpiBytes = EWG * (4 * 4096 /*staging*/ + 2 * 2048 /*GroupNorm partials, double buffered*/);
   static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes - 512;
@@ -103,10 +107,16 @@ __device__ __forceinline__ int residual_steps(int n0, int N) {
   return (min(BLOCK_N, N - n0) + 63) >> 6;
 }
 
-template <int BLOCK_N, int MT, int MODE, bool UPS2, bool LIGHT = false, int EWG = 1>
+template <int BLOCK_N, int MT, int MODE, bool UPS2, bool LIGHT = false, int EWG = 1, bool PAIR = false>
 __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BLOCK_N, MT, LIGHT, EWG>;
+  using Cfg = ConvGemmCfg<BLOCK_N, MT, LIGHT, EWG, PAIR>;
   static_assert(EWG == 1 || EWG == 2, "one or two epilogue warpgroups");
+  static_assert(!PAIR || (MT == 1 && EWG == 1 && !LIGHT && MODE == EPI_F16 && BLOCK_N % 128 == 0), "CTA-pair configuration");
+  // PAIR: p.total_tiles counts 256-row pair tiles (as for MT = 2); this CTA works on sub-tile `rank` of every pair tile
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int SUBS = PAIR ? 2 : MT;  // M sub-tiles per (pair) tile
   static_assert(!LIGHT || Cfg::kTmemCols <= 256, "two CTAs per SM need <= 256 TMEM columns each");
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -131,14 +141,18 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), (EWG == 2 && MT == 2) ? 8 : 4);
+      mbar_init(tempty_bar(a), ((EWG == 2 && MT == 2) || PAIR) ? 8 : 4);  // PAIR: 4 epilogue warps of each CTA (leader's barrier)
     }
     fence_barrier_init();
     fence_proxy_async_smem();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -153,13 +167,19 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
       tma_prefetch_desc(&p.b_map);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      // PAIR: every transaction byte of both CTAs is accounted on the LEADER's full barrier
+      uint32_t full_remote[PAIR ? kStages : 1];
+      if constexpr (PAIR) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) full_remote[s] = mapa_shared(full_bar(s), 0);
+      }
+      for (int tile = tile_first; tile < p.total_tiles; tile += tile_step) {
         const int nt = tile % p.n_tiles;
         const int n0 = nt * BLOCK_N;
         int x0[MT], y0[MT], bb[MT];
 #pragma unroll
         for (int u = 0; u < MT; ++u) {
-          const int mt = (tile / p.n_tiles) * MT + u;
+          const int mt = (tile / p.n_tiles) * SUBS + (PAIR ? (int)rank : u);
           const int tx = mt % p.tiles_x;
           const int ty = (mt / p.tiles_x) % p.tiles_y;
           x0[u] = tx * p.tw; y0[u] = ty * p.th;
@@ -169,8 +189,8 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
         // tile's main loop instead of stalling the 4-stage ring (ncu r1i, 128->128 conv: 20 % of the A sectors missed L2,
         // tensor pipe 64 % busy with L2 at 52 % and DRAM at 22 %: latency, not bandwidth)
         {
-          const int nxt = tile + (int)gridDim.x;
-          if (p.prefetch && nxt < p.total_tiles && (nxt % p.n_tiles) == 0) {
+          const int nxt = tile + tile_step;
+          if (!PAIR && p.prefetch && nxt < p.total_tiles && (nxt % p.n_tiles) == 0) {
 #pragma unroll
             for (int u = 0; u < MT; ++u) {
               const int mt = (nxt / p.n_tiles) * MT + u;
@@ -194,6 +214,11 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
               mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
               const uint32_t b_dst = a_dst + MT * Cfg::kABytes;
+              if constexpr (PAIR) {
+                if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+                tma_load_4d_pair(a_dst, amap, full_remote[stage], c0, x0[0] + p.tap_dx[tap], y0[0] + p.tap_dy[tap], bb[0]);
+                tma_load_2d_pair(b_dst, &p.b_map, full_remote[stage], koff + c0, n0 + (int)rank * (BLOCK_N / 2));
+              } else {
               mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
 #pragma unroll
               for (int u = 0; u < MT; ++u)
@@ -202,6 +227,7 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
                 tma_load_3d(b_dst, &p.b_map, full_bar(stage), koff + c0, n0, bb[0]);
               else
                 tma_load_2d(b_dst, &p.b_map, full_bar(stage), koff + c0, n0);
+              }
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
             koff += p.src_c[s];
@@ -213,10 +239,16 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
             const uint32_t b_dst = a_dst + MT * Cfg::kABytes;
+            if constexpr (PAIR) {  // identity block: 32 of its 64 rows per CTA (i_map box = 64 x 32)
+              if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * (Cfg::kABytes + 32 * 128));
+              tma_load_4d_pair(a_dst, &p.r_map, full_remote[stage], n0 + i * 64, x0[0], y0[0], bb[0]);
+              tma_load_2d_pair(b_dst, &p.i_map, full_remote[stage], 0, (int)rank * 32);
+            } else {
             mbar_expect_tx(full_bar(stage), MT * Cfg::kABytes + 64 * 128);
 #pragma unroll
             for (int u = 0; u < MT; ++u) tma_load_4d(a_dst + u * Cfg::kABytes, &p.r_map, full_bar(stage), n0 + i * 64, x0[u], y0[u], bb[u]);
             tma_load_2d(b_dst, &p.i_map, full_bar(stage), 0, 0);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -224,13 +256,13 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BLOCK_N);
+    if (lane == 0 && rank == 0) {  // PAIR: only the leader issues (its MMAs drive both CTAs' tensor cores)
+      constexpr uint32_t idesc = PAIR ? umma_idesc_f16_m256(BLOCK_N) : umma_idesc_f16(BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < p.total_tiles; tile += tile_step) {
         const int n0 = (tile % p.n_tiles) * BLOCK_N;
         const int nres = p.has_res ? residual_steps<BLOCK_N>(n0, p.N) : 0;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -242,7 +274,7 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
           const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
           const uint64_t bdesc = umma_desc_k128(a_addr + MT * Cfg::kABytes);
           const int ri = ks - num_ksteps;  // >= 0: residual slice index
-          const uint32_t id = ri < 0 ? idesc : umma_idesc_f16(min(64, BLOCK_N - ri * 64));
+          const uint32_t id = ri < 0 ? idesc : (PAIR ? umma_idesc_f16_m256(64) : umma_idesc_f16(min(64, BLOCK_N - ri * 64)));
           const uint32_t dcol = ri < 0 ? 0u : (uint32_t)(ri * 64);
 #pragma unroll
           for (int u = 0; u < MT; ++u) {
@@ -250,13 +282,16 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // +32 B per 16-element K step (start-address field is in 16-byte units)
-              umma_f16(d_tmem + u * Cfg::kSubStride + dcol, adesc + 2 * k, bdesc + 2 * k, id, (ks | k) != 0);
+              if constexpr (PAIR) umma_f16_pair(d_tmem + dcol, adesc + 2 * k, bdesc + 2 * k, id, (ks | k) != 0);
+              else umma_f16(d_tmem + u * Cfg::kSubStride + dcol, adesc + 2 * k, bdesc + 2 * k, id, (ks | k) != 0);
             }
           }
-          umma_commit(empty_bar(stage));
+          if constexpr (PAIR) umma_commit_pair(empty_bar(stage));  // frees the stage in both CTAs
+          else umma_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
+        if constexpr (PAIR) umma_commit_pair(tfull_bar(acc));
+        else umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -280,15 +315,17 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
     constexpr bool kAlternate = (EWG == 2 && MT == 1);
     int acc = kAlternate ? ewg : 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x + (kAlternate ? ewg * (int)gridDim.x : 0); tile < p.total_tiles;
-         tile += (kAlternate ? 2 : 1) * (int)gridDim.x) {
+    const uint32_t tempty_leader0 = PAIR ? mapa_shared(tempty_bar(0), 0) : 0u;
+    const uint32_t tempty_leader1 = PAIR ? mapa_shared(tempty_bar(1), 0) : 0u;
+    for (int tile = tile_first + (kAlternate ? ewg * tile_step : 0); tile < p.total_tiles;
+         tile += (kAlternate ? 2 : 1) * tile_step) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int nt = tile % p.n_tiles;
       const int n0 = nt * BLOCK_N;
 #pragma unroll 1
       for (int u = (EWG == 2 && MT == 2) ? ewg : 0; u < ((EWG == 2 && MT == 2) ? ewg + 1 : MT); ++u) {
-        const int mt = (tile / p.n_tiles) * MT + u;
+        const int mt = (tile / p.n_tiles) * SUBS + (PAIR ? (int)rank : u);
         if (mt >= p.m_tiles) break;  // warp-uniform
         const int tx = mt % p.tiles_x;
         const int ty = (mt / p.tiles_x) % p.tiles_y;
@@ -602,17 +639,22 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
       }  // M sub-tile
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);  // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (kAlternate) acc_phase ^= 1u;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA may free tensor memory (or exit) while the pair's MMAs / remote arrives are in flight
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 

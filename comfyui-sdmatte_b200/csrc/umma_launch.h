@@ -21,4 +21,30 @@ void conv_gemm_launch(const ConvGemmParams& p, int grid, cudaStream_t st);
     conv_gemm_kernel<BN, MT, MODE, UPS2, LIGHT, EWG><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(p);                                   \
     SDM_CUDA_OK(cudaGetLastError());                                                                                         \
   }
+
+// CTA-pair (cta_group::2) variant: cluster of 2 CTAs, grid = an even number of CTAs
+template <int BN, int MODE>
+void conv_gemm_launch_pair(const ConvGemmParams& p, int grid, cudaStream_t st);
+#define SDM_DEFINE_CONV_GEMM_LAUNCH_PAIR(BN, MODE)                                                                           \
+  template <>                                                                                                                \
+  void conv_gemm_launch_pair<BN, MODE>(const ConvGemmParams& p, int grid, cudaStream_t st) {                                 \
+    using Cfg = ConvGemmCfg<BN, 1, false, 1, true>;                                                                          \
+    auto kern = conv_gemm_kernel<BN, 1, MODE, false, false, 1, true>;                                                        \
+    static bool attr = false;                                                                                                \
+    if (!attr) {                                                                                                             \
+      SDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));                 \
+      attr = true;                                                                                                           \
+    }                                                                                                                        \
+    cudaLaunchConfig_t cfg = {};                                                                                             \
+    cfg.gridDim = dim3((unsigned)grid);                                                                                      \
+    cfg.blockDim = dim3(Cfg::kThreads);                                                                                      \
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;                                                                                  \
+    cfg.stream = st;                                                                                                         \
+    cudaLaunchAttribute at[1];                                                                                               \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                                                          \
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                                      \
+    cfg.attrs = at;                                                                                                          \
+    cfg.numAttrs = 1;                                                                                                        \
+    SDM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));                                                                          \
+  }
 }  // namespace sdm

@@ -110,6 +110,7 @@ typedef struct {
   int force_mt;                 /* tests: 1 / 2 = force M sub-tiles per CTA tile (BLOCK_N 128 only), 0 = auto */
   int force_light;              /* tests: 1 = force the 2-CTAs-per-SM short-K config, -1 = forbid it, 0 = auto */
   float* stats;                 /* mode 0 without ups2: GroupNorm partials [B][sdm_k_conv_tiles_per_image][N][2] (sum, sumsq), or NULL */
+  int force_pair;               /* tests: 1 = force the CTA-pair (tcgen05 cta_group::2, M = 256) kernel, -1 = forbid it, 0 = auto */
 } sdm_conv_gemm_args;
 int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream);
 int sdm_k_conv_tiles_per_image(int Hout, int Wout);

@@ -538,8 +538,9 @@ def test_key_compact_and_gather(eng_mod, B, L):
         n = rn * 128
         assert torch.equal(idx[b, :n].long(), ri), f"idx sample {b}"
         assert torch.equal(cb[b, :n], rc), f"cbias sample {b}"
-        assert torch.equal(dst[b, :n], src[b, ri]), f"gather sample {b}"
-        assert torch.count_nonzero(dst[b, n:]) == 0  # rows beyond the padded count are left alone
+        m = min(n, L)  # dst holds L rows; a padded count beyond L (L < 128) is covered by the TMA zero fill of the K/V tiles
+        assert torch.equal(dst[b, :m], src[b, ri[:m]]), f"gather sample {b}"
+        assert torch.count_nonzero(dst[b, m:]) == 0  # rows beyond the padded count are left alone
 
 
 @pytest.mark.parametrize("B,heads,L", [(3, 2, 1024), (2, 5, 4096)])
@@ -589,3 +590,31 @@ def test_conv1x1_two_m_subtiles_dual_epilogue(eng_mod, B, H, W, Cin, Cout):
     o = out.double().view(B, H * W, Cout)
     assert torch.allclose(tot[..., 0], o.sum(1), rtol=1e-4, atol=1e-2)
     assert torch.allclose(tot[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,res", [(2, 32, 32, 128, True), (3, 16, 8, 128, True), (1, 128, 128, 64, False), (2, 64, 64, 256, True),
+                                           (5, 8, 16, 192, False)])
+def test_conv3x3_cta_pair(eng_mod, B, H, W, Cin, res):
+    """256x128 tile computed by a CTA pair (tcgen05 cta_group::2, M = 256): output, residual K steps and GroupNorm partials
+    must equal the single-CTA kernel bit for bit (same K order), incl. an odd number of 128-row M tiles."""
+    Cout = 128
+    x = _rand(B, H, W, Cin, seed=1).half()
+    r = _rand(B, H, W, Cout, seed=5).half() if res else None
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2).half()
+    b = _rand(Cout, seed=3).float()
+    slots = eng_mod.conv_tiles_per_image(H, W)
+    outs, stats = [], []
+    for fp in (1, -1):
+        out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
+        st = torch.full((B, slots, Cout, 2), float("nan"), device=DEV)
+        eng_mod.k_conv_gemm([(x, Cin, Cin)], _pack_conv_w(w), Cout, out, B=B, Hin=H, Win=W, ksize=3, bias=b, out_ld=Cout,
+                            out_bstride=H * W * Cout, res=(r, Cout, H * W * Cout) if res else None, force_mt=2, stats=st, force_pair=fp)
+        torch.cuda.synchronize()
+        outs.append(out)
+        stats.append(st)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).half().float().permute(0, 2, 3, 1)
+    if res:
+        ref = ref + r.float()
+    _close(outs[0], ref, 2e-3, 2e-3, "conv3x3 CTA pair")
+    assert torch.equal(outs[0], outs[1]), "pair kernel differs from the single-CTA kernel"
+    assert torch.equal(stats[0], stats[1]), "GroupNorm partials differ"
