@@ -128,7 +128,7 @@ int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream) {
   d.bias = a->bias; d.bias_sel = a->bias_sel;
   d.res = reinterpret_cast<const __half*>(a->res); d.res_ld = a->res_ld; d.res_bstride = a->res_bstride;
   d.scale = a->scale; d.force_block_n = a->force_block_n;
-  d.post_div = a->post_div == 0.f ? 1.f : a->post_div; d.n_store = a->n_store; d.out2 = a->out2; d.force_mt = a->force_mt; d.stats = a->stats; d.force_light = a->force_light; d.force_pair = a->force_pair;
+  d.post_div = a->post_div == 0.f ? 1.f : a->post_div; d.n_store = a->n_store; d.out2 = a->out2; d.force_mt = a->force_mt; d.stats = a->stats; d.force_light = a->force_light; d.force_pair = a->force_pair; d.force_halo = a->force_halo; d.force_swap = a->force_swap;
   auto l = sdm::conv_gemm_build(d, sdm::device_sm_count());
   sdm::conv_gemm_run(*l, reinterpret_cast<cudaStream_t>(stream));
   SDM_API_END
@@ -154,6 +154,13 @@ int sdm_k_attention(const sdm_attn_args* a, uintptr_t stream) {
 int sdm_k_key_compact(const float* bias, float* cbias, int32_t* idx, int32_t* ntiles, int B, int L, int lpad, uintptr_t stream) {
   SDM_API_BEGIN
   sdm::key_compact_level_run(bias, cbias, idx, ntiles, B, L, lpad, reinterpret_cast<cudaStream_t>(stream));
+  SDM_API_END
+}
+
+int sdm_k_probe_halo(const void* x, const void* eye, float* out, int dy, int dx, int mode, uintptr_t stream) {
+  SDM_API_BEGIN
+  sdm::probe_halo_run(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(eye), out, dy, dx, mode,
+                      reinterpret_cast<cudaStream_t>(stream));
   SDM_API_END
 }
 

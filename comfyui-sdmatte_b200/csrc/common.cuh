@@ -211,7 +211,10 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (release at CTA scope) as in CUTLASS' umma_arrive_2x1SM_sm0: the hand-off only orders tcgen05.ld (already
+  // fenced with tcgen05.fence::before_thread_sync) against the leader's next MMAs; .release.cluster added a cluster-wide
+  // membar (ERRBAR, 5 % of the epilogue warps' samples in ncu r1r) that waits for the tile's global stores
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: destination in this CTA, completion bytes on the barrier at `bar_cluster` (any CTA of the pair)
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* desc, uint32_t bar_cluster, int c0, int c1) {
@@ -290,6 +293,18 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;             // SBO
   d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+// Same with an explicit stride between 8-row groups: a window of a wider tile (rows of the window `sbo_bytes` / 8 ... apart).
+// The start address need not sit on a 1024-byte boundary: the 128-byte swizzle is applied to absolute shared-memory address
+// bits, so any 128-byte-row-aligned window of a TMA-written (SWIZZLE_128B) tile is a valid operand (tests/probe_halo.py).
+__device__ __forceinline__ uint64_t umma_desc_k128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
   return d;
 }
 // Instruction descriptor: kind::f16, A/B = fp16 K-major, D = fp32, M=128, N=n.

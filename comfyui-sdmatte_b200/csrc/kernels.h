@@ -45,6 +45,8 @@ struct ConvGemmDesc {
   int force_mt = 0;       // tests only: 1 / 2 = force the number of M sub-tiles per CTA tile
   int force_light = 0;    // tests only: 1 = force the two-CTAs-per-SM config, -1 = forbid it
   int force_pair = 0;     // tests only: 1 = force the CTA-pair (cta_group::2) kernel, -1 = forbid it, 0 = auto
+  int force_halo = 0;     // tests only: 1 = force the resident-halo 3x3 kernel, -1 = forbid it, 0 = auto
+  int force_swap = 0;     // tests only: 1 = force the swapped-operand 3x3 kernel (channels on M), -1 = forbid it, 0 = auto
 };
 
 struct ConvGemmLaunch;  // opaque: prebuilt tensor maps + params
@@ -153,6 +155,9 @@ void preprocess_run(const float* image, const float* trimap, int B, int H, int W
 // resize alpha [B][R][R] fp16 back to (H, W), clamp, mask_refine, output_mode composition (sdmatte_nodes.py:362-397)
 void postprocess_run(const __half* alpha, int B, int R, int H, int W, const float* image, const float* trimap, int mask_refine,
                      double trimap_constraint, int output_mode, __half* alpha_out, float* matted_out, cudaStream_t st);
+
+// hardware probe (probe.cu): shifted window of a swizzled halo tile as a tcgen05 A operand; out [128][64] fp32
+void probe_halo_run(const __half* x /*[16][8][64]*/, const __half* eye /*[64][64]*/, float* out, int dy, int dx, int mode, cudaStream_t st);
 
 int device_sm_count();
 }  // namespace sdm

@@ -10,6 +10,8 @@
 
 namespace sdm {
 
+void conv_swap_launch(const ConvGemmParams& p, int grid, cudaStream_t st);  // conv_swap.cu
+
 struct ConvGemmLaunch {
   ConvGemmParams p;
   int block_n = 0;
@@ -17,6 +19,8 @@ struct ConvGemmLaunch {
   bool light = false;
   int ewg = 1;
   bool pair = false;  // CTA-pair (cta_group::2) kernel
+  bool halo = false;  // 3x3 stride-1 conv with a resident halo tile per 64-channel slice
+  bool swap = false;  // conv_swap_kernel: channels on M, 256 pixels on N (128-channel 3x3 convs)
   int grid = 0;
   double flops = 0;
 };
@@ -113,14 +117,54 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   // CTA pairs for the 256 x 128 tiles of the long-K convs (SDM_PAIR=0 keeps the single-CTA MT=2 kernel for A/B; force_pair = 1 / -1
   // from the kernel tests).  Restrictions of the pair kernel: one weight set, N % 128 == 0, fp16 epilogue without the 2x scatter.
   {
-    static const int env_pair = [] { const char* e = getenv("SDM_PAIR"); return e ? atoi(e) : 1; }();
+    // measured r1r/r1s: the pair kernel is SLOWER on the 128->128 convs (711 vs 1098 TFLOP/s): those layers are bound by the
+    // L2 -> shared-memory fill rate (51 B/clk/SM), which a CTA pair does not reduce (each CTA still fetches its own activation
+    // tile per tap), and the 2-CTA TMA/MMA round trips add latency -> off by default; the halo path below is what cuts the fill
+    static const int env_pair = [] { const char* e = getenv("SDM_PAIR"); return e ? atoi(e) : 0; }();
     const long long ksteps_all = (long long)d.ksize * d.ksize * (cin_total / 64);
     const bool can = bn == 128 && L->mt == 2 && d.mode == EPI_F16 && !d.ups2 && !d.w_bstride && d.N % 128 == 0 && (d.n_store == 0 || d.n_store == d.N);
     L->pair = can && (d.force_pair == 1 || (d.force_pair == 0 && env_pair != 0 && ksteps_all > 4));
     if (d.force_pair == 1) SDM_CHECK(can, "force_pair: configuration not supported by the CTA-pair kernel");
   }
-  p.m_tiles = (int)m_tiles;
-  const long long total = ((m_tiles + L->mt - 1) / L->mt) * p.n_tiles;
+  // swapped operands for the 128-channel 3x3 convs (conv_swap.cu; SDM_SWAP=0 for A/B, force_swap = 1 / -1 from the tests):
+  // 16 x 16 pixel patches, two GroupNorm-partials slots per patch -> only where that equals the default slot count
+  {
+    static const int env_swap = [] { const char* e = getenv("SDM_SWAP"); return e ? atoi(e) : 1; }();
+    const long long swap_tiles = (long long)((Wout + 15) / 16) * ((Hout + 15) / 16) * d.B;
+    const bool can = d.ksize == 3 && d.stride == 1 && d.mode == EPI_F16 && !d.ups2 && !light && !L->pair && !d.w_bstride && d.N % 128 == 0 &&
+                     Hout >= 16 && Wout >= 16 && 2 * swap_tiles == m_tiles && (d.n_store == 0 || d.n_store == d.N) &&
+                     (!d.res || d.N <= kIdentityN);
+    L->swap = can && (d.force_swap == 1 || (d.force_swap == 0 && env_swap != 0 && d.N == 128 && L->mt == 2));
+    if (d.force_swap == 1) SDM_CHECK(can, "force_swap: configuration not supported by the swapped-operand kernel");
+  }
+  // resident halo tile for the 3x3 stride-1 convs (SDM_HALO=0: one TMA box per tap as before; force_halo = 1 / -1 from the tests).
+  // The halo kernel tiles the image in 8 x 16 pixel patches; it is only used where that gives the same number of M tiles as
+  // the default patch (the GroupNorm-partials slot count, conv_gemm_tiles_per_image, must not depend on the kernel choice).
+  {
+    static const int env_halo = [] { const char* e = getenv("SDM_HALO"); return e ? atoi(e) : 1; }();
+    const long long halo_tiles = (long long)((Wout + 7) / 8) * ((Hout + 15) / 16) * d.B;
+    const bool can = d.ksize == 3 && d.stride == 1 && d.mode == EPI_F16 && !light && !L->pair && !L->swap && Hout >= 16 && Wout >= 8 &&
+                     halo_tiles == m_tiles && (bn == 256 || bn == 160 || (bn == 128 && L->mt == 2)) && (d.n_store == 0 || d.n_store == d.N);
+    L->halo = can && (d.force_halo == 1 || (d.force_halo == 0 && env_halo != 0));
+    if (d.force_halo == 1) SDM_CHECK(can, "force_halo: configuration not supported by the halo kernel");
+    if (L->halo) {
+      p.tw = 8; p.th = 16;
+      p.tiles_x = (Wout + 7) / 8;
+      p.tiles_y = (Hout + 15) / 16;
+    }
+  }
+  long long m_tiles_eff = m_tiles;
+  if (L->swap) {
+    p.tw = 16; p.th = 16;
+    p.tiles_x = (Wout + 15) / 16;
+    p.tiles_y = (Hout + 15) / 16;
+    m_tiles_eff = (long long)p.tiles_x * p.tiles_y * d.B;
+    L->mt = 1;
+    L->block_n = 128;
+    p.n_tiles = d.N / 128;
+  }
+  p.m_tiles = (int)m_tiles_eff;
+  const long long total = ((m_tiles_eff + L->mt - 1) / L->mt) * p.n_tiles;
   SDM_CHECK(total < (1ll << 31), "too many tiles");
   p.total_tiles = (int)total;
   p.ntaps = d.ksize * d.ksize;
@@ -135,7 +179,8 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
       const long long bs = d.src_bstride[s] ? d.src_bstride[s] : (long long)d.Hin * d.Win * d.src[s].ld;
       const uint64_t dims[4] = {(uint64_t)d.src[s].C, (uint64_t)d.Win, (uint64_t)d.Hin, (uint64_t)d.B};
       const uint64_t strides[3] = {(uint64_t)d.src[s].ld * 2, (uint64_t)d.Win * d.src[s].ld * 2, (uint64_t)bs * 2};
-      make_tmap(&p.a_map[s], d.src[s].ptr, 4, dims, strides, box);
+      const uint32_t hbox[4] = {64u, (uint32_t)p.tw + 2u, (uint32_t)p.th + 2u, 1u};  // halo: (8+2) x (16+2) pixels, loaded at (x0-1, y0-1)
+      make_tmap(&p.a_map[s], d.src[s].ptr, 4, dims, strides, L->halo ? hbox : box);
     }
     for (int s = d.nsrc; s < 4; ++s) p.a_map[s] = p.a_map[0];
     for (int t = 0; t < p.ntaps; ++t) {
@@ -180,7 +225,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   } else {
     const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d.N};
     const uint64_t strides[1] = {(uint64_t)ktot * 2};
-    const uint32_t bbox[2] = {64u, (uint32_t)(L->pair ? bn / 2 : bn)};  // pair: each CTA loads half of the tile's weight rows
+    const uint32_t bbox[2] = {64u, (uint32_t)(L->swap ? 128 : (L->pair ? bn / 2 : bn))};  // pair: each CTA loads half of the tile's weight rows
     make_tmap(&p.b_map, d.w, 2, dims, strides, bbox);
   }
   // ---- residual: extra K steps  A = residual tile, B = identity columns
@@ -193,7 +238,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
     make_tmap(&p.r_map, d.res, 4, dims, strides, box);
     const uint64_t idims[2] = {(uint64_t)kIdentityN, (uint64_t)kIdentityN};
     const uint64_t istr[1] = {(uint64_t)kIdentityN * 2};
-    const uint32_t ibox[2] = {64u, L->pair ? 32u : 64u};
+    const uint32_t ibox[2] = {64u, L->swap ? 128u : (L->pair ? 32u : 64u)};  // swap: 128 channel rows x one 64-column slice
     make_tmap(&p.i_map, identity_matrix(), 2, idims, istr, ibox);
     p.has_res = 1;
   } else {
@@ -236,6 +281,8 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   }
   {
     static const int env_pf = [] { const char* e = getenv("SDM_PREFETCH"); return e ? atoi(e) : 0; }();
+    static const int env_prof = [] { const char* e = getenv("SDM_GEMM_PROF"); return e ? atoi(e) : 0; }();
+    p.prof = env_prof;
     p.prefetch = env_pf;  // measured (A/B, one box): L2 prefetch of the next tile slows the large convs by 3-9 % -> off by default
   }
   L->grid = (int)std::min<long long>(total, light ? 2 * num_sms : num_sms);
@@ -252,7 +299,16 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
     if (l.ewg == 2) return conv_gemm_launch<BN, MT, MODE, UPS2, false, 2>(p, g, st); \
     return conv_gemm_launch<BN, MT, MODE, UPS2, false, 1>(p, g, st);                 \
   } while (0)
+  if (l.swap) return conv_swap_launch(p, g, st);
   if (l.pair) return conv_gemm_launch_pair<128, EPI_F16>(p, g, st);
+  if (l.halo) {
+    if (bn == 256 && !p.ups2) return conv_gemm_launch_halo<256, 1, false, 1>(p, g, st);
+    if (bn == 256 && p.ups2) return conv_gemm_launch_halo<256, 1, true, 1>(p, g, st);
+    if (bn == 160 && !p.ups2) return conv_gemm_launch_halo<160, 1, false, 2>(p, g, st);
+    if (bn == 160 && p.ups2) return conv_gemm_launch_halo<160, 1, true, 2>(p, g, st);
+    if (bn == 128 && mt == 2 && !p.ups2) return conv_gemm_launch_halo<128, 2, false, 1>(p, g, st);
+    throw Error{"conv_gemm: no halo instantiation for this configuration"};
+  }
   if (l.light) {
     if (p.mode == EPI_F16 && !p.ups2) return conv_gemm_launch<128, 1, EPI_F16, false, true>(p, g, st);
     if (p.mode == EPI_F16_T) return conv_gemm_launch<128, 1, EPI_F16_T, false, true>(p, g, st);

@@ -57,6 +57,7 @@ struct alignas(64) ConvGemmParams {
   int b_batched;      // weight map has a batch coordinate
   int has_res;        // residual K steps present
   int prefetch;       // L2-prefetch the next tile's activation rows
+  int prof;           // SDM_GEMM_PROF=1: CTAs 0/1 print the cycles their producer / MMA / epilogue threads spent waiting
   int mode;
   int ups2;           // EPI_F16 only: write each pixel to the 2x2 block of a (2H,2W) output
   void* out;
@@ -83,19 +84,33 @@ struct alignas(64) ConvGemmParams {
 // its own 128-row A sub-tile and HALF of the B rows, and owns 128 accumulator lanes.  Per MMA each SM then reads 4 KB (A) +
 // N/2 x 32 B (B) of shared memory instead of 4 KB + N x 32 B: the N=128 convs sat exactly at the 128 B/clk shared-memory limit
 // (tensor pipe 59-62 %, ncu r1k/r1n) while the N=256 tiles (96 B/clk) reach 80 %+.  MT must be 1 (the pair IS the two sub-tiles).
-template <int BLOCK_N, int MT = 1, bool LIGHT = false, int EWG = 1, bool PAIR = false>
+// HALO (r1s): 3x3 stride-1 convolutions keep ONE (8+2) x (16+2)-pixel halo tile per M sub-tile and 64-channel slice resident in
+// shared memory and issue all NINE taps from it: the A operand of tap (dy, dx) is the descriptor of the same tile started
+// (dy*10 + dx) pixel rows later with SBO = 10 rows (1280 B) — the 128-byte swizzle is a function of the absolute shared-memory
+// address, so shifted windows of a TMA-written tile are valid operands (tests/probe_halo.py, all 9 windows exact on B200).
+// Measured motivation (SDM_GEMM_PROF, r1s): the 128->128 convs at 1024^2 moved 51 B/clk/SM from L2 into shared memory (the nine
+// taps re-fetch the activation tile nine times) and each MMA took 109 clk instead of 64: shared-memory bandwidth = 8 KB operand
+// reads + 6 KB TMA writes per MMA.  With the halo tile the fill traffic per 64-channel slice drops from 9 x 16 KB to 23 KB per
+// sub-tile.  Shared memory = 2 halo slots (x MT) + a ring of weight tiles.
+template <int BLOCK_N, int MT = 1, bool LIGHT = false, int EWG = 1, bool PAIR = false, bool HALO = false>
 struct ConvGemmCfg {
   static constexpr int kABytes = 128 * 128;          // 128 rows x 64 fp16 (per M sub-tile)
   static constexpr int kBBytes = (PAIR ? BLOCK_N / 2 : BLOCK_N) * 128;  // B rows held by this CTA x 64 fp16
-  static constexpr int kStageBytes = MT * kABytes + kBBytes;
+  static constexpr int kHaloBytes = 23 * 1024;       // 10 x 18 pixel rows of 128 B (23 040 B) rounded up to the 1024-byte swizzle atom
+  static constexpr int kHaloTx = 10 * 18 * 128;      // bytes one halo box delivers
+  static constexpr int kASlots = 2;
   static constexpr int kEpiBytes = EWG * (4 * 4096 /*staging*/ + 2 * 2048 /*GroupNorm partials, double buffered*/);
   static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes - 512;
-  static constexpr int kStages = LIGHT ? 2 : ((kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes));
+  static constexpr int kStageBytes = HALO ? kBBytes : MT * kABytes + kBBytes;
+  static constexpr int kRingBudget = HALO ? kBudget - kASlots * MT * kHaloBytes : kBudget;
+  static constexpr int kStages = LIGHT ? 2 : ((kRingBudget / kStageBytes) > 8 ? 8 : (kRingBudget / kStageBytes));
   static constexpr int kSubStride = BLOCK_N < 32 ? 32 : BLOCK_N;  // TMEM columns per M sub-tile accumulator
   static constexpr int kAccStride = MT * kSubStride;              // TMEM columns between the two accumulator stages
   static constexpr int kTmemCols = (2 * kAccStride <= 64) ? 64 : (2 * kAccStride <= 128) ? 128 : (2 * kAccStride <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
+  static constexpr int kPipeBytes = kStages * kStageBytes + (HALO ? kASlots * MT * kHaloBytes : 0);  // ring first, halo slots behind it
+  static constexpr int kSmemBytes = kPipeBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
   static constexpr int kThreads = 64 + 128 * EWG;
+  static_assert(kStages >= 2, "pipeline depth");
 };
 
 // residual K steps of the tile starting at output column n0: one per 64-channel slice of the tile's own columns.
@@ -107,9 +122,10 @@ __device__ __forceinline__ int residual_steps(int n0, int N) {
   return (min(BLOCK_N, N - n0) + 63) >> 6;
 }
 
-template <int BLOCK_N, int MT, int MODE, bool UPS2, bool LIGHT = false, int EWG = 1, bool PAIR = false>
+template <int BLOCK_N, int MT, int MODE, bool UPS2, bool LIGHT = false, int EWG = 1, bool PAIR = false, bool HALO = false>
 __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BLOCK_N, MT, LIGHT, EWG, PAIR>;
+  using Cfg = ConvGemmCfg<BLOCK_N, MT, LIGHT, EWG, PAIR, HALO>;
+  static_assert(!HALO || (!PAIR && !LIGHT && MODE == EPI_F16), "halo configuration");
   static_assert(EWG == 1 || EWG == 2, "one or two epilogue warpgroups");
   static_assert(!PAIR || (MT == 1 && EWG == 1 && !LIGHT && MODE == EPI_F16 && BLOCK_N % 128 == 0), "CTA-pair configuration");
   // PAIR: p.total_tiles counts 256-row pair tiles (as for MT = 2); this CTA works on sub-tile `rank` of every pair tile
@@ -121,13 +137,17 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
-  // barrier layout (8 B each): full[kStages], empty[kStages], tfull[2], tempty[2], then tmem ptr (4 B)
+  const uint32_t bar_base = smem_base + Cfg::kPipeBytes;
+  const uint32_t halo_base = smem_base + kStages * Cfg::kStageBytes;  // HALO: kASlots x MT halo tiles
+  // barrier layout (8 B each): full[kStages], empty[kStages], tfull[2], tempty[2], then tmem ptr (4 B), then (HALO) afull[2], aempty[2]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  auto afull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 5 + a); };
+  auto aempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 7 + a); };
+  static_assert(8 * (2 * 8 + 9) <= 256, "barrier area");
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -142,6 +162,7 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), ((EWG == 2 && MT == 2) || PAIR) ? 8 : 4);  // PAIR: 4 epilogue warps of each CTA (leader's barrier)
+      if (HALO) { mbar_init(afull_bar(a), 1); mbar_init(aempty_bar(a), 1); }
     }
     fence_barrier_init();
     fence_proxy_async_smem();
@@ -167,6 +188,10 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
       tma_prefetch_desc(&p.b_map);
       int stage = 0;
       uint32_t phase = 0;
+      int aslot = 0;        // HALO: halo-slot ring
+      uint32_t aphase = 0;
+      long long prof_wait = 0;
+      const long long prof_t0 = p.prof ? clock64() : 0;
       // PAIR: every transaction byte of both CTAs is accounted on the LEADER's full barrier
       uint32_t full_remote[PAIR ? kStages : 1];
       if constexpr (PAIR) {
@@ -206,12 +231,53 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
             }
           }
         }
+        if constexpr (HALO) {
+          // per 64-channel slice: ONE halo box per M sub-tile (x0-1 .. x0+8, y0-1 .. y0+16; zero fill = conv padding), then the
+          // nine weight tiles of the slice through the ring
+          int coff = 0;
+          for (int s = 0; s < p.nsrc; ++s) {
+            for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
+              mbar_wait(aempty_bar(aslot), aphase ^ 1u);
+              mbar_expect_tx(afull_bar(aslot), MT * Cfg::kHaloTx);
+#pragma unroll
+              for (int u = 0; u < MT; ++u)
+                tma_load_4d(halo_base + (aslot * MT + u) * Cfg::kHaloBytes, &p.a_map[s], afull_bar(aslot), c0, x0[u] - 1, y0[u] - 1, bb[u]);
+              if (++aslot == Cfg::kASlots) { aslot = 0; aphase ^= 1u; }
+              for (int tap = 0; tap < 9; ++tap) {
+                if (p.prof) { const long long t = clock64(); mbar_wait(empty_bar(stage), phase ^ 1u); prof_wait += clock64() - t; }
+                else mbar_wait(empty_bar(stage), phase ^ 1u);
+                mbar_expect_tx(full_bar(stage), Cfg::kBBytes);
+                const uint32_t b_dst = smem_base + stage * Cfg::kStageBytes;
+                if (p.b_batched) tma_load_3d(b_dst, &p.b_map, full_bar(stage), tap * p.cin_total + coff + c0, n0, bb[0]);
+                else tma_load_2d(b_dst, &p.b_map, full_bar(stage), tap * p.cin_total + coff + c0, n0);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              }
+            }
+            coff += p.src_c[s];
+          }
+          if (p.has_res) {  // residual K steps: dense 8 x 16 residual boxes in a halo slot, identity block in a ring stage
+            const int nres = residual_steps<BLOCK_N>(n0, p.N);
+            for (int i = 0; i < nres; ++i) {
+              mbar_wait(aempty_bar(aslot), aphase ^ 1u);
+              mbar_expect_tx(afull_bar(aslot), MT * Cfg::kABytes);
+#pragma unroll
+              for (int u = 0; u < MT; ++u)
+                tma_load_4d(halo_base + (aslot * MT + u) * Cfg::kHaloBytes, &p.r_map, afull_bar(aslot), n0 + i * 64, x0[u], y0[u], bb[u]);
+              if (++aslot == Cfg::kASlots) { aslot = 0; aphase ^= 1u; }
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              mbar_expect_tx(full_bar(stage), 64 * 128);
+              tma_load_2d(smem_base + stage * Cfg::kStageBytes, &p.i_map, full_bar(stage), 0, 0);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        } else {
         for (int tap = 0; tap < p.ntaps; ++tap) {
           int koff = tap * p.cin_total;
           for (int s = 0; s < p.nsrc; ++s) {
             const CUtensorMap* amap = &p.a_map[p.tap_map[tap] + s];
             for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
+              if (p.prof) { const long long t = clock64(); mbar_wait(empty_bar(stage), phase ^ 1u); prof_wait += clock64() - t; }
+              else mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
               const uint32_t b_dst = a_dst + MT * Cfg::kABytes;
               if constexpr (PAIR) {
@@ -252,7 +318,10 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
+        }  // !HALO
       }
+      if (p.prof && blockIdx.x < 2)
+        printf("sdm prof: cta %d producer   total %lld clk, waiting for a free stage %lld\n", blockIdx.x, clock64() - prof_t0, prof_wait);
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
@@ -262,14 +331,52 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int aslot = 0;        // HALO: halo-slot ring
+      uint32_t aphase = 0;
+      long long prof_full = 0, prof_tempty = 0;
+      const long long prof_t0 = p.prof ? clock64() : 0;
       for (int tile = tile_first; tile < p.total_tiles; tile += tile_step) {
         const int n0 = (tile % p.n_tiles) * BLOCK_N;
         const int nres = p.has_res ? residual_steps<BLOCK_N>(n0, p.N) : 0;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        if (p.prof) { const long long t = clock64(); mbar_wait(tempty_bar(acc), acc_phase ^ 1u); prof_tempty += clock64() - t; }
+        else mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+        if constexpr (HALO) {
+          // 64-channel slices: wait for the slice's halo tiles once, then nine taps x MT sub-tiles x four K16 steps, each tap
+          // reading the SAME halo tile through a descriptor started (dy*10 + dx) pixel rows later (rows of a window are 10 rows apart)
+          const int nslices = chunks_per_tap;
+          for (int sl = 0; sl < nslices + nres; ++sl) {
+            if (p.prof) { const long long t = clock64(); mbar_wait(afull_bar(aslot), aphase); prof_full += clock64() - t; }
+            else mbar_wait(afull_bar(aslot), aphase);
+            const uint32_t h_addr = halo_base + aslot * MT * Cfg::kHaloBytes;
+            const int ri = sl - nslices;  // >= 0: residual slice index (dense 8 x 16 box, identity weight tile)
+            const int ntap = ri < 0 ? 9 : 1;
+            const uint32_t id = ri < 0 ? idesc : umma_idesc_f16(min(64, BLOCK_N - ri * 64));
+            const uint32_t dcol = ri < 0 ? 0u : (uint32_t)(ri * 64);
+            for (int tap = 0; tap < ntap; ++tap) {
+              if (p.prof) { const long long t = clock64(); mbar_wait(full_bar(stage), phase); prof_full += clock64() - t; }
+              else mbar_wait(full_bar(stage), phase);
+              tc_fence_after();
+              const uint64_t bdesc = umma_desc_k128(smem_base + stage * Cfg::kStageBytes);
+              const uint32_t woff = ri < 0 ? (uint32_t)((tap / 3) * 10 + tap % 3) * 128u : 0u;
+#pragma unroll
+              for (int u = 0; u < MT; ++u) {
+                const uint64_t adesc = ri < 0 ? umma_desc_k128_sbo(h_addr + u * Cfg::kHaloBytes + woff, 1280) : umma_desc_k128(h_addr + u * Cfg::kHaloBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(d_tmem + u * Cfg::kSubStride + dcol, adesc + 2 * k, bdesc + 2 * k, id, (sl | tap | k) != 0);
+              }
+              umma_commit(empty_bar(stage));
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(aempty_bar(aslot));
+            if (++aslot == Cfg::kASlots) { aslot = 0; aphase ^= 1u; }
+          }
+        } else
         for (int ks = 0; ks < num_ksteps + nres; ++ks) {
-          mbar_wait(full_bar(stage), phase);
+          if (p.prof) { const long long t = clock64(); mbar_wait(full_bar(stage), phase); prof_full += clock64() - t; }
+          else mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
           const uint64_t bdesc = umma_desc_k128(a_addr + MT * Cfg::kABytes);
@@ -294,6 +401,9 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
         else umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
+      if (p.prof && blockIdx.x < 2)
+        printf("sdm prof: cta %d MMA issuer total %lld clk, waiting for operands %lld, for a free accumulator %lld\n", blockIdx.x,
+               clock64() - prof_t0, prof_full, prof_tempty);
     }
   } else {
     // ============================== epilogue (4 warps, one TMEM lane quadrant each) ==============
@@ -315,11 +425,14 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
     constexpr bool kAlternate = (EWG == 2 && MT == 1);
     int acc = kAlternate ? ewg : 0;
     uint32_t acc_phase = 0;
+    long long prof_tfull = 0;
+    const long long prof_t0 = p.prof ? clock64() : 0;
     const uint32_t tempty_leader0 = PAIR ? mapa_shared(tempty_bar(0), 0) : 0u;
     const uint32_t tempty_leader1 = PAIR ? mapa_shared(tempty_bar(1), 0) : 0u;
     for (int tile = tile_first + (kAlternate ? ewg * tile_step : 0); tile < p.total_tiles;
          tile += (kAlternate ? 2 : 1) * tile_step) {
-      mbar_wait(tfull_bar(acc), acc_phase);
+      if (p.prof) { const long long t = clock64(); mbar_wait(tfull_bar(acc), acc_phase); prof_tfull += clock64() - t; }
+      else mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int nt = tile % p.n_tiles;
       const int n0 = nt * BLOCK_N;
@@ -646,6 +759,8 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
       if (kAlternate) acc_phase ^= 1u;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (p.prof && blockIdx.x < 2 && (warp == 2 || warp == 6) && lane == 0)
+      printf("sdm prof: cta %d epilogue warp %d total %lld clk, waiting for an accumulator %lld\n", blockIdx.x, warp, clock64() - prof_t0, prof_tfull);
   }
 
   tc_fence_before();

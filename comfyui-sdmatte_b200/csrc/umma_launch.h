@@ -22,6 +22,23 @@ void conv_gemm_launch(const ConvGemmParams& p, int grid, cudaStream_t st);
     SDM_CUDA_OK(cudaGetLastError());                                                                                         \
   }
 
+// resident-halo variant for the 3x3 stride-1 convs (EPI_F16)
+template <int BN, int MT, bool UPS2, int EWG>
+void conv_gemm_launch_halo(const ConvGemmParams& p, int grid, cudaStream_t st);
+#define SDM_DEFINE_CONV_GEMM_LAUNCH_HALO(BN, MT, UPS2, EWG)                                                                  \
+  template <>                                                                                                                \
+  void conv_gemm_launch_halo<BN, MT, UPS2, EWG>(const ConvGemmParams& p, int grid, cudaStream_t st) {                         \
+    using Cfg = ConvGemmCfg<BN, MT, false, EWG, false, true>;                                                                \
+    auto kern = conv_gemm_kernel<BN, MT, EPI_F16, UPS2, false, EWG, false, true>;                                            \
+    static bool attr = false;                                                                                                \
+    if (!attr) {                                                                                                             \
+      SDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));                 \
+      attr = true;                                                                                                           \
+    }                                                                                                                        \
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(p);                                                                   \
+    SDM_CUDA_OK(cudaGetLastError());                                                                                         \
+  }
+
 // CTA-pair (cta_group::2) variant: cluster of 2 CTAs, grid = an even number of CTAs
 template <int BN, int MODE>
 void conv_gemm_launch_pair(const ConvGemmParams& p, int grid, cudaStream_t st);

@@ -31,7 +31,7 @@ class sdm_conv_gemm_args(C.Structure):
         ("out", C.c_void_p), ("out_ld", C.c_int64), ("out_bstride", C.c_int64),
         ("bias", C.c_void_p), ("bias_sel", C.c_void_p),
         ("res", C.c_void_p), ("res_ld", C.c_int64), ("res_bstride", C.c_int64),
-        ("scale", C.c_float), ("force_block_n", C.c_int), ("post_div", C.c_float), ("n_store", C.c_int), ("out2", C.c_void_p), ("force_mt", C.c_int), ("force_light", C.c_int), ("stats", C.c_void_p), ("force_pair", C.c_int),
+        ("scale", C.c_float), ("force_block_n", C.c_int), ("post_div", C.c_float), ("n_store", C.c_int), ("out2", C.c_void_p), ("force_mt", C.c_int), ("force_light", C.c_int), ("stats", C.c_void_p), ("force_pair", C.c_int), ("force_halo", C.c_int), ("force_swap", C.c_int),
     ]
 
 
@@ -68,7 +68,7 @@ EXPORTS = [
     "sdm_workspace_bytes", "sdm_forward", "sdm_forward_host", "sdm_forward_profiled", "sdm_profile_count", "sdm_profile_entry",
     "sdm_last_forward_stats", "sdm_debug_tensor", "sdm_preprocess", "sdm_postprocess",
     "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
-    "sdm_k_softmax_rows", "sdm_k_direct_conv", "sdm_k_key_compact", "sdm_k_gather_rows",
+    "sdm_k_softmax_rows", "sdm_k_direct_conv", "sdm_k_key_compact", "sdm_k_gather_rows", "sdm_k_probe_halo",
 ]
 
 
@@ -323,7 +323,7 @@ def _p(t):
 
 
 def k_conv_gemm(srcs, w, N, out, *, B, Hin, Win, ksize=1, stride=1, pad=0, mode=0, ups2=0, bias=None, bias_sel=None,
-                res=None, scale=1.0, w_bstride=0, out_ld=None, out_bstride=None, force_block_n=0, post_div=1.0, n_store=0, out2=None, force_mt=0, stats=None, force_light=0, force_pair=0):
+                res=None, scale=1.0, w_bstride=0, out_ld=None, out_bstride=None, force_block_n=0, post_div=1.0, n_store=0, out2=None, force_mt=0, stats=None, force_light=0, force_pair=0, force_halo=0, force_swap=0):
     lib = load_library()
     a = sdm_conv_gemm_args()
     a.B, a.Hin, a.Win, a.nsrc = B, Hin, Win, len(srcs)
@@ -339,7 +339,7 @@ def k_conv_gemm(srcs, w, N, out, *, B, Hin, Win, ksize=1, stride=1, pad=0, mode=
         a.res, a.res_ld, a.res_bstride = res[0].data_ptr(), res[1], res[2]
     a.scale, a.force_block_n = scale, force_block_n
     a.post_div, a.n_store, a.out2, a.force_mt, a.stats, a.force_light = post_div, n_store, _p(out2), force_mt, _p(stats), force_light
-    a.force_pair = force_pair
+    a.force_pair, a.force_halo, a.force_swap = force_pair, force_halo, force_swap
     _check(lib.sdm_k_conv_gemm(C.byref(a), _stream_ptr(out.device)))
 
 
@@ -358,6 +358,12 @@ def k_key_compact(bias, cbias, idx, ntiles, *, B, L, lpad):
     """bias/cbias float32 [B][lpad], idx int32 [B][lpad], ntiles int32 [B] (see include/sdmatte_b200.h)."""
     _check(load_library().sdm_k_key_compact(bias.data_ptr(), cbias.data_ptr(), idx.data_ptr(), ntiles.data_ptr(), B, L, lpad,
                                            _stream_ptr(bias.device)))
+
+
+def k_probe_halo(x, eye, out, dy, dx, mode):
+    lib = load_library()
+    lib.sdm_k_probe_halo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    _check(lib.sdm_k_probe_halo(x.data_ptr(), eye.data_ptr(), out.data_ptr(), dy, dx, mode, _stream_ptr(x.device)))
 
 
 def k_gather_rows(src, dst, idx, ntiles, *, B, L, C_, idx_bstride):

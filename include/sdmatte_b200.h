@@ -111,6 +111,8 @@ typedef struct {
   int force_light;              /* tests: 1 = force the 2-CTAs-per-SM short-K config, -1 = forbid it, 0 = auto */
   float* stats;                 /* mode 0 without ups2: GroupNorm partials [B][sdm_k_conv_tiles_per_image][N][2] (sum, sumsq), or NULL */
   int force_pair;               /* tests: 1 = force the CTA-pair (tcgen05 cta_group::2, M = 256) kernel, -1 = forbid it, 0 = auto */
+  int force_halo;               /* tests: 1 = force the resident-halo 3x3 kernel (one halo tile per 64 channels, nine taps from it), -1 = forbid */
+  int force_swap;               /* tests: 1 = force the swapped-operand 3x3 kernel (channels on M, 256 pixels on N), -1 = forbid it */
 } sdm_conv_gemm_args;
 int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream);
 int sdm_k_conv_tiles_per_image(int Hout, int Wout);
@@ -131,6 +133,10 @@ int sdm_k_attention(const sdm_attn_args* a, uintptr_t stream);
    bias [B][lpad] (log2 domain, -inf padded) -> idx [B][lpad] kept key indices in order (padded to a multiple of 128 with a
    valid index), cbias [B][lpad] their biases (-inf padding), ntiles [B] = padded count / 128.  L = real key count. */
 int sdm_k_key_compact(const float* bias, float* cbias, int32_t* idx, int32_t* ntiles, int B, int L, int lpad, uintptr_t stream);
+/* Hardware probe (tests/probe_halo.py): D = shifted 16x8 window of a TMA-swizzled (18x10) halo tile, as a tcgen05 A operand
+   with SBO = 1280 B and an unaligned start; x [16][8][64] fp16, eye [64][64] fp16 identity, out [128][64] fp32;
+   mode 0: descriptor base_offset 0, mode 1: base_offset = (start >> 7) & 7 */
+int sdm_k_probe_halo(const void* x, const void* eye, float* out, int dy, int dx, int mode, uintptr_t stream);
 /* dst[b][i][:] = src[b][idx[b][i]][:] for i < 128 * ntiles[b]; src/dst [B][L][C] fp16 */
 int sdm_k_gather_rows(const void* src, void* dst, const int32_t* idx, const int32_t* ntiles, int B, int L, int C, int idx_bstride,
                       uintptr_t stream);

@@ -608,7 +608,7 @@ def test_conv3x3_cta_pair(eng_mod, B, H, W, Cin, res):
         out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
         st = torch.full((B, slots, Cout, 2), float("nan"), device=DEV)
         eng_mod.k_conv_gemm([(x, Cin, Cin)], _pack_conv_w(w), Cout, out, B=B, Hin=H, Win=W, ksize=3, bias=b, out_ld=Cout,
-                            out_bstride=H * W * Cout, res=(r, Cout, H * W * Cout) if res else None, force_mt=2, stats=st, force_pair=fp)
+                            out_bstride=H * W * Cout, res=(r, Cout, H * W * Cout) if res else None, force_block_n=128, force_mt=2, stats=st, force_pair=fp)
         torch.cuda.synchronize()
         outs.append(out)
         stats.append(st)
@@ -618,3 +618,99 @@ def test_conv3x3_cta_pair(eng_mod, B, H, W, Cin, res):
     _close(outs[0], ref, 2e-3, 2e-3, "conv3x3 CTA pair")
     assert torch.equal(outs[0], outs[1]), "pair kernel differs from the single-CTA kernel"
     assert torch.equal(stats[0], stats[1]), "GroupNorm partials differ"
+
+
+# ------------------------------------------------------------------------------------------------ resident-halo 3x3 convs
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,bn,mt,res,ups2", [
+    (2, 32, 32, 128, 0, 128, 128, 2, True, 0),    # 256x128 tiles, residual K steps, GroupNorm partials
+    (3, 16, 8, 64, 0, 128, 128, 2, False, 0),     # one patch per image, odd number of M tiles (past-the-end sub-tile)
+    (1, 64, 64, 64, 0, 256, 256, 1, True, 0),     # 256-wide tiles
+    (2, 16, 16, 320, 0, 320, 160, 1, True, 0),    # 160-wide tiles, two epilogue warpgroups
+    (1, 32, 32, 192, 128, 256, 256, 1, False, 0),  # cat([h, skip]) input: two sources
+    (1, 40, 40, 128, 0, 512, 256, 1, True, 0),    # ragged image (40 = 5 x 8 = 2.5 x 16): halo and tile rows outside the image, two N tiles
+    (1, 16, 16, 128, 0, 256, 256, 1, True, 1),    # fused nearest-2x scatter store
+    (2, 24, 24, 640, 0, 640, 160, 1, False, 1),
+])
+def test_conv3x3_halo(eng_mod, B, H, W, C0, C1, Cout, bn, mt, res, ups2):
+    """3x3 conv issued from ONE resident (8+2) x (16+2) halo tile per 64-channel slice (nine shifted descriptor windows) against
+    the reference and against the tap-per-TMA-box kernel (different K order: equal up to fp32 summation order)."""
+    Cin = C0 + C1
+    a = _rand(B, H, W, C0, seed=1).half()
+    s2 = _rand(B, H, W, C1, seed=6).half() if C1 else None
+    r = _rand(B, H, W, Cout, seed=5).half() if res else None
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2).half()
+    b = _rand(Cout, seed=3).float()
+    srcs = [(a, C0, C0)] + ([(s2, C1, C1)] if C1 else [])
+    slots = eng_mod.conv_tiles_per_image(H, W)
+    sc = 2 if ups2 else 1
+    outs, stats = [], []
+    for fh in (1, -1):
+        out = torch.zeros(B, sc * H, sc * W, Cout, dtype=torch.float16, device=DEV)
+        st = None if ups2 else torch.full((B, slots, Cout, 2), float("nan"), device=DEV)
+        eng_mod.k_conv_gemm(srcs, _pack_conv_w(w), Cout, out, B=B, Hin=H, Win=W, ksize=3, bias=b, ups2=ups2, out_ld=Cout,
+                            out_bstride=sc * sc * H * W * Cout, res=(r, Cout, H * W * Cout) if res else None, force_block_n=bn,
+                            force_mt=mt, stats=st, force_halo=fh)
+        torch.cuda.synchronize()
+        outs.append(out)
+        stats.append(st)
+    xin = torch.cat([a, s2], -1) if C1 else a
+    y = F.conv2d(xin.float().permute(0, 3, 1, 2), w.float(), b, padding=1).half().float()
+    if res:
+        y = y + r.float().permute(0, 3, 1, 2)
+    if ups2:
+        y = F.interpolate(y, scale_factor=2, mode="nearest")
+    ref = y.permute(0, 2, 3, 1)
+    _close(outs[0], ref, 2e-3, 2e-3, "conv3x3 halo")
+    d = (outs[0].float() - outs[1].float()).abs()
+    assert d.max().item() <= 4e-3 and (d > 0).float().mean().item() < 0.05, f"halo vs tap kernels: max {d.max():.3e}, differing {(d > 0).float().mean():.4f}"
+    if not ups2:
+        assert torch.isfinite(stats[0]).all()
+        tot = stats[0].double().sum(1)
+        o = outs[0].double().view(B, H * W, Cout)
+        assert torch.allclose(tot[..., 0], o.sum(1), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(tot[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ swapped-operand 3x3 convs
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,res", [
+    (2, 32, 32, 128, 0, 128, True),     # the VAE case: 128 -> 128 with residual and GroupNorm partials
+    (1, 64, 64, 256, 0, 128, False),    # 256 -> 128 (decoder conv1 of the last block)
+    (3, 16, 16, 64, 0, 128, True),      # one patch per image
+    (1, 48, 80, 128, 64, 256, True),    # two sources, two 128-channel N tiles
+    (1, 40, 24, 64, 0, 128, True),      # ragged image: patch rows / columns outside the image
+])
+def test_conv3x3_swapped_operands(eng_mod, B, H, W, C0, C1, Cout, res):
+    """3x3 conv computed as D^T = W . X^T (channels on the MMA's M, 256 pixels on N; conv_swap.cu): output, residual K steps and
+    GroupNorm partials against the reference and the pixels-on-M kernel."""
+    Cin = C0 + C1
+    a = _rand(B, H, W, C0, seed=1).half()
+    s2 = _rand(B, H, W, C1, seed=6).half() if C1 else None
+    r = _rand(B, H, W, Cout, seed=5).half() if res else None
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2).half()
+    b = _rand(Cout, seed=3).float()
+    srcs = [(a, C0, C0)] + ([(s2, C1, C1)] if C1 else [])
+    slots = eng_mod.conv_tiles_per_image(H, W)
+    if 2 * ((W + 15) // 16) * ((H + 15) // 16) != slots:
+        pytest.skip("default patch gives a different GroupNorm slot count: the engine would not select the swapped kernel here")
+    outs, stats = [], []
+    for fs in (1, -1):
+        out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
+        st = torch.full((B, slots, Cout, 2), float("nan"), device=DEV)
+        eng_mod.k_conv_gemm(srcs, _pack_conv_w(w), Cout, out, B=B, Hin=H, Win=W, ksize=3, bias=b, out_ld=Cout, out_bstride=H * W * Cout,
+                            res=(r, Cout, H * W * Cout) if res else None, stats=st, force_swap=fs, force_halo=-1)
+        torch.cuda.synchronize()
+        outs.append(out)
+        stats.append(st)
+    xin = torch.cat([a, s2], -1) if C1 else a
+    y = F.conv2d(xin.float().permute(0, 3, 1, 2), w.float(), b, padding=1).half().float()
+    if res:
+        y = y + r.float().permute(0, 3, 1, 2)
+    ref = y.permute(0, 2, 3, 1)
+    _close(outs[0], ref, 2e-3, 2e-3, "conv3x3 swapped operands")
+    d = (outs[0].float() - outs[1].float()).abs()
+    assert d.max().item() <= 4e-3 and (d > 0).float().mean().item() < 0.05
+    assert torch.isfinite(stats[0]).all()
+    tot = stats[0].double().sum(1)
+    o = outs[0].double().view(B, H * W, Cout)
+    assert torch.allclose(tot[..., 0], o.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(tot[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)
