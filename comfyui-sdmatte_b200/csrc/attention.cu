@@ -11,7 +11,7 @@
 //   warps 0-3  : softmax warpgroup for tile A (thread r owns query row r == TMEM lane r)
 //   warps 4-7  : softmax warpgroup for tile B
 //   warp  8    : TMA producer (Q once; K, V^T and the per-key bias per tile; 5-stage ring)
-//   warp  9    : tcgen05.mma issuer + TMEM alloc
+//   warps 9,10 : tcgen05.mma issuers, ONE PER QUERY TILE (warp 9 also owns the TMEM allocation)
 //                S_X  = Q_X K^T : two M128 N64 K64 halves (keys 0-63 / 64-127), both operands from shared memory
 //                O_X += P_X V   : M128 N64 K128, A = P_X read from TENSOR MEMORY ("TS" MMA), B = V^T from shared memory
 // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)   (P = packed fp16x2).
@@ -39,6 +39,16 @@
 // P_lo = chunks 0-1 published after chunk 1 and P_hi after chunk 3, O += P_lo V_lo runs half a tile earlier, the chunk-0
 // store of tile j waits for an MMA issued two chunks before the end of tile j-1, the chunk-2 store for the one issued at
 // its end: both have >= 2 chunks of exponentials of slack.
+// v9 (r1q): one MMA issuer warp per query tile running the tile's fixed event sequence with BLOCKING mbarrier waits
+//   S_lo(t+1) <- s_free_lo(t),  [P.V_lo(t) <- p_full_lo(t)],  S_hi(t+1) <- s_free_hi(t),  P.V(t) <- p_full(t)
+// instead of one thread polling the ~12 barriers of both tiles round-robin.  ncu r1p/r1q: the single poller was the bottleneck
+// (with the extra events of SPLIT_PV the softmax warps waited 25 % of their time for S_hi(j), issued late): same box,
+// B2 h5 16384 x 16384: 501 -> 622 TFLOP/s (whole-tile P.V) / 631 (split); in the step cross attention 54.1 -> 42.4 / 45.1 ms.
+// The polling issuer is gone; SPLIT_PV stays as a switch (SDM_ATTN_SPLIT=1), whole-tile P.V is the default.
+// An FMA-pipe polynomial exp2 (degree 4, packed fp32x2) for 4 / 8 of the 16 column pairs of a chunk was measured twice and
+// removed: under the polling issuer (r1o) 519 -> 494 / 464 TFLOP/s at L0, under the sequenced issuers (r1v) 623 -> 603 / 550:
+// the softmax warps are bound by their dependent instruction chain, not by MUFU throughput (XU pipe 65 % in ncu r1q).
+// Self-attention only streams the keys that can have a non-zero probability (p.ntiles, see key_compact_kernel).
 // The per-key bias is expected pre-multiplied by log2(e); scores are handled in the log2 domain, statistics in fp32,
 // and scores are NOT rounded to fp16 before the softmax (the reference does).
 #include "common.cuh"
@@ -63,8 +73,7 @@ struct alignas(64) AttnParams {
 
 namespace a7 {
 constexpr int kStages = 5;
-constexpr int kThreads = 320;      // 8 softmax warps + TMA producer + one MMA issuer
-constexpr int kThreadsDual = 352;  // ... + a second MMA issuer (one per query tile)
+constexpr int kThreads = 352;  // 8 softmax warps + TMA producer + two MMA issuers (one per query tile)
 constexpr uint32_t kQBytes = 128 * 128;        // one 128x64 fp16 tile
 constexpr uint32_t kKBytes = 128 * 128;        // 128 keys x 64 d
 constexpr uint32_t kVBytes = 2 * 64 * 128;     // 64 d x 128 keys as two 64-key blocks
@@ -85,15 +94,9 @@ __device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, __half2 s) {
 
 // TAIL: Lk is not a multiple of 128 and there is no bias to carry the -inf padding (never the case inside the engine;
 // kept out of the common instantiations: even skipped, the masking code cost a BSSY/branch per chunk and i-cache misses)
-// SPLIT_PV: see the v8 note above (false = v7c behaviour, kept as the A/B baseline: SDM_ATTN_SPLIT=0)
-// (An FMA-pipe polynomial exp2 for 4/6/8 of the 16 column pairs of a chunk was measured on B200 in r1o: 519 -> 494 / 475 /
-// 464 TFLOP/s at L0 — the softmax warps are latency-, not MUFU-throughput-bound — and removed.)
-// DUAL (v9, r1q): one MMA issuer warp PER QUERY TILE running the tile's fixed event sequence with blocking mbarrier waits
-//   S_lo(t+1) <- s_free_lo(t),  [P.V_lo(t) <- p_full_lo(t)],  S_hi(t+1) <- s_free_hi(t),  P.V(t) <- p_full(t)
-// instead of one thread polling all ~12 barriers of both tiles round-robin (ncu r1p: with the extra events of SPLIT_PV the
-// single poller became the bottleneck — the softmax warps then waited 25 % of their time for S_hi(j), issued late).
-template <bool HAS_BIAS, bool TAIL, bool SPLIT_PV, bool DUAL>
-__global__ void __launch_bounds__(a7::kThreadsDual, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+// SPLIT_PV: P.V in two 64-key halves (v8 note above)
+template <bool HAS_BIAS, bool TAIL, bool SPLIT_PV>
+__global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   using namespace a7;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(a7::kThreadsDual, 1) attention_kernel(const __
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < kStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), DUAL ? 2 : 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2); }  // both issuers commit
     for (int x = 0; x < 2; ++x) {
       for (int hf = 0; hf < 2; ++hf) {
         mbar_init(s_full(x, hf), 1); mbar_init(s_free(x, hf), 128);
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(a7::kThreadsDual, 1) attention_kernel(const __
         umma_commit(commit_bar);
       };
       mbar_wait(q_full, 0);
-      if constexpr (DUAL) {
+      {
         const int x = warp - 9;  // this issuer's query tile
         auto wait_kv = [&](int t) { mbar_wait(kv_full(t % kStages), (uint32_t)(t / kStages) & 1u); };
         wait_kv(0);
@@ -210,72 +213,7 @@ __global__ void __launch_bounds__(a7::kThreadsDual, 1) attention_kernel(const __
           else issue_pv(x, st, t, 0, 8, o_full(x, 1));
           umma_commit(kv_empty(st));  // this tile's MMAs on the stage are done (the barrier counts both issuers)
         }
-      } else {
-      // Event-driven issue.  Per query tile x the streams are  S_lo(t), S_hi(t), P.V_lo(t), P.V_hi(t)  with
-      //   S_lo_x(t+1) as soon as the warpgroup holds chunks 0-1 of S_x(t) in registers (right at the start of its tile t),
-      //   S_hi_x(t+1) once chunks 2-3 are in registers, P.V_lo/hi_x(t) once that half of P_x(t) is in TMEM.
-      // S is issued with priority: it sits on the softmax warps' critical path (ncu r1n: with whole-tile S and in-order /
-      // round-robin issue the warpgroups waited 12 % of their time for S(j+1)); P.V is only needed later.
-      int js[2][2] = {{0, 0}, {0, 0}};   // S halves issued per query tile
-      int jp[2][2] = {{0, 0}, {0, 0}};   // P.V halves issued per query tile ([x][1] = whole tiles when !SPLIT_PV)
-      int released = 0;                  // K/V stages handed back to the producer
-      uint32_t idle = 0;
-      long long t0 = 0;
-      while (jp[0][1] < n || jp[1][1] < n) {
-        bool progress = false;
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            const int t = js[x][hf];
-            if (t < n && mbar_test(kv_full(t % kStages), (uint32_t)(t / kStages) & 1u) &&
-                (t == 0 || mbar_test(s_free(x, hf), (uint32_t)(t - 1) & 1u))) {
-              tc_fence_after();
-              issue_s(x, hf, t % kStages);
-              js[x][hf] = t + 1;
-              progress = true;
-            }
-          }
-        }
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          // older half first: hi(t) is issued after lo(t) and before lo(t+1), so every commit also covers all earlier P.V
-          {
-            const int t = jp[x][1];
-            if (t < js[x][1] && (!SPLIT_PV || t < jp[x][0]) && mbar_test(p_full(x, 1), (uint32_t)t & 1u)) {
-              tc_fence_after();
-              if (SPLIT_PV) issue_pv(x, t % kStages, t, 4, 8, o_full(x, 1));
-              else issue_pv(x, t % kStages, t, 0, 8, o_full(x, 1));
-              jp[x][1] = t + 1;
-              progress = true;
-              while (released < min(jp[0][1], jp[1][1])) {  // both tiles have issued all their P.V for this stage
-                umma_commit(kv_empty(released % kStages));
-                ++released;
-              }
-            }
-          }
-          if (SPLIT_PV) {
-            const int t = jp[x][0];
-            if (t == jp[x][1] && t < js[x][0] && mbar_test(p_full(x, 0), (uint32_t)t & 1u)) {
-              tc_fence_after();
-              issue_pv(x, t % kStages, t, 0, 4, o_full(x, 0));
-              jp[x][0] = t + 1;
-              progress = true;
-            }
-          }
-        }
-        if (progress) { idle = 0; t0 = 0; }
-        else if ((++idle & 0xFFFFu) == 0) {  // a pipeline bug must trap instead of hanging the GPU box
-          const long long now = clock64();
-          if (t0 == 0) t0 = now;
-          else if (now - t0 > 20000000000LL) {
-            printf("sdm: attention MMA issue loop timeout (block %d,%d,%d js %d %d %d %d jp %d %d %d %d)\n", blockIdx.x, blockIdx.y,
-                   blockIdx.z, js[0][0], js[0][1], js[1][0], js[1][1], jp[0][0], jp[0][1], jp[1][0], jp[1][1]);
-            __trap();
-          }
-        }
       }
-      }  // !DUAL
     }
   } else if (warp < 8) {
     // ======================================= softmax warpgroups =================================
@@ -516,31 +454,26 @@ std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d) {
   return L;
 }
 
-template <bool HB, bool TL, bool SP, bool DU>
+template <bool HB, bool TL, bool SP>
 static void attn_launch(const AttnLaunch& l, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<HB, TL, SP, DU>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
+    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<HB, TL, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
     attr = true;
   }
-  attention_kernel<HB, TL, SP, DU><<<l.grid, DU ? a7::kThreadsDual : a7::kThreads, a7::kSmem, st>>>(l.p);
+  attention_kernel<HB, TL, SP><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
 }
 
 void attn_run(const AttnLaunch& l, cudaStream_t st) {
-  // SDM_ATTN_VARIANT (A/B switch, read once): 0 = v7c (one polling issuer, whole-tile P.V), 1 = v8 (polling, split P.V),
-  // 2 = v9 (two sequenced issuers, whole-tile P.V), 3 = v9 + split P.V
-  static const int variant = [] { const char* e = getenv("SDM_ATTN_VARIANT"); return e ? atoi(e) : 2; }();
-  if (!l.has_bias && (l.p.Lk & 127) != 0) attn_launch<false, true, false, false>(l, st);
+  // SDM_ATTN_SPLIT=1: P.V in two 64-key halves (A/B switch, read once)
+  static const bool split = [] { const char* e = getenv("SDM_ATTN_SPLIT"); return e ? atoi(e) != 0 : false; }();
+  if (!l.has_bias && (l.p.Lk & 127) != 0) attn_launch<false, true, false>(l, st);
   else if (l.has_bias) {
-    if (variant == 3) attn_launch<true, false, true, true>(l, st);
-    else if (variant == 2) attn_launch<true, false, false, true>(l, st);
-    else if (variant == 1) attn_launch<true, false, true, false>(l, st);
-    else attn_launch<true, false, false, false>(l, st);
+    if (split) attn_launch<true, false, true>(l, st);
+    else attn_launch<true, false, false>(l, st);
   } else {
-    if (variant == 3) attn_launch<false, false, true, true>(l, st);
-    else if (variant == 2) attn_launch<false, false, false, true>(l, st);
-    else if (variant == 1) attn_launch<false, false, true, false>(l, st);
-    else attn_launch<false, false, false, false>(l, st);
+    if (split) attn_launch<false, false, true>(l, st);
+    else attn_launch<false, false, false>(l, st);
   }
   SDM_CUDA_OK(cudaGetLastError());
 }

@@ -150,66 +150,19 @@ __global__ void __launch_bounds__(NT) gn_finalize_kernel(const float* __restrict
 // apply: same (channel-vector, pixel-row) thread layout as the stats kernel, so each thread keeps the scale/shift of its
 // 8 channels in registers and streams pixels with 4 independent 16-byte loads in flight (r1c ncu: the grid-stride version
 // was latency/issue-bound at 3.4 TB/s: one load in flight per thread, 64 B of scale/shift re-fetched per vector).
-// v0 (r1c-r1o): scalar fp32 arithmetic; kept as the A/B baseline (SDM_GN_APPLY=0)
-__global__ void gn_apply_kernel_v0(const __half* __restrict__ s0, const __half* __restrict__ s1, int C0, int Ctot, long long ld0,
-                                long long ld1, int HW, int pix_per_slab, const float* __restrict__ ab, int silu,
-                                __half* __restrict__ out) {
-  const int v = threadIdx.x, y = threadIdx.y, ny = blockDim.y;
-  const int b = blockIdx.y;
-  const int p0 = blockIdx.x * pix_per_slab;
-  const int p1 = min(HW, p0 + pix_per_slab);
-  const int c = v * 8;
-  const __half* base;
-  long long ld;
-  if (c < C0) { base = s0 + (long long)b * HW * ld0 + c; ld = ld0; }
-  else { base = s1 + (long long)b * HW * ld1 + (c - C0); ld = ld1; }
-  __half* obase = out + (long long)b * HW * Ctot + c;
-  float ka[8], ks[8];
-  {
-    const float4* abp = reinterpret_cast<const float4*>(ab + ((size_t)b * Ctot + c) * 2);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 k = __ldg(abp + j);  // (a0, s0, a1, s1)
-      ka[2 * j] = k.x; ks[2 * j] = k.y; ka[2 * j + 1] = k.z; ks[2 * j + 1] = k.w;
-    }
-  }
-  auto emit = [&](const uint4& raw, int p) {
-    const __half2* h = reinterpret_cast<const __half2*>(&raw);
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(h[j]);
-      float y0 = fmaf(f.x, ka[2 * j], ks[2 * j]);
-      float y1 = fmaf(f.y, ka[2 * j + 1], ks[2 * j + 1]);
-      if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
-      w[j] = pack_h2(y0, y1);
-    }
-    *reinterpret_cast<uint4*>(obase + (long long)p * Ctot) = make_uint4(w[0], w[1], w[2], w[3]);
-  };
-  int p = p0 + y;
-  for (; p + 3 * ny < p1; p += 4 * ny) {
-    uint4 r[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) r[u] = __ldg(reinterpret_cast<const uint4*>(base + (long long)(p + u * ny) * ld));
-#pragma unroll
-    for (int u = 0; u < 4; ++u) emit(r[u], p + u * ny);
-  }
-  for (; p < p1; p += ny) emit(__ldg(reinterpret_cast<const uint4*>(base + (long long)p * ld)), p);
-}
-
 // r1p: packed fp32x2 arithmetic (FFMA2/FMUL2/FADD2) and sign-folded constants.  Inside a step the SM clock sits at
 // 1.3-1.4 GHz (power cap) and this kernel was issue-bound there (ncu r1k: 59 % issue-active at 5.4 TB/s unthrottled,
 // 4.0 TB/s in the step): 12.5 -> 8.5 instructions per element.  SiLU(y) = y / (1 + 2^(-y log2 e)) with ONE MUFU op: the
 // reciprocal of d = 1 + e is the bit-trick guess (negated for free through the magic constant) + two Newton steps,
 //   n0 = -r0,  p1 = n0 (2 + d n0) = -r1,  p2 = p1 (2 + d p1) = -r2,  result = (-y) p2,
 // with -y produced directly by the scale/shift FMA (negated per-channel constants).
-// JOIN: make the arithmetic of pixel 0 depend on all four loads of the iteration (a never-taken trap on the xor of their
+// The arithmetic of pixel 0 is made to depend on all four loads of the iteration (a never-taken trap on the AND of their
 // first words): ptxas otherwise sinks loads 2 and 3 below the arithmetic of pixel 0 — two 16-byte loads in flight per
 // thread instead of four (volatile accesses did not help: it then parks them right before the first store).
-// PACKED = false: scalar fp32 arithmetic (silu_f) inside the same loop structure (measured r1p: packed math alone was slower
-// than v0, 4.5 vs 5.1 TB/s at 1024^2 x 128 ch; packed + joined loads 5.5)
+// Measured r1p/r1q at 1024^2 x 128 ch (isolated, GB/s algorithmic): scalar v0 5.1-5.2, packed without the load join 4.5,
+// packed + joined loads 5.5, scalar + joined loads 5.5; in the step 4.0-4.2 -> 4.5-4.7 TB/s.
 // MAXT: launch bound (256 for up to 2048 channels at 8 per thread, 1024 beyond)
-template <bool SILU, bool JOIN, bool PACKED, int MAXT>
+template <bool SILU, int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 1) gn_apply_kernel(const __half* __restrict__ s0, const __half* __restrict__ s1, int C0, int Ctot,
                                                           long long ld0, long long ld1, int HW, int pix_per_slab,
                                                           const float* __restrict__ ab, __half* __restrict__ out) {
@@ -226,7 +179,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 1) gn_apply_kernel(con
   uint64_t ka[4], ks[4];  // channel pairs (2j, 2j+1); negated when SILU
   {
     const float4* abp = reinterpret_cast<const float4*>(ab + ((size_t)b * Ctot + c) * 2);
-    const float sg = (SILU && PACKED) ? -1.0f : 1.0f;
+    const float sg = SILU ? -1.0f : 1.0f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float4 k = __ldg(abp + j);  // (a0, s0, a1, s1)
@@ -242,15 +195,6 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 1) gn_apply_kernel(con
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = __half22float2(h[j]);
-      if (!PACKED) {
-        float a0, a1, b0, b1;
-        unpack_f2(ka[j], a0, a1);
-        unpack_f2(ks[j], b0, b1);
-        float y0 = fmaf(f.x, a0, b0), y1 = fmaf(f.y, a1, b1);
-        if (SILU) { y0 = silu_f(y0); y1 = silu_f(y1); }
-        w[j] = pack_h2(y0, y1);
-        continue;
-      }
       uint64_t r = fma_f2(pack_f2(f.x, f.y), ka[j], ks[j]);  // y, or -y when SILU
       if (SILU) {
         float t0, t1;
@@ -279,10 +223,8 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 1) gn_apply_kernel(con
     uint4 r[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) r[u] = __ldg(reinterpret_cast<const uint4*>(src + u * ss));
-    if (JOIN) {
-      // four fp16 NaN payloads that a finite tensor can never hold all at once
-      if (((r[0].x & r[1].x & r[2].x & r[3].x) & 0x7fff7fffu) == 0x7fff7fffu) __trap();
-    }
+    // four fp16 NaN payloads that a finite tensor can never hold all at once
+    if (((r[0].x & r[1].x & r[2].x & r[3].x) & 0x7fff7fffu) == 0x7fff7fffu) __trap();
 #pragma unroll
     for (int u = 0; u < 4; ++u) emit(r[u], dst + u * ds);
     src += 4 * ss;
@@ -360,25 +302,15 @@ void groupnorm_run(const GroupNormDesc& d, cudaStream_t st) {
   SDM_CUDA_OK(cudaGetLastError());
   const int app_pps = ny * 16;  // 16 pixels per thread
   const int app_slabs = (d.HW + app_pps - 1) / app_pps;
-  // SDM_GN_APPLY = 0 (scalar v0) | 1 (packed) | 2 (packed + joined loads) | 3 (scalar + joined loads); A/B switch read once
-  static const int variant = [] { const char* e = getenv("SDM_GN_APPLY"); return e ? atoi(e) : 2; }();
   const dim3 ag(app_slabs, d.B), ab_(nvec, ny);
 #define SDM_GN_APPLY_ARGS d.src[0], s1, C0, Ctot, d.ld[0], ld1, d.HW, app_pps, ab
-#define SDM_GN_GO(JOIN, PACKED)                                                                                                  \
-  do {                                                                                                                           \
-    if (nvec * ny <= 256) {                                                                                                      \
-      if (d.silu) gn_apply_kernel<true, JOIN, PACKED, 256><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);                         \
-      else gn_apply_kernel<false, JOIN, PACKED, 256><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);                               \
-    } else {                                                                                                                     \
-      if (d.silu) gn_apply_kernel<true, JOIN, PACKED, 1024><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);                        \
-      else gn_apply_kernel<false, JOIN, PACKED, 1024><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);                              \
-    }                                                                                                                            \
-  } while (0)
-  if (variant == 0) gn_apply_kernel_v0<<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.silu, d.out);
-  else if (variant == 1) SDM_GN_GO(false, true);
-  else if (variant == 3) SDM_GN_GO(true, false);
-  else SDM_GN_GO(true, true);
-#undef SDM_GN_GO
+  if (nvec * ny <= 256) {
+    if (d.silu) gn_apply_kernel<true, 256><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);
+    else gn_apply_kernel<false, 256><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);
+  } else {
+    if (d.silu) gn_apply_kernel<true, 1024><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);
+    else gn_apply_kernel<false, 1024><<<ag, ab_, 0, st>>>(SDM_GN_APPLY_ARGS, d.out);
+  }
 #undef SDM_GN_APPLY_ARGS
   SDM_CUDA_OK(cudaGetLastError());
 }

@@ -77,7 +77,18 @@ def gn(B, H, W, C):
     return ms, 4.0 * B * H * W * C / ms / 1e9  # "TFLOP/s" column = TB/s here
 
 
+def scores(B, L, D):
+    """VAE mid-block attention scores: fp32 [B][L][L] = scale * Q K^T (batched weights, EPI_F32)."""
+    q = torch.randn(B, L, D, device=DEV).half()
+    k = torch.randn(B, L, D, device=DEV).half()
+    out = torch.empty(B, L, L, dtype=torch.float32, device=DEV)
+    ms = timeit(lambda: E.k_conv_gemm([(q, D, D)], k, L, out, B=B, Hin=1, Win=L, mode=3, scale=D ** -0.5, w_bstride=L * D, out_ld=L,
+                                      out_bstride=L * L), iters=5, warm=2)
+    return ms, 2.0 * B * L * L * D / ms / 1e9
+
+
 CASES = {
+    "vae_qk scores 16384x16384x512 B2 f32": lambda: scores(2, 16384, 512),
     "gn+silu 128ch @1024^2 B4 (TB/s)": lambda: gn(4, 1024, 1024, 128),
     "gn+silu 256ch @512^2 B4 (TB/s)": lambda: gn(4, 512, 512, 256),
     "gn+silu 320ch @128^2 B8 (TB/s)": lambda: gn(8, 128, 128, 320),

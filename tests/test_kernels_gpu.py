@@ -608,7 +608,7 @@ def test_conv3x3_cta_pair(eng_mod, B, H, W, Cin, res):
         out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
         st = torch.full((B, slots, Cout, 2), float("nan"), device=DEV)
         eng_mod.k_conv_gemm([(x, Cin, Cin)], _pack_conv_w(w), Cout, out, B=B, Hin=H, Win=W, ksize=3, bias=b, out_ld=Cout,
-                            out_bstride=H * W * Cout, res=(r, Cout, H * W * Cout) if res else None, force_block_n=128, force_mt=2, stats=st, force_pair=fp)
+                            out_bstride=H * W * Cout, res=(r, Cout, H * W * Cout) if res else None, force_block_n=128, force_mt=2, stats=st, force_pair=fp, force_swap=-1, force_halo=-1)
         torch.cuda.synchronize()
         outs.append(out)
         stats.append(st)
@@ -649,7 +649,7 @@ def test_conv3x3_halo(eng_mod, B, H, W, C0, C1, Cout, bn, mt, res, ups2):
         st = None if ups2 else torch.full((B, slots, Cout, 2), float("nan"), device=DEV)
         eng_mod.k_conv_gemm(srcs, _pack_conv_w(w), Cout, out, B=B, Hin=H, Win=W, ksize=3, bias=b, ups2=ups2, out_ld=Cout,
                             out_bstride=sc * sc * H * W * Cout, res=(r, Cout, H * W * Cout) if res else None, force_block_n=bn,
-                            force_mt=mt, stats=st, force_halo=fh)
+                            force_mt=mt, stats=st, force_halo=fh, force_swap=-1)
         torch.cuda.synchronize()
         outs.append(out)
         stats.append(st)
