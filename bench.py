@@ -174,6 +174,10 @@ def run_b200(args):
     # global batch = world*B; this rank's shard (weak scaling: B per GPU)
     lo, hi = shard_range(world * B, rank, world)
     image, trimap = synth.make_inputs(B, R, seed=1000 + lo)
+    # attn1 only streams the keys whose probability can be non-zero under the -10000 trimap bias (key_compact_kernel):
+    # fraction of the level-0 keys kept for this batch (same rule on the host: mask >= max - 0.25), reported in `config`
+    m0 = trimap[:, ::8, ::8].reshape(B, -1)
+    kept_l0 = float((m0 >= m0.max(dim=1, keepdim=True).values - 0.25).float().mean())
     img_d, tri_d = image.to(dev), trimap.to(dev)
     img_h, tri_h = image.pin_memory(), trimap.pin_memory()
     alpha_h = torch.empty((B, R, R), dtype=torch.float16).pin_memory()
@@ -282,12 +286,15 @@ def run_b200(args):
         "dtype": "f16", "data": "synthetic",
         "config": {"workload": f"bs={B} per GPU, {R}x{R} synthetic RGB+trimap, synthetic SDMatte checkpoint (seed 1234), is_transparent=False",
                    "global_batch": world * B, "resolution": R, "parallelism": f"dp{world} batch shard + one NCCL all-gather of alpha" if world > 1 else "single GPU",
-                   "l2": "256 MiB buffer written between timed iterations (inside the loop)"},
+                   "l2": "256 MiB buffer written between timed iterations (inside the loop)",
+                   "self_attn_keys_streamed_L0": round(kept_l0, 4),
+                   "note": "FLOP figures are ALGORITHMIC (all keys); attn1 skips keys whose softmax probability is exactly 0 under the "
+                           "reference's -10000 bias, so tc:attention_self reports algorithmic TFLOP/s above what it executes"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "mattes/s", "h2d_bytes_per_step": B * R * R * 16, "d2h_bytes_per_step": B * R * R * 2,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": stats["launches"] * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel<BLOCK_N> (tcgen05 implicit-GEMM conv/linear, all launches of one step)",
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv/linear kernels (conv_gemm_kernel<...> incl. the resident-halo 3x3 variants, conv_swap_kernel), all launches of one step",
                      "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
                      "traffic": None, "launches_per_step": gemm_launches, "share_of_step": gemm_ms / tot_ms if tot_ms else None,
                      "peak_source": peaks["source"] + " (bf16 sustained)"},
