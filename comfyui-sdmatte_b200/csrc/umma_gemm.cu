@@ -108,45 +108,48 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   (void)light_ok;  // measured (r1i): the two-CTAs-per-SM config is slower than 160/256-wide tiles -> only on request
   const bool light = d.force_light == 1;
   L->light = light;
-  const int bn = light ? 128 : (d.force_block_n ? d.force_block_n : pick_block_n(d.N, d.mode, m_tiles, num_sms));
+  // ---- kernel variant of the 3x3 stride-1 convs: decided from the per-sample GEOMETRY only (never from the batch size), because
+  // the variants differ in K order (halo: slice-major, taps inner) and in how pixels are grouped into GroupNorm-partials slots:
+  // a sample must produce the same bits alone and inside a batch (test_batch_independence_and_determinism).
+  const bool conv3 = d.ksize == 3 && d.stride == 1 && d.mode == EPI_F16 && !light && (d.n_store == 0 || d.n_store == d.N);
+  const long long tiles_img = (long long)p.tiles_x * p.tiles_y;  // default patch, per sample
+  // swapped operands (conv_swap.cu; SDM_SWAP=0 for A/B, force_swap = 1 / -1 from the tests): 16 x 16 pixel patches, two
+  // GroupNorm-partials slots per patch -> only where that equals the default slot count
+  static const int env_swap = [] { const char* e = getenv("SDM_SWAP"); return e ? atoi(e) : 1; }();
+  const bool swap_can = conv3 && !d.ups2 && !d.w_bstride && d.N % 128 == 0 && Hout >= 16 && Wout >= 16 &&
+                        2ll * ((Wout + 15) / 16) * ((Hout + 15) / 16) == tiles_img && (!d.res || d.N <= kIdentityN);
+  if (d.force_swap == 1) SDM_CHECK(swap_can, "force_swap: configuration not supported by the swapped-operand kernel");
+  L->swap = swap_can && d.force_pair != 1 && d.force_halo != 1 &&
+            (d.force_swap == 1 || (d.force_swap == 0 && env_swap != 0 && d.N == 128 && d.force_block_n == 0 && d.force_mt == 0));
+  // resident halo tile (SDM_HALO=0: one TMA box per tap; force_halo = 1 / -1 from the tests): 8 x 16 pixel patches, used where that
+  // gives the default number of M tiles (the slot count conv_gemm_tiles_per_image must not depend on the kernel choice).
+  // Tile width by N alone: 256 | 160 (the small-problem narrowing of pick_block_n depends on the batch size).
+  static const int env_halo = [] { const char* e = getenv("SDM_HALO"); return e ? atoi(e) : 1; }();
+  const bool halo_geom = conv3 && !L->swap && Hout >= 16 && Wout >= 8 && (long long)((Wout + 7) / 8) * ((Hout + 15) / 16) == tiles_img;
+  const int halo_bn = d.N % 256 == 0 ? 256 : (d.N % 160 == 0 ? 160 : 0);
+  const bool halo_auto = halo_geom && halo_bn != 0 && d.force_halo == 0 && env_halo != 0 && d.force_block_n == 0 && d.force_mt == 0 && d.force_pair != 1;
+  const int bn = light ? 128 : (halo_auto ? halo_bn : (d.force_block_n ? d.force_block_n : pick_block_n(d.N, d.mode, m_tiles, num_sms)));
   if (d.mode == EPI_GEGLU) SDM_CHECK(bn == 256 && d.N % 256 == 0, "GEGLU needs N % 256 == 0");
   L->block_n = bn;
   p.n_tiles = (d.N + bn - 1) / bn;
   // 256 x 128 CTA tiles (two M sub-tiles per B tile) when there is enough work to keep every SM busy
   L->mt = (bn == 128 && !light && d.mode == EPI_F16 && d.force_mt != 1 && (d.force_mt == 2 || (m_tiles / 2) * p.n_tiles >= 2 * num_sms)) ? 2 : 1;
-  // CTA pairs for the 256 x 128 tiles of the long-K convs (SDM_PAIR=0 keeps the single-CTA MT=2 kernel for A/B; force_pair = 1 / -1
-  // from the kernel tests).  Restrictions of the pair kernel: one weight set, N % 128 == 0, fp16 epilogue without the 2x scatter.
+  // CTA pairs for the 256 x 128 tiles of the long-K convs (SDM_PAIR=1 / force_pair = 1 from the kernel tests; bit-identical to the
+  // single-CTA MT=2 kernel).  Restrictions: one weight set, N % 128 == 0, fp16 epilogue without the 2x scatter.
   {
     // measured r1r/r1s: the pair kernel is SLOWER on the 128->128 convs (711 vs 1098 TFLOP/s): those layers are bound by the
-    // L2 -> shared-memory fill rate (51 B/clk/SM), which a CTA pair does not reduce (each CTA still fetches its own activation
-    // tile per tap), and the 2-CTA TMA/MMA round trips add latency -> off by default; the halo path below is what cuts the fill
+    // operand fetch / L2 -> shared-memory fill, which a CTA pair does not reduce (each CTA still fetches its own activation
+    // tile per tap), and the 2-CTA TMA/MMA round trips add latency -> off by default
     static const int env_pair = [] { const char* e = getenv("SDM_PAIR"); return e ? atoi(e) : 0; }();
     const long long ksteps_all = (long long)d.ksize * d.ksize * (cin_total / 64);
-    const bool can = bn == 128 && L->mt == 2 && d.mode == EPI_F16 && !d.ups2 && !d.w_bstride && d.N % 128 == 0 && (d.n_store == 0 || d.n_store == d.N);
+    const bool can = !L->swap && bn == 128 && L->mt == 2 && d.mode == EPI_F16 && !d.ups2 && !d.w_bstride && d.N % 128 == 0 && (d.n_store == 0 || d.n_store == d.N);
     L->pair = can && (d.force_pair == 1 || (d.force_pair == 0 && env_pair != 0 && ksteps_all > 4));
     if (d.force_pair == 1) SDM_CHECK(can, "force_pair: configuration not supported by the CTA-pair kernel");
   }
-  // swapped operands for the 128-channel 3x3 convs (conv_swap.cu; SDM_SWAP=0 for A/B, force_swap = 1 / -1 from the tests):
-  // 16 x 16 pixel patches, two GroupNorm-partials slots per patch -> only where that equals the default slot count
   {
-    static const int env_swap = [] { const char* e = getenv("SDM_SWAP"); return e ? atoi(e) : 1; }();
-    const long long swap_tiles = (long long)((Wout + 15) / 16) * ((Hout + 15) / 16) * d.B;
-    const bool can = d.ksize == 3 && d.stride == 1 && d.mode == EPI_F16 && !d.ups2 && !light && !L->pair && !d.w_bstride && d.N % 128 == 0 &&
-                     Hout >= 16 && Wout >= 16 && 2 * swap_tiles == m_tiles && (d.n_store == 0 || d.n_store == d.N) &&
-                     (!d.res || d.N <= kIdentityN);
-    L->swap = can && (d.force_swap == 1 || (d.force_swap == 0 && env_swap != 0 && d.N == 128 && L->mt == 2));
-    if (d.force_swap == 1) SDM_CHECK(can, "force_swap: configuration not supported by the swapped-operand kernel");
-  }
-  // resident halo tile for the 3x3 stride-1 convs (SDM_HALO=0: one TMA box per tap as before; force_halo = 1 / -1 from the tests).
-  // The halo kernel tiles the image in 8 x 16 pixel patches; it is only used where that gives the same number of M tiles as
-  // the default patch (the GroupNorm-partials slot count, conv_gemm_tiles_per_image, must not depend on the kernel choice).
-  {
-    static const int env_halo = [] { const char* e = getenv("SDM_HALO"); return e ? atoi(e) : 1; }();
-    const long long halo_tiles = (long long)((Wout + 7) / 8) * ((Hout + 15) / 16) * d.B;
-    const bool can = d.ksize == 3 && d.stride == 1 && d.mode == EPI_F16 && !light && !L->pair && !L->swap && Hout >= 16 && Wout >= 8 &&
-                     halo_tiles == m_tiles && (bn == 256 || bn == 160 || (bn == 128 && L->mt == 2)) && (d.n_store == 0 || d.n_store == d.N);
-    L->halo = can && (d.force_halo == 1 || (d.force_halo == 0 && env_halo != 0));
+    const bool can = halo_geom && !L->pair && (bn == 256 || bn == 160 || (bn == 128 && L->mt == 2));
     if (d.force_halo == 1) SDM_CHECK(can, "force_halo: configuration not supported by the halo kernel");
+    L->halo = can && (d.force_halo == 1 || halo_auto);
     if (L->halo) {
       p.tw = 8; p.th = 16;
       p.tiles_x = (Wout + 7) / 8;
