@@ -69,6 +69,7 @@ EXPORTS = [
     "sdm_last_forward_stats", "sdm_debug_tensor", "sdm_preprocess", "sdm_postprocess",
     "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
     "sdm_k_softmax_rows", "sdm_k_direct_conv", "sdm_k_key_compact", "sdm_k_gather_rows", "sdm_k_probe_halo",
+    "sdm_safetensors_open", "sdm_safetensors_count", "sdm_safetensors_entry", "sdm_safetensors_close",
 ]
 
 
@@ -115,6 +116,11 @@ def load_library():
     lib.sdm_k_conv_gemm.argtypes = [C.POINTER(sdm_conv_gemm_args), C.c_void_p]
     lib.sdm_k_conv_tiles_per_image.argtypes = [C.c_int, C.c_int]
     lib.sdm_k_attention.argtypes = [C.POINTER(sdm_attn_args), C.c_void_p]
+    lib.sdm_safetensors_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.sdm_safetensors_count.argtypes = [C.c_void_p]
+    lib.sdm_safetensors_entry.argtypes = [C.c_void_p, C.c_int, C.POINTER(sdm_tensor_desc)]
+    lib.sdm_safetensors_close.argtypes = [C.c_void_p]
+    lib.sdm_safetensors_close.restype = None
     lib.sdm_k_key_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.sdm_k_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.sdm_k_groupnorm_scratch_floats.argtypes = [C.c_int, C.c_int, C.c_int]
@@ -137,6 +143,50 @@ def _stream_ptr(device) -> int:
 
 
 _DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+class SafeTensorsReader:
+    """Native .safetensors reader (csrc/safetensors.cu): header parse + read-only mmap, no torch tensors are created.
+    `descs()` yields the sdm_tensor_desc array the engine's loader takes, filtered exactly like Engine.load_state_dict
+    (unet.* / vae.* keys, floating-point dtypes, rank <= 4); the descriptors point into the mapping, so the reader must stay
+    open until sdm_load_weights has returned."""
+
+    def __init__(self, path: str):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        _check(self.lib.sdm_safetensors_open(os.fsencode(path), C.byref(self.h)))
+
+    def __len__(self):
+        return self.lib.sdm_safetensors_count(self.h)
+
+    def entry(self, i: int) -> "sdm_tensor_desc":
+        d = sdm_tensor_desc()
+        _check(self.lib.sdm_safetensors_entry(self.h, i, C.byref(d)))
+        return d
+
+    def descs(self):
+        n_all = len(self)
+        arr = (sdm_tensor_desc * max(1, n_all))()
+        n = 0
+        for i in range(n_all):
+            d = self.entry(i)
+            name = d.name.decode()
+            if not (name.startswith("unet.") or name.startswith("vae.")) or d.dtype < 0 or d.ndim > 4:
+                continue
+            arr[n] = d
+            n += 1
+        return arr, n
+
+    def close(self):
+        if self.h:
+            self.lib.sdm_safetensors_close(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 class Engine:
@@ -187,6 +237,18 @@ class Engine:
             d.data = t.data_ptr()
             n += 1
         _check(self.lib.sdm_load_weights(self.h, descs, n))
+        used, unexpected = C.c_int(), C.c_int()
+        _check(self.lib.sdm_load_report(self.h, C.byref(used), C.byref(unexpected)))
+        self.load_report = (used.value, unexpected.value)
+        self._ws = None
+        return self.load_report
+
+    def load_safetensors(self, path: str):
+        """Load a checkpoint file through the native reader: the engine repacks straight from the file mapping
+        (the reference builds torch CPU tensors with safe_open first, sdmatte_nodes.py:298-304)."""
+        with SafeTensorsReader(path) as rd:
+            descs, n = rd.descs()
+            _check(self.lib.sdm_load_weights(self.h, descs, n))
         used, unexpected = C.c_int(), C.c_int()
         _check(self.lib.sdm_load_report(self.h, C.byref(used), C.byref(unexpected)))
         self.load_report = (used.value, unexpected.value)

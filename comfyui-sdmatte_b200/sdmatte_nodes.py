@@ -86,10 +86,13 @@ def get_engine(ckpt_name: str, device: torch.device) -> "_engine.Engine":
     eng = _ENGINE_CACHE.get(key)
     if eng is None:
         sd = _STATE_DICT_OVERRIDES.get(ckpt_name)
-        if sd is None:
-            sd = _load_state_dict(find_checkpoint(ckpt_name))
         eng = _engine.Engine(device)
-        used, unexpected = eng.load_state_dict(sd)
+        if sd is not None:
+            used, unexpected = eng.load_state_dict(sd)
+        elif os.environ.get("SDMATTE_PY_SAFETENSORS") == "1":  # the safetensors package instead of the native reader
+            used, unexpected = eng.load_state_dict(_load_state_dict(find_checkpoint(ckpt_name)))
+        else:  # native reader: header parse + mmap, repacked straight from the mapping (no torch CPU tensors)
+            used, unexpected = eng.load_safetensors(find_checkpoint(ckpt_name))
         print(f"[SDMatte-B200] loaded {ckpt_name}: {used} tensors used, {unexpected} ignored")
         _ENGINE_CACHE[key] = eng
     return eng

@@ -40,6 +40,16 @@ void sdm_destroy(sdm_handle* h);
 int sdm_load_weights(sdm_handle* h, const sdm_tensor_desc* tensors, int n);
 int sdm_load_report(sdm_handle* h, int* n_used, int* n_unexpected);
 
+/* Native .safetensors reader: replaces the safe_open / get_tensor loop of sdmatte_nodes.py:298-304.
+ * The file is mapped read-only; sdm_safetensors_entry fills a descriptor whose `data` points INTO the mapping (valid until
+ * sdm_safetensors_close), ready to be passed to sdm_load_weights.  dtype: 0 = F32, 1 = F16, 2 = BF16, -1 = anything else
+ * (not a weight of this model); ndim is the tensor's true rank (shape[] holds at most the first four extents). */
+typedef struct sdm_safetensors sdm_safetensors;
+int sdm_safetensors_open(const char* path, sdm_safetensors** out);
+int sdm_safetensors_count(const sdm_safetensors* f);
+int sdm_safetensors_entry(sdm_safetensors* f, int i, sdm_tensor_desc* out);
+void sdm_safetensors_close(sdm_safetensors* f);
+
 /* Workspace the caller must provide for a (B, R) forward; R in {64k}, multiples of 64. */
 size_t sdm_workspace_bytes(sdm_handle* h, int B, int R);
 

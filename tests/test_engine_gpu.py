@@ -219,3 +219,26 @@ def test_key_compaction_is_transparent(pkg, ckpt, engine, R, B):
     _record(f"compact_on_off_R{R}_B{B}", max_abs=d.max().item(), mean_abs=d.mean().item())
     assert n_on == n_off + 17  # 16 gathers + the compaction kernel
     assert d.max().item() <= 4e-3 and d.mean().item() <= 5e-4
+
+
+def test_native_safetensors_load_equals_state_dict_load(pkg, ckpt, tmp_path):
+    """the engine loaded through the native .safetensors reader (header parse + mmap, repacked straight from the
+    mapping) produces the same bits as the engine loaded from the same tensors passed as a state dict."""
+    safetensors_torch = pytest.importorskip("safetensors.torch")
+    from oracle import synth
+
+    sd16 = {k: v.half().contiguous() for k, v in ckpt.items()}  # fp16 file: half the bytes on disk, same path through the loader
+    path = str(tmp_path / "SDMatte_synth.safetensors")
+    safetensors_torch.save_file(sd16, path)
+    image, trimap = synth.make_inputs(1, 64, seed=17)
+    a = pkg.engine.Engine(0)
+    used_a, _ = a.load_state_dict(sd16)
+    alpha_a = a.forward(image.cuda(), trimap.cuda(), False).clone()
+    a.close()
+    b = pkg.engine.Engine(0)
+    used_b, unexpected_b = b.load_safetensors(path)
+    alpha_b = b.forward(image.cuda(), trimap.cuda(), False).clone()
+    b.close()
+    os.remove(path)
+    assert used_a == used_b and unexpected_b == 0
+    assert torch.equal(alpha_a, alpha_b)

@@ -59,6 +59,23 @@ def test_attention_scores_match_reference(lifted):
     np.testing.assert_allclose(probs0.numpy(), lifted["att_probs_nomask"], rtol=1e-5, atol=1e-7)
 
 
+def test_key_compaction_drops_only_exact_zero_probabilities(lifted):
+    """The engine's attn1 streams only the keys with bias >= max(bias) - 2500 (key_compact_kernel).  Against the output of the
+    reference's OWN custom_get_attention_scores (golden `att_probs`, replace.py:75-122): every dropped key has probability
+    exactly 0.0 there, and the softmax over the kept keys alone reproduces the reference's probabilities of those keys."""
+    q, k = torch.from_numpy(lifted["att_q"]), torch.from_numpy(lifted["att_k"])
+    m1 = torch.from_numpy(lifted["att_m1"])                  # (B*heads, 1, L) additive mask: 0 / -5000 / -10000
+    probs = torch.from_numpy(lifted["att_probs"])            # (B*heads, Lq, L)
+    keep = m1 >= m1.max(dim=-1, keepdim=True).values - 2500.0
+    assert 0 < keep.float().mean().item() < 1                # the golden trimap has foreground AND non-foreground keys
+    assert (probs[(~keep).expand_as(probs)] == 0).all(), "a dropped key has a non-zero probability in the reference"
+    scale = 8 ** -0.5
+    for i in range(q.shape[0]):
+        kk = keep[i, 0]
+        sub = (torch.matmul(q[i], k[i][kk].t()) * scale + m1[i, :, kk]).softmax(-1)
+        np.testing.assert_allclose(sub.numpy(), probs[i][:, kk].numpy(), rtol=1e-5, atol=1e-7)
+
+
 def test_unet_surgery_semantics(lifted):
     """replace_unet_conv_in / add_aux_conv_in (utils.py:13-41): conv_in becomes 8-ch = tiled weights / 2; aux_conv_in 4->1024."""
     w = lifted["sur_w_before"]
