@@ -526,6 +526,7 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
             // of branched around, so the accumulators stay in place (the branchy form cost 16 register moves per row).
             auto store_rows = [&](auto with_stats) {
               constexpr bool WITH_STATS = decltype(with_stats)::value;
+              (void)WITH_STATS;  // unused in the UPS2 instantiations
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int rl = i * 4 + t_row0;
