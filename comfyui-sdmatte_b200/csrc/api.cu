@@ -135,6 +135,9 @@ int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream) {
 }
 
 int sdm_k_conv_tiles_per_image(int Hout, int Wout) { return sdm::conv_gemm_tiles_per_image(Hout, Wout); }
+int sdm_k_conv_variant(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout) {
+  return sdm::conv_gemm_variant_code(ksize, stride, mode, ups2, N, has_res, Hout, Wout);
+}
 
 int sdm_k_attention(const sdm_attn_args* a, uintptr_t stream) {
   SDM_API_BEGIN

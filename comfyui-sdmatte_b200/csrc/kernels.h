@@ -55,6 +55,9 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st);
 void conv_gemm_set_outputs(ConvGemmLaunch& l, void* out, void* out2);  // run-time output slots (EPI_ALPHA)
 double conv_gemm_flops(const ConvGemmLaunch& l);
 int conv_gemm_tiles_per_image(int Hout, int Wout);  // number of 128-pixel M tiles per batch element
+// kernel variant the engine uses for a conv of this per-sample geometry (no batch size in the signature, on purpose):
+// 0 = one TMA box per tap, 1 / 2 = resident halo tile with 256- / 160-wide tiles, 3 = swapped operands
+int conv_gemm_variant_code(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout);
 
 // ------------------------------------------------------------------ flash attention (d = 64)
 struct AttnDesc {

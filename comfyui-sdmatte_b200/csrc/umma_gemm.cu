@@ -80,6 +80,44 @@ static const __half* identity_matrix() {
   return m;
 }
 
+// Kernel variant of a 3x3 stride-1 conv, decided from the per-sample GEOMETRY only: neither the batch size nor the SM count is
+// an argument.  The variants differ in K order (halo: slice-major with the taps inner; the others tap-major) and in how pixels
+// are grouped into GroupNorm-partials slots, and a sample must produce the same bits alone and inside a batch
+// (test_batch_independence_and_determinism; tests/test_oracle_cpu.py::test_conv_variant_is_a_function_of_geometry).
+struct ConvVariant {
+  bool swap_can = false, swap = false;      // conv_swap_kernel possible / selected
+  bool halo_geom = false, halo_auto = false;  // resident-halo patches fit / selected without a force flag
+  int halo_bn = 0;                          // tile width of the halo kernel by N alone (256 | 160 | 0 = none)
+};
+static ConvVariant conv3x3_variant(int ksize, int stride, int mode, bool light, int ups2, bool batched_w, int N, int n_store, bool has_res,
+                                   int Hout, int Wout, int force_swap, int force_halo, int force_pair, int force_block_n, int force_mt) {
+  ConvVariant v;
+  const bool conv3 = ksize == 3 && stride == 1 && mode == EPI_F16 && !light && (n_store == 0 || n_store == N);
+  int tw = 128, th = 1;
+  pick_patch(Hout, Wout, tw, th);
+  const long long tiles_img = (long long)((Wout + tw - 1) / tw) * ((Hout + th - 1) / th);  // default patch, per sample
+  // swapped operands (conv_swap.cu; SDM_SWAP=0 for A/B, force_swap = 1 / -1 from the tests): 16 x 16 pixel patches, two
+  // GroupNorm-partials slots per patch -> only where that equals the default slot count
+  static const int env_swap = [] { const char* e = getenv("SDM_SWAP"); return e ? atoi(e) : 1; }();
+  v.swap_can = conv3 && !ups2 && !batched_w && N % 128 == 0 && Hout >= 16 && Wout >= 16 &&
+               2ll * ((Wout + 15) / 16) * ((Hout + 15) / 16) == tiles_img && (!has_res || N <= kIdentityN);
+  v.swap = v.swap_can && force_pair != 1 && force_halo != 1 &&
+           (force_swap == 1 || (force_swap == 0 && env_swap != 0 && N == 128 && force_block_n == 0 && force_mt == 0));
+  // resident halo tile (SDM_HALO=0: one TMA box per tap; force_halo = 1 / -1 from the tests): 8 x 16 pixel patches, used where that
+  // gives the default number of M tiles (the slot count conv_gemm_tiles_per_image must not depend on the kernel choice).
+  // Tile width by N alone: 256 | 160 (the small-problem narrowing of pick_block_n depends on the batch size).
+  static const int env_halo = [] { const char* e = getenv("SDM_HALO"); return e ? atoi(e) : 1; }();
+  v.halo_geom = conv3 && !v.swap && Hout >= 16 && Wout >= 8 && (long long)((Wout + 7) / 8) * ((Hout + 15) / 16) == tiles_img;
+  v.halo_bn = N % 256 == 0 ? 256 : (N % 160 == 0 ? 160 : 0);
+  v.halo_auto = v.halo_geom && v.halo_bn != 0 && force_halo == 0 && env_halo != 0 && force_block_n == 0 && force_mt == 0 && force_pair != 1;
+  return v;
+}
+// 0 = one TMA box per tap (conv_gemm_kernel), 1 / 2 = resident halo with 256- / 160-wide tiles, 3 = swapped operands
+int conv_gemm_variant_code(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout) {
+  const ConvVariant v = conv3x3_variant(ksize, stride, mode, false, ups2, false, N, 0, has_res != 0, Hout, Wout, 0, 0, 0, 0, 0);
+  return v.swap ? 3 : (v.halo_auto ? (v.halo_bn == 256 ? 1 : 2) : 0);
+}
+
 std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_sms) {
   auto L = std::make_shared<ConvGemmLaunch>();
   ConvGemmParams& p = L->p;
@@ -108,26 +146,13 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   (void)light_ok;  // measured (r1i): the two-CTAs-per-SM config is slower than 160/256-wide tiles -> only on request
   const bool light = d.force_light == 1;
   L->light = light;
-  // ---- kernel variant of the 3x3 stride-1 convs: decided from the per-sample GEOMETRY only (never from the batch size), because
-  // the variants differ in K order (halo: slice-major, taps inner) and in how pixels are grouped into GroupNorm-partials slots:
-  // a sample must produce the same bits alone and inside a batch (test_batch_independence_and_determinism).
-  const bool conv3 = d.ksize == 3 && d.stride == 1 && d.mode == EPI_F16 && !light && (d.n_store == 0 || d.n_store == d.N);
-  const long long tiles_img = (long long)p.tiles_x * p.tiles_y;  // default patch, per sample
-  // swapped operands (conv_swap.cu; SDM_SWAP=0 for A/B, force_swap = 1 / -1 from the tests): 16 x 16 pixel patches, two
-  // GroupNorm-partials slots per patch -> only where that equals the default slot count
-  static const int env_swap = [] { const char* e = getenv("SDM_SWAP"); return e ? atoi(e) : 1; }();
-  const bool swap_can = conv3 && !d.ups2 && !d.w_bstride && d.N % 128 == 0 && Hout >= 16 && Wout >= 16 &&
-                        2ll * ((Wout + 15) / 16) * ((Hout + 15) / 16) == tiles_img && (!d.res || d.N <= kIdentityN);
-  if (d.force_swap == 1) SDM_CHECK(swap_can, "force_swap: configuration not supported by the swapped-operand kernel");
-  L->swap = swap_can && d.force_pair != 1 && d.force_halo != 1 &&
-            (d.force_swap == 1 || (d.force_swap == 0 && env_swap != 0 && d.N == 128 && d.force_block_n == 0 && d.force_mt == 0));
-  // resident halo tile (SDM_HALO=0: one TMA box per tap; force_halo = 1 / -1 from the tests): 8 x 16 pixel patches, used where that
-  // gives the default number of M tiles (the slot count conv_gemm_tiles_per_image must not depend on the kernel choice).
-  // Tile width by N alone: 256 | 160 (the small-problem narrowing of pick_block_n depends on the batch size).
-  static const int env_halo = [] { const char* e = getenv("SDM_HALO"); return e ? atoi(e) : 1; }();
-  const bool halo_geom = conv3 && !L->swap && Hout >= 16 && Wout >= 8 && (long long)((Wout + 7) / 8) * ((Hout + 15) / 16) == tiles_img;
-  const int halo_bn = d.N % 256 == 0 ? 256 : (d.N % 160 == 0 ? 160 : 0);
-  const bool halo_auto = halo_geom && halo_bn != 0 && d.force_halo == 0 && env_halo != 0 && d.force_block_n == 0 && d.force_mt == 0 && d.force_pair != 1;
+  // ---- kernel variant of the 3x3 stride-1 convs: conv3x3_variant() sees the per-sample geometry only
+  const ConvVariant cv = conv3x3_variant(d.ksize, d.stride, d.mode, light, d.ups2, d.w_bstride != 0, d.N, d.n_store, d.res != nullptr, Hout, Wout,
+                                         d.force_swap, d.force_halo, d.force_pair, d.force_block_n, d.force_mt);
+  if (d.force_swap == 1) SDM_CHECK(cv.swap_can, "force_swap: configuration not supported by the swapped-operand kernel");
+  L->swap = cv.swap;
+  const bool halo_geom = cv.halo_geom, halo_auto = cv.halo_auto;
+  const int halo_bn = cv.halo_bn;
   const int bn = light ? 128 : (halo_auto ? halo_bn : (d.force_block_n ? d.force_block_n : pick_block_n(d.N, d.mode, m_tiles, num_sms)));
   if (d.mode == EPI_GEGLU) SDM_CHECK(bn == 256 && d.N % 256 == 0, "GEGLU needs N % 256 == 0");
   L->block_n = bn;

@@ -67,7 +67,7 @@ EXPORTS = [
     "sdm_version", "sdm_last_error", "sdm_create", "sdm_destroy", "sdm_load_weights", "sdm_load_report",
     "sdm_workspace_bytes", "sdm_forward", "sdm_forward_host", "sdm_forward_profiled", "sdm_profile_count", "sdm_profile_entry",
     "sdm_last_forward_stats", "sdm_debug_tensor", "sdm_preprocess", "sdm_postprocess",
-    "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
+    "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_conv_variant", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
     "sdm_k_softmax_rows", "sdm_k_direct_conv", "sdm_k_key_compact", "sdm_k_gather_rows", "sdm_k_probe_halo",
     "sdm_safetensors_open", "sdm_safetensors_count", "sdm_safetensors_entry", "sdm_safetensors_close",
 ]
@@ -431,6 +431,13 @@ def k_probe_halo(x, eye, out, dy, dx, mode):
 def k_gather_rows(src, dst, idx, ntiles, *, B, L, C_, idx_bstride):
     _check(load_library().sdm_k_gather_rows(src.data_ptr(), dst.data_ptr(), idx.data_ptr(), ntiles.data_ptr(), B, L, C_, idx_bstride,
                                            _stream_ptr(src.device)))
+
+
+def conv_variant(ksize, stride, N, H, W, *, mode=0, ups2=0, has_res=0):
+    """Kernel variant for a conv of this per-sample geometry: 0 tap-per-box, 1 / 2 halo (256 / 160 wide), 3 swapped operands."""
+    lib = load_library()
+    lib.sdm_k_conv_variant.argtypes = [C.c_int] * 8
+    return lib.sdm_k_conv_variant(ksize, stride, mode, ups2, N, has_res, H, W)
 
 
 def conv_tiles_per_image(H, W):

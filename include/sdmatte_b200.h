@@ -126,6 +126,10 @@ typedef struct {
 } sdm_conv_gemm_args;
 int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream);
 int sdm_k_conv_tiles_per_image(int Hout, int Wout);
+/* Kernel variant the engine picks for a conv of this PER-SAMPLE geometry (host logic only; the batch size is not an argument
+   on purpose: a sample must give the same bits alone and in a batch).  mode as in sdm_conv_gemm_args.
+   0 = one TMA box per tap, 1 / 2 = resident halo tile with 256- / 160-wide tiles, 3 = swapped operands (conv_swap_kernel) */
+int sdm_k_conv_variant(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout);
 
 typedef struct {
   int B, heads, Lq, Lk;

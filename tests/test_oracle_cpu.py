@@ -174,6 +174,36 @@ def test_cabi_exports_every_declared_symbol():
     assert lib.sdm_version() >= 100
 
 
+def test_conv_variant_is_a_function_of_geometry(pkg):
+    """The engine's choice between the tap-per-box, resident-halo and swapped-operand 3x3 kernels (they differ in K order and in
+    the GroupNorm-partials grouping, i.e. in output bits) is host logic with NO batch size in its signature, so a sample gives
+    the same bits alone and in a batch.  Pin the choice for every 3x3 conv geometry of the model at all node resolutions."""
+    E = pkg.engine
+    for R in (512, 640, 768, 896, 1024):
+        S = R // 8
+        # VAE: 128 ch @R, 256 @R/2, 512 @R/4 and R/8 (encoder and decoder); decoder upsample convs at 2x of the 512 / 512 / 256 levels
+        assert E.conv_variant(3, 1, 128, R, R, has_res=1) == 3, R          # swapped operands (channels on M)
+        assert E.conv_variant(3, 1, 128, R, R) == 3
+        assert E.conv_variant(3, 1, 256, R // 2, R // 2, has_res=1) == 1   # resident halo, 256-wide tiles
+        assert E.conv_variant(3, 1, 512, R // 4, R // 4) == 1
+        assert E.conv_variant(3, 1, 512, R // 8, R // 8, ups2=1) == 1
+        assert E.conv_variant(3, 1, 256, R, R) == 1
+        # UNet: 320 @S, 640 @S/2 (160-wide tiles), 1280 @S/4
+        assert E.conv_variant(3, 1, 320, S, S) == 2
+        assert E.conv_variant(3, 1, 640, S // 2, S // 2, has_res=1) == 2
+        # 1280 ch @S/4, S/8: halo where the 8 x 16 patches tile the grid like the default patch does (same GroupNorm slot count)
+        assert E.conv_variant(3, 1, 1280, S // 4, S // 4) in (0, 1)
+        assert E.conv_variant(3, 1, 1280, S // 8, S // 8) == (1 if S // 8 == 16 else 0)  # below 16 rows: no halo patch
+        # everything else keeps one TMA box per tap
+        assert E.conv_variant(3, 2, 320, S, S) == 0       # Downsample2D
+        assert E.conv_variant(1, 1, 256, R // 2, R // 2) == 0   # 1x1 shortcut
+        assert E.conv_variant(3, 1, 8, S, S) == 0         # skinny outputs
+        assert E.conv_variant(3, 1, 256, R // 2, R // 2, mode=3) == 0  # only the fp16 epilogue has the variants
+    assert E.conv_variant(3, 1, 1280, 32, 32) == 1 and E.conv_variant(3, 1, 1280, 20, 20) == 0  # R = 1024 / 640 at S/4
+    for hw in (8, 12):  # tiny latents (tests at R = 64 / 96): no variant kernel
+        assert E.conv_variant(3, 1, 1280, hw, hw) == 0 and E.conv_variant(3, 1, 128, hw, hw) == 0
+
+
 def test_no_cpu_fallback_and_no_oracle_on_product_path():
     import __graft_entry__ as ge
 
