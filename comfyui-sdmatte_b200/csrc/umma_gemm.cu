@@ -83,7 +83,7 @@ static const __half* identity_matrix() {
 // Kernel variant of a 3x3 stride-1 conv, decided from the per-sample GEOMETRY only: neither the batch size nor the SM count is
 // an argument.  The variants differ in K order (halo: slice-major with the taps inner; the others tap-major) and in how pixels
 // are grouped into GroupNorm-partials slots, and a sample must produce the same bits alone and inside a batch
-// (test_batch_independence_and_determinism; tests/test_oracle_cpu.py::test_conv_variant_is_a_function_of_geometry).
+// (test_batch_independence_and_determinism on the GPU, test_conv_variant_is_a_function_of_geometry in the CPU suite).
 struct ConvVariant {
   bool swap_can = false, swap = false;      // conv_swap_kernel possible / selected
   bool halo_geom = false, halo_auto = false;  // resident-halo patches fit / selected without a force flag
