@@ -1,0 +1,218 @@
+// STAGED FOR THE NEXT ROUND — compiled, reachable only with SDM_SWAP_HALO=1, NOT yet run on hardware (written after this
+// round's GPU budget was spent).  The default path never launches it.
+//
+// conv_swap_kernel (channels on the MMA's M, 256 pixels on N) with a RESIDENT PIXEL HALO TILE: per 64-channel slice ONE TMA box
+// of (8+2) x (32+2) pixels is fetched, and the nine taps are nine B-operand descriptors of that tile started (dy*10 + dx) pixel
+// rows later with SBO = 10 rows (1280 B) — the mechanism tests/probe_halo.py verified for A operands (the 128-byte swizzle
+// is a function of absolute shared-memory address bits).  conv_swap_kernel is bound by the L2 -> shared-memory fill (48 KB per
+// K step, ~51 B/clk/SM measured); here the fill per slice is 43.5 KB + 9 x 16 KB of weights instead of 9 x 48 KB.
+// Tile = 8 wide x 32 tall pixel patch (N = 256 = 32 groups of 8 rows) x 128 output channels; GroupNorm partials: two slots per
+// patch (128 pixels each), as in conv_swap_kernel.
+#include "umma_gemm.cuh"
+
+namespace sdm {
+
+namespace swh {
+constexpr int kWBytes = 128 * 128;    // weight tile: 128 channels x 64 k (fp16)
+constexpr int kWStages = 6;
+constexpr int kXSlot = 44 * 1024;     // halo tile: 10 x 34 pixel rows of 128 B = 43 520 B, rounded up to the 1024-byte swizzle atom
+constexpr int kXTx = 10 * 34 * 128;   // bytes one halo box delivers
+constexpr int kXDense = 256 * 128;    // residual: dense 8 x 32 box
+constexpr int kXSlots = 2;
+constexpr int kStgBytes = 4 * 2048;
+constexpr int kPipe = kWStages * kWBytes + kXSlots * kXSlot;
+constexpr int kSmem = kPipe + 1024 + 256 + kStgBytes;
+constexpr int kThreads = 192;
+static_assert(kSmem <= 232448, "shared memory budget");
+}  // namespace swh
+
+__global__ void __launch_bounds__(swh::kThreads, 1) conv_swap_halo_kernel(const __grid_constant__ ConvGemmParams p) {
+  using namespace swh;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t x_base = smem_base + kWStages * kWBytes;
+  const uint32_t bar_base = smem_base + kPipe;
+  auto wfull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto wempty_bar = [&](int s) { return bar_base + 8u * (kWStages + s); };
+  auto xfull_bar = [&](int s) { return bar_base + 8u * (2 * kWStages + s); };
+  auto xempty_bar = [&](int s) { return bar_base + 8u * (2 * kWStages + 2 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kWStages + 4 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kWStages + 6 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kWStages + 8);
+  static_assert(8 * (2 * kWStages + 8) + 4 <= 256, "barrier area");
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWStages; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
+    for (int s = 0; s < kXSlots; ++s) { mbar_init(xfull_bar(s), 1); mbar_init(xempty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int nres = p.has_res ? 2 : 0;
+  int nslices = 0;
+  for (int s = 0; s < p.nsrc; ++s) nslices += p.src_c[s] >> 6;
+  const int per_image = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      tma_prefetch_desc(&p.a_map[0]); tma_prefetch_desc(&p.a_map[1]); tma_prefetch_desc(&p.b_map);
+      int ws = 0, xs = 0;
+      uint32_t wph = 0, xph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles) * 128;
+        const int mt = tile / p.n_tiles;
+        const int t_img = mt % per_image;
+        const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32, b = mt / per_image;
+        int coff = 0;
+        for (int s = 0; s < p.nsrc; ++s) {
+          for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
+            mbar_wait(xempty_bar(xs), xph ^ 1u);
+            mbar_expect_tx(xfull_bar(xs), kXTx);
+            tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, x0 - 1, y0 - 1, b);  // zero fill = conv padding
+            if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(wempty_bar(ws), wph ^ 1u);
+              mbar_expect_tx(wfull_bar(ws), kWBytes);
+              tma_load_2d(smem_base + ws * kWBytes, &p.b_map, wfull_bar(ws), tap * p.cin_total + coff + c0, n0);
+              if (++ws == kWStages) { ws = 0; wph ^= 1u; }
+            }
+          }
+          coff += p.src_c[s];
+        }
+        for (int i = 0; i < nres; ++i) {  // D^T[c][pix] += I[c][64 i + k] . R[pix][n0 + 64 i + k]: dense residual box in a halo slot
+          mbar_wait(xempty_bar(xs), xph ^ 1u);
+          mbar_expect_tx(xfull_bar(xs), kXDense);
+          tma_load_4d(x_base + xs * kXSlot, &p.r_map, xfull_bar(xs), n0 + 64 * i, x0, y0, b);
+          if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
+          mbar_wait(wempty_bar(ws), wph ^ 1u);
+          mbar_expect_tx(wfull_bar(ws), kWBytes);
+          tma_load_2d(smem_base + ws * kWBytes, &p.i_map, wfull_bar(ws), 64 * i, 0);
+          if (++ws == kWStages) { ws = 0; wph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(256);
+      int ws = 0, xs = 0, acc = 0;
+      uint32_t wph = 0, xph = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int sl = 0; sl < nslices + nres; ++sl) {
+          mbar_wait(xfull_bar(xs), xph);
+          const uint32_t x_addr = x_base + xs * kXSlot;
+          const bool resid = sl >= nslices;
+          const int ntap = resid ? 1 : 9;
+          for (int tap = 0; tap < ntap; ++tap) {
+            mbar_wait(wfull_bar(ws), wph);
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_k128(smem_base + ws * kWBytes);
+            const uint64_t bdesc = resid ? umma_desc_k128(x_addr)
+                                         : umma_desc_k128_sbo(x_addr + (uint32_t)((tap / 3) * 10 + tap % 3) * 128u, 1280);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (sl | tap | k) != 0);
+            umma_commit(wempty_bar(ws));
+            if (++ws == kWStages) { ws = 0; wph ^= 1u; }
+          }
+          umma_commit(xempty_bar(xs));
+          if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ============================== epilogue: thread = output channel; column j = pixel (y = j / 8, x = j % 8) ==============
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    uint8_t* stg = smem_raw + (bar_base - smem_u32(smem_raw)) + 256 + (warp - 2) * 2048;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int n0 = (tile % p.n_tiles) * 128;
+      const int mt = tile / p.n_tiles;
+      const int t_img = mt % per_image;
+      const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32, b = mt / per_image;
+      const float bias = p.bias ? p.bias[(p.bias_sel ? (long long)p.bias_sel[b] * p.N : 0) + n0 + m] : 0.f;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256;
+      __half* obase = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + n0 + quad * 32;
+      float sum = 0.f, sq = 0.f;
+      uint32_t ra[32], rb[32];
+      // one block = 32 pixels = patch rows 4 blk .. 4 blk + 3, held in r; `nxt` receives the following block meanwhile
+      auto block = [&](const uint32_t (&r)[32], uint32_t (&nxt)[32], int blk) {
+        tmem_ld_wait();
+        __syncwarp();
+        if (blk + 1 < 8) tmem_ld32(taddr + (blk + 1) * 32, nxt);
+        const int ya = y0 + 4 * blk;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const __half h = __float2half_rn(fmaf(__uint_as_float(r[i]), p.scale, bias));
+          const bool ok = (x0 + (i & 7) < p.W) && (ya + (i >> 3) < p.H);
+          const float f = ok ? __half2float(h) : 0.f;
+          sum += f;
+          sq = fmaf(f, f, sq);
+          *reinterpret_cast<__half*>(stg + i * 64 + lane * 2) = h;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int idx = lane + 32 * t;
+          const int px = idx >> 2, piece = idx & 3;
+          const int xx = x0 + (px & 7), yy = ya + (px >> 3);
+          const uint4 v = *reinterpret_cast<const uint4*>(stg + px * 64 + piece * 16);
+          if (xx < p.W && yy < p.H) *reinterpret_cast<uint4*>(obase + ((long long)yy * p.W + xx) * p.out_ld + piece * 8) = v;
+        }
+        if (p.stats && (blk & 3) == 3) {
+          const long long slot = (long long)b * (2 * per_image) + 2 * t_img + (blk >> 2);
+          *reinterpret_cast<float2*>(p.stats + (slot * p.N + n0 + m) * 2) = make_float2(sum, sq);
+          sum = 0.f;
+          sq = 0.f;
+        }
+      };
+      __syncwarp();
+      tmem_ld32(taddr, ra);
+#pragma unroll 1
+      for (int b2 = 0; b2 < 4; ++b2) {
+        block(ra, rb, 2 * b2);
+        block(rb, ra, 2 * b2 + 1);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+void conv_swap_halo_launch(const ConvGemmParams& p, int grid, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::kSmem));
+    attr = true;
+  }
+  conv_swap_halo_kernel<<<grid, swh::kThreads, swh::kSmem, st>>>(p);
+  SDM_CUDA_OK(cudaGetLastError());
+}
+
+}  // namespace sdm

@@ -10,7 +10,8 @@
 
 namespace sdm {
 
-void conv_swap_launch(const ConvGemmParams& p, int grid, cudaStream_t st);  // conv_swap.cu
+void conv_swap_launch(const ConvGemmParams& p, int grid, cudaStream_t st);       // conv_swap.cu
+void conv_swap_halo_launch(const ConvGemmParams& p, int grid, cudaStream_t st);  // conv_swap_halo.cu (staged, SDM_SWAP_HALO=1)
 
 struct ConvGemmLaunch {
   ConvGemmParams p;
@@ -21,6 +22,7 @@ struct ConvGemmLaunch {
   bool pair = false;  // CTA-pair (cta_group::2) kernel
   bool halo = false;  // 3x3 stride-1 conv with a resident halo tile per 64-channel slice
   bool swap = false;  // conv_swap_kernel: channels on M, 256 pixels on N (128-channel 3x3 convs)
+  bool swap_halo = false;  // ... with a resident 8 x 32 pixel halo tile (staged for the next round, SDM_SWAP_HALO=1)
   int grid = 0;
   double flops = 0;
 };
@@ -183,9 +185,14 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   }
   long long m_tiles_eff = m_tiles;
   if (L->swap) {
-    p.tw = 16; p.th = 16;
-    p.tiles_x = (Wout + 15) / 16;
-    p.tiles_y = (Hout + 15) / 16;
+    // staged (not yet run on hardware): resident 8 x 32 halo tile, only on request and where the patch count matches
+    static const int env_swap_halo = [] { const char* e = getenv("SDM_SWAP_HALO"); return e ? atoi(e) : 0; }();
+    L->swap_halo = env_swap_halo != 0 && Hout >= 32 && Wout >= 8 &&
+                   2ll * ((Wout + 7) / 8) * ((Hout + 31) / 32) == (long long)p.tiles_x * p.tiles_y;
+    p.tw = L->swap_halo ? 8 : 16;
+    p.th = L->swap_halo ? 32 : 16;
+    p.tiles_x = (Wout + p.tw - 1) / p.tw;
+    p.tiles_y = (Hout + p.th - 1) / p.th;
     m_tiles_eff = (long long)p.tiles_x * p.tiles_y * d.B;
     L->mt = 1;
     L->block_n = 128;
@@ -208,7 +215,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
       const uint64_t dims[4] = {(uint64_t)d.src[s].C, (uint64_t)d.Win, (uint64_t)d.Hin, (uint64_t)d.B};
       const uint64_t strides[3] = {(uint64_t)d.src[s].ld * 2, (uint64_t)d.Win * d.src[s].ld * 2, (uint64_t)bs * 2};
       const uint32_t hbox[4] = {64u, (uint32_t)p.tw + 2u, (uint32_t)p.th + 2u, 1u};  // halo: (8+2) x (16+2) pixels, loaded at (x0-1, y0-1)
-      make_tmap(&p.a_map[s], d.src[s].ptr, 4, dims, strides, L->halo ? hbox : box);
+      make_tmap(&p.a_map[s], d.src[s].ptr, 4, dims, strides, (L->halo || L->swap_halo) ? hbox : box);
     }
     for (int s = d.nsrc; s < 4; ++s) p.a_map[s] = p.a_map[0];
     for (int t = 0; t < p.ntaps; ++t) {
@@ -327,7 +334,7 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
     if (l.ewg == 2) return conv_gemm_launch<BN, MT, MODE, UPS2, false, 2>(p, g, st); \
     return conv_gemm_launch<BN, MT, MODE, UPS2, false, 1>(p, g, st);                 \
   } while (0)
-  if (l.swap) return conv_swap_launch(p, g, st);
+  if (l.swap) return l.swap_halo ? conv_swap_halo_launch(p, g, st) : conv_swap_launch(p, g, st);
   if (l.pair) return conv_gemm_launch_pair<128, EPI_F16>(p, g, st);
   if (l.halo) {
     if (bn == 256 && !p.ups2) return conv_gemm_launch_halo<256, 1, false, 1>(p, g, st);
