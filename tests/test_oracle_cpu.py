@@ -204,6 +204,26 @@ def test_conv_variant_is_a_function_of_geometry(pkg):
         assert E.conv_variant(3, 1, 1280, hw, hw) == 0 and E.conv_variant(3, 1, 128, hw, hw) == 0
 
 
+def test_conv_variant_keeps_the_groupnorm_slot_count(pkg):
+    """The conv epilogues write one GroupNorm-partials slot per 128 output pixels into a buffer sized by
+    sdm_k_conv_tiles_per_image(H, W) (default patch).  The halo kernel (8 x 16 patches) and the swapped-operand kernel (16 x 16
+    patches, two slots each) must cover exactly that many slots wherever the engine selects them."""
+    E = pkg.engine
+    checked = 0
+    for H in range(8, 1025, 8):
+        for W in {H, max(8, H // 2), min(1024, H + 24)}:
+            slots = E.conv_tiles_per_image(H, W)
+            for N in (128, 256, 320, 512, 640, 1280):
+                v = E.conv_variant(3, 1, N, H, W)
+                if v == 3:
+                    assert 2 * (-(-W // 16)) * (-(-H // 16)) == slots, (H, W, N)
+                    checked += 1
+                elif v in (1, 2):
+                    assert (-(-W // 8)) * (-(-H // 16)) == slots, (H, W, N)
+                    checked += 1
+    assert checked > 500
+
+
 def test_no_cpu_fallback_and_no_oracle_on_product_path():
     import __graft_entry__ as ge
 
