@@ -1,20 +1,28 @@
 #!/usr/bin/env python
 """bench.py — mattes/sec of the SDMatte single-pass matte path at 1024^2, bs=8 per GPU (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            # B200 engine (this repo)
-  python bench.py --impl reference [--gpus N] --steps K --warmup W   # the reference graph on the host CPU (oracle port)
+  python bench.py [--gpus N] [--steps K] [--warmup W]                  # B200 engine (this repo)
+  python bench.py --impl reference [--gpus N] --steps K --warmup W     # the reference graph on the host CPU (oracle port)
+  python bench.py --size 768 --batch 8 / --batch 1 / --trimap allfg / --graph 0      # other BASELINE configs, A/B switches
 
-One "step" = one pass of the hot path over one batch of 8 synthetic 1024x1024 RGB+trimap inputs per GPU.
-N > 1: launched by torchrun, one rank per GPU, batch-sharded (weak scaling: 8 mattes per GPU), one NCCL all-gather of
+One "step" = one pass of the hot path over one batch of `--batch` synthetic `--size`^2 RGB+trimap inputs per GPU.
+N > 1: launched by torchrun, one rank per GPU, batch-sharded (weak scaling: `--batch` mattes per GPU), one NCCL all-gather of
 the fp16 alpha per step (north_star); timing = CUDA events, barrier + synchronize on both sides, max over ranks.
 
 JSON keys beyond the base contract:
-  roofline     : the dominant kernel family (tcgen05 implicit-GEMM conv/linear): achieved = algorithmic FLOPs / CUDA-event time
-                 of those launches inside one profiled step; peak = MEASURED_PEAKS.json bf16 sustained TFLOP/s.
-  path_roofline: whole step: B * 28.785 TFLOP (SURVEY.md §8d, R=1024) / step time / sustained peak.
+  roofline      : the dominant kernel family, the tcgen05 3x3 convolutions (half of the step): achieved = algorithmic FLOPs of
+                  those launches / their CUDA-event time inside one profiled step; peak = MEASURED_PEAKS.json bf16 sustained;
+                  traffic = ncu dram bytes per launch of the same family (profiles/r2_traffic.json, captured by
+                  profiles/scripts/run_r2_traffic.sh) or null.
+  gemm_roofline : same for all non-attention tcgen05 kernels (round 1's `roofline`).
+  path_roofline : whole step: B * TFLOP(R) / step time / sustained peak.
   kernel_breakdown: per kernel family ms / share / achieved TFLOP/s or GB/s (from the same profiled step).
-  cpu_baseline : the oracle (torch fp32 restatement of the reference graph, kind "port") timed on the host cores.
-  e2e          : same metric through the host-buffer C-ABI call (pinned host inputs, H2D + forward + D2H of alpha).
+  e2e           : same metric through the NODE: SDMatteApply.apply_matte(..., mask_refine=True) with pageable ComfyUI-style host
+                  tensors in and host tensors out (staging + H2D + forward + post-processing + D2H inside the timed region).
+  gpu_baseline  : the real competitor: the reference graph under torch.autocast(fp16) with
+                  SlicedAttnProcessor(1) semantics (oracle mode "autocast": cuDNN / cuBLAS) on the SAME B200, CUDA events.
+  cpu_baseline  : the oracle (torch fp32 restatement of the reference graph, kind "port") timed on the host cores.
+  worst_case    : the same step with an all-foreground trimap (attn1 streams 100 % of the keys instead of ~30 %).
 """
 from __future__ import annotations
 
@@ -40,6 +48,16 @@ def measured_peaks():
         return {"tflops_sustained": d.get("bf16_tflops_sustained", 1438.8), "tflops_burst": d.get("bf16_tflops", 1677.1),
                 "hbm_gbs": d.get("hbm_gbs", 6566.1), "source": "measured"}
     return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def cpu_time_ratio_1024_over_512():
+    """Measured wall-time ratio of one 1024^2 (sliced attention) to one 512^2 matte of the CPU oracle on a gpurun host
+    (profiles/r2_cpu_1024.json, written by profiles/scripts/run_r2_cpu1024.sh); None if that measurement is not in the tree."""
+    p = os.path.join(ROOT, "profiles", "r2_cpu_1024.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["seconds_per_matte_1024"] / d["seconds_per_matte_512"], p
+    return None, None
 
 
 class ClockSampler:
@@ -98,9 +116,10 @@ def shard_range(total: int, rank: int, world: int):
     return rank * per, (rank + 1) * per
 
 
-def cpu_oracle_rate(R: int, n_mattes: int, threads: int, sd=None, min_seconds: float = 0.0, max_mattes: int = 16):
-    """Time the oracle (fp32, sliced attention at large R) on the host: at least `n_mattes` mattes and, when `min_seconds` is
-    given, as many more (up to `max_mattes`) as it takes to fill that much wall time.  Returns (mattes/s, seconds, description)."""
+def cpu_oracle_rate(R: int, n_mattes: int, threads: int, sd=None, min_seconds: float = 0.0, max_mattes: int = 16, max_seconds: float = 1e9):
+    """Time the oracle (fp32; sliced attention above 512^2, as the fp32 score tensor of one un-sliced L0 attention would be 5.4 GB)
+    on the host: at least one matte, at most `n_mattes`; stops early once `max_seconds` of wall time are spent, continues beyond
+    `n_mattes` (up to `max_mattes`) until `min_seconds` are filled.  Returns (mattes/s, seconds, mattes done, description)."""
     import torch
     from oracle import sdmatte_oracle as orc
     from oracle import synth
@@ -111,18 +130,25 @@ def cpu_oracle_rate(R: int, n_mattes: int, threads: int, sd=None, min_seconds: f
     image, trimap = synth.make_inputs(1, R, seed=0)
     t0 = time.perf_counter()
     done = 0
-    while done < n_mattes or (time.perf_counter() - t0 < min_seconds and done < max_mattes):
+    while True:
         orc.forward(sd, image, trimap, is_transparent=False, sliced=R > 512)
         done += 1
+        el = time.perf_counter() - t0
+        if el >= max_seconds:
+            break
+        if done >= n_mattes and (el >= min_seconds or done >= max_mattes):
+            break
     dt = time.perf_counter() - t0
-    return done / dt, dt, f"{done} matte(s) at {R}x{R}, fp32 torch CPU, {threads} threads"
+    return done / dt, dt, done, f"{done} matte(s) at {R}x{R}, fp32 torch CPU oracle, {threads} threads, {dt:.1f} s"
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU path does not run (hard-coded .cuda(), meta_arch.py:128; diffusers absent),
-    so this times the oracle port of the same graph on the host cores.  Each step = ONE matte (a bounded sample of the
-    bs=8 workload); if 1024^2 would not finish in a few minutes the sample resolution is reduced and the rate is converted
-    to 1024^2-equivalent mattes by the FLOP ratio of SURVEY.md §8(d) (stated in `sample`)."""
+    """--impl reference: the reference's own CPU path does not run as written (hard-coded .cuda(), meta_arch.py:128; diffusers is
+    absent), so this times the oracle port of the same graph on the host cores, on THE HEADLINE GEOMETRY: every step is one real
+    1024 x 1024 matte (one sample of the bs=8 batch; samples are independent, so a batch costs 8x) with per-head sliced attention.
+    One such matte takes minutes on 16-32 host cores, so the run is time-bounded: mattes are executed until `--ref-budget-s`
+    (default 240 s) is spent, at least one; `steps_executed` says how many of the K requested steps really ran and nothing is
+    extrapolated from another resolution."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -132,25 +158,52 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     sd = synth.make_checkpoint(seed=1234)
-    # bounded sample: ONE matte at --ref-size (default 512x512: 4-20 s on 8-16 host cores; a 1024^2 matte needs the sliced
-    # attention and 30 s to minutes) per step; the rate is converted to 1024^2-equivalent mattes by the algorithmic FLOP ratio.
-    R = args.ref_size
-    if args.warmup > 0:
-        cpu_oracle_rate(R, args.warmup, threads, sd)
-    rate, dt, desc = cpu_oracle_rate(R, args.steps, threads, sd)
-    equiv = rate * TFLOP_PER_MATTE[R] / TFLOP_PER_MATTE[1024]
-    sample = desc + ("" if R == 1024 else f"; converted to 1024^2-equivalent mattes by the FLOP ratio {TFLOP_PER_MATTE[R]}/{TFLOP_PER_MATTE[1024]} (SURVEY App. D model)")
+    R = args.ref_size or args.size
+    rate, dt, done, desc = cpu_oracle_rate(R, max(1, args.steps), threads, sd, max_seconds=args.ref_budget_s)
+    sample = (f"{desc}; each step = ONE matte of the bs={args.batch} batch at the workload's own resolution; {done} of {args.steps} requested "
+              f"steps executed (time-bounded at {args.ref_budget_s:.0f} s, no warm-up: a matte takes minutes)")
     line = {
-        "impl": "reference", "metric": "mattes/sec @1024^2 bs=8", "value": equiv, "unit": "mattes/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps), "higher_is_better": True,
+        "impl": "reference", "metric": f"mattes/sec @{args.size}^2 bs={args.batch}", "value": rate, "unit": "mattes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "steps_executed": done, "ms_per_step": 1000.0 * dt / done, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "bs=8 1024x1024 synthetic RGB+trimap, synthetic SDMatte checkpoint (seed 1234), is_transparent=False"},
-        "cpu_baseline": {"value": equiv, "unit": "mattes/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": equiv, "unit": "mattes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": f"bs={args.batch} {args.size}x{args.size} synthetic RGB+trimap, synthetic SDMatte checkpoint (seed 1234), is_transparent=False",
+                   "resolution": R},
+        "cpu_baseline": {"value": rate, "unit": "mattes/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "mattes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+def gpu_baseline(R: int, batches, dev, steps: int = 2):
+    """The competitor on the same GPU: the reference graph under a genuine torch.autocast(fp16) with per-(sample, head) sliced
+    attention (oracle mode "autocast" == sdmatte_nodes.py:331-358), fp32 master weights, cuDNN / cuBLAS kernels, CUDA events."""
+    import torch
+    from oracle import sdmatte_oracle as orc
+    from oracle import synth
+
+    sd = orc.to_device(synth.make_checkpoint(seed=1234), dev)
+    out = {"impl": "oracle graph, torch.autocast(cuda, fp16) + SlicedAttnProcessor(1) semantics, cuDNN/cuBLAS, inputs resident on the device",
+           "torch": torch.__version__, "resolution": R}
+    for B in batches:
+        image, trimap = synth.make_inputs(B, R, seed=1000)
+        img, tri = image.to(dev), trimap.to(dev)
+        orc.forward(sd, img, tri, mode="autocast", device=dev)  # warm-up (cuDNN autotune, allocator)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            orc.forward(sd, img, tri, mode="autocast", device=dev)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        out[f"bs{B}"] = {"ms_per_step": ms, "mattes_per_s": B / (ms * 1e-3), "steps": steps, "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2**30}
+        del img, tri
+        torch.cuda.empty_cache()
+    del sd
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_b200(args):
@@ -168,32 +221,38 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     pkg = ge.load_package()
+    nodes = pkg.sdmatte_nodes
 
     R, B = args.size, args.batch
     sd = synth.make_checkpoint(seed=1234)
-    eng = pkg.engine.Engine(dev)
-    eng.load_state_dict(sd)
+    nodes.register_state_dict("SDMatte.safetensors", sd)
+    nodes.set_devices([dev])
+    eng = nodes.get_engine("SDMatte.safetensors", dev)  # the same cached engine the node call uses
+    if not args.graph:
+        eng.set_option("cuda_graph", 0)
     del sd
     # global batch = world*B; this rank's shard (weak scaling: B per GPU)
     lo, hi = shard_range(world * B, rank, world)
     image, trimap = synth.make_inputs(B, R, seed=1000 + lo)
+    if args.trimap == "allfg":
+        trimap = torch.ones_like(trimap)
     # attn1 only streams the keys whose probability can be non-zero under the -10000 trimap bias (key_compact_kernel):
     # fraction of the level-0 keys kept for this batch (same rule on the host: mask >= max - 0.25), reported in `config`
-    m0 = trimap[:, ::8, ::8].reshape(B, -1)
-    kept_l0 = float((m0 >= m0.max(dim=1, keepdim=True).values - 0.25).float().mean())
+    def kept_fraction(t):
+        m0 = t[:, ::8, ::8].reshape(t.shape[0], -1)
+        return float((m0 >= m0.max(dim=1, keepdim=True).values - 0.25).float().mean())
+
+    kept_l0 = kept_fraction(trimap)
     img_d, tri_d = image.to(dev), trimap.to(dev)
-    img_h, tri_h = image.pin_memory(), trimap.pin_memory()
-    alpha_h = torch.empty((B, R, R), dtype=torch.float16).pin_memory()
+    alpha_d = torch.empty((B, R, R), dtype=torch.float16, device=dev)
     gathered = torch.empty((world * B, R, R), dtype=torch.float16, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB)
-    eng.workspace(B, R, host_staging=True)
 
-    def step_device():
+    def step_device(tri=tri_d):
         flush.zero_()  # L2 flush between iterations (inside the loop; ~0.1 ms of a >100 ms step)
-        a = eng.forward(img_d, tri_d, False)
+        eng.forward(img_d, tri, False, out=alpha_d)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, a)
-        return a
+            dist.all_gather_into_tensor(gathered, alpha_d)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -201,41 +260,57 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     for _ in range(args.warmup):
         step_device()
     sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_device()
-    e1.record()
-    sync_all()
-    ms = e0.elapsed_time(e1)
+    ms_total = timed(step_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = t.item()
     stats = eng.stats()
+    graph = eng.graph_stats()
 
-    # ---- end to end through the host-buffer call (pinned host inputs -> H2D -> forward -> D2H alpha), same K steps
-    for _ in range(0 if args.quick else min(2, args.warmup)):
-        eng.forward_host(img_h, tri_h, False, out=alpha_h)
-    sync_all()
-    e0.record()
-    for _ in range(1 if args.quick else args.steps):
-        eng.forward_host(img_h, tri_h, False, out=alpha_h)
+    # ---- worst case for the key compaction: all-foreground trimap (every key kept at every level), same step otherwise
+    worst = None
+    if args.trimap != "allfg" and not args.quick and not args.no_worst_case:
+        tri_fg = torch.ones_like(tri_d)
+        for _ in range(2):
+            step_device(tri_fg)
+        wsteps = max(2, min(5, args.steps))
+        ms_w = timed(lambda: step_device(tri_fg), wsteps)
+        worst = {"trimap": "all foreground (attn1 streams 100 % of the keys)", "ms_per_step": ms_w / wsteps,
+                 "value": world * B * wsteps / (ms_w * 1e-3), "unit": "mattes/s", "steps": wsteps}
+        del tri_fg
+
+    # ---- end to end through the NODE (the call a ComfyUI user makes): pageable host tensors in, host tensors out
+    node = nodes.SDMatteApply()
+    img_h, tri_h = image.clone(), trimap.clone()  # plain pageable tensors, like ComfyUI's
+    e2e_alpha = [None]
+
+    def step_node():
+        a, _ = node.apply_matte("SDMatte.safetensors", img_h, tri_h, R, False, "alpha_only", True, 0.8)
+        e2e_alpha[0] = a
         if world > 1:
-            dist.all_gather_into_tensor(gathered, alpha_h.to(dev, non_blocking=True))
-    e1.record()
-    sync_all()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = t.item()
+            dist.all_gather_into_tensor(gathered, a.to(dev, non_blocking=True))
+
+    e2e_steps = 1 if args.quick else args.steps
+    for _ in range(0 if args.quick else min(2, args.warmup)):
+        step_node()
+    ms_e2e = timed(step_node, e2e_steps)
 
     if rank != 0:
         if world > 1:
@@ -263,46 +338,84 @@ def run_b200(args):
         elif f["bytes"] > 0:
             e["gbs"] = round(f["bytes"] / (f["ms"] * 1e-3) / 1e9, 1)
         breakdown[k] = e
-    gemm_ms = sum(f["ms"] for k, f in fam.items() if k.startswith("tc:") and "attention" not in k)
-    gemm_fl = sum(f["flops"] for k, f in fam.items() if k.startswith("tc:") and "attention" not in k)
-    gemm_launches = sum(f["launches"] for k, f in fam.items() if k.startswith("tc:") and "attention" not in k)
-    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+
+    def family(pred):
+        ms = sum(f["ms"] for k, f in fam.items() if pred(k))
+        fl = sum(f["flops"] for k, f in fam.items() if pred(k))
+        n = sum(f["launches"] for k, f in fam.items() if pred(k))
+        return ms, fl, n
+
+    conv_ms, conv_fl, conv_n = family(lambda k: k == "tc:conv3x3")
+    gemm_ms, gemm_fl, gemm_n = family(lambda k: k.startswith("tc:") and "attention" not in k)
+    conv_ach = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    gemm_ach = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(tp) and R == 1024 and B == 8:
+        try:
+            td = json.load(open(tp))
+            traffic = {"dram_bytes_per_launch": td["conv3x3"]["dram_bytes"] / td["conv3x3"]["launches"],
+                       "algorithmic_bytes_per_launch": fam["tc:conv3x3"]["bytes"] / conv_n, "source": "profiles/r2_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one bs=8 1024^2 step)"}
+        except Exception:
+            traffic = None
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
-    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
     path_tflops = B * TFLOP_PER_MATTE.get(R, 0.0) / (ms_step * 1e-3)
+
+    # ---- the real competitor on the same GPU
+    gpu_base = None
+    if world == 1 and not args.no_gpu_baseline and not args.quick:
+        eng._ws = None  # hand the workspace back to the allocator while the baseline runs
+        torch.cuda.empty_cache()
+        try:
+            gpu_base = gpu_baseline(R, sorted({1, B}), dev)
+            gpu_base["speedup_device_timed"] = value / gpu_base[f"bs{B}"]["mattes_per_s"]
+            gpu_base["speedup_e2e_node_vs_device_resident_baseline"] = e2e_value / gpu_base[f"bs{B}"]["mattes_per_s"]
+        except Exception as ex:  # the baseline must never take the bench line down
+            gpu_base = {"error": f"{type(ex).__name__}: {ex}"}
 
     # ---- CPU baseline: the oracle on the host cores, bounded sample (N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline and not args.quick:
         threads = os.cpu_count() or 1
-        Rc = args.ref_size
-        rate, dt, desc = cpu_oracle_rate(Rc, 1, threads, min_seconds=10.0, max_mattes=8)  # about 10-30 s of CPU work
-        equiv = rate * TFLOP_PER_MATTE[Rc] / TFLOP_PER_MATTE[1024]
-        cpu = {"value": equiv, "unit": "mattes/s", "cores": threads, "kind": "port",
-               "sample": desc + f"; {dt:.1f} s; converted to 1024^2-equivalent mattes by the FLOP ratio {TFLOP_PER_MATTE[Rc]}/{TFLOP_PER_MATTE[1024]}"}
+        Rc = 512
+        rate, dt, done, desc = cpu_oracle_rate(Rc, 1, threads, min_seconds=10.0, max_mattes=8)  # about 10-30 s of CPU work
+        ratio, src = cpu_time_ratio_1024_over_512()
+        if ratio is not None and R == 1024:
+            equiv, how = rate / ratio, f"converted to {R}^2 mattes with the MEASURED wall-time ratio t(1024^2)/t(512^2) = {ratio:.1f} of the same oracle ({os.path.relpath(src, ROOT)}); `bench.py --impl reference` times real 1024^2 mattes"
+        else:
+            equiv, how = rate * TFLOP_PER_MATTE[Rc] / TFLOP_PER_MATTE[R], f"converted to {R}^2 mattes by the algorithmic FLOP ratio {TFLOP_PER_MATTE[Rc]}/{TFLOP_PER_MATTE[R]} (an upper bound: sliced attention at 1024^2 is slower than that)"
+        cpu = {"value": equiv, "unit": "mattes/s", "cores": threads, "kind": "port", "sample": desc + "; " + how,
+               "measured_512": {"value": rate, "unit": "mattes/s at 512^2"}}
 
     line = {
-        "metric": "mattes/sec @1024^2 bs=8", "value": value, "unit": "mattes/s", "n_gpus": world, "steps": args.steps,
+        "metric": f"mattes/sec @{R}^2 bs={B}", "value": value, "unit": "mattes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"bs={B} per GPU, {R}x{R} synthetic RGB+trimap, synthetic SDMatte checkpoint (seed 1234), is_transparent=False",
+        "config": {"workload": f"bs={B} per GPU, {R}x{R} synthetic RGB+trimap, synthetic SDMatte checkpoint (seed 1234), is_transparent=False, mask_refine on (e2e leg)",
                    "global_batch": world * B, "resolution": R, "parallelism": f"dp{world} batch shard + one NCCL all-gather of alpha" if world > 1 else "single GPU",
                    "l2": "256 MiB buffer written between timed iterations (inside the loop)",
-                   "self_attn_keys_streamed_L0": round(kept_l0, 4),
+                   "trimap": args.trimap, "self_attn_keys_streamed_L0": round(kept_l0, 4),
+                   "cuda_graph": {"enabled": bool(args.graph), **graph},
                    "note": "FLOP figures are ALGORITHMIC (all keys); attn1 skips keys whose softmax probability is exactly 0 under the "
-                           "reference's -10000 bias, so tc:attention_self reports algorithmic TFLOP/s above what it executes"},
+                           "reference's -10000 bias, so tc:attention_self reports algorithmic TFLOP/s above what it executes; see worst_case"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "mattes/s", "h2d_bytes_per_step": B * R * R * 16, "d2h_bytes_per_step": B * R * R * 2,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                "api": "SDMatteApply.apply_matte(ckpt, image, trimap, R, False, 'alpha_only', mask_refine=True, 0.8) with pageable host tensors"},
         "gpu_launches": stats["launches"] * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv/linear kernels (conv_gemm_kernel<...> incl. the resident-halo 3x3 variants, conv_swap_kernel), all launches of one step",
-                     "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"],
-                     "traffic": None, "launches_per_step": gemm_launches, "share_of_step": gemm_ms / tot_ms if tot_ms else None,
-                     "peak_source": peaks["source"] + " (bf16 sustained)"},
+        "roofline": {"bound": "tensor", "kernel": "tc:conv3x3 — the tcgen05 implicit-GEMM 3x3 stride-1 convolutions (conv_gemm_kernel<..., HALO>, conv_swap_kernel), all launches of one step",
+                     "achieved": conv_ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": conv_ach / peaks["tflops_sustained"],
+                     "traffic": traffic, "launches_per_step": conv_n, "share_of_step": conv_ms / tot_ms if tot_ms else None,
+                     "peak_source": peaks["source"] + " (bf16 sustained: the kernels are timed inside a long step)"},
+        "gemm_roofline": {"kernel": "all non-attention tcgen05 kernels (3x3 / 1x1 convs, linears, GEGLU, V^T, VAE QK^T / PV)", "achieved": gemm_ach,
+                          "frac": gemm_ach / peaks["tflops_sustained"], "launches_per_step": gemm_n, "share_of_step": gemm_ms / tot_ms if tot_ms else None},
         "path_roofline": {"algorithmic_tflop_per_matte": TFLOP_PER_MATTE.get(R), "achieved_tflops": path_tflops,
                           "frac_of_sustained_peak": path_tflops / peaks["tflops_sustained"]},
         "kernel_breakdown": breakdown,
+        "worst_case": worst,
+        "gpu_baseline": gpu_base,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
@@ -319,10 +432,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--batch", type=int, default=8, help="mattes per GPU per step")
+    ap.add_argument("--trimap", default="synthetic", choices=["synthetic", "allfg"], help="allfg: every pixel foreground (worst case of the key compaction)")
+    ap.add_argument("--graph", type=int, default=1, help="0: launch the plan kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-worst-case", action="store_true")
     ap.add_argument("--dump-ops", default=None, help="write the per-op profile of one step to this CSV")
-    ap.add_argument("--ref-size", type=int, default=512, choices=[128, 256, 384, 512, 1024], help="CPU-baseline sample resolution")
-    ap.add_argument("--quick", action="store_true", help="profiling aid: no e2e / cpu-baseline legs, warm-up as given (not a bench value)")
+    ap.add_argument("--ref-size", type=int, default=0, choices=[0, 128, 256, 384, 512, 1024], help="--impl reference: resolution of the timed mattes (0 = --size)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="--impl reference: wall-time bound of the whole run")
+    ap.add_argument("--quick", action="store_true", help="profiling aid: no e2e repeat / baselines, warm-up as given (not a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -33,7 +33,7 @@ int device_sm_count() {
 
 extern "C" {
 
-int sdm_version(void) { return 100; }
+int sdm_version(void) { return 200; }
 const char* sdm_last_error(void) { return sdm::g_last_error.c_str(); }
 
 int sdm_create(sdm_handle** out, int device) {
@@ -75,6 +75,23 @@ int sdm_forward_host(sdm_handle* h, const float* image_host, const float* trimap
                            workspace_dev, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
   SDM_API_END
 }
+size_t sdm_node_workspace_bytes(sdm_handle* h, int B, int H, int W, int R, int output_mode) {
+  try {
+    return sdm::engine_node_workspace_bytes(reinterpret_cast<sdm::Engine*>(h), B, H, W, R, output_mode);
+  } catch (const sdm::Error& e) {
+    sdm::set_last_error(e.msg);
+    return 0;
+  }
+}
+int sdm_apply_matte_host(sdm_handle* h, const float* image_host, const float* trimap_host, int B, int H, int W, int R,
+                         const int32_t* is_trans, int mask_refine, double trimap_constraint, int output_mode, void* alpha_out_host_f16,
+                         float* matted_out_host, void* workspace_dev, size_t workspace_bytes, uintptr_t stream) {
+  SDM_API_BEGIN
+  sdm::engine_apply_host(reinterpret_cast<sdm::Engine*>(h), image_host, trimap_host, B, H, W, R, is_trans, mask_refine, trimap_constraint,
+                         output_mode, alpha_out_host_f16, matted_out_host, workspace_dev, workspace_bytes,
+                         reinterpret_cast<cudaStream_t>(stream));
+  SDM_API_END
+}
 int sdm_preprocess(const float* image_dev, const float* trimap_dev, int B, int H, int W, int R, float* image_out_dev,
                    float* trimap_out_dev, uintptr_t stream) {
   SDM_API_BEGIN
@@ -111,6 +128,23 @@ int sdm_last_forward_stats(sdm_handle* h, int* n_launches, double* tensor_flops)
 int sdm_debug_tensor(sdm_handle* h, const char* name, void* dst_dev, size_t dst_bytes, int64_t* shape4, int* dtype) {
   SDM_API_BEGIN
   sdm::engine_debug_tensor(reinterpret_cast<sdm::Engine*>(h), name, dst_dev, dst_bytes, shape4, dtype);
+  SDM_API_END
+}
+
+int sdm_debug_tensor_count(sdm_handle* h) { return sdm::engine_debug_tensor_count(reinterpret_cast<sdm::Engine*>(h)); }
+int sdm_debug_tensor_name(sdm_handle* h, int i, char* name, int name_len) {
+  SDM_API_BEGIN
+  snprintf(name, name_len, "%s", sdm::engine_debug_tensor_name(reinterpret_cast<sdm::Engine*>(h), i));
+  SDM_API_END
+}
+int sdm_graph_stats(sdm_handle* h, int* captures, int* launches) {
+  SDM_API_BEGIN
+  sdm::engine_graph_stats(reinterpret_cast<sdm::Engine*>(h), captures, launches);
+  SDM_API_END
+}
+int sdm_set_option(sdm_handle* h, const char* name, int value) {
+  SDM_API_BEGIN
+  sdm::engine_set_option(reinterpret_cast<sdm::Engine*>(h), name, value);
   SDM_API_END
 }
 

@@ -456,11 +456,8 @@ std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d) {
 
 template <bool HB, bool TL, bool SP>
 static void attn_launch(const AttnLaunch& l, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<HB, TL, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem));
-    attr = true;
-  }
+  static PerDeviceOnce attr;  // function attributes are per device: a second GPU in the same process needs them too
+  attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<HB, TL, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem)); });
   attention_kernel<HB, TL, SP><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
 }
 

@@ -370,3 +370,21 @@ void set_last_error(const std::string& s);
     if (!(cond)) throw ::sdm::Error{std::string("check failed: ") + #cond + " — " + (msg)};        \
   } while (0)
 }  // namespace sdm
+
+#include <atomic>
+namespace sdm {
+// Kernel function attributes (cudaFuncSetAttribute: dynamic shared-memory limit) are per DEVICE: one process driving several
+// GPUs (one handle + one host thread per device) must set them once on each.  One instance per launch shim.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  template <class F>
+  void operator()(F&& f) {
+    int dev = 0;
+    SDM_CUDA_OK(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return;
+    f();  // idempotent, so two threads of the same device racing here is harmless
+    done.fetch_or(bit, std::memory_order_release);
+  }
+};
+}  // namespace sdm

@@ -191,11 +191,8 @@ __global__ void __launch_bounds__(sw::kThreads, 1) conv_swap_kernel(const __grid
 }
 
 void conv_swap_launch(const ConvGemmParams& p, int grid, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sw::kSmem));
-    attr = true;
-  }
+  static PerDeviceOnce attr;
+  attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sw::kSmem)); });
   conv_swap_kernel<<<grid, sw::kThreads, sw::kSmem, st>>>(p);
   SDM_CUDA_OK(cudaGetLastError());
 }

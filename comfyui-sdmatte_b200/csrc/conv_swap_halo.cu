@@ -206,11 +206,8 @@ __global__ void __launch_bounds__(swh::kThreads, 1) conv_swap_halo_kernel(const 
 }
 
 void conv_swap_halo_launch(const ConvGemmParams& p, int grid, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::kSmem));
-    attr = true;
-  }
+  static PerDeviceOnce attr;
+  attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::kSmem)); });
   conv_swap_halo_kernel<<<grid, swh::kThreads, swh::kSmem, st>>>(p);
   SDM_CUDA_OK(cudaGetLastError());
 }

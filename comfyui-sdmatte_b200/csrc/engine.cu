@@ -284,14 +284,32 @@ struct Plan {
   __half* d_alpha = nullptr;
   const float** image_slot = nullptr;
   std::map<std::string, T> taps;
+  std::vector<std::string> tap_order;
+  bool keep_taps = false;
+  // CUDA graph of the op list (engine option "cuda_graph"): kernel arguments are baked at capture, so a graph is valid for
+  // exactly one set of run-time pointers (`graph_slots`) and one set of per-sample flags
+  cudaGraphExec_t graph_exec = nullptr;
+  std::vector<int32_t> flags;   // is_trans values currently resident in d_is_trans
+  bool flags_valid = false;
+  int eager_runs = 0;
+  ~Plan() { if (graph_exec) cudaGraphExecDestroy(graph_exec); }
   // run-time argument slots (device pointers change per call without rebuilding the plan)
-  struct Slots { const float* image; const float* trimap; __half* alpha; __half* premean; } slots{};
+  struct Slots { const float* image; const float* trimap; __half* alpha; __half* premean; } slots{}, graph_slots{}, last_slots{};
   int* d_is_trans = nullptr;
 };
 
 struct Engine {
   int device = 0;
   int num_sms = 148;
+  bool keep_taps = false;  // parity diagnostics: tapped block outputs are never recycled by the arena (bigger workspace)
+  bool use_graph = true;   // replay the plan as one CUDA graph when the caller's pointers repeat (option "cuda_graph")
+  cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream, which cannot capture)
+  int32_t* flags_pinned = nullptr;    // staging for the per-sample is_transparent flags (uploaded only when they change)
+  char* pinned = nullptr;             // page-locked staging of the node call's host tensors (grown on demand, engine_apply_host)
+  size_t pinned_bytes = 0;
+  int copy_threads = 8;
+  cudaEvent_t flags_event = nullptr;
+  int graph_launches = 0, graph_captures = 0;
   Weights W;
   std::unique_ptr<Plan> plan;
   int last_launches = 0;
@@ -329,8 +347,19 @@ struct Builder {
     *off_out = off;
     return dry ? nullptr : (void*)(ws + off);
   }
+  // parity taps: the named block output stays readable after the forward (sdm_debug_tensor).  Without the engine's keep_taps
+  // option only tensors that are never recycled anyway (unet_in, ctx, unet_out_scaled) are valid afterwards.
+  std::vector<size_t> pinned;
+  void tap(const std::string& name, const T& t) {
+    if (E.keep_taps) pinned.push_back(t.off);
+    if (plan && (E.keep_taps || name == "unet_in" || name == "ctx" || name == "unet_out_scaled")) {
+      plan->taps[name] = t;
+      plan->tap_order.push_back(name);
+    }
+  }
   void free(T& t) {
-    if (t.valid()) arena.release(t.off, t.bytes);
+    const bool keep = t.valid() && std::find(pinned.begin(), pinned.end(), t.off) != pinned.end();
+    if (t.valid() && !keep) arena.release(t.off, t.bytes);
     if (t.stats_bytes) arena.release(t.stats_off, t.stats_bytes);
     t.bytes = 0;
     t.stats_bytes = 0;
@@ -760,6 +789,7 @@ struct Builder {
       { GemmOpt o; o.bias = W.vec(e + ".conv_in.bias", 128); o.stats_for = &h; o.label = "conv_in_im2col";
         conv_tc(x0, nullptr, W.conv_im2col(e + ".conv_in", 128, 3), 128, 1, h, o); }
       free(x0);
+      tap("enc.conv_in", h);
       const int ch[4] = {128, 256, 512, 512};
       for (int i = 0; i < 4; ++i) {
         for (int j = 0; j < 2; ++j) {
@@ -770,10 +800,13 @@ struct Builder {
           T o = conv3_plain(h, e + ".down_blocks." + std::to_string(i) + ".downsamplers.0.conv", ch[i], 2, PAD_VAE_DOWN);
           free(h); h = o;
         }
+        tap("enc.down" + std::to_string(i), h);
       }
       { T o = resnet(h, nullptr, e + ".mid_block.resnets.0", 512, 1e-6f, false, 0); free(h); h = o; }
       { T o = vae_attention(h, e + ".mid_block.attentions.0"); free(h); h = o; }
+      tap("enc.mid_attn", h);
       { T o = resnet(h, nullptr, e + ".mid_block.resnets.1", 512, 1e-6f, false, 0); free(h); h = o; }
+      tap("enc.mid", h);
       T n = groupnorm(h, nullptr, e + ".conv_norm_out", 1e-6f, 1);
       free(h);
       T mom = alloc(B2, S, S, 8);
@@ -790,13 +823,13 @@ struct Builder {
       }
       free(mom);
     }
-    if (plan) plan->taps["unet_in"] = unet_in;
+    tap("unet_in", unet_in);
 
     // ---- a5: trimap tokens = aux_conv_in(trimap latent) (meta_arch.py:215-218, utils.py:33-41)
     T ctx = alloc(B, S, S, 1024);
     { DirectConvDesc d; d.B = B; d.H = S; d.W = S; d.Cin = 4; d.Cout = 1024; d.ksize = 3; d.x = dry ? nullptr : unet_in.p + 4; d.x_ld = 8;
       d.w = W.conv("unet.aux_conv_in", 1024, 4, 3); d.bias = W.vec("unet.aux_conv_in.bias", 1024); d.out = ctx.p; d.out_ld = 1024; direct(d); }
-    if (plan) plan->taps["ctx"] = ctx;
+    tap("ctx", ctx);
 
     // ---- a7..a14: UNet (replace.py:462-544)
     T unet_out = alloc(B, S, S, 4);
@@ -807,6 +840,7 @@ struct Builder {
       T h = alloc(B, S, S, 320);
       { DirectConvDesc d; d.B = B; d.H = S; d.W = S; d.Cin = 8; d.Cout = 320; d.ksize = 3; d.x = unet_in.p; d.x_ld = 8;
         d.w = W.conv("unet.conv_in", 320, 8, 3); d.bias = W.vec("unet.conv_in.bias", 320); d.out = h.p; d.out_ld = 320; direct(d); }
+      tap("unet.conv_in", h);
       skips.push_back(h);
       for (int i = 0; i < 4; ++i) {
         const std::string bp = "unet.down_blocks." + std::to_string(i);
@@ -817,10 +851,12 @@ struct Builder {
             free(o); o = o2;
           }
           h = o;
+          tap("unet.down" + std::to_string(i) + "." + std::to_string(j), h);
           skips.push_back(h);
         }
         if (i < 3) {
           h = conv3_plain(h, bp + ".downsamplers.0.conv", ch[i], 2, PAD_SAME);
+          tap("unet.down" + std::to_string(i) + ".ds", h);
           skips.push_back(h);
         }
       }
@@ -832,6 +868,7 @@ struct Builder {
         T o3 = resnet(o2, nullptr, "unet.mid_block.resnets.1", 1280, 1e-5f, true, 0);
         free(o2);
         h = o3;
+        tap("unet.mid", h);
       }
       const int rch[4] = {1280, 1280, 640, 320};
       const int rheads[4] = {20, 20, 10, 5};
@@ -850,10 +887,12 @@ struct Builder {
             free(o); o = o2;
           }
           h = o;
+          tap("unet.up" + std::to_string(i) + "." + std::to_string(j), h);  // j == 2, i < 3: already nearest-x2 upsampled
         }
         if (i < 3) {  // Upsample2D: nearest x2 (fused into the producer's store) + conv3x3
           T o = conv3_plain(h, bp + ".upsamplers.0.conv", rch[i], 1, PAD_SAME);
           free(h); h = o;
+          tap("unet.up" + std::to_string(i) + ".us", h);
         }
       }
       T n = groupnorm(h, nullptr, "unet.conv_norm_out", 1e-5f, 1);
@@ -865,7 +904,7 @@ struct Builder {
       SDM_CHECK(skips.empty(), "skip bookkeeping");
     }
     // ctx / unet_in / unet_out stay allocated: they are small and double as parity-test taps
-    if (plan) plan->taps["unet_out_scaled"] = unet_out;
+    tap("unet_out_scaled", unet_out);
 
     // ---- a15: VAE decode (meta_arch.py:255-256)
     {
@@ -877,9 +916,11 @@ struct Builder {
       { DirectConvDesc d; d.B = B; d.H = S; d.W = S; d.Cin = 4; d.Cout = 512; d.ksize = 3; d.x = z.p; d.x_ld = 4;
         d.w = W.conv(dcd + ".conv_in", 512, 4, 3); d.bias = W.vec(dcd + ".conv_in.bias", 512); d.out = h.p; d.out_ld = 512; direct(d); }
       free(z);
+      tap("dec.conv_in", h);
       { T o = resnet(h, nullptr, dcd + ".mid_block.resnets.0", 512, 1e-6f, false, 0); free(h); h = o; }
       { T o = vae_attention(h, dcd + ".mid_block.attentions.0"); free(h); h = o; }
       { T o = resnet(h, nullptr, dcd + ".mid_block.resnets.1", 512, 1e-6f, false, 0); free(h); h = o; }
+      tap("dec.mid", h);
       const int ch[4] = {512, 512, 256, 128};
       for (int i = 0; i < 4; ++i) {
         const std::string bp = dcd + ".up_blocks." + std::to_string(i);
@@ -888,6 +929,7 @@ struct Builder {
           free(h); h = o;
         }
         if (i < 3) { T o = conv3_plain(h, bp + ".upsamplers.0.conv", ch[i], 1, PAD_SAME); free(h); h = o; }
+        tap("dec.up" + std::to_string(i), h);
       }
       T n = groupnorm(h, nullptr, dcd + ".conv_norm_out", 1e-6f, 1);
       free(h);
@@ -944,6 +986,12 @@ Engine* engine_create(int device) {
 void engine_destroy(Engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  e->plan.reset();
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->flags_event) cudaEventDestroy(e->flags_event);
+  if (e->flags_pinned) cudaFreeHost(e->flags_pinned);
+  if (e->pinned) cudaFreeHost(e->pinned);
   e->W.free_all();
   delete e;
 }
@@ -1000,17 +1048,35 @@ size_t engine_workspace_bytes(Engine* e, int B, int R) {
 static Plan& get_plan(Engine* e, int B, int R, void* ws, size_t ws_bytes) {
   SDM_CHECK(e->W.loaded, "weights not loaded");
   SDM_CHECK((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
-  if (e->plan && e->plan->B == B && e->plan->R == R && e->plan->ws == ws && e->plan->ws_bytes == ws_bytes) return *e->plan;
+  if (e->plan && e->plan->B == B && e->plan->R == R && e->plan->ws == ws && e->plan->ws_bytes == ws_bytes && e->plan->keep_taps == e->keep_taps) return *e->plan;
   const size_t need = engine_workspace_bytes(e, B, R);
   if (ws_bytes < need) throw Error{"workspace too small: need " + std::to_string(need) + " bytes, got " + std::to_string(ws_bytes)};
   auto plan = std::make_unique<Plan>();
-  plan->B = B; plan->R = R; plan->ws = ws; plan->ws_bytes = ws_bytes;
+  plan->B = B; plan->R = R; plan->ws = ws; plan->ws_bytes = ws_bytes; plan->keep_taps = e->keep_taps;
   Builder b(*e, plan.get(), B, R, ws);
   b.build();
   plan->n_launches = b.n_launches;
   plan->tensor_flops = b.flops;
   e->plan = std::move(plan);
   return *e->plan;
+}
+
+// per-sample flags: uploaded from a pinned staging buffer, and only when they differ from what the device already holds
+static void upload_flags(Engine* e, Plan& p, const int32_t* is_trans, int B, cudaStream_t st) {
+  for (int i = 0; i < B; ++i) SDM_CHECK(is_trans[i] == 0 || is_trans[i] == 1, "is_trans must be 0/1");
+  if (p.flags_valid && (int)p.flags.size() == B && memcmp(p.flags.data(), is_trans, (size_t)B * 4) == 0) return;
+  SDM_CHECK(B <= 1024, "batch too large for the flag staging buffer");
+  if (!e->flags_pinned) {
+    SDM_CUDA_OK(cudaHostAlloc((void**)&e->flags_pinned, 1024 * sizeof(int32_t), cudaHostAllocDefault));
+    SDM_CUDA_OK(cudaEventCreateWithFlags(&e->flags_event, cudaEventDisableTiming));
+  } else {
+    SDM_CUDA_OK(cudaEventSynchronize(e->flags_event));  // the previous upload has left the staging buffer
+  }
+  memcpy(e->flags_pinned, is_trans, (size_t)B * 4);
+  SDM_CUDA_OK(cudaMemcpyAsync(p.d_is_trans, e->flags_pinned, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  SDM_CUDA_OK(cudaEventRecord(e->flags_event, st));
+  p.flags.assign(is_trans, is_trans + B);
+  p.flags_valid = true;
 }
 
 void engine_forward(Engine* e, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
@@ -1021,11 +1087,42 @@ void engine_forward(Engine* e, const float* image_dev, const float* trimap_dev, 
   p.slots.trimap = trimap_dev;
   p.slots.alpha = (__half*)alpha_dev;
   p.slots.premean = (__half*)premean_dev;
-  for (int i = 0; i < B; ++i) SDM_CHECK(is_trans[i] == 0 || is_trans[i] == 1, "is_trans must be 0/1");
-  SDM_CUDA_OK(cudaMemcpyAsync(p.d_is_trans, is_trans, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-  for (auto& op : p.ops) op.fn(st);
+  upload_flags(e, p, is_trans, B, st);
   e->last_launches = p.n_launches;
   e->last_flops = p.tensor_flops;
+  auto same = [](const Plan::Slots& a, const Plan::Slots& b) { return memcmp(&a, &b, sizeof(Plan::Slots)) == 0; };
+  if (e->use_graph && p.graph_exec && same(p.graph_slots, p.slots)) {
+    SDM_CUDA_OK(cudaGraphLaunch(p.graph_exec, st));
+    e->graph_launches++;
+    return;
+  }
+  // capture when the same pointers come back (first run of a plan is always eager: it also sets the per-device kernel
+  // attributes); callers that hand in fresh buffers every time simply stay on the eager path
+  if (e->use_graph && p.eager_runs >= 1 && same(p.last_slots, p.slots)) {
+    if (!e->cap_stream) SDM_CUDA_OK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    SDM_CUDA_OK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      for (auto& op : p.ops) op.fn(e->cap_stream);
+    } catch (...) {
+      cudaStreamEndCapture(e->cap_stream, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    SDM_CUDA_OK(cudaStreamEndCapture(e->cap_stream, &g));
+    if (p.graph_exec) { cudaGraphExecDestroy(p.graph_exec); p.graph_exec = nullptr; }
+    const cudaError_t ie = cudaGraphInstantiate(&p.graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    SDM_CUDA_OK(ie);
+    p.graph_slots = p.slots;
+    e->graph_captures++;
+    SDM_CUDA_OK(cudaGraphLaunch(p.graph_exec, st));
+    e->graph_launches++;
+    return;
+  }
+  for (auto& op : p.ops) op.fn(st);
+  p.eager_runs++;
+  p.last_slots = p.slots;
 }
 
 void engine_forward_profiled(Engine* e, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
@@ -1036,7 +1133,7 @@ void engine_forward_profiled(Engine* e, const float* image_dev, const float* tri
   p.slots.trimap = trimap_dev;
   p.slots.alpha = (__half*)alpha_dev;
   p.slots.premean = nullptr;
-  SDM_CUDA_OK(cudaMemcpyAsync(p.d_is_trans, is_trans, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  upload_flags(e, p, is_trans, B, st);
   std::vector<cudaEvent_t> ev(p.ops.size() + 1);
   for (auto& x : ev) SDM_CUDA_OK(cudaEventCreate(&x));
   SDM_CUDA_OK(cudaEventRecord(ev[0], st));
@@ -1079,9 +1176,121 @@ void engine_forward_host(Engine* e, const float* image_host, const float* trimap
   SDM_CUDA_OK(cudaStreamSynchronize(st));
 }
 
+// ================================================================================================
+// the node call: host tensors of ANY size in, host tensors out (replaces sdmatte_nodes.py:339-397 around the forward)
+// ================================================================================================
+// Layout of the caller's workspace: [ plan arena (engine_workspace_bytes) | image HxW | trimap HxW | image RxR | trimap RxR |
+// alpha RxR | alpha HxW | matted HxW ] — fixed offsets for a given geometry, so the plan's CUDA graph sees the same pointers
+// on every call.
+struct NodeLayout {
+  size_t main_bytes, img, tri, img_r, tri_r, alpha_r, out, matted, total;
+  int mch;
+};
+static NodeLayout node_layout(Engine* e, int B, int H, int W, int R, int output_mode) {
+  auto al = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  NodeLayout L{};
+  L.mch = output_mode == 1 ? 4 : (output_mode == 0 ? 0 : 3);
+  const size_t hw = (size_t)B * H * W, rr = (size_t)B * R * R;
+  const bool resize = !(H == R && W == R);
+  L.main_bytes = al(engine_workspace_bytes(e, B, R));
+  size_t o = L.main_bytes;
+  L.img = o; o += al(hw * 12);
+  L.tri = o; o += al(hw * 4);
+  L.img_r = resize ? o : L.img; if (resize) o += al(rr * 12);
+  L.tri_r = resize ? o : L.tri; if (resize) o += al(rr * 4);
+  L.alpha_r = o; o += al(rr * 2);
+  L.out = o; o += al(hw * 2);
+  L.matted = o; o += al(hw * 4 * L.mch);
+  L.total = o + 1024;
+  return L;
+}
+size_t engine_node_workspace_bytes(Engine* e, int B, int H, int W, int R, int output_mode) {
+  SDM_CHECK(B >= 1 && H >= 1 && W >= 1, "node geometry");
+  SDM_CHECK(output_mode >= 0 && output_mode <= 3, "output_mode");
+  return node_layout(e, B, H, W, R, output_mode).total;
+}
+
+// pageable -> pinned -> device: `nt` host threads copy disjoint chunks into the page-locked buffer and each enqueues the H2D of
+// its chunk right behind it, so the staging memcpy (the slow half: host DRAM bandwidth) overlaps the DMA of earlier chunks
+static void stage_h2d(Engine* e, char* pin, void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st) {
+  const size_t chunk = 4u << 20;
+  const size_t nchunks = (bytes + chunk - 1) / chunk;
+  const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->copy_threads, nchunks));
+  std::vector<std::thread> th;
+  std::vector<cudaError_t> err((size_t)nt, cudaSuccess);
+  const int device = e->device;
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([=, &err] {
+      cudaSetDevice(device);
+      for (size_t c = (size_t)t; c < nchunks; c += (size_t)nt) {
+        const size_t off = c * chunk, n = std::min(chunk, bytes - off);
+        memcpy(pin + off, (const char*)src_host + off, n);
+        const cudaError_t r = cudaMemcpyAsync((char*)dst_dev + off, pin + off, n, cudaMemcpyHostToDevice, st);
+        if (r != cudaSuccess) err[(size_t)t] = r;
+      }
+    });
+  for (auto& x : th) x.join();
+  for (auto r : err) SDM_CUDA_OK(r);
+}
+static void parallel_memcpy(Engine* e, void* dst, const void* src, size_t bytes) {
+  const size_t chunk = 4u << 20;
+  const size_t nchunks = (bytes + chunk - 1) / chunk;
+  const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)e->copy_threads, nchunks));
+  if (nt == 1) { memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([=] {
+      for (size_t c = (size_t)t; c < nchunks; c += (size_t)nt) {
+        const size_t off = c * chunk, n = std::min(chunk, bytes - off);
+        memcpy((char*)dst + off, (const char*)src + off, n);
+      }
+    });
+  for (auto& x : th) x.join();
+}
+
+void engine_apply_host(Engine* e, const float* image_host, const float* trimap_host, int B, int H, int W, int R, const int32_t* is_trans,
+                       int mask_refine, double trimap_constraint, int output_mode, void* alpha_out_host_f16, float* matted_out_host,
+                       void* ws, size_t ws_bytes, cudaStream_t st) {
+  SDM_CUDA_OK(cudaSetDevice(e->device));
+  SDM_CHECK(image_host && trimap_host && alpha_out_host_f16, "null host tensor");
+  const NodeLayout L = node_layout(e, B, H, W, R, output_mode);
+  SDM_CHECK(ws_bytes >= L.total, "workspace too small for the node call (sdm_node_workspace_bytes)");
+  SDM_CHECK(L.mch == 0 || matted_out_host != nullptr, "matted_out needed for this output_mode");
+  char* base = (char*)ws;
+  const size_t hw = (size_t)B * H * W, rr = (size_t)B * R * R;
+  const size_t in_b = hw * 16, out_b = hw * 2 + hw * 4 * L.mch;
+  const size_t need = ((in_b + 4095) & ~(size_t)4095) + out_b;
+  if (e->pinned_bytes < need) {
+    if (e->pinned) { cudaFreeHost(e->pinned); e->pinned = nullptr; e->pinned_bytes = 0; }
+    SDM_CUDA_OK(cudaHostAlloc((void**)&e->pinned, need, cudaHostAllocDefault));
+    e->pinned_bytes = need;
+  }
+  char* pin_in = e->pinned;
+  char* pin_out = e->pinned + ((in_b + 4095) & ~(size_t)4095);
+  // trimap first (the key-bias / compaction kernels need only it), then the image
+  stage_h2d(e, pin_in, base + L.tri, trimap_host, hw * 4, st);
+  stage_h2d(e, pin_in + hw * 4, base + L.img, image_host, hw * 12, st);
+  if (!(H == R && W == R))
+    preprocess_run((const float*)(base + L.img), (const float*)(base + L.tri), B, H, W, R, (float*)(base + L.img_r), (float*)(base + L.tri_r), st);
+  engine_forward(e, (const float*)(base + L.img_r), (const float*)(base + L.tri_r), B, R, is_trans, base + L.alpha_r, nullptr, ws, L.main_bytes, st);
+  postprocess_run((const __half*)(base + L.alpha_r), B, R, H, W, (const float*)(base + L.img), (const float*)(base + L.tri), mask_refine,
+                  trimap_constraint, output_mode, (__half*)(base + L.out), L.mch ? (float*)(base + L.matted) : nullptr, st);
+  SDM_CUDA_OK(cudaMemcpyAsync(pin_out, base + L.out, hw * 2, cudaMemcpyDeviceToHost, st));
+  if (L.mch) SDM_CUDA_OK(cudaMemcpyAsync(pin_out + hw * 2, base + L.matted, hw * 4 * L.mch, cudaMemcpyDeviceToHost, st));
+  SDM_CUDA_OK(cudaStreamSynchronize(st));
+  parallel_memcpy(e, alpha_out_host_f16, pin_out, hw * 2);
+  if (L.mch) parallel_memcpy(e, matted_out_host, pin_out + hw * 2, hw * 4 * L.mch);
+  (void)rr;
+}
+
 void engine_stats(Engine* e, int* n_launches, double* tensor_flops) {
   if (n_launches) *n_launches = e->last_launches;
   if (tensor_flops) *tensor_flops = e->last_flops;
+}
+
+void engine_graph_stats(Engine* e, int* captures, int* launches) {
+  if (captures) *captures = e->graph_captures;
+  if (launches) *launches = e->graph_launches;
 }
 
 void engine_debug_tensor(Engine* e, const char* name, void* dst_dev, size_t dst_bytes, int64_t* shape4, int* dtype) {
@@ -1090,10 +1299,26 @@ void engine_debug_tensor(Engine* e, const char* name, void* dst_dev, size_t dst_
   if (it == e->plan->taps.end()) throw Error{std::string("unknown debug tensor '") + name + "'"};
   const T& t = it->second;
   const size_t bytes = (size_t)t.B * t.H * t.W * t.C * 2;
-  SDM_CHECK(dst_bytes >= bytes, "debug tensor destination too small");
-  SDM_CUDA_OK(cudaMemcpy(dst_dev, (const char*)e->plan->ws + t.off, bytes, cudaMemcpyDeviceToDevice));
   if (shape4) { shape4[0] = t.B; shape4[1] = t.H; shape4[2] = t.W; shape4[3] = t.C; }
   if (dtype) *dtype = 1;
+  if (!dst_dev) return;  // shape query
+  SDM_CHECK(dst_bytes >= bytes, "debug tensor destination too small");
+  SDM_CUDA_OK(cudaSetDevice(e->device));
+  SDM_CUDA_OK(cudaMemcpy(dst_dev, (const char*)e->plan->ws + t.off, bytes, cudaMemcpyDeviceToDevice));
+}
+
+int engine_debug_tensor_count(Engine* e) { return e->plan ? (int)e->plan->tap_order.size() : 0; }
+const char* engine_debug_tensor_name(Engine* e, int i) {
+  SDM_CHECK(e->plan && i >= 0 && i < (int)e->plan->tap_order.size(), "tap index");
+  return e->plan->tap_order[i].c_str();
+}
+
+void engine_set_option(Engine* e, const char* name, int value) {
+  const std::string n = name ? name : "";
+  if (n == "keep_taps") { e->keep_taps = value != 0; e->plan.reset(); return; }
+  if (n == "cuda_graph") { e->use_graph = value != 0; e->plan.reset(); return; }
+  if (n == "copy_threads") { e->copy_threads = std::max(1, std::min(64, value)); return; }
+  throw Error{"unknown engine option '" + n + "'"};
 }
 
 }  // namespace sdm

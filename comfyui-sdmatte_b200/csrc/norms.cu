@@ -263,11 +263,8 @@ void groupnorm_run(const GroupNormDesc& d, cudaStream_t st) {
   const __half* s1 = d.nsrc > 1 ? d.src[1] : d.src[0];
   const long long ld1 = d.nsrc > 1 ? d.ld[1] : d.ld[0];
   const size_t smem = (size_t)ny * nvec * 16 * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SDM_CUDA_OK(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_set;
+  attr_set([] { SDM_CUDA_OK(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); });
   const int path = gn_stats_path(d);
   if (path != 0) {
     // statistics were produced by the epilogue of the conv(s) that wrote the input: only reduce them

@@ -12,12 +12,11 @@ void conv_gemm_launch(const ConvGemmParams& p, int grid, cudaStream_t st);
   template <>                                                                                                                \
   void conv_gemm_launch<BN, MT, MODE, UPS2, LIGHT, EWG>(const ConvGemmParams& p, int grid, cudaStream_t st) {                            \
     using Cfg = ConvGemmCfg<BN, MT, LIGHT, EWG>;                                                                                       \
-    static bool attr = false;                                                                                                \
-    if (!attr) {                                                                                                             \
+    static PerDeviceOnce attr;                                                                                               \
+    attr([] {                                                                                                                \
       SDM_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, MT, MODE, UPS2, LIGHT, EWG>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                        Cfg::kSmemBytes));                                                                    \
-      attr = true;                                                                                                           \
-    }                                                                                                                        \
+    });                                                                                                                      \
     conv_gemm_kernel<BN, MT, MODE, UPS2, LIGHT, EWG><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(p);                                   \
     SDM_CUDA_OK(cudaGetLastError());                                                                                         \
   }
@@ -30,11 +29,8 @@ void conv_gemm_launch_halo(const ConvGemmParams& p, int grid, cudaStream_t st);
   void conv_gemm_launch_halo<BN, MT, UPS2, EWG>(const ConvGemmParams& p, int grid, cudaStream_t st) {                         \
     using Cfg = ConvGemmCfg<BN, MT, false, EWG, false, true>;                                                                \
     auto kern = conv_gemm_kernel<BN, MT, EPI_F16, UPS2, false, EWG, false, true>;                                            \
-    static bool attr = false;                                                                                                \
-    if (!attr) {                                                                                                             \
-      SDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));                 \
-      attr = true;                                                                                                           \
-    }                                                                                                                        \
+    static PerDeviceOnce attr;                                                                                               \
+    attr([&] { SDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes)); });    \
     kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(p);                                                                   \
     SDM_CUDA_OK(cudaGetLastError());                                                                                         \
   }
@@ -47,11 +43,8 @@ void conv_gemm_launch_pair(const ConvGemmParams& p, int grid, cudaStream_t st);
   void conv_gemm_launch_pair<BN, MODE>(const ConvGemmParams& p, int grid, cudaStream_t st) {                                 \
     using Cfg = ConvGemmCfg<BN, 1, false, 1, true>;                                                                          \
     auto kern = conv_gemm_kernel<BN, 1, MODE, false, false, 1, true>;                                                        \
-    static bool attr = false;                                                                                                \
-    if (!attr) {                                                                                                             \
-      SDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));                 \
-      attr = true;                                                                                                           \
-    }                                                                                                                        \
+    static PerDeviceOnce attr;                                                                                               \
+    attr([&] { SDM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes)); });    \
     cudaLaunchConfig_t cfg = {};                                                                                             \
     cfg.gridDim = dim3((unsigned)grid);                                                                                      \
     cfg.blockDim = dim3(Cfg::kThreads);                                                                                      \

@@ -14,6 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libsdmatte_b200.so")
 _lib = None
+ABI_VERSION = 200  # sdm_version(): bumped whenever a struct or signature of include/sdmatte_b200.h changes
 
 
 class sdm_tensor_desc(C.Structure):
@@ -65,8 +66,9 @@ class sdm_direct_conv_args(C.Structure):
 
 EXPORTS = [
     "sdm_version", "sdm_last_error", "sdm_create", "sdm_destroy", "sdm_load_weights", "sdm_load_report",
-    "sdm_workspace_bytes", "sdm_forward", "sdm_forward_host", "sdm_forward_profiled", "sdm_profile_count", "sdm_profile_entry",
-    "sdm_last_forward_stats", "sdm_debug_tensor", "sdm_preprocess", "sdm_postprocess",
+    "sdm_workspace_bytes", "sdm_forward", "sdm_forward_host", "sdm_node_workspace_bytes", "sdm_apply_matte_host", "sdm_forward_profiled", "sdm_profile_count", "sdm_profile_entry",
+    "sdm_last_forward_stats", "sdm_debug_tensor", "sdm_debug_tensor_count", "sdm_debug_tensor_name", "sdm_set_option", "sdm_graph_stats",
+    "sdm_preprocess", "sdm_postprocess",
     "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_conv_variant", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
     "sdm_k_softmax_rows", "sdm_k_direct_conv", "sdm_k_key_compact", "sdm_k_gather_rows", "sdm_k_probe_halo",
     "sdm_safetensors_open", "sdm_safetensors_count", "sdm_safetensors_entry", "sdm_safetensors_close",
@@ -82,14 +84,19 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
-        import importlib.util
+    # always go through build_ext.build(): it is gated by a digest of csrc/ + the public header, so it only compiles when the
+    # sources changed — a stale .so from an older tree must never be loaded silently (struct layouts may have moved)
+    import importlib.util
 
-        spec = importlib.util.spec_from_file_location("_sdm_build_ext", os.path.join(_HERE, "build_ext.py"))
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-        mod.build()
+    spec = importlib.util.spec_from_file_location("_sdm_build_ext", os.path.join(_HERE, "build_ext.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
     lib = C.CDLL(_LIB_PATH)
+    lib.sdm_version.restype = C.c_int
+    if lib.sdm_version() != ABI_VERSION:
+        raise RuntimeError(f"libsdmatte_b200.so reports ABI {lib.sdm_version()}, this binding expects {ABI_VERSION}: rebuild "
+                           f"(python comfyui-sdmatte_b200/build_ext.py --force)")
     lib.sdm_version.restype = C.c_int
     lib.sdm_last_error.restype = C.c_char_p
     lib.sdm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
@@ -103,6 +110,10 @@ def load_library():
                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.sdm_forward_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_void_p,
                                      C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sdm_node_workspace_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.sdm_node_workspace_bytes.restype = C.c_size_t
+    lib.sdm_apply_matte_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32),
+                                         C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.sdm_preprocess.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sdm_postprocess.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -113,6 +124,10 @@ def load_library():
                                       C.POINTER(C.c_double)]
     lib.sdm_last_forward_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     lib.sdm_debug_tensor.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+    lib.sdm_debug_tensor_count.argtypes = [C.c_void_p]
+    lib.sdm_debug_tensor_name.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+    lib.sdm_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    lib.sdm_graph_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.sdm_k_conv_gemm.argtypes = [C.POINTER(sdm_conv_gemm_args), C.c_void_p]
     lib.sdm_k_conv_tiles_per_image.argtypes = [C.c_int, C.c_int]
     lib.sdm_k_attention.argtypes = [C.POINTER(sdm_attn_args), C.c_void_p]
@@ -267,8 +282,10 @@ class Engine:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
-    def forward(self, image: torch.Tensor, trimap: torch.Tensor, is_transparent=False, want_premean: bool = False):
-        """image [B,R,R,3] fp32 cuda, trimap [B,R,R] fp32 cuda -> alpha [B,R,R] fp16 cuda (and pre-clip mean)."""
+    def forward(self, image: torch.Tensor, trimap: torch.Tensor, is_transparent=False, want_premean: bool = False,
+                out: Optional[torch.Tensor] = None):
+        """image [B,R,R,3] fp32 cuda, trimap [B,R,R] fp32 cuda -> alpha [B,R,R] fp16 cuda (and pre-clip mean).
+        `out`: optional preallocated alpha; calling again with the same input/output tensors replays the plan's CUDA graph."""
         B, R = image.shape[0], image.shape[1]
         assert image.shape == (B, R, R, 3) and trimap.shape == (B, R, R), "inputs must already be R x R"
         assert image.dtype == torch.float32 and trimap.dtype == torch.float32
@@ -276,7 +293,9 @@ class Engine:
         image = image.contiguous()
         trimap = trimap.contiguous()
         ws = self.workspace(B, R)
-        alpha = torch.empty((B, R, R), dtype=torch.float16, device=self.device)
+        if out is not None:
+            assert out.shape == (B, R, R) and out.dtype == torch.float16 and out.is_cuda and out.is_contiguous()
+        alpha = out if out is not None else torch.empty((B, R, R), dtype=torch.float16, device=self.device)
         pre = torch.empty((B, R, R), dtype=torch.float16, device=self.device) if want_premean else None
         flags = is_transparent if isinstance(is_transparent, (list, tuple)) else [is_transparent] * B
         it = (C.c_int32 * B)(*[1 if f else 0 for f in flags])
@@ -303,6 +322,38 @@ class Engine:
                                              ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
         return out
 
+    def apply_host(self, image: torch.Tensor, trimap: torch.Tensor, R: int, is_transparent=False, output_mode: str = "alpha_only",
+                   mask_refine: bool = True, trimap_constraint: float = 0.8, alpha_out: Optional[torch.Tensor] = None,
+                   matted_out: Optional[torch.Tensor] = None):
+        """The node call (include/sdmatte_b200.h: sdm_apply_matte_host): HOST image [B,H,W,3] / trimap [B,H,W] fp32 of any size
+        (pageable is fine) -> HOST alpha [B,H,W] fp16 and matted [B,H,W,3|4] fp32 (None for "alpha_only").  One library call:
+        staging, H2D, resize, forward, post-processing, D2H, sync."""
+        B, H, W, _ = image.shape
+        assert image.shape == (B, H, W, 3) and trimap.shape == (B, H, W)
+        assert not image.is_cuda and not trimap.is_cuda
+        image = image.contiguous().float()
+        trimap = trimap.contiguous().float()
+        mode = OUTPUT_MODES.get(output_mode, 3)
+        need = self.lib.sdm_node_workspace_bytes(self.h, B, H, W, int(R), mode)
+        if need == 0:
+            _check(1)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if alpha_out is None:
+            alpha_out = torch.empty((B, H, W), dtype=torch.float16)
+        mch = 4 if mode == 1 else 3
+        if mode != 0 and matted_out is None:
+            matted_out = torch.empty((B, H, W, mch), dtype=torch.float32)
+        flags = is_transparent if isinstance(is_transparent, (list, tuple)) else [is_transparent] * B
+        it = (C.c_int32 * B)(*[1 if f else 0 for f in flags])
+        with torch.cuda.device(self.device):
+            _check(self.lib.sdm_apply_matte_host(self.h, image.data_ptr(), trimap.data_ptr(), B, H, W, int(R), it, int(bool(mask_refine)),
+                                                 float(trimap_constraint), mode, alpha_out.data_ptr(),
+                                                 matted_out.data_ptr() if mode != 0 else None, self._ws.data_ptr(), self._ws.numel(),
+                                                 _stream_ptr(self.device)))
+        return alpha_out, (matted_out if mode != 0 else None)
+
     def forward_profiled(self, image: torch.Tensor, trimap: torch.Tensor, is_transparent=False):
         """One forward with CUDA events around every op; returns [(kind, ms, flops, bytes), ...] (measurement aid)."""
         B, R = image.shape[0], image.shape[1]
@@ -325,13 +376,32 @@ class Engine:
         _check(self.lib.sdm_last_forward_stats(self.h, C.byref(n), C.byref(f)))
         return {"launches": n.value, "tensor_flops": f.value}
 
+    def set_option(self, name: str, value: int):
+        """Diagnostics switches of the handle (include/sdmatte_b200.h: sdm_set_option); drops the cached plan and workspace."""
+        _check(self.lib.sdm_set_option(self.h, name.encode(), int(value)))
+        self._ws = None
+
+    def graph_stats(self):
+        c, l = C.c_int(), C.c_int()
+        _check(self.lib.sdm_graph_stats(self.h, C.byref(c), C.byref(l)))
+        return {"captures": c.value, "launches": l.value}
+
+    def tap_names(self):
+        """Names of the block taps of the last forward, in graph order (all of them only with set_option("keep_taps", 1))."""
+        buf = C.create_string_buffer(64)
+        out = []
+        for i in range(self.lib.sdm_debug_tensor_count(self.h)):
+            _check(self.lib.sdm_debug_tensor_name(self.h, i, buf, 64))
+            out.append(buf.value.decode())
+        return out
+
     def debug_tensor(self, name: str) -> torch.Tensor:
         shape = (C.c_int64 * 4)()
         dt = C.c_int()
-        buf = torch.empty(64 << 20, dtype=torch.float16, device=self.device)
-        _check(self.lib.sdm_debug_tensor(self.h, name.encode(), buf.data_ptr(), buf.numel() * 2, shape, C.byref(dt)))
-        n = shape[0] * shape[1] * shape[2] * shape[3]
-        return buf[:n].view(shape[0], shape[1], shape[2], shape[3]).clone()
+        _check(self.lib.sdm_debug_tensor(self.h, name.encode(), None, 0, shape, C.byref(dt)))
+        out = torch.empty((shape[0], shape[1], shape[2], shape[3]), dtype=torch.float16, device=self.device)
+        _check(self.lib.sdm_debug_tensor(self.h, name.encode(), out.data_ptr(), out.numel() * 2, shape, C.byref(dt)))
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -63,10 +63,24 @@ size_t sdm_workspace_bytes(sdm_handle* h, int B, int R);
 int sdm_forward(sdm_handle* h, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
                 void* alpha_dev, void* premean_dev, void* workspace_dev, size_t workspace_bytes, uintptr_t stream);
 
-/* Same, with HOST buffers (pinned or pageable): H2D of image/trimap and D2H of alpha on `stream`, then a stream sync.
- * This is the call the node makes (replaces the .to(device) / .cpu() pair at sdmatte_nodes.py:342,349,363). */
+/* Same, with HOST buffers (pinned or pageable) already at R x R: H2D of image/trimap and D2H of alpha on `stream`, then a
+ * stream sync (replaces the .to(device) / .cpu() pair at sdmatte_nodes.py:342,349,363 for pre-sized inputs; bench / tests). */
 int sdm_forward_host(sdm_handle* h, const float* image_host, const float* trimap_host, int B, int R, const int32_t* is_trans,
                      void* alpha_host_f16, void* workspace_dev, size_t workspace_bytes, uintptr_t stream);
+
+/* THE call the `Apply SDMatte` node makes — everything between the argument checks and the return of
+ * SDMatteApply.apply_matte (sdmatte_nodes.py:339-397) for host tensors of ANY size:
+ *   image_host [B][H][W][3] fp32 / trimap_host [B][H][W] fp32 (pageable ComfyUI tensors are fine: they are staged through a
+ *   page-locked buffer owned by the handle, by several host threads, chunk by chunk, each chunk's H2D enqueued behind its memcpy)
+ *   -> antialiased resize to R x R (only if (H, W) != (R, R)) -> sdm_forward -> resize back + clamp + mask_refine + output_mode
+ *   composition -> D2H -> alpha_out_host_f16 [B][H][W] fp16 and matted_out_host [B][H][W][3|4] fp32 (NULL / untouched for
+ *   output_mode 0 "alpha_only": the caller returns zeros, sdmatte_nodes.py:384-385).  Synchronises `stream` before returning.
+ * The device-side staging lives behind the plan arena in the caller's workspace (sdm_node_workspace_bytes), at fixed offsets,
+ * so repeated calls of one geometry replay the plan's CUDA graph. */
+size_t sdm_node_workspace_bytes(sdm_handle* h, int B, int H, int W, int R, int output_mode);
+int sdm_apply_matte_host(sdm_handle* h, const float* image_host, const float* trimap_host, int B, int H, int W, int R,
+                         const int32_t* is_trans, int mask_refine, double trimap_constraint, int output_mode, void* alpha_out_host_f16,
+                         float* matted_out_host, void* workspace_dev, size_t workspace_bytes, uintptr_t stream);
 
 /* Node-side pre/post-processing on the device, all pointers are device pointers.
  * sdm_preprocess replaces torchvision Resize(antialias=True) of image and trimap to R x R
@@ -96,9 +110,23 @@ int sdm_profile_entry(sdm_handle* h, int i, char* kind, int kind_len, float* ms,
 int sdm_last_forward_stats(sdm_handle* h, int* n_launches, double* tensor_flops);
 
 /* Intermediate taps for block-level parity tests: copies the named activation of the LAST forward into dst (device).
- * Names: "unet_in" [B,S,S,8] (rgb latent | trimap latent), "ctx" [B,S,S,1024] (trimap tokens),
- * "unet_out_scaled" [B,S,S,4] (UNet output / scaling_factor).  shape4 receives (B,H,W,C); dtype 1 = fp16. */
+ * Always available: "unet_in" [B,S,S,8] (rgb latent | trimap latent), "ctx" [B,S,S,1024] (trimap tokens),
+ * "unet_out_scaled" [B,S,S,4] (UNet output / scaling_factor).  With sdm_set_option(h, "keep_taps", 1) one tap per block of the
+ * graph (SDMatte.forward meta_arch.py:127-261 / CustomUNet.forward replace.py:462-544 / the VAE, in graph order, enumerated by
+ * sdm_debug_tensor_count / _name): "enc.conv_in", "enc.down0..3", "enc.mid_attn", "enc.mid" (batch 2B: rgb samples, then
+ * trimap samples), "unet.conv_in", "unet.down{i}.{j}", "unet.down{i}.ds", "unet.mid", "unet.up{i}.{j}" (the last block of an
+ * up stage is tapped after its fused nearest-x2 store), "unet.up{i}.us", "dec.conv_in", "dec.mid", "dec.up0..3".
+ * shape4 receives (B,H,W,C); dtype 1 = fp16.  dst_dev == NULL: shape query only. */
 int sdm_debug_tensor(sdm_handle* h, const char* name, void* dst_dev, size_t dst_bytes, int64_t* shape4, int* dtype);
+int sdm_debug_tensor_count(sdm_handle* h);
+int sdm_debug_tensor_name(sdm_handle* h, int i, char* name, int name_len);
+/* Engine options (changing one drops the cached plan): "keep_taps" 0/1 (diagnostics) — tapped block outputs are not recycled
+ * by the workspace arena, so sdm_workspace_bytes grows.  "cuda_graph" 0/1 (default 1): when a forward is called again with
+ * the same (B, R, workspace, image/trimap/alpha pointers) the ~700 launches of the plan are replayed as ONE CUDA graph
+ * (captured on an internal stream, launched on the caller's); sdm_forward_host always qualifies (it stages through fixed
+ * buffers in the workspace).  sdm_graph_stats: graphs captured / graph launches so far. */
+int sdm_set_option(sdm_handle* h, const char* name, int value);
+int sdm_graph_stats(sdm_handle* h, int* captures, int* launches);
 
 /* ---- single-kernel entry points (parity tests at the kernel level; all pointers are device pointers) ---- */
 typedef struct {

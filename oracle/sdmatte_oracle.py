@@ -22,8 +22,16 @@ The functions below follow, line by line:
 with node flags frozen as sdmatte_nodes.py:286-296 sets them (aux_input="trimap", use_coor_input=True, ...).
 State-dict keys are the reference's (`unet.*`, `vae.*`), so a real SDMatte.safetensors drops in.
 
-mode="fp32"   : everything in fp32 (what the reference's CPU branch computes, sdmatte_nodes.py:359-360)
-mode="fp16sim": fp32 math with the fp16 rounding points of the reference's CUDA autocast path emulated
+mode="fp32"    : everything in fp32 (what the reference's CPU branch computes, sdmatte_nodes.py:359-360)
+mode="fp16sim" : fp32 math with the fp16 rounding points of the reference's CUDA autocast path emulated
+mode="autocast": the reference's real CUDA branch (sdmatte_nodes.py:355-358): the same graph on a CUDA device under a
+                 genuine `torch.autocast("cuda", dtype=torch.float16)` with fp32 master weights (cuDNN / cuBLAS kernels — allowed
+                 for the checker, never for the product), UNet attention = SlicedAttnProcessor(slice_size=1) semantics
+                 (sdmatte_nodes.py:331-335): one (sample, head) slice at a time through `torch.baddbmm` + softmax + `torch.bmm`
+                 exactly as custom_get_attention_scores (replace.py:75-122); VAE attention = SDPA (diffusers default processor).
+`device`: where the graph runs ("cpu" default; "cuda" for the GPU-resident checker and the GPU baseline of bench.py).  fp32 on a
+CUDA device runs with TF32 disabled.  `capture`: receives, besides the outputs, one tensor per block ("taps", graph order kept in
+capture["_order"]) for the per-block error-growth curves of tests/test_parity_gpu.py.
 """
 from __future__ import annotations
 
@@ -40,10 +48,18 @@ VAE_CH = (128, 256, 512, 512)
 
 
 class _Ctx:
-    def __init__(self, sd, mode, sliced):
+    def __init__(self, sd, mode, sliced, device="cpu", capture=None):
         self.sd = sd
         self.mode = mode
         self.sliced = sliced
+        self.device = torch.device(device)
+        self.capture = capture
+
+    def tap(self, name, x):
+        """Record a block output (NCHW) for the per-block parity curves; no-op unless a capture dict was given."""
+        if self.capture is not None:
+            self.capture[name] = x.detach()
+            self.capture.setdefault("_order", []).append(name)
 
     def r(self, x):  # fp16 rounding point of the autocast path
         return x.half().float() if self.mode == "fp16sim" else x
@@ -57,7 +73,7 @@ class _Ctx:
 def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
     """diffusers get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0) as called at meta_arch.py:181-186."""
     half = dim // 2
-    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half
+    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half
     emb = t[:, None].float() * torch.exp(exponent)[None, :]
     return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
 
@@ -106,7 +122,7 @@ def prepare_key_bias(attention_mask: torch.Tensor, target_length: int) -> torch.
 
 
 def _attention(c, x, ctx, p, heads, key_bias):
-    """diffusers Attention with AttnProcessor + custom_get_attention_scores (replace.py:75-122)."""
+    """diffusers Attention with AttnProcessor / SlicedAttnProcessor(1) + custom_get_attention_scores (replace.py:75-122)."""
     B, L, C = x.shape
     q = _linear(c, x, p + ".to_q", bias=False)
     k = _linear(c, ctx, p + ".to_k", bias=False)
@@ -120,13 +136,31 @@ def _attention(c, x, ctx, p, heads, key_bias):
     bias = None
     if key_bias is not None:
         bias = prepare_key_bias(key_bias, Lk)[:, :, None, :]  # (B,1,1,Lk) -> every head, every query row
-    out = torch.empty(B, heads, L, d)
+    if c.mode == "autocast":
+        # SlicedAttnProcessor(slice_size=1): the (B*heads) slices one at a time; per slice replace.py:92-120 verbatim in effect:
+        # baddbmm(mask or empty, q, k^T, beta, alpha=scale) [autocast: fp16 out] -> softmax [autocast: fp32] -> .to(q.dtype) -> bmm
+        out = torch.zeros(B, heads, L, d, device=q.device, dtype=q.dtype)
+        for b in range(B):
+            for h in range(heads):
+                qs, ks, vs = q[b, h:h + 1], k[b, h:h + 1], v[b, h:h + 1]
+                if bias is not None:
+                    s = torch.baddbmm(bias[b], qs, ks.transpose(-1, -2), beta=1, alpha=scale)
+                else:
+                    empty = torch.empty(1, L, Lk, dtype=qs.dtype, device=qs.device)
+                    s = torch.baddbmm(empty, qs, ks.transpose(-1, -2), beta=0, alpha=scale)
+                pr = s.softmax(dim=-1).to(qs.dtype)
+                del s
+                out[b, h:h + 1] = torch.bmm(pr, vs)
+                del pr
+        out = out.transpose(1, 2).reshape(B, L, C)
+        return _linear(c, out, p + ".to_out.0")
+    out = torch.empty(B, heads, L, d, device=q.device)
     for b in range(B):
         for h in range(heads if c.sliced else 1):
             hs = slice(h, h + 1) if c.sliced else slice(None)
             s = torch.matmul(q[b, hs], k[b, hs].transpose(-1, -2)) * scale  # baddbmm(beta, alpha=scale)
             if bias is not None:
-                s = s + bias[b]
+                s = s + c.r(bias[b])  # autocast casts the additive mask to fp16 too (exact for 0 / -5000 / -10000)
             s = c.r(s)
             pr = c.r(s.softmax(dim=-1))
             out[b, hs] = c.r(torch.matmul(pr, v[b, hs]))
@@ -159,6 +193,7 @@ def unet_forward(c, sample, trans, ctx, bbox_coords_emb, attention_mask, capture
     aug_emb = _time_mlp(c, bbox_coords_emb.reshape(B, -1), "unet.bbox_embedding")  # :451-455
     emb = c.r(op_emb + aug_emb)  # :459
     x = _conv(c, sample, "unet.conv_in")  # :462
+    c.tap("unet.conv_in", x)
     skips = [x]
     for i in range(4):
         bp = f"unet.down_blocks.{i}"
@@ -166,13 +201,16 @@ def unet_forward(c, sample, trans, ctx, bbox_coords_emb, attention_mask, capture
             x = _resnet(c, x, f"{bp}.resnets.{j}", emb, 1e-5)
             if i < 3:
                 x = _transformer(c, x, f"{bp}.attentions.{j}", UNET_HEADS[i], ctx, key_bias)
+            c.tap(f"unet.down{i}.{j}", x)
             skips.append(x)
         if i < 3:
             x = _conv(c, x, f"{bp}.downsamplers.0.conv", stride=2, padding=1)
+            c.tap(f"unet.down{i}.ds", x)
             skips.append(x)
     x = _resnet(c, x, "unet.mid_block.resnets.0", emb, 1e-5)
     x = _transformer(c, x, "unet.mid_block.attentions.0", 20, ctx, key_bias)
     x = _resnet(c, x, "unet.mid_block.resnets.1", emb, 1e-5)
+    c.tap("unet.mid", x)
     rheads = (20, 20, 10, 5)
     for i in range(4):
         bp = f"unet.up_blocks.{i}"
@@ -181,9 +219,13 @@ def unet_forward(c, sample, trans, ctx, bbox_coords_emb, attention_mask, capture
             x = _resnet(c, x, f"{bp}.resnets.{j}", emb, 1e-5)
             if i > 0:
                 x = _transformer(c, x, f"{bp}.attentions.{j}", rheads[i], ctx, key_bias)
+            if not (i < 3 and j == 2):
+                c.tap(f"unet.up{i}.{j}", x)
         if i < 3:
             x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+            c.tap(f"unet.up{i}.2", x)  # tapped AFTER the nearest x2 (the engine fuses the upsampling into the block's store)
             x = _conv(c, x, f"{bp}.upsamplers.0.conv")
+            c.tap(f"unet.up{i}.us", x)
     assert not skips
     x = F.silu(_gn(c, x, "unet.conv_norm_out", 1e-5))
     return _conv(c, x, "unet.conv_out")
@@ -196,24 +238,32 @@ def _vae_attention(c, x, p):
     q, k, v = _linear(c, h, p + ".to_q"), _linear(c, h, p + ".to_k"), _linear(c, h, p + ".to_v")
     out = torch.empty_like(q)
     for b in range(B):
+        if c.mode == "autocast":  # AttnProcessor2_0: F.scaled_dot_product_attention on the fp16 q/k/v, one head of 512
+            out[b] = F.scaled_dot_product_attention(q[b][None, None], k[b][None, None], v[b][None, None])[0, 0]
+            continue
         s = torch.matmul(q[b], k[b].transpose(0, 1)) * (C ** -0.5)
         out[b] = c.r(torch.matmul(s.softmax(dim=-1), v[b]))
+        del s
     out = _linear(c, out, p + ".to_out.0").transpose(1, 2).reshape(B, C, H, W)
     return c.r(out + x)
 
 
-def vae_encode(c, x):
+def vae_encode(c, x, tag="enc"):
     """AutoencoderKL.encoder + quant_conv, mean half, * scaling_factor (meta_arch.py:142-145,209-212)."""
     e = "vae.encoder"
     h = _conv(c, x, e + ".conv_in")
+    c.tap(f"{tag}.conv_in", h)
     for i in range(4):
         for j in range(2):
             h = _resnet(c, h, f"{e}.down_blocks.{i}.resnets.{j}", None, 1e-6)
         if i < 3:
             h = _conv(c, F.pad(h, (0, 1, 0, 1)), f"{e}.down_blocks.{i}.downsamplers.0.conv", stride=2, padding=0)
+        c.tap(f"{tag}.down{i}", h)
     h = _resnet(c, h, e + ".mid_block.resnets.0", None, 1e-6)
     h = _vae_attention(c, h, e + ".mid_block.attentions.0")
+    c.tap(f"{tag}.mid_attn", h)
     h = _resnet(c, h, e + ".mid_block.resnets.1", None, 1e-6)
+    c.tap(f"{tag}.mid", h)
     h = _conv(c, F.silu(_gn(c, h, e + ".conv_norm_out", 1e-6)), e + ".conv_out")
     moments = _conv(c, h, "vae.quant_conv", padding=0)
     mean, _ = torch.chunk(moments, 2, dim=1)
@@ -225,39 +275,66 @@ def vae_decode(c, z):
     d = "vae.decoder"
     h = _conv(c, z, "vae.post_quant_conv", padding=0)
     h = _conv(c, h, d + ".conv_in")
+    c.tap("dec.conv_in", h)
     h = _resnet(c, h, d + ".mid_block.resnets.0", None, 1e-6)
     h = _vae_attention(c, h, d + ".mid_block.attentions.0")
     h = _resnet(c, h, d + ".mid_block.resnets.1", None, 1e-6)
+    c.tap("dec.mid", h)
     for i in range(4):
         for j in range(3):
             h = _resnet(c, h, f"{d}.up_blocks.{i}.resnets.{j}", None, 1e-6)
         if i < 3:
             h = F.interpolate(h, scale_factor=2.0, mode="nearest")
             h = _conv(c, h, f"{d}.up_blocks.{i}.upsamplers.0.conv")
+        c.tap(f"dec.up{i}", h)
     return _conv(c, F.silu(_gn(c, h, d + ".conv_norm_out", 1e-6)), d + ".conv_out")
+
+
+def to_device(sd: Dict[str, torch.Tensor], device) -> Dict[str, torch.Tensor]:
+    """fp32 master copy of the checkpoint on `device` (what `.to(device)` leaves at sdmatte_nodes.py:323)."""
+    return {k: v.float().to(device) for k, v in sd.items() if k.startswith(("unet.", "vae."))}
 
 
 @torch.no_grad()
 def forward(sd: Dict[str, torch.Tensor], image: torch.Tensor, trimap: torch.Tensor, is_transparent=False,
-            mode: str = "fp32", sliced: bool = False, capture: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+            mode: str = "fp32", sliced: bool = False, capture: Optional[dict] = None, device="cpu") -> Dict[str, torch.Tensor]:
     """image (B,R,R,3) fp32 in [0,1] and trimap (B,R,R) fp32 in [0,1], both ALREADY at inference size R.
 
-    Returns {"alpha": (B,1,R,R) in [0,1], "label_mean": pre-clip decoder channel mean, + intermediates}.
+    Returns {"alpha": (B,1,R,R) in [0,1], "label_mean": pre-clip decoder channel mean, + intermediates} on `device`.
     Follows sdmatte_nodes.py:339-360 (pre-processing at native size) then meta_arch.py:127-261.
+    `sd` must already live on `device` (see to_device) — the reference moves the model once, before the forward.
     """
-    c = _Ctx(sd, mode, sliced)
+    device = torch.device(device)
+    if mode == "autocast":
+        assert device.type == "cuda", "mode='autocast' is the reference's CUDA branch (sdmatte_nodes.py:355-358)"
+        with torch.autocast(device_type="cuda", dtype=torch.float16):
+            return _forward(sd, image, trimap, is_transparent, mode, True, capture, device)
+    if device.type == "cuda":  # fp32 checker on the GPU: no TF32 anywhere
+        old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            return _forward(sd, image, trimap, is_transparent, mode, sliced, capture, device)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return _forward(sd, image, trimap, is_transparent, mode, sliced, capture, device)
+
+
+def _forward(sd, image, trimap, is_transparent, mode, sliced, capture, device):
+    c = _Ctx(sd, mode, sliced, device, capture)
     B = image.shape[0]
+    image, trimap = image.to(device), trimap.to(device)
     rgb = (image.permute(0, 3, 1, 2).float() - 0.5) / 0.5  # Normalize(0.5, 0.5), sdmatte_nodes.py:204-209
     tri = trimap.unsqueeze(1).float() * 2 - 1  # sdmatte_nodes.py:351
     flags = is_transparent if isinstance(is_transparent, (list, tuple)) else [is_transparent] * B
-    is_trans = torch.tensor([1 if f else 0 for f in flags])
+    is_trans = torch.tensor([1 if f else 0 for f in flags], device=device)
 
-    aux_latent = vae_encode(c, tri.repeat(1, 3, 1, 1))  # meta_arch.py:139-145
-    coor = torch.tensor([[0.0, 0.0, 1.0, 1.0]] * B)  # sdmatte_nodes.py:353
+    aux_latent = vae_encode(c, tri.repeat(1, 3, 1, 1), "enc_tri")  # meta_arch.py:139-145
+    coor = torch.tensor([[0.0, 0.0, 1.0, 1.0]] * B, device=device)  # sdmatte_nodes.py:353
     coor_emb = timestep_embedding(coor.flatten(), 320)  # meta_arch.py:181-187
     attention_mask = (tri + 1) / 2  # meta_arch.py:200-204
     attention_mask = F.interpolate(attention_mask, scale_factor=1 / 8, mode="nearest").flatten(start_dim=1)
-    rgb_latent = vae_encode(c, rgb)  # meta_arch.py:209-212
+    rgb_latent = vae_encode(c, rgb, "enc_rgb")  # meta_arch.py:209-212
     ehs = _conv(c, aux_latent, "unet.aux_conv_in")  # meta_arch.py:215-218
     ehs = ehs.view(B, 1024, -1).permute(0, 2, 1)
     trans = 1 - is_trans  # meta_arch.py:237-238

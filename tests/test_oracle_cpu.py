@@ -111,15 +111,16 @@ def test_postprocess_matches_reference(lifted, mode, refine):
 
 
 def test_node_runs_pre_and_post_on_the_device():
-    """§8(f) n1: the node has no torch/CPU resize or refine code of its own any more — both sides of the model call go
-    through the C ABI (sdm_preprocess / sdm_postprocess; GPU parity in tests/test_prepost_gpu.py)."""
+    """§8(f) n1: the node has no torch/CPU resize or refine code of its own — everything between its argument checks and its
+    return is the C-ABI node call (sdm_apply_matte_host: staging, resize, forward, post-processing; GPU parity of the pre/post
+    kernels in tests/test_prepost_gpu.py, of the whole call in tests/test_multigpu_gpu.py)."""
     import inspect
 
     import __graft_entry__ as ge
 
     nodes = ge.load_package().sdmatte_nodes
     src = inspect.getsource(nodes.SDMatteApply.apply_matte)
-    assert "_engine.preprocess(" in src and "_engine.postprocess(" in src
+    assert "eng.apply_host(" in src and ".cuda(" not in src and ".to(device=device" not in src
     assert "interpolate(" not in inspect.getsource(nodes) and ".clamp(" not in src and "refined" not in src
     node = nodes.SDMatteApply()
     assert node.RETURN_TYPES == ("MASK", "IMAGE") and node.FUNCTION == "apply_matte"
@@ -265,10 +266,14 @@ def test_node_surface_matches_reference_schema():
     assert list(inspect.signature(cls.apply_matte).parameters) == ["self", "ckpt_name", "image", "trimap", "inference_size", "is_transparent",
                                                                     "output_mode", "mask_refine", "trimap_constraint", "force_cpu"]
     nodes = pkg.sdmatte_nodes
-    with pytest.raises(ValueError):
-        nodes.find_checkpoint("nope.safetensors")
-    with pytest.raises(FileNotFoundError):
-        nodes.find_checkpoint("SDMatte.safetensors")
+    os.environ["SDMATTE_OFFLINE"] = "1"  # no network here: a missing checkpoint must be a clear error, not a download attempt
+    try:
+        with pytest.raises(ValueError):
+            nodes.find_checkpoint("nope.safetensors")
+        with pytest.raises(FileNotFoundError):
+            nodes.find_checkpoint("SDMatte.safetensors")
+    finally:
+        del os.environ["SDMATTE_OFFLINE"]
 
 
 def test_flop_model_matches_survey():
