@@ -163,6 +163,7 @@ int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream) {
   d.res = reinterpret_cast<const __half*>(a->res); d.res_ld = a->res_ld; d.res_bstride = a->res_bstride;
   d.scale = a->scale; d.force_block_n = a->force_block_n;
   d.post_div = a->post_div == 0.f ? 1.f : a->post_div; d.n_store = a->n_store; d.out2 = a->out2; d.force_mt = a->force_mt; d.stats = a->stats; d.force_light = a->force_light; d.force_pair = a->force_pair; d.force_halo = a->force_halo; d.force_swap = a->force_swap;
+  d.gn_ab = a->gn_ab; d.gn_silu = a->gn_silu;
   auto l = sdm::conv_gemm_build(d, sdm::device_sm_count());
   sdm::conv_gemm_run(*l, reinterpret_cast<cudaStream_t>(stream));
   SDM_API_END
@@ -171,6 +172,10 @@ int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream) {
 int sdm_k_conv_tiles_per_image(int Hout, int Wout) { return sdm::conv_gemm_tiles_per_image(Hout, Wout); }
 int sdm_k_conv_variant(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout) {
   return sdm::conv_gemm_variant_code(ksize, stride, mode, ups2, N, has_res, Hout, Wout);
+}
+
+int sdm_k_conv_can_fuse_gn(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout) {
+  return sdm::conv_gemm_can_fuse_gn(ksize, stride, mode, ups2, N, has_res, Hout, Wout) ? 1 : 0;
 }
 
 int sdm_k_attention(const sdm_attn_args* a, uintptr_t stream) {
@@ -210,6 +215,7 @@ int sdm_k_gather_rows(const void* src, void* dst, const int32_t* idx, const int3
 }
 
 size_t sdm_k_groupnorm_scratch_floats(int B, int HW, int C) { return sdm::groupnorm_scratch_floats(B, HW, C); }
+size_t sdm_k_groupnorm_ab_offset(int B, int HW, int C) { return sdm::groupnorm_ab_offset_floats(B, HW, C); }
 int sdm_k_groupnorm(const sdm_groupnorm_args* a, uintptr_t stream) {
   SDM_API_BEGIN
   sdm::GroupNormDesc d;

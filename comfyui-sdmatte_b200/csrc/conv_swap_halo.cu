@@ -1,5 +1,5 @@
-// STAGED FOR THE NEXT ROUND — compiled, reachable only with SDM_SWAP_HALO=1, NOT yet run on hardware (written after this
-// round's GPU budget was spent).  The default path never launches it.
+// Swapped-operand 3x3 convolution with a RESIDENT PIXEL HALO TILE, optionally with the input's GroupNorm(+SiLU) fused in.
+// (written in round 1, first run on hardware in round 2: tests/test_kernels_gpu.py -k swapped)
 //
 // conv_swap_kernel (channels on the MMA's M, 256 pixels on N) with a RESIDENT PIXEL HALO TILE: per 64-channel slice ONE TMA box
 // of (8+2) x (32+2) pixels is fetched, and the nine taps are nine B-operand descriptors of that tile started (dy*10 + dx) pixel
@@ -8,6 +8,16 @@
 // K step, ~51 B/clk/SM measured); here the fill per slice is 43.5 KB + 9 x 16 KB of weights instead of 9 x 48 KB.
 // Tile = 8 wide x 32 tall pixel patch (N = 256 = 32 groups of 8 rows) x 128 output channels; GroupNorm partials: two slots per
 // patch (128 pixels each), as in conv_swap_kernel.
+//
+// GNF (round 2): the conv of a ResnetBlock2D consumes GroupNorm(32) -> SiLU of its input (reference: diffusers ResnetBlock2D, built at
+// /root/reference/src/utils/replace.py:239,268,321).  As a separate pass that is one full HBM read + write of the activation per
+// conv (27 ms of a 280 ms step).  With the halo tile an activation slice sits in shared memory exactly ONCE per 64 channels, so
+// four TRANSFORM warps apply y = silu(a x + s) in place (per-(sample, channel) (a, s) from gn_finalize_kernel, the same arithmetic
+// as gn_apply_kernel: identical fp16 bits) between the TMA's arrival (xfull) and the MMA's use (xready).  Rows outside the image
+// were zero-filled by the TMA unit and stay zero: the convolution pads the NORMALISED tensor.  The 128-byte swizzle is undone
+// per thread: 16-byte piece j of tile row r holds channel chunk j ^ (r & 7); a thread keeps (piece, r mod 16), hence one fixed
+// chunk and its 16 constants in registers.
+#include "gn_math.cuh"
 #include "umma_gemm.cuh"
 
 namespace sdm {
@@ -22,11 +32,14 @@ constexpr int kXSlots = 2;
 constexpr int kStgBytes = 4 * 2048;
 constexpr int kPipe = kWStages * kWBytes + kXSlots * kXSlot;
 constexpr int kSmem = kPipe + 1024 + 256 + kStgBytes;
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kThreadsGN = 320;    // + warps 6..9: GroupNorm transform
+constexpr int kXRows = 10 * 34;    // pixel rows of a halo tile
 static_assert(kSmem <= 232448, "shared memory budget");
 }  // namespace swh
 
-__global__ void __launch_bounds__(swh::kThreads, 1) conv_swap_halo_kernel(const __grid_constant__ ConvGemmParams p) {
+template <bool GNF>
+__global__ void __launch_bounds__(GNF ? swh::kThreadsGN : swh::kThreads, 1) conv_swap_halo_kernel(const __grid_constant__ ConvGemmParams p) {
   using namespace swh;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -39,7 +52,8 @@ __global__ void __launch_bounds__(swh::kThreads, 1) conv_swap_halo_kernel(const 
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kWStages + 4 + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kWStages + 6 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kWStages + 8);
-  static_assert(8 * (2 * kWStages + 8) + 4 <= 256, "barrier area");
+  auto xready_bar = [&](int s) { return bar_base + 8u * (2 * kWStages + 9 + s); };  // GNF: the slot's tile has been normalised
+  static_assert(8 * (2 * kWStages + 11) <= 256, "barrier area");
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -47,6 +61,7 @@ __global__ void __launch_bounds__(swh::kThreads, 1) conv_swap_halo_kernel(const 
     for (int s = 0; s < kWStages; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
     for (int s = 0; s < kXSlots; ++s) { mbar_init(xfull_bar(s), 1); mbar_init(xempty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    if (GNF) for (int s = 0; s < kXSlots; ++s) mbar_init(xready_bar(s), 4);  // one arrive per transform warp
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -111,7 +126,7 @@ __global__ void __launch_bounds__(swh::kThreads, 1) conv_swap_halo_kernel(const 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int sl = 0; sl < nslices + nres; ++sl) {
-          mbar_wait(xfull_bar(xs), xph);
+          mbar_wait(GNF ? xready_bar(xs) : xfull_bar(xs), xph);
           const uint32_t x_addr = x_base + xs * kXSlot;
           const bool resid = sl >= nslices;
           const int ntap = resid ? 1 : 9;
@@ -131,6 +146,56 @@ __global__ void __launch_bounds__(swh::kThreads, 1) conv_swap_halo_kernel(const 
         }
         umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (GNF && warp >= 6) {
+    // ============================== GroupNorm transform (4 warps) ==============================
+    const int t = threadIdx.x - kThreads;      // 0..127
+    const int piece = t & 7, r0 = t >> 3;      // rows r0, r0 + 16, ... of the tile; r & 7 == r0 & 7 for all of them
+    const int chunk = piece ^ (r0 & 7);        // channel chunk (8 channels) this thread's pieces hold
+    int xs = 0;
+    uint32_t xph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles;
+      const int t_img = mt % per_image;
+      const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32, b = mt / per_image;
+      const float* ab_b = p.gn_ab + (size_t)b * p.cin_total * 2;
+      // validity of this thread's rows depends on the tile position only: bit k = row r0 + 16 k lies inside the image
+      uint32_t inside = 0;
+#pragma unroll 1
+      for (int k = 0; k < 22; ++k) {
+        const int r = r0 + 16 * k;
+        const int px = x0 - 1 + r % 10, py = y0 - 1 + r / 10;
+        if (r < kXRows && px >= 0 && px < p.W && py >= 0 && py < p.H) inside |= 1u << k;
+      }
+      int coff = 0;
+      for (int s = 0; s < p.nsrc; ++s) {
+        for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
+          uint64_t ka[4], ks[4];
+          if (p.gn_silu) gn_load_consts<true>(ab_b + (size_t)(coff + c0 + chunk * 8) * 2, ka, ks);
+          else gn_load_consts<false>(ab_b + (size_t)(coff + c0 + chunk * 8) * 2, ka, ks);
+          mbar_wait(xfull_bar(xs), xph);
+          uint8_t* tile_p = smem_raw + (x_base + xs * kXSlot - smem_u32(smem_raw)) + r0 * 128 + piece * 16;
+#pragma unroll 2
+          for (int k = 0; k < 22; ++k) {
+            if (inside & (1u << k)) {
+              uint4* q = reinterpret_cast<uint4*>(tile_p + k * 2048);
+              const uint4 v = *q;
+              *q = p.gn_silu ? gn_piece<true>(v, ka, ks) : gn_piece<false>(v, ka, ks);
+            }
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(xready_bar(xs));
+          if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
+        }
+        coff += p.src_c[s];
+      }
+      for (int i = 0; i < nres; ++i) {  // residual boxes pass through untouched
+        mbar_wait(xfull_bar(xs), xph);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xready_bar(xs));
+        if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
       }
     }
   } else {
@@ -206,9 +271,15 @@ __global__ void __launch_bounds__(swh::kThreads, 1) conv_swap_halo_kernel(const 
 }
 
 void conv_swap_halo_launch(const ConvGemmParams& p, int grid, cudaStream_t st) {
-  static PerDeviceOnce attr;
-  attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::kSmem)); });
-  conv_swap_halo_kernel<<<grid, swh::kThreads, swh::kSmem, st>>>(p);
+  if (p.gn_ab) {
+    static PerDeviceOnce attr;
+    attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::kSmem)); });
+    conv_swap_halo_kernel<true><<<grid, swh::kThreadsGN, swh::kSmem, st>>>(p);
+  } else {
+    static PerDeviceOnce attr;
+    attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::kSmem)); });
+    conv_swap_halo_kernel<false><<<grid, swh::kThreads, swh::kSmem, st>>>(p);
+  }
   SDM_CUDA_OK(cudaGetLastError());
 }
 

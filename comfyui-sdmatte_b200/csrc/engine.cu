@@ -383,6 +383,8 @@ struct Builder {
     int n_store = 0;
     bool alpha_slots = false;  // EPI_ALPHA: outputs come from the per-call slots
     T* stats_for = nullptr;    // EPI_F16 (no ups2): attach GroupNorm partial statistics of the output to this tensor
+    const float* gn_ab = nullptr;  // fused GroupNorm(+SiLU) of the input (the conv normalises its resident halo tile itself)
+    int gn_silu = 0;
     const char* label = nullptr;
   };
   // generic tensor-core conv (ksize 1/3) over one or two channel-concatenated sources
@@ -421,6 +423,7 @@ struct Builder {
     d.post_div = o.post_div;
     d.n_store = o.n_store;
     d.stats = stats_ptr;
+    d.gn_ab = o.gn_ab; d.gn_silu = o.gn_silu;
     if (o.mode == EPI_ALPHA) { d.out_ld = 1; d.out_bstride = (long long)Hout * Wout; }
     auto l = conv_gemm_build(d, E.num_sms);
     const double by = 2.0 * a.B * ((double)a.HW() * (a.C + (a2 ? a2->C : 0)) + (double)Hout * Wout * N * (o.ups2 ? 4 : 1) * (o.mode == EPI_GEGLU ? 0.5 : 1.0) +
@@ -470,6 +473,33 @@ struct Builder {
     arena.release(soff, sbytes);
     return out;
   }
+  // GroupNorm whose apply pass is fused into the consuming 3x3 conv (conv_gemm_can_fuse_gn): statistics + finalize only.
+  // The (scale, shift) table lives in the scratch block, which must stay allocated until the consuming conv has been emitted.
+  struct GnFused { const float* ab = nullptr; size_t soff = 0, sbytes = 0; };
+  GnFused groupnorm_stats_only(const T& a, const T* a2, const std::string& name, float eps) {
+    const int Ctot = a.C + (a2 ? a2->C : 0);
+    const float* gamma = W.vec(name + ".weight", Ctot);
+    const float* beta = W.vec(name + ".bias", Ctot);
+    GnFused g;
+    g.sbytes = groupnorm_scratch_floats(a.B, (int)a.HW(), Ctot) * 4;
+    float* scratch = (float*)alloc_raw(g.sbytes, &g.soff);
+    if (!dry) {
+      GroupNormDesc d;
+      d.B = a.B; d.HW = (int)a.HW(); d.nsrc = a2 ? 2 : 1;
+      d.src[0] = a.p; d.C[0] = a.C; d.ld[0] = a.ld();
+      if (a2) { d.src[1] = a2->p; d.C[1] = a2->C; d.ld[1] = a2->ld(); }
+      d.gamma = gamma; d.beta = beta; d.eps = eps; d.silu = 1;
+      d.out = nullptr; d.scratch = scratch;
+      if (a.stats && (!a2 || (a2->stats && a2->stat_slots == a.stat_slots))) {
+        d.pre_partial[0] = a.stats;
+        d.pre_partial[1] = a2 ? a2->stats : nullptr;
+        d.pre_slots = a.stat_slots;
+      }
+      g.ab = groupnorm_ab(d);
+      push([d](cudaStream_t st) { groupnorm_run(d, st); }, groupnorm_num_launches(d), "groupnorm_stats", 0, 0);
+    } else n_launches += 2;
+    return g;
+  }
   T layernorm(const T& x, const std::string& name) {
     T out = alloc(x.B, x.H, x.W, x.C);
     const float* g = W.vec(name + ".weight", x.C);
@@ -506,18 +536,31 @@ struct Builder {
   // conv1.bias + time_emb_proj(silu(emb)) with two rows (is_transparent = 0 / 1), or null for the VAE.
   T resnet(const T& x, const T* x2, const std::string& p, int Cout, float eps, bool has_temb, int ups2) {
     const int Cin = x.C + (x2 ? x2->C : 0);
-    T n1 = groupnorm(x, x2, p + ".norm1", eps, 1);
+    // GroupNorm -> SiLU -> conv3x3: where the consuming conv can normalise its resident input tile (conv_gemm_can_fuse_gn, a
+    // function of the per-sample geometry only) there is no apply pass and no normalised copy of the activation
+    const bool fuse1 = conv_gemm_can_fuse_gn(3, 1, EPI_F16, 0, Cout, 0, x.H, x.W);
+    const bool fuse2 = conv_gemm_can_fuse_gn(3, 1, EPI_F16, ups2, Cout, 1, x.H, x.W);
     T h = alloc(x.B, x.H, x.W, Cout);
     {
       GemmOpt o;
       if (has_temb) { o.bias = W.raw_vec("temb:" + p, {}); o.bias_sel = d_is_trans; }
       else o.bias = W.vec(p + ".conv1.bias", Cout);
       o.stats_for = &h;  // norm2 statistics come out of this conv's epilogue
-      conv_tc(n1, nullptr, W.conv(p + ".conv1", Cout, Cin, 3), Cout, 3, h, o);
+      if (fuse1) {
+        GnFused g = groupnorm_stats_only(x, x2, p + ".norm1", eps);
+        o.gn_ab = g.ab; o.gn_silu = 1;
+        conv_tc(x, x2, W.conv(p + ".conv1", Cout, Cin, 3), Cout, 3, h, o);
+        arena.release(g.soff, g.sbytes);
+      } else {
+        T n1 = groupnorm(x, x2, p + ".norm1", eps, 1);
+        conv_tc(n1, nullptr, W.conv(p + ".conv1", Cout, Cin, 3), Cout, 3, h, o);
+        free(n1);
+      }
     }
-    free(n1);
-    T n2 = groupnorm(h, nullptr, p + ".norm2", eps, 1);
-    free(h);
+    T n2;
+    GnFused g2;
+    if (fuse2) g2 = groupnorm_stats_only(h, nullptr, p + ".norm2", eps);
+    else { n2 = groupnorm(h, nullptr, p + ".norm2", eps, 1); free(h); }
     T sc;
     const T* resid = &x;
     if (Cin != Cout) {
@@ -536,9 +579,11 @@ struct Builder {
       o.res = resid;
       o.ups2 = ups2;
       o.stats_for = ups2 ? nullptr : &out;
-      conv_tc(n2, nullptr, W.conv(p + ".conv2", Cout, Cout, 3), Cout, 3, out, o);
+      if (fuse2) { o.gn_ab = g2.ab; o.gn_silu = 1; }
+      conv_tc(fuse2 ? h : n2, nullptr, W.conv(p + ".conv2", Cout, Cout, 3), Cout, 3, out, o);
     }
-    free(n2);
+    if (fuse2) { arena.release(g2.soff, g2.sbytes); free(h); }
+    else free(n2);
     free(sc);
     return out;
   }
@@ -999,11 +1044,21 @@ void engine_destroy(Engine* e) {
 void engine_load(Engine* e, const sdm_tensor_desc* tensors, int n) {
   SDM_CUDA_OK(cudaSetDevice(e->device));
   Weights& W = e->W;
+  W.loaded = false;  // a failed (re)load must leave the engine "not loaded", never half-loaded
   W.free_all();
   W.host.clear();
   W.missing.clear();
   e->plan.reset();
+  SDM_CHECK(n >= 0 && (n == 0 || tensors != nullptr), "sdm_load_weights: null descriptor array");
   for (int i = 0; i < n; ++i) {
+    // the descriptors come across the C ABI: validate before touching shape[] (4 entries) or dereferencing anything
+    SDM_CHECK(tensors[i].name != nullptr, "sdm_load_weights: descriptor without a name");
+    if (tensors[i].ndim < 0 || tensors[i].ndim > 4)
+      throw Error{std::string("sdm_load_weights: '") + tensors[i].name + "' has rank " + std::to_string(tensors[i].ndim) + " (0..4 supported)"};
+    if (tensors[i].dtype < 0 || tensors[i].dtype > 2)
+      throw Error{std::string("sdm_load_weights: '") + tensors[i].name + "' has an unsupported dtype code " + std::to_string(tensors[i].dtype)};
+    SDM_CHECK(tensors[i].data != nullptr, "sdm_load_weights: descriptor without data");
+    for (int d = 0; d < tensors[i].ndim; ++d) SDM_CHECK(tensors[i].shape[d] >= 0, "sdm_load_weights: negative extent");
     HostT t;
     t.dtype = tensors[i].dtype;
     for (int d = 0; d < tensors[i].ndim; ++d) t.shape.push_back(tensors[i].shape[d]);

@@ -46,7 +46,11 @@ struct ConvGemmDesc {
   int force_light = 0;    // tests only: 1 = force the two-CTAs-per-SM config, -1 = forbid it
   int force_pair = 0;     // tests only: 1 = force the CTA-pair (cta_group::2) kernel, -1 = forbid it, 0 = auto
   int force_halo = 0;     // tests only: 1 = force the resident-halo 3x3 kernel, -1 = forbid it, 0 = auto
-  int force_swap = 0;     // tests only: 1 = force the swapped-operand 3x3 kernel (channels on M), -1 = forbid it, 0 = auto
+  int force_swap = 0;     // tests only: 1 = force the swapped-operand 3x3 kernel (channels on M), 2 = its resident-halo form, -1 = forbid, 0 = auto
+  // fused GroupNorm(+SiLU) of the INPUT: the conv reads the raw producer output and normalises its resident halo tile in shared
+  // memory with this [B][cin_total][2] (scale, shift) table (groupnorm_ab); only where conv_gemm_can_fuse_gn() says so
+  const float* gn_ab = nullptr;
+  int gn_silu = 0;
 };
 
 struct ConvGemmLaunch;  // opaque: prebuilt tensor maps + params
@@ -58,6 +62,8 @@ int conv_gemm_tiles_per_image(int Hout, int Wout);  // number of 128-pixel M til
 // kernel variant the engine uses for a conv of this per-sample geometry (no batch size in the signature, on purpose):
 // 0 = one TMA box per tap, 1 / 2 = resident halo tile with 256- / 160-wide tiles, 3 = swapped operands
 int conv_gemm_variant_code(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout);
+// can a conv of this per-sample geometry take its input GroupNorm fused (ConvGemmDesc::gn_ab)?  Geometry only, like the variant.
+bool conv_gemm_can_fuse_gn(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout);
 
 // ------------------------------------------------------------------ flash attention (d = 64)
 struct AttnDesc {
@@ -92,7 +98,7 @@ struct GroupNormDesc {
   const float* beta = nullptr;
   float eps = 1e-5f;
   int silu = 1;
-  __half* out = nullptr;   // [B][HW][C0+C1]
+  __half* out = nullptr;   // [B][HW][C0+C1]; null = statistics + finalize only (the (scale, shift) table stays in scratch: groupnorm_ab)
   float* scratch = nullptr;  // >= groupnorm_scratch_floats(...) floats
   // optional: per-(image tile, channel) partial sums written by the producing conv's epilogue (one buffer per source)
   const float* pre_partial[2] = {nullptr, nullptr};
@@ -100,6 +106,8 @@ struct GroupNormDesc {
 };
 size_t groupnorm_scratch_floats(int B, int HW, int Ctot);
 void groupnorm_run(const GroupNormDesc& d, cudaStream_t st);
+size_t groupnorm_ab_offset_floats(int B, int HW, int Ctot);
+const float* groupnorm_ab(const GroupNormDesc& d);  // [B][C0+C1][2] (scale, shift) inside d.scratch
 int groupnorm_num_launches(const GroupNormDesc& d);  // kernels groupnorm_run will launch for this descriptor (2..4)
 
 void layernorm_run(const __half* x, __half* y, const float* gamma, const float* beta, long long rows, int C, float eps,

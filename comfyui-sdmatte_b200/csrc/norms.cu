@@ -3,6 +3,7 @@
 // nn.LayerNorm in BasicTransformerBlock, softmax in the VAE mid-block attention.
 // All statistics are fp32/fp64; inputs and outputs are fp16 NHWC (the reference's autocast rounding points, A.6).
 #include "common.cuh"
+#include "gn_math.cuh"
 #include "kernels.h"
 
 #include <algorithm>
@@ -177,42 +178,8 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 1) gn_apply_kernel(con
   else { base = s1 + (long long)b * HW * ld1 + (c - C0); ld = ld1; }
   __half* obase = out + (long long)b * HW * Ctot + c;
   uint64_t ka[4], ks[4];  // channel pairs (2j, 2j+1); negated when SILU
-  {
-    const float4* abp = reinterpret_cast<const float4*>(ab + ((size_t)b * Ctot + c) * 2);
-    const float sg = SILU ? -1.0f : 1.0f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 k = __ldg(abp + j);  // (a0, s0, a1, s1)
-      ka[j] = pack_f2(sg * k.x, sg * k.z);
-      ks[j] = pack_f2(sg * k.y, sg * k.w);
-    }
-  }
-  const uint64_t kLog2e = pack_f2(1.4426950408889634f, 1.4426950408889634f);
-  const uint64_t kOne = pack_f2(1.0f, 1.0f), kTwo = pack_f2(2.0f, 2.0f);
-  auto emit = [&](const uint4& raw, __half* dst) {
-    const __half2* h = reinterpret_cast<const __half2*>(&raw);
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(h[j]);
-      uint64_t r = fma_f2(pack_f2(f.x, f.y), ka[j], ks[j]);  // y, or -y when SILU
-      if (SILU) {
-        float t0, t1;
-        unpack_f2(mul_f2(r, kLog2e), t0, t1);                // -y log2(e)
-        const uint64_t d = add_f2(pack_f2(ex2f(fminf(t0, 80.0f)), ex2f(fminf(t1, 80.0f))), kOne);
-        float d0, d1;
-        unpack_f2(d, d0, d1);
-        uint64_t n = pack_f2(__int_as_float(0xFEF311C7 - __float_as_int(d0)), __int_as_float(0xFEF311C7 - __float_as_int(d1)));
-        n = mul_f2(n, fma_f2(d, n, kTwo));
-        n = mul_f2(n, fma_f2(d, n, kTwo));
-        r = mul_f2(r, n);
-      }
-      float y0, y1;
-      unpack_f2(r, y0, y1);
-      w[j] = pack_h2(y0, y1);
-    }
-    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-  };
+  gn_load_consts<SILU>(ab + ((size_t)b * Ctot + c) * 2, ka, ks);
+  auto emit = [&](const uint4& raw, __half* dst) { *reinterpret_cast<uint4*>(dst) = gn_piece<SILU>(raw, ka, ks); };
   // pointer-increment addressing: the 64-bit (pixel * ld) products were 7 instructions per 16-byte load
   int p = p0 + y;
   const __half* src = base + (long long)p * ld;
@@ -246,7 +213,12 @@ static int gn_stats_path(const GroupNormDesc& d) {
 }
 int groupnorm_num_launches(const GroupNormDesc& d) {
   const int path = gn_stats_path(d);
-  return path == 0 ? 3 : path == 1 ? 2 : 2 + d.nsrc;
+  return (path == 0 ? 3 : path == 1 ? 2 : 2 + d.nsrc) - (d.out ? 0 : 1);
+}
+// per-(sample, channel) (scale, shift) table [B][Ctot][2] inside the scratch buffer, valid after groupnorm_run
+size_t groupnorm_ab_offset_floats(int B, int HW, int Ctot) { return (size_t)B * gn_nslab(B, HW, Ctot) * Ctot * 2; }
+const float* groupnorm_ab(const GroupNormDesc& d) {
+  return d.scratch + groupnorm_ab_offset_floats(d.B, d.HW, d.C[0] + (d.nsrc > 1 ? d.C[1] : 0));
 }
 
 void groupnorm_run(const GroupNormDesc& d, cudaStream_t st) {
@@ -297,6 +269,7 @@ void groupnorm_run(const GroupNormDesc& d, cudaStream_t st) {
     gn_finalize_kernel<128><<<d.B * 32, 128, 0, st>>>(partial, partial, Ctot, nslab, Ctot, d.HW, d.eps, d.gamma, d.beta, ab);
   }
   SDM_CUDA_OK(cudaGetLastError());
+  if (!d.out) return;  // finalize only: the consuming conv normalises its resident input tile itself (groupnorm_ab)
   const int app_pps = ny * 16;  // 16 pixels per thread
   const int app_slabs = (d.HW + app_pps - 1) / app_pps;
   const dim3 ag(app_slabs, d.B), ab_(nvec, ny);

@@ -16,6 +16,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <climits>
+#include <cstdint>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -91,20 +94,28 @@ struct Json {
     ws();
     if (p >= e || *p < '0' || *p > '9') fail("expected an unsigned integer");
     uint64_t v = 0;
-    while (p < e && *p >= '0' && *p <= '9') v = v * 10 + (uint64_t)(*p++ - '0');
+    while (p < e && *p >= '0' && *p <= '9') {
+      const uint64_t d = (uint64_t)(*p++ - '0');
+      if (v > (UINT64_MAX - d) / 10) fail("integer does not fit 64 bits");
+      v = v * 10 + d;
+    }
     return v;
   }
-  void skip_value() {  // strings, numbers, literals, nested objects / arrays
+  // unknown per-tensor keys: strings, numbers, literals, nested objects / arrays — the file is untrusted, so the nesting depth
+  // is capped (a header of 100 MB of '[' must not overflow the stack of the ComfyUI process)
+  static constexpr int kMaxDepth = 4;
+  void skip_value(int depth = 0) {
     ws();
     if (p >= e) fail("truncated");
     if (*p == '"') { str(); return; }
     if (*p == '{' || *p == '[') {
+      if (depth >= kMaxDepth) fail("nesting too deep");
       const char close = *p == '{' ? '}' : ']';
       ++p;
       if (peek(close)) { ++p; return; }
       for (;;) {
         if (close == '}') { str(); expect(':'); }
-        skip_value();
+        skip_value(depth + 1);
         if (peek(',')) { ++p; continue; }
         expect(close);
         return;
@@ -112,7 +123,34 @@ struct Json {
     }
     while (p < e && *p != ',' && *p != '}' && *p != ']') ++p;
   }
+  // "__metadata__" must be a flat string -> string object (the format's rule; the safetensors package rejects anything else)
+  void metadata() {
+    expect('{');
+    if (peek('}')) { ++p; return; }
+    for (;;) {
+      str();
+      expect(':');
+      ws();
+      if (p >= e || *p != '"') fail("__metadata__ must map strings to strings");
+      str();
+      if (peek(',')) { ++p; continue; }
+      expect('}');
+      return;
+    }
+  }
 };
+// numel = prod(shape) with overflow detection; false if it does not fit an int64
+static bool checked_numel(const int64_t* shape, int ndim, int64_t* out) {
+  uint64_t n = 1;
+  for (int d = 0; d < ndim; ++d) {
+    const uint64_t s = (uint64_t)shape[d];
+    if (shape[d] < 0) return false;
+    if (s != 0 && n > (uint64_t)INT64_MAX / s) return false;
+    n *= s;
+  }
+  *out = (int64_t)n;
+  return true;
+}
 }  // namespace
 
 std::unique_ptr<SafeTensorsFile> safetensors_open(const char* path) {
@@ -137,7 +175,7 @@ std::unique_ptr<SafeTensorsFile> safetensors_open(const char* path) {
       std::string name = j.str();
       j.expect(':');
       if (name == "__metadata__") {
-        j.skip_value();
+        j.metadata();
       } else {
         StEntry en;
         en.name = std::move(name);
@@ -152,7 +190,9 @@ std::unique_ptr<SafeTensorsFile> safetensors_open(const char* path) {
             if (!j.peek(']')) {
               for (;;) {
                 if (en.ndim >= 8) j.fail("more than 8 dimensions");
-                en.shape[en.ndim++] = (int64_t)j.uint();
+                const uint64_t ext = j.uint();
+                if (ext > (uint64_t)INT64_MAX) j.fail("shape extent does not fit 63 bits");
+                en.shape[en.ndim++] = (int64_t)ext;
                 if (j.peek(',')) { ++j.p; continue; }
                 break;
               }
@@ -172,6 +212,8 @@ std::unique_ptr<SafeTensorsFile> safetensors_open(const char* path) {
         }
         if (!have_off || en.dtype.empty()) j.fail("tensor entry without dtype / data_offsets");
         if (en.begin > en.end || en.end > data_bytes) throw Error{"safetensors: data_offsets of '" + en.name + "' outside the file"};
+        int64_t numel = 0;
+        if (!checked_numel(en.shape, en.ndim, &numel)) throw Error{"safetensors: shape of '" + en.name + "' overflows"};
         f->entries.push_back(std::move(en));
       }
       if (j.peek(',')) { ++j.p; continue; }
@@ -180,6 +222,23 @@ std::unique_ptr<SafeTensorsFile> safetensors_open(const char* path) {
     }
   } else {
     ++j.p;
+  }
+  // the package the reference reads checkpoints with rejects duplicate names and any layout in which the tensors do not tile the
+  // byte buffer exactly (sorted by offset: first begins at 0, each begins where the previous ended, the last ends at the end of
+  // the file): same rules here, so that a file is either valid for both readers or for neither
+  {
+    std::vector<const StEntry*> by_name, by_off;
+    for (auto& en : f->entries) { by_name.push_back(&en); by_off.push_back(&en); }
+    std::sort(by_name.begin(), by_name.end(), [](const StEntry* a, const StEntry* b) { return a->name < b->name; });
+    for (size_t i = 1; i < by_name.size(); ++i)
+      if (by_name[i]->name == by_name[i - 1]->name) throw Error{"safetensors: duplicate tensor name '" + by_name[i]->name + "'"};
+    std::sort(by_off.begin(), by_off.end(), [](const StEntry* a, const StEntry* b) { return a->begin != b->begin ? a->begin < b->begin : a->end < b->end; });
+    uint64_t pos = 0;
+    for (const StEntry* en : by_off) {
+      if (en->begin != pos) throw Error{"safetensors: tensor '" + en->name + "' " + (en->begin < pos ? "overlaps the previous tensor" : "leaves a gap in the byte buffer")};
+      pos = en->end;
+    }
+    if (pos != data_bytes) throw Error{"safetensors: the tensors do not cover the byte buffer (incomplete metadata or trailing bytes)"};
   }
   return f;
 }
@@ -234,10 +293,10 @@ int sdm_safetensors_entry(sdm_safetensors* h, int i, sdm_tensor_desc* out) {
     out->ndim = en.ndim;  // may exceed 4: such tensors are not weights of this model (shape[] holds the first four)
     int64_t numel = 1;
     for (int d = 0; d < 4; ++d) out->shape[d] = d < en.ndim ? en.shape[d] : 0;
-    for (int d = 0; d < en.ndim; ++d) numel *= en.shape[d];
+    if (!sdm::checked_numel(en.shape, en.ndim, &numel)) throw sdm::Error{"safetensors: shape of '" + en.name + "' overflows"};
     const uint8_t* p = h->f->map + h->f->data_start + en.begin;
     if (elem > 0) {
-      if ((uint64_t)numel * (uint64_t)elem != en.end - en.begin) throw sdm::Error{"safetensors: byte size of '" + en.name + "' does not match its shape"};
+      if ((uint64_t)numel > UINT64_MAX / (uint64_t)elem || (uint64_t)numel * (uint64_t)elem != en.end - en.begin) throw sdm::Error{"safetensors: byte size of '" + en.name + "' does not match its shape"};
       if ((reinterpret_cast<uintptr_t>(p) % (uintptr_t)elem) != 0) {  // header length not a multiple of the element size
         if (en.aligned.empty()) en.aligned.assign(p, p + (en.end - en.begin));
         p = en.aligned.data();

@@ -88,11 +88,13 @@ static const __half* identity_matrix() {
 // (test_batch_independence_and_determinism on the GPU, test_conv_variant_is_a_function_of_geometry in the CPU suite).
 struct ConvVariant {
   bool swap_can = false, swap = false;      // conv_swap_kernel possible / selected
+  bool swap_halo_geom = false, swap_halo = false;  // its resident-halo form (8 x 32 patches) possible / selected
   bool halo_geom = false, halo_auto = false;  // resident-halo patches fit / selected without a force flag
   int halo_bn = 0;                          // tile width of the halo kernel by N alone (256 | 160 | 0 = none)
 };
 static ConvVariant conv3x3_variant(int ksize, int stride, int mode, bool light, int ups2, bool batched_w, int N, int n_store, bool has_res,
-                                   int Hout, int Wout, int force_swap, int force_halo, int force_pair, int force_block_n, int force_mt) {
+                                   int Hout, int Wout, int force_swap, int force_halo, int force_pair, int force_block_n, int force_mt,
+                                   bool want_gn = false) {
   ConvVariant v;
   const bool conv3 = ksize == 3 && stride == 1 && mode == EPI_F16 && !light && (n_store == 0 || n_store == N);
   int tw = 128, th = 1;
@@ -103,8 +105,13 @@ static ConvVariant conv3x3_variant(int ksize, int stride, int mode, bool light, 
   static const int env_swap = [] { const char* e = getenv("SDM_SWAP"); return e ? atoi(e) : 1; }();
   v.swap_can = conv3 && !ups2 && !batched_w && N % 128 == 0 && Hout >= 16 && Wout >= 16 &&
                2ll * ((Wout + 15) / 16) * ((Hout + 15) / 16) == tiles_img && (!has_res || N <= kIdentityN);
+  // resident-halo form: 8 x 32 pixel patches, two GroupNorm-partials slots per patch -> only where that equals the default count
+  v.swap_halo_geom = v.swap_can && Hout >= 32 && Wout >= 8 && 2ll * ((Wout + 7) / 8) * ((Hout + 31) / 32) == tiles_img;
+  static const int env_swap_halo = [] { const char* e = getenv("SDM_SWAP_HALO"); return e ? atoi(e) : 0; }();
   v.swap = v.swap_can && force_pair != 1 && force_halo != 1 &&
-           (force_swap == 1 || (force_swap == 0 && env_swap != 0 && N == 128 && force_block_n == 0 && force_mt == 0));
+           (force_swap >= 1 || (want_gn && v.swap_halo_geom) ||
+            (force_swap == 0 && env_swap != 0 && N == 128 && force_block_n == 0 && force_mt == 0));
+  v.swap_halo = v.swap && v.swap_halo_geom && (force_swap == 2 || want_gn || (force_swap == 0 && env_swap_halo != 0));
   // resident halo tile (SDM_HALO=0: one TMA box per tap; force_halo = 1 / -1 from the tests): 8 x 16 pixel patches, used where that
   // gives the default number of M tiles (the slot count conv_gemm_tiles_per_image must not depend on the kernel choice).
   // Tile width by N alone: 256 | 160 (the small-problem narrowing of pick_block_n depends on the batch size).
@@ -115,6 +122,14 @@ static ConvVariant conv3x3_variant(int ksize, int stride, int mode, bool light, 
   return v;
 }
 // 0 = one TMA box per tap (conv_gemm_kernel), 1 / 2 = resident halo with 256- / 160-wide tiles, 3 = swapped operands
+// GroupNorm fusion is available where the resident-halo swapped-operand kernel applies.  SDM_GN_FUSE: 0 = never, 1 = the
+// 128-channel convs only, 2 = every N % 128 == 0 conv (A/B switch of round 2)
+bool conv_gemm_can_fuse_gn(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout) {
+  static const int level = [] { const char* e = getenv("SDM_GN_FUSE"); return e ? atoi(e) : 1; }();
+  if (level <= 0 || (level == 1 && N != 128)) return false;
+  const ConvVariant v = conv3x3_variant(ksize, stride, mode, false, ups2, false, N, 0, has_res != 0, Hout, Wout, 0, 0, 0, 0, 0, true);
+  return v.swap && v.swap_halo;
+}
 int conv_gemm_variant_code(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout) {
   const ConvVariant v = conv3x3_variant(ksize, stride, mode, false, ups2, false, N, 0, has_res != 0, Hout, Wout, 0, 0, 0, 0, 0);
   return v.swap ? 3 : (v.halo_auto ? (v.halo_bn == 256 ? 1 : 2) : 0);
@@ -150,8 +165,10 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   L->light = light;
   // ---- kernel variant of the 3x3 stride-1 convs: conv3x3_variant() sees the per-sample geometry only
   const ConvVariant cv = conv3x3_variant(d.ksize, d.stride, d.mode, light, d.ups2, d.w_bstride != 0, d.N, d.n_store, d.res != nullptr, Hout, Wout,
-                                         d.force_swap, d.force_halo, d.force_pair, d.force_block_n, d.force_mt);
-  if (d.force_swap == 1) SDM_CHECK(cv.swap_can, "force_swap: configuration not supported by the swapped-operand kernel");
+                                         d.force_swap, d.force_halo, d.force_pair, d.force_block_n, d.force_mt, d.gn_ab != nullptr);
+  if (d.force_swap >= 1) SDM_CHECK(cv.swap_can, "force_swap: configuration not supported by the swapped-operand kernel");
+  if (d.force_swap == 2) SDM_CHECK(cv.swap_halo, "force_swap = 2: geometry not supported by the resident-halo swapped-operand kernel");
+  if (d.gn_ab) SDM_CHECK(cv.swap && cv.swap_halo, "fused GroupNorm needs the resident-halo swapped-operand kernel (conv_gemm_can_fuse_gn)");
   L->swap = cv.swap;
   const bool halo_geom = cv.halo_geom, halo_auto = cv.halo_auto;
   const int halo_bn = cv.halo_bn;
@@ -185,10 +202,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   }
   long long m_tiles_eff = m_tiles;
   if (L->swap) {
-    // staged (not yet run on hardware): resident 8 x 32 halo tile, only on request and where the patch count matches
-    static const int env_swap_halo = [] { const char* e = getenv("SDM_SWAP_HALO"); return e ? atoi(e) : 0; }();
-    L->swap_halo = env_swap_halo != 0 && Hout >= 32 && Wout >= 8 &&
-                   2ll * ((Wout + 7) / 8) * ((Hout + 31) / 32) == (long long)p.tiles_x * p.tiles_y;
+    L->swap_halo = cv.swap_halo;  // resident 8 x 32 halo tile (conv_swap_halo.cu)
     p.tw = L->swap_halo ? 8 : 16;
     p.th = L->swap_halo ? 32 : 16;
     p.tiles_x = (Wout + p.tw - 1) / p.tw;
@@ -296,6 +310,8 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   SDM_CHECK(p.post_div == 1.0f || p.mode == EPI_SKINNY, "post_div is only implemented for skinny (n_store < 8) outputs");
   if (p.mode == EPI_SKINNY) SDM_CHECK(bn == 16 && !d.res && !d.ups2, "skinny output needs N <= 16 and no residual");
   p.out2 = d.out2;
+  p.gn_ab = d.gn_ab;
+  p.gn_silu = d.gn_silu;
   p.stats = (d.mode == EPI_F16 && !d.ups2) ? d.stats : nullptr;
   if (d.mode == EPI_ALPHA) SDM_CHECK(d.N >= 3 && d.N <= 16 && d.bias != nullptr, "EPI_ALPHA needs 3..16 columns and a bias");
   {

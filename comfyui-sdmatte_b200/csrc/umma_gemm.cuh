@@ -69,6 +69,8 @@ struct alignas(64) ConvGemmParams {
   float post_div;   // EPI_SKINNY only: fp16(result) / post_div, rounded again (label_latent / scaling_factor); 1 = off
   int n_store;      // EPI_SKINNY: number of output columns stored
   void* out2;       // EPI_ALPHA: optional pre-clip mean
+  const float* gn_ab;  // fused input GroupNorm (conv_swap_halo_kernel<true>): [B][cin_total][2] (scale, shift), or null
+  int gn_silu;
   float* stats;     // EPI_F16 (no ups2): per-(M tile, channel) partial (sum, sumsq) of the STORED fp16 values for the next GroupNorm:
                     // stats[((b * tiles_per_image + tile_in_image) * N + col) * 2 + {0,1}]  (deterministic: one writer per slot)
 };

@@ -33,6 +33,7 @@ class sdm_conv_gemm_args(C.Structure):
         ("bias", C.c_void_p), ("bias_sel", C.c_void_p),
         ("res", C.c_void_p), ("res_ld", C.c_int64), ("res_bstride", C.c_int64),
         ("scale", C.c_float), ("force_block_n", C.c_int), ("post_div", C.c_float), ("n_store", C.c_int), ("out2", C.c_void_p), ("force_mt", C.c_int), ("force_light", C.c_int), ("stats", C.c_void_p), ("force_pair", C.c_int), ("force_halo", C.c_int), ("force_swap", C.c_int),
+        ("gn_ab", C.c_void_p), ("gn_silu", C.c_int),
     ]
 
 
@@ -69,7 +70,7 @@ EXPORTS = [
     "sdm_workspace_bytes", "sdm_forward", "sdm_forward_host", "sdm_node_workspace_bytes", "sdm_apply_matte_host", "sdm_forward_profiled", "sdm_profile_count", "sdm_profile_entry",
     "sdm_last_forward_stats", "sdm_debug_tensor", "sdm_debug_tensor_count", "sdm_debug_tensor_name", "sdm_set_option", "sdm_graph_stats",
     "sdm_preprocess", "sdm_postprocess",
-    "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_conv_variant", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
+    "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_conv_variant", "sdm_k_conv_can_fuse_gn", "sdm_k_groupnorm_ab_offset", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
     "sdm_k_softmax_rows", "sdm_k_direct_conv", "sdm_k_key_compact", "sdm_k_gather_rows", "sdm_k_probe_halo",
     "sdm_safetensors_open", "sdm_safetensors_count", "sdm_safetensors_entry", "sdm_safetensors_close",
 ]
@@ -455,7 +456,7 @@ def _p(t):
 
 
 def k_conv_gemm(srcs, w, N, out, *, B, Hin, Win, ksize=1, stride=1, pad=0, mode=0, ups2=0, bias=None, bias_sel=None,
-                res=None, scale=1.0, w_bstride=0, out_ld=None, out_bstride=None, force_block_n=0, post_div=1.0, n_store=0, out2=None, force_mt=0, stats=None, force_light=0, force_pair=0, force_halo=0, force_swap=0):
+                res=None, scale=1.0, w_bstride=0, out_ld=None, out_bstride=None, force_block_n=0, post_div=1.0, n_store=0, out2=None, force_mt=0, stats=None, force_light=0, force_pair=0, force_halo=0, force_swap=0, gn_ab=None, gn_silu=0):
     lib = load_library()
     a = sdm_conv_gemm_args()
     a.B, a.Hin, a.Win, a.nsrc = B, Hin, Win, len(srcs)
@@ -472,6 +473,7 @@ def k_conv_gemm(srcs, w, N, out, *, B, Hin, Win, ksize=1, stride=1, pad=0, mode=
     a.scale, a.force_block_n = scale, force_block_n
     a.post_div, a.n_store, a.out2, a.force_mt, a.stats, a.force_light = post_div, n_store, _p(out2), force_mt, _p(stats), force_light
     a.force_pair, a.force_halo, a.force_swap = force_pair, force_halo, force_swap
+    a.gn_ab, a.gn_silu = _p(gn_ab), int(gn_silu)
     _check(lib.sdm_k_conv_gemm(C.byref(a), _stream_ptr(out.device)))
 
 
@@ -510,6 +512,12 @@ def conv_variant(ksize, stride, N, H, W, *, mode=0, ups2=0, has_res=0):
     return lib.sdm_k_conv_variant(ksize, stride, mode, ups2, N, has_res, H, W)
 
 
+def conv_can_fuse_gn(ksize, stride, N, H, W, *, mode=0, ups2=0, has_res=0):
+    lib = load_library()
+    lib.sdm_k_conv_can_fuse_gn.argtypes = [C.c_int] * 8
+    return bool(lib.sdm_k_conv_can_fuse_gn(ksize, stride, mode, ups2, N, has_res, H, W))
+
+
 def conv_tiles_per_image(H, W):
     return load_library().sdm_k_conv_tiles_per_image(H, W)
 
@@ -524,13 +532,23 @@ def k_groupnorm(srcs, gamma, beta, out, *, B, HW, eps, silu, pre=None, pre_slots
         a.src1, a.c1, a.ld1 = srcs[1][0].data_ptr(), srcs[1][1], srcs[1][2]
         ctot += srcs[1][1]
     n = lib.sdm_k_groupnorm_scratch_floats(B, HW, ctot)
-    scratch = torch.empty(n, dtype=torch.float32, device=out.device)
+    dev = srcs[0][0].device
+    scratch = torch.empty(n, dtype=torch.float32, device=dev)
     a.gamma, a.beta, a.eps, a.silu = gamma.data_ptr(), beta.data_ptr(), eps, int(silu)
-    a.out, a.scratch, a.scratch_floats = out.data_ptr(), scratch.data_ptr(), n
+    a.out, a.scratch, a.scratch_floats = _p(out), scratch.data_ptr(), n
     if pre is not None:
         a.pre0, a.pre1, a.pre_slots = _p(pre[0]), _p(pre[1]) if len(pre) > 1 else None, pre_slots
-    _check(lib.sdm_k_groupnorm(C.byref(a), _stream_ptr(out.device)))
+    _check(lib.sdm_k_groupnorm(C.byref(a), _stream_ptr(dev)))
     return scratch
+
+
+def groupnorm_ab(scratch, B, HW, Ctot):
+    """The [B][Ctot][2] (scale, shift) table k_groupnorm left in its scratch buffer (view, no copy)."""
+    lib = load_library()
+    lib.sdm_k_groupnorm_ab_offset.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.sdm_k_groupnorm_ab_offset.restype = C.c_size_t
+    off = lib.sdm_k_groupnorm_ab_offset(B, HW, Ctot)
+    return scratch[off: off + B * Ctot * 2]
 
 
 def k_layernorm(x, y, gamma, beta, rows, Cc, eps=1e-5):

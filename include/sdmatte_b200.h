@@ -150,7 +150,10 @@ typedef struct {
   float* stats;                 /* mode 0 without ups2: GroupNorm partials [B][sdm_k_conv_tiles_per_image][N][2] (sum, sumsq), or NULL */
   int force_pair;               /* tests: 1 = force the CTA-pair (tcgen05 cta_group::2, M = 256) kernel, -1 = forbid it, 0 = auto */
   int force_halo;               /* tests: 1 = force the resident-halo 3x3 kernel (one halo tile per 64 channels, nine taps from it), -1 = forbid */
-  int force_swap;               /* tests: 1 = force the swapped-operand 3x3 kernel (channels on M, 256 pixels on N), -1 = forbid it */
+  int force_swap;               /* tests: 1 = force the swapped-operand 3x3 kernel (channels on M, 256 pixels on N), 2 = its resident-halo form, -1 = forbid it */
+  const float* gn_ab;           /* fused GroupNorm(+SiLU) of the INPUT: [B][c0+c1][2] (scale, shift) as sdm_k_groupnorm leaves them in its scratch
+                                   (offset sdm_k_groupnorm_ab_offset); the conv then reads the raw tensor.  Only where sdm_k_conv_can_fuse_gn() != 0 */
+  int gn_silu;
 } sdm_conv_gemm_args;
 int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream);
 int sdm_k_conv_tiles_per_image(int Hout, int Wout);
@@ -158,6 +161,8 @@ int sdm_k_conv_tiles_per_image(int Hout, int Wout);
    on purpose: a sample must give the same bits alone and in a batch).  mode as in sdm_conv_gemm_args.
    0 = one TMA box per tap, 1 / 2 = resident halo tile with 256- / 160-wide tiles, 3 = swapped operands (conv_swap_kernel) */
 int sdm_k_conv_variant(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout);
+/* 1 if a conv of this per-sample geometry can take its input GroupNorm fused (sdm_conv_gemm_args.gn_ab) */
+int sdm_k_conv_can_fuse_gn(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout);
 
 typedef struct {
   int B, heads, Lq, Lk;
@@ -192,6 +197,9 @@ typedef struct {
   const float* pre0; const float* pre1; int pre_slots;   /* optional partial statistics from the producing convs' epilogues */
 } sdm_groupnorm_args;
 size_t sdm_k_groupnorm_scratch_floats(int B, int HW, int C);
+/* float offset of the [B][C][2] (scale, shift) table inside the scratch buffer; out == NULL in sdm_groupnorm_args: statistics +
+   finalize only (no apply pass) */
+size_t sdm_k_groupnorm_ab_offset(int B, int HW, int C);
 int sdm_k_groupnorm(const sdm_groupnorm_args* a, uintptr_t stream);
 int sdm_k_layernorm(const void* x, void* y, const float* gamma, const float* beta, int64_t rows, int C, float eps, uintptr_t stream);
 int sdm_k_softmax_rows(const float* s, void* p, int64_t rows, int L, uintptr_t stream);

@@ -714,3 +714,67 @@ def test_conv3x3_swapped_operands(eng_mod, B, H, W, C0, C1, Cout, res):
     o = outs[0].double().view(B, H * W, Cout)
     assert torch.allclose(tot[..., 0], o.sum(1), rtol=1e-4, atol=1e-2)
     assert torch.allclose(tot[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ GroupNorm fused into the consuming conv
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,res,silu", [
+    (2, 64, 64, 128, 0, 128, False, 1),   # VAE 128 -> 128 resnet conv1
+    (1, 64, 64, 128, 0, 128, True, 1),    # conv2: + residual K steps (the residual boxes must pass the transform warps untouched)
+    (1, 96, 40, 128, 64, 128, True, 1),   # concat input: groups straddle the two sources; ragged 8 x 32 patches
+    (1, 32, 64, 256, 0, 256, False, 0),   # two N tiles, no SiLU
+    (2, 128, 128, 64, 0, 128, False, 1),  # many tiles per CTA: slot ring wraps, per-tile validity masks change
+])
+def test_conv3x3_fused_groupnorm(eng_mod, B, H, W, C0, C1, Cout, res, silu):
+    """GroupNorm(32)(+SiLU) applied to the conv's resident input halo tile by the transform warps of conv_swap_halo_kernel<true>
+    == the stand-alone apply pass followed by the same conv kernel, BIT FOR BIT (same arithmetic on the same fp16 values, same
+    summation order), incl. the zero padding of the NORMALISED tensor; and within fp16 tolerance of the fp32 torch reference
+    (ResnetBlock2D: norm -> silu -> conv, /root/reference/src/utils/replace.py:239,268,321 via diffusers)."""
+    Cin = C0 + C1
+    a = (_rand(B, H, W, C0, seed=1) * 1.5 + 0.4).half()
+    s2 = (_rand(B, H, W, C1, seed=6) * 0.7 - 0.2).half() if C1 else None
+    r = _rand(B, H, W, Cout, seed=5).half() if res else None
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2).half()
+    bias = _rand(Cout, seed=3).float()
+    g = _rand(Cin, seed=7).float() * 0.2 + 1.0
+    bt = _rand(Cin, seed=8).float() * 0.2
+    srcs = [(a, C0, C0)] + ([(s2, C1, C1)] if C1 else [])
+    flat = [(t.view(B, H * W, c), c, ld) for t, c, ld in srcs]
+    assert eng_mod.conv_tiles_per_image(H, W) == 2 * ((W + 7) // 8) * ((H + 31) // 32), "pick a geometry the fused kernel supports"
+    slots = eng_mod.conv_tiles_per_image(H, W)
+    # (1) unfused: apply pass -> normalised tensor -> conv (resident-halo swapped kernel)
+    n = torch.zeros(B, H * W, Cin, dtype=torch.float16, device=DEV)
+    eng_mod.k_groupnorm(flat, g, bt, n, B=B, HW=H * W, eps=1e-6, silu=silu)
+    out_u = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    st_u = torch.full((B, slots, Cout, 2), float("nan"), device=DEV)
+    eng_mod.k_conv_gemm([(n.view(B, H, W, Cin), Cin, Cin)], _pack_conv_w(w), Cout, out_u, B=B, Hin=H, Win=W, ksize=3, bias=bias, out_ld=Cout,
+                        out_bstride=H * W * Cout, res=(r, Cout, H * W * Cout) if res else None, stats=st_u, force_swap=2)
+    # (2) fused: statistics + finalize only, the conv reads the RAW tensors
+    scratch = eng_mod.k_groupnorm(flat, g, bt, None, B=B, HW=H * W, eps=1e-6, silu=silu)
+    ab = eng_mod.groupnorm_ab(scratch, B, H * W, Cin)
+    out_f = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    st_f = torch.full((B, slots, Cout, 2), float("nan"), device=DEV)
+    eng_mod.k_conv_gemm(srcs, _pack_conv_w(w), Cout, out_f, B=B, Hin=H, Win=W, ksize=3, bias=bias, out_ld=Cout, out_bstride=H * W * Cout,
+                        res=(r, Cout, H * W * Cout) if res else None, stats=st_f, gn_ab=ab, gn_silu=silu)
+    torch.cuda.synchronize()
+    assert torch.equal(out_f, out_u), f"fused != unfused: {(out_f.float() - out_u.float()).abs().max().item():.3e}"
+    assert torch.equal(st_f, st_u)
+    # the raw inputs must not have been modified (the transform works on the shared-memory copy)
+    assert torch.equal(a, (_rand(B, H, W, C0, seed=1) * 1.5 + 0.4).half())
+    x = torch.cat([a, s2], -1) if C1 else a
+    y = F.group_norm(x.float().permute(0, 3, 1, 2), 32, g, bt, 1e-6)
+    if silu:
+        y = F.silu(y)
+    y = F.conv2d(y.half().float(), w.float(), bias, padding=1)
+    if res:
+        y = y + r.float().permute(0, 3, 1, 2)
+    _close(out_f, y.permute(0, 2, 3, 1), 4e-3, 4e-3, "conv3x3 with fused GroupNorm")
+
+
+def test_conv_can_fuse_gn_is_geometry_only(eng_mod):
+    assert eng_mod.conv_can_fuse_gn(3, 1, 128, 1024, 1024)
+    assert eng_mod.conv_can_fuse_gn(3, 1, 128, 64, 64, has_res=1)
+    assert not eng_mod.conv_can_fuse_gn(3, 2, 128, 64, 64)       # stride 2
+    assert not eng_mod.conv_can_fuse_gn(1, 1, 128, 64, 64)       # 1x1
+    assert not eng_mod.conv_can_fuse_gn(3, 1, 128, 64, 64, ups2=1)
+    assert not eng_mod.conv_can_fuse_gn(3, 1, 320, 64, 64)       # N % 128 != 0
+    assert not eng_mod.conv_can_fuse_gn(3, 1, 128, 16, 16)       # too small for 8 x 32 patches

@@ -101,3 +101,60 @@ def test_reader_rejects_broken_files(pkg, tmp_path, case):
     else:
         with pytest.raises(RuntimeError):
             E.SafeTensorsReader(path)
+
+
+@pytest.mark.parametrize("case", ["deep_nesting", "metadata_not_flat", "uint_overflow", "numel_overflow", "duplicate_name", "overlap", "gap",
+                                  "trailing_bytes", "huge_shape"])
+def test_reader_is_hardened_against_malformed_headers(pkg, tmp_path, case):
+    """Checkpoint files are untrusted input: bounded recursion, overflow-checked integers and products, and the
+    safetensors package's own layout rules (no duplicate names, tensors tile the byte buffer exactly)."""
+    E = pkg.engine
+    path = str(tmp_path / f"{case}.safetensors")
+    w = {"dtype": "F32", "shape": [2], "data_offsets": [0, 8]}
+    payload = b"\0" * 16
+    raw = None
+    if case == "deep_nesting":  # 4 MB of '[' inside an unknown per-tensor key: must fail cleanly, not overflow the stack
+        raw = b'{"unet.w":{"dtype":"F32","shape":[2],"data_offsets":[0,8],"x":' + b"[" * (4 << 20) + b"}}"
+        payload = b"\0" * 8
+    elif case == "metadata_not_flat":
+        raw = b'{"__metadata__":{"a":{"b":"c"}},"unet.w":{"dtype":"F32","shape":[2],"data_offsets":[0,8]}}'
+        payload = b"\0" * 8
+    elif case == "uint_overflow":
+        raw = b'{"unet.w":{"dtype":"F32","shape":[2],"data_offsets":[0,99999999999999999999999]}}'
+    elif case == "numel_overflow":  # 2^32 * 2^32 wraps to 0 in 64 bits
+        raw = b'{"unet.w":{"dtype":"F32","shape":[4294967296,4294967296],"data_offsets":[0,0]}}'
+        payload = b""
+    elif case == "huge_shape":
+        raw = b'{"unet.w":{"dtype":"F32","shape":[9223372036854775807,3],"data_offsets":[0,8]}}'
+        payload = b"\0" * 8
+    elif case == "duplicate_name":
+        raw = b'{"unet.w":{"dtype":"F32","shape":[2],"data_offsets":[0,8]},"unet.w":{"dtype":"F32","shape":[2],"data_offsets":[8,16]}}'
+    elif case == "overlap":
+        hdr = {"unet.a": w, "unet.b": {"dtype": "F32", "shape": [2], "data_offsets": [4, 12]}}
+        payload = b"\0" * 12
+    elif case == "gap":
+        hdr = {"unet.a": w, "unet.b": {"dtype": "F32", "shape": [1], "data_offsets": [12, 16]}}
+    else:  # trailing_bytes
+        hdr = {"unet.a": w}
+    if raw is not None:
+        with open(path, "wb") as f:
+            f.write(struct.pack("<Q", len(raw)) + raw + payload)
+    else:
+        _write_raw(path, hdr, payload)
+    with pytest.raises(RuntimeError):
+        E.SafeTensorsReader(path)
+    if case in ("duplicate_name", "overlap", "gap", "trailing_bytes", "metadata_not_flat"):  # ...and the package agrees
+        with pytest.raises(Exception):
+            safetensors_torch.load_file(path)
+
+
+def test_reader_accepts_flat_metadata_and_empty_tensor(pkg, tmp_path):
+    E = pkg.engine
+    path = str(tmp_path / "ok.safetensors")
+    _write_raw(path, {"__metadata__": {"format": "pt"}, "unet.e": {"dtype": "F32", "shape": [0, 4], "data_offsets": [0, 0]},
+                      "unet.w": {"dtype": "F16", "shape": [2, 2], "data_offsets": [0, 8]}}, b"\1" * 8)
+    with E.SafeTensorsReader(path) as rd:
+        assert len(rd) == 2
+        for i in range(2):
+            rd.entry(i)
+    assert set(safetensors_torch.load_file(path)) == {"unet.e", "unet.w"}
