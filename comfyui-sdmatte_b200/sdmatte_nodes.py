@@ -16,6 +16,7 @@ samples are independent, so the sharded result is bit-identical to the single-GP
 from __future__ import annotations
 
 import os
+import sys
 import threading
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -143,7 +144,7 @@ def get_engine(ckpt_name: str, device: torch.device) -> "_engine.Engine":
             used, unexpected = eng.load_state_dict(_load_state_dict(find_checkpoint(ckpt_name)))
         else:  # native reader: header parse + mmap, repacked straight from the mapping (no torch CPU tensors)
             used, unexpected = eng.load_safetensors(find_checkpoint(ckpt_name))
-        print(f"[SDMatte-B200] loaded {ckpt_name} on {device}: {used} tensors used, {unexpected} ignored")
+        print(f"[SDMatte-B200] loaded {ckpt_name} on {device}: {used} tensors used, {unexpected} ignored", file=sys.stderr)
         with _CACHE_LOCK:
             _ENGINE_CACHE[key] = eng
     return eng
