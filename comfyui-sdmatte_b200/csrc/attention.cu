@@ -94,8 +94,7 @@ __device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, __half2 s) {
 
 // TAIL: Lk is not a multiple of 128 and there is no bias to carry the -inf padding (never the case inside the engine;
 // kept out of the common instantiations: even skipped, the masking code cost a BSSY/branch per chunk and i-cache misses)
-// SPLIT_PV: P.V in two 64-key halves (v8 note above)
-template <bool HAS_BIAS, bool TAIL, bool SPLIT_PV>
+template <bool HAS_BIAS, bool TAIL>
 __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   using namespace a7;
   extern __shared__ uint8_t smem_raw[];
@@ -108,7 +107,8 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
   // S is produced and released in two 64-key halves (hf = 0: keys 0-63, 1: keys 64-127)
   auto s_full = [&](int x, int hf) { return bar + 8u * (1 + 2 * kStages + x * 2 + hf); };
   auto s_free = [&](int x, int hf) { return bar + 8u * (5 + 2 * kStages + x * 2 + hf); };
-  // P is published and P.V committed per 64-key half when SPLIT_PV (otherwise only index hf = 1 is used: whole tile)
+  // P is published and P.V committed per whole 128-key tile (only index hf = 1 is used; the per-half variant of r1p was
+  // measured neutral to -2 % in the step and removed in round 2)
   auto p_full = [&](int x, int hf) { return bar + 8u * (9 + 2 * kStages + x * 2 + hf); };
   auto o_full = [&](int x, int hf) { return bar + 8u * (13 + 2 * kStages + x * 2 + hf); };
   const uint32_t tmem_slot = bar + 8u * (17 + 2 * kStages);
@@ -197,11 +197,6 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
             tc_fence_after();
             issue_s(x, 0, (t + 1) % kStages);
           }
-          if (SPLIT_PV) {
-            mbar_wait(p_full(x, 0), (uint32_t)t & 1u);
-            tc_fence_after();
-            issue_pv(x, st, t, 0, 4, o_full(x, 0));
-          }
           if (more) {
             mbar_wait(s_free(x, 1), (uint32_t)t & 1u);
             tc_fence_after();
@@ -209,8 +204,7 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           }
           mbar_wait(p_full(x, 1), (uint32_t)t & 1u);
           tc_fence_after();
-          if (SPLIT_PV) issue_pv(x, st, t, 4, 8, o_full(x, 1));
-          else issue_pv(x, st, t, 0, 8, o_full(x, 1));
+          issue_pv(x, st, t, 0, 8, o_full(x, 1));
           umma_commit(kv_empty(st));  // this tile's MMAs on the stage are done (the barrier counts both issuers)
         }
       }
@@ -297,12 +291,9 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           }
           const float m_new = fmaxf(m2, cm);
           const float alpha = (m_new == m2) ? 1.0f : ex2f(m2 - m_new);  // 0 when m2 = -inf
-          // every P.V issued so far must have landed in O before its rows are rescaled: all of tile j-1, and with
-          // SPLIT_PV the low half of this tile once it has been published (c >= 2)
-          const bool lo_consumed = SPLIT_PV && c >= 2;
+          // every P.V issued so far (all of tile j-1) must have landed in O before its rows are rescaled
           if (j > 0) mbar_wait(o_full(x, 1), (uint32_t)(j - 1) & 1u);
-          if (lo_consumed) mbar_wait(o_full(x, 0), (uint32_t)j & 1u);
-          if (j > 0 || lo_consumed) {
+          if (j > 0) {
             tc_fence_after();
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
@@ -330,17 +321,10 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           m2 = m_new;
           exp_pack();
         }
-        // P(j) overwrites the columns P.V(j-1) reads: chunks 0-1 the low half's, chunks 2-3 the high half's
-        if (j > 0) {
-          if (SPLIT_PV) {
-            if ((c & 1) == 0) {
-              mbar_wait(o_full(x, c >> 1), (uint32_t)(j - 1) & 1u);
-              tc_fence_after();
-            }
-          } else if (c == 0) {
-            mbar_wait(o_full(x, 1), (uint32_t)(j - 1) & 1u);
-            tc_fence_after();
-          }
+        // P(j) overwrites the columns P.V(j-1) reads
+        if (j > 0 && c == 0) {
+          mbar_wait(o_full(x, 1), (uint32_t)(j - 1) & 1u);
+          tc_fence_after();
         }
         tmem_st16(t_p + c * 16, pk);
         rowsum += csum;
@@ -366,11 +350,6 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
         if (cp == 0) {
           tmem_ld_wait();
           tmem_ld32(t_s + 96, r1);   // chunk 3 in flight while chunk 2 is processed
-          if (SPLIT_PV) {            // chunks 0-1 of P(j) are complete: O += P_lo V_lo may start
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(p_full(x, 0));
-          }
         }
       }
       l += rowsum;
@@ -454,24 +433,17 @@ std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d) {
   return L;
 }
 
-template <bool HB, bool TL, bool SP>
+template <bool HB, bool TL>
 static void attn_launch(const AttnLaunch& l, cudaStream_t st) {
   static PerDeviceOnce attr;  // function attributes are per device: a second GPU in the same process needs them too
-  attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<HB, TL, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem)); });
-  attention_kernel<HB, TL, SP><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
+  attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<HB, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem)); });
+  attention_kernel<HB, TL><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
 }
 
 void attn_run(const AttnLaunch& l, cudaStream_t st) {
-  // SDM_ATTN_SPLIT=1: P.V in two 64-key halves (A/B switch, read once)
-  static const bool split = [] { const char* e = getenv("SDM_ATTN_SPLIT"); return e ? atoi(e) != 0 : false; }();
-  if (!l.has_bias && (l.p.Lk & 127) != 0) attn_launch<false, true, false>(l, st);
-  else if (l.has_bias) {
-    if (split) attn_launch<true, false, true>(l, st);
-    else attn_launch<true, false, false>(l, st);
-  } else {
-    if (split) attn_launch<false, false, true>(l, st);
-    else attn_launch<false, false, false>(l, st);
-  }
+  if (!l.has_bias && (l.p.Lk & 127) != 0) attn_launch<false, true>(l, st);
+  else if (l.has_bias) attn_launch<true, false>(l, st);
+  else attn_launch<false, false>(l, st);
   SDM_CUDA_OK(cudaGetLastError());
 }
 

@@ -24,23 +24,58 @@ namespace sdm {
 
 namespace swh {
 constexpr int kWBytes = 128 * 128;    // weight tile: 128 channels x 64 k (fp16)
-constexpr int kWStages = 6;
 constexpr int kXSlot = 44 * 1024;     // halo tile: 10 x 34 pixel rows of 128 B = 43 520 B, rounded up to the 1024-byte swizzle atom
 constexpr int kXTx = 10 * 34 * 128;   // bytes one halo box delivers
 constexpr int kXDense = 256 * 128;    // residual: dense 8 x 32 box
-constexpr int kXSlots = 2;
 constexpr int kStgBytes = 4 * 2048;
-constexpr int kPipe = kWStages * kWBytes + kXSlots * kXSlot;
-constexpr int kSmem = kPipe + 1024 + 256 + kStgBytes;
-constexpr int kThreads = 192;      // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
-constexpr int kThreadsGN = 320;    // + warps 6..9: GroupNorm transform
+constexpr int kBaseThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int kXRows = 10 * 34;    // pixel rows of a halo tile
-static_assert(kSmem <= 232448, "shared memory budget");
+// GNF: the slot of a halo tile is busy for (TMA flight + transform + nine taps of MMAs) instead of (TMA flight + MMAs): a third
+// slot (paid for with one weight stage) keeps the tensor core fed; 8 transform warps (r2b: 4 warps with a branch per piece made
+// the fused conv 35 % slower than conv + separate apply pass, i.e. no net gain)
+template <bool GNF>
+struct Cfg {
+  static constexpr int kWStages = GNF ? 5 : 6;
+  static constexpr int kXSlots = GNF ? 3 : 2;
+  static constexpr int kTWarps = GNF ? 8 : 0;
+  static constexpr int kThreads = kBaseThreads + 32 * kTWarps;
+  static constexpr int kPipe = kWStages * kWBytes + kXSlots * kXSlot;
+  static constexpr int kSmem = kPipe + 1024 + 256 + kStgBytes;
+  static_assert(kSmem <= 232448, "shared memory budget");
+  static_assert(8 * (2 * kWStages + 3 * kXSlots + 4) + 8 <= 256, "barrier area");
+};
+
+// one thread's share of a halo tile: pieces (r0 + 32 k, piece), k = 0..10; `exist` bit k: the row is part of the tile,
+// `inside` bit k: its pixel lies inside the image (rows outside stay / become zero: the conv pads the NORMALISED tensor).
+// Branch-free and unrolled four pieces deep, so that 16 independent channel-pair chains are in flight per thread.
+template <bool SILU>
+__device__ __forceinline__ void gn_transform_tile(uint8_t* tp, uint32_t inside, uint32_t exist, const uint64_t (&ka)[4], const uint64_t (&ks)[4]) {
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = g * 4 + j;
+      v[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (k < 11 && ((exist >> k) & 1u)) v[j] = *reinterpret_cast<const uint4*>(tp + k * 4096);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = g * 4 + j;
+      if (k < 11) {
+        uint4 o = gn_piece<SILU>(v[j], ka, ks);
+        if (!((inside >> k) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);
+        if ((exist >> k) & 1u) *reinterpret_cast<uint4*>(tp + k * 4096) = o;
+      }
+    }
+  }
+}
 }  // namespace swh
 
 template <bool GNF>
-__global__ void __launch_bounds__(GNF ? swh::kThreadsGN : swh::kThreads, 1) conv_swap_halo_kernel(const __grid_constant__ ConvGemmParams p) {
+__global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_kernel(const __grid_constant__ ConvGemmParams p) {
   using namespace swh;
+  constexpr int kWStages = Cfg<GNF>::kWStages, kXSlots = Cfg<GNF>::kXSlots, kPipe = Cfg<GNF>::kPipe;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t x_base = smem_base + kWStages * kWBytes;
@@ -48,12 +83,11 @@ __global__ void __launch_bounds__(GNF ? swh::kThreadsGN : swh::kThreads, 1) conv
   auto wfull_bar = [&](int s) { return bar_base + 8u * s; };
   auto wempty_bar = [&](int s) { return bar_base + 8u * (kWStages + s); };
   auto xfull_bar = [&](int s) { return bar_base + 8u * (2 * kWStages + s); };
-  auto xempty_bar = [&](int s) { return bar_base + 8u * (2 * kWStages + 2 + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kWStages + 4 + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kWStages + 6 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kWStages + 8);
-  auto xready_bar = [&](int s) { return bar_base + 8u * (2 * kWStages + 9 + s); };  // GNF: the slot's tile has been normalised
-  static_assert(8 * (2 * kWStages + 11) <= 256, "barrier area");
+  auto xempty_bar = [&](int s) { return bar_base + 8u * (2 * kWStages + kXSlots + s); };
+  auto xready_bar = [&](int s) { return bar_base + 8u * (2 * kWStages + 2 * kXSlots + s); };  // GNF: the slot's tile has been normalised
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kWStages + 3 * kXSlots + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kWStages + 3 * kXSlots + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kWStages + 3 * kXSlots + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -61,7 +95,7 @@ __global__ void __launch_bounds__(GNF ? swh::kThreadsGN : swh::kThreads, 1) conv
     for (int s = 0; s < kWStages; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
     for (int s = 0; s < kXSlots; ++s) { mbar_init(xfull_bar(s), 1); mbar_init(xempty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
-    if (GNF) for (int s = 0; s < kXSlots; ++s) mbar_init(xready_bar(s), 4);  // one arrive per transform warp
+    if (GNF) for (int s = 0; s < kXSlots; ++s) mbar_init(xready_bar(s), Cfg<GNF>::kTWarps);  // one arrive per transform warp
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -149,10 +183,11 @@ __global__ void __launch_bounds__(GNF ? swh::kThreadsGN : swh::kThreads, 1) conv
       }
     }
   } else if (GNF && warp >= 6) {
-    // ============================== GroupNorm transform (4 warps) ==============================
-    const int t = threadIdx.x - kThreads;      // 0..127
-    const int piece = t & 7, r0 = t >> 3;      // rows r0, r0 + 16, ... of the tile; r & 7 == r0 & 7 for all of them
+    // ============================== GroupNorm transform (8 warps) ==============================
+    const int t = threadIdx.x - kBaseThreads;  // 0..255
+    const int piece = t & 7, r0 = t >> 3;      // rows r0, r0 + 32, ... of the tile; r & 7 == r0 & 7 for all of them
     const int chunk = piece ^ (r0 & 7);        // channel chunk (8 channels) this thread's pieces hold
+    const uint32_t exist = r0 < kXRows - 320 ? 0x7ffu : 0x3ffu;  // row r0 + 320 exists for r0 < 20
     int xs = 0;
     uint32_t xph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -160,30 +195,26 @@ __global__ void __launch_bounds__(GNF ? swh::kThreadsGN : swh::kThreads, 1) conv
       const int t_img = mt % per_image;
       const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32, b = mt / per_image;
       const float* ab_b = p.gn_ab + (size_t)b * p.cin_total * 2;
-      // validity of this thread's rows depends on the tile position only: bit k = row r0 + 16 k lies inside the image
+      // validity of this thread's rows depends on the tile position only: bit k = row r0 + 32 k lies inside the image
       uint32_t inside = 0;
-#pragma unroll 1
-      for (int k = 0; k < 22; ++k) {
-        const int r = r0 + 16 * k;
+#pragma unroll
+      for (int k = 0; k < 11; ++k) {
+        const int r = r0 + 32 * k;
         const int px = x0 - 1 + r % 10, py = y0 - 1 + r / 10;
-        if (r < kXRows && px >= 0 && px < p.W && py >= 0 && py < p.H) inside |= 1u << k;
+        if (px >= 0 && px < p.W && py >= 0 && py < p.H) inside |= 1u << k;
       }
+      inside &= exist;
       int coff = 0;
       for (int s = 0; s < p.nsrc; ++s) {
         for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
           uint64_t ka[4], ks[4];
-          if (p.gn_silu) gn_load_consts<true>(ab_b + (size_t)(coff + c0 + chunk * 8) * 2, ka, ks);
-          else gn_load_consts<false>(ab_b + (size_t)(coff + c0 + chunk * 8) * 2, ka, ks);
+          const float* ab8 = ab_b + (size_t)(coff + c0 + chunk * 8) * 2;
+          if (p.gn_silu) gn_load_consts<true>(ab8, ka, ks);
+          else gn_load_consts<false>(ab8, ka, ks);
           mbar_wait(xfull_bar(xs), xph);
-          uint8_t* tile_p = smem_raw + (x_base + xs * kXSlot - smem_u32(smem_raw)) + r0 * 128 + piece * 16;
-#pragma unroll 2
-          for (int k = 0; k < 22; ++k) {
-            if (inside & (1u << k)) {
-              uint4* q = reinterpret_cast<uint4*>(tile_p + k * 2048);
-              const uint4 v = *q;
-              *q = p.gn_silu ? gn_piece<true>(v, ka, ks) : gn_piece<false>(v, ka, ks);
-            }
-          }
+          uint8_t* tp = smem_raw + (x_base + xs * kXSlot - smem_u32(smem_raw)) + r0 * 128 + piece * 16;
+          if (p.gn_silu) gn_transform_tile<true>(tp, inside, exist, ka, ks);
+          else gn_transform_tile<false>(tp, inside, exist, ka, ks);
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
           __syncwarp();
           if (lane == 0) mbar_arrive(xready_bar(xs));
@@ -273,12 +304,12 @@ __global__ void __launch_bounds__(GNF ? swh::kThreadsGN : swh::kThreads, 1) conv
 void conv_swap_halo_launch(const ConvGemmParams& p, int grid, cudaStream_t st) {
   if (p.gn_ab) {
     static PerDeviceOnce attr;
-    attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::kSmem)); });
-    conv_swap_halo_kernel<true><<<grid, swh::kThreadsGN, swh::kSmem, st>>>(p);
+    attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::Cfg<true>::kSmem)); });
+    conv_swap_halo_kernel<true><<<grid, swh::Cfg<true>::kThreads, swh::Cfg<true>::kSmem, st>>>(p);
   } else {
     static PerDeviceOnce attr;
-    attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::kSmem)); });
-    conv_swap_halo_kernel<false><<<grid, swh::kThreads, swh::kSmem, st>>>(p);
+    attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::Cfg<false>::kSmem)); });
+    conv_swap_halo_kernel<false><<<grid, swh::Cfg<false>::kThreads, swh::Cfg<false>::kSmem, st>>>(p);
   }
   SDM_CUDA_OK(cudaGetLastError());
 }

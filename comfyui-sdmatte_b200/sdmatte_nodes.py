@@ -193,8 +193,14 @@ class SDMatteApply:
         tri = trimap.detach().to(device="cpu", dtype=torch.float32).contiguous()
         mode = _engine.OUTPUT_MODES.get(output_mode, 3)
         alpha = torch.empty((B, H, W), dtype=torch.float16)  # fp16 like the reference's CUDA branch
-        if mode == 0:  # "alpha_only": zeros_like(image) (sdmatte_nodes.py:384-385)
-            matted = torch.zeros_like(img)
+        zeros_box: List[torch.Tensor] = []
+        zeros_thread = None
+        if mode == 0:
+            # "alpha_only": zeros_like(image) (sdmatte_nodes.py:384-385).  Clearing 100 MB of host memory takes ~10 ms of one
+            # core: it runs on a helper thread while the GPU works (the library call below releases the GIL)
+            zeros_thread = threading.Thread(target=lambda: zeros_box.append(torch.zeros_like(img)))
+            zeros_thread.start()
+            matted = None
         else:
             matted = torch.empty((B, H, W, 4 if mode == 1 else 3), dtype=torch.float32)
 
@@ -224,6 +230,9 @@ class SDMatteApply:
                 t.join()
             if errors:
                 raise errors[0]
+        if zeros_thread is not None:
+            zeros_thread.join()
+            matted = zeros_box[0]
         if os.environ.get("SDMATTE_KEEP_RESIDENT", "1") == "0":
             unload_engines()
         return (alpha, matted)
