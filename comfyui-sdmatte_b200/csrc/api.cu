@@ -162,7 +162,7 @@ int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream) {
   d.bias = a->bias; d.bias_sel = a->bias_sel;
   d.res = reinterpret_cast<const __half*>(a->res); d.res_ld = a->res_ld; d.res_bstride = a->res_bstride;
   d.scale = a->scale; d.force_block_n = a->force_block_n;
-  d.post_div = a->post_div == 0.f ? 1.f : a->post_div; d.n_store = a->n_store; d.out2 = a->out2; d.force_mt = a->force_mt; d.stats = a->stats; d.force_light = a->force_light; d.force_pair = a->force_pair; d.force_halo = a->force_halo; d.force_swap = a->force_swap;
+  d.post_div = a->post_div == 0.f ? 1.f : a->post_div; d.n_store = a->n_store; d.out2 = a->out2; d.force_mt = a->force_mt; d.stats = a->stats; d.force_halo = a->force_halo; d.force_swap = a->force_swap;
   d.gn_ab = a->gn_ab; d.gn_silu = a->gn_silu;
   auto l = sdm::conv_gemm_build(d, sdm::device_sm_count());
   sdm::conv_gemm_run(*l, reinterpret_cast<cudaStream_t>(stream));

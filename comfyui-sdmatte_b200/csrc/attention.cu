@@ -33,18 +33,12 @@
 // alpha = 2^(m2_old - m2_new), and exponentiate the chunk again from the S registers that are still live.  Steady state is
 // one basic block per chunk: 16 FFMA2 -> 32 MUFU.EX2 -> 16 FADD2 / 16 F2FP -> tcgen05.st (fp32x2 packed arithmetic).
 // Measured (B2 h5 16384x16384, same box): v5 (row max -> vote -> exp, P via smem) 532 TFLOP/s, v6 (optimistic, P via smem) 478.
-// v8 (r1p): P.V is issued in two 64-key halves as well (SPLIT_PV).  ncu source view of v7c (profiles/r1o): 19 % of the
-// softmax warps' samples sat on ONE instruction, the wait for P.V(j-1) before chunk 0 of P(j) may overwrite the P columns
-// it reads (P.V(j-1) is only issued at the very end of tile j-1 and queues behind the other warpgroup's MMAs).  With
-// P_lo = chunks 0-1 published after chunk 1 and P_hi after chunk 3, O += P_lo V_lo runs half a tile earlier, the chunk-0
-// store of tile j waits for an MMA issued two chunks before the end of tile j-1, the chunk-2 store for the one issued at
-// its end: both have >= 2 chunks of exponentials of slack.
+// v8 (r1p) also issued P.V in two 64-key halves; measured neutral to -2 % in the step, removed in round 2 (history: profiles/r1q_*).
 // v9 (r1q): one MMA issuer warp per query tile running the tile's fixed event sequence with BLOCKING mbarrier waits
-//   S_lo(t+1) <- s_free_lo(t),  [P.V_lo(t) <- p_full_lo(t)],  S_hi(t+1) <- s_free_hi(t),  P.V(t) <- p_full(t)
+//   S_lo(t+1) <- s_free_lo(t),  S_hi(t+1) <- s_free_hi(t),  P.V(t) <- p_full(t)
 // instead of one thread polling the ~12 barriers of both tiles round-robin.  ncu r1p/r1q: the single poller was the bottleneck
-// (with the extra events of SPLIT_PV the softmax warps waited 25 % of their time for S_hi(j), issued late): same box,
-// B2 h5 16384 x 16384: 501 -> 622 TFLOP/s (whole-tile P.V) / 631 (split); in the step cross attention 54.1 -> 42.4 / 45.1 ms.
-// The polling issuer is gone; SPLIT_PV stays as a switch (SDM_ATTN_SPLIT=1), whole-tile P.V is the default.
+// (the softmax warps waited 25 % of their time for S_hi(j), issued late): same box, B2 h5 16384 x 16384: 501 -> 622 TFLOP/s;
+// in the step cross attention 54.1 -> 42.4 ms.
 // An FMA-pipe polynomial exp2 (degree 4, packed fp32x2) for 4 / 8 of the 16 column pairs of a chunk was measured twice and
 // removed: under the polling issuer (r1o) 519 -> 494 / 464 TFLOP/s at L0, under the sequenced issuers (r1v) 623 -> 603 / 550:
 // the softmax warps are bound by their dependent instruction chain, not by MUFU throughput (XU pipe 65 % in ncu r1q).
@@ -307,8 +301,8 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           }
           const __half2 a2 = __float2half2_rn(alpha);
           tmem_st_wait();  // this tile's earlier P chunks are in TMEM before they are read back
-          // chunks of this tile stored but not yet handed to the tensor core (chunks 0-1 already are when lo_consumed)
-          for (int cc = lo_consumed ? 2 : 0; cc < c; ++cc) {
+          // chunks of this tile stored but not yet handed to the tensor core
+          for (int cc = 0; cc < c; ++cc) {
             uint32_t pp[16];
             tmem_ld16(t_p + cc * 16, pp);
             tmem_ld_wait();

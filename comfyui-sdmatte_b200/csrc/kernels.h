@@ -43,8 +43,6 @@ struct ConvGemmDesc {
   float* stats = nullptr;  // EPI_F16 without ups2: GroupNorm partials [B][tiles_per_image][N][2] (see conv_gemm_tiles_per_image)
   int force_block_n = 0;  // tests only
   int force_mt = 0;       // tests only: 1 / 2 = force the number of M sub-tiles per CTA tile
-  int force_light = 0;    // tests only: 1 = force the two-CTAs-per-SM config, -1 = forbid it
-  int force_pair = 0;     // tests only: 1 = force the CTA-pair (cta_group::2) kernel, -1 = forbid it, 0 = auto
   int force_halo = 0;     // tests only: 1 = force the resident-halo 3x3 kernel, -1 = forbid it, 0 = auto
   int force_swap = 0;     // tests only: 1 = force the swapped-operand 3x3 kernel (channels on M), 2 = its resident-halo form, -1 = forbid, 0 = auto
   // fused GroupNorm(+SiLU) of the INPUT: the conv reads the raw producer output and normalises its resident halo tile in shared

@@ -11,18 +11,16 @@
 namespace sdm {
 
 void conv_swap_launch(const ConvGemmParams& p, int grid, cudaStream_t st);       // conv_swap.cu
-void conv_swap_halo_launch(const ConvGemmParams& p, int grid, cudaStream_t st);  // conv_swap_halo.cu (staged, SDM_SWAP_HALO=1)
+void conv_swap_halo_launch(const ConvGemmParams& p, int grid, cudaStream_t st);  // conv_swap_halo.cu
 
 struct ConvGemmLaunch {
   ConvGemmParams p;
   int block_n = 0;
   int mt = 1;
-  bool light = false;
   int ewg = 1;
-  bool pair = false;  // CTA-pair (cta_group::2) kernel
   bool halo = false;  // 3x3 stride-1 conv with a resident halo tile per 64-channel slice
   bool swap = false;  // conv_swap_kernel: channels on M, 256 pixels on N (128-channel 3x3 convs)
-  bool swap_halo = false;  // ... with a resident 8 x 32 pixel halo tile (staged for the next round, SDM_SWAP_HALO=1)
+  bool swap_halo = false;  // ... with a resident 8 x 32 pixel halo tile (conv_swap_halo.cu; carries the fused GroupNorm)
   int grid = 0;
   double flops = 0;
 };
@@ -92,11 +90,11 @@ struct ConvVariant {
   bool halo_geom = false, halo_auto = false;  // resident-halo patches fit / selected without a force flag
   int halo_bn = 0;                          // tile width of the halo kernel by N alone (256 | 160 | 0 = none)
 };
-static ConvVariant conv3x3_variant(int ksize, int stride, int mode, bool light, int ups2, bool batched_w, int N, int n_store, bool has_res,
-                                   int Hout, int Wout, int force_swap, int force_halo, int force_pair, int force_block_n, int force_mt,
+static ConvVariant conv3x3_variant(int ksize, int stride, int mode, int ups2, bool batched_w, int N, int n_store, bool has_res,
+                                   int Hout, int Wout, int force_swap, int force_halo, int force_block_n, int force_mt,
                                    bool want_gn = false) {
   ConvVariant v;
-  const bool conv3 = ksize == 3 && stride == 1 && mode == EPI_F16 && !light && (n_store == 0 || n_store == N);
+  const bool conv3 = ksize == 3 && stride == 1 && mode == EPI_F16 && (n_store == 0 || n_store == N);
   int tw = 128, th = 1;
   pick_patch(Hout, Wout, tw, th);
   const long long tiles_img = (long long)((Wout + tw - 1) / tw) * ((Hout + th - 1) / th);  // default patch, per sample
@@ -108,7 +106,7 @@ static ConvVariant conv3x3_variant(int ksize, int stride, int mode, bool light, 
   // resident-halo form: 8 x 32 pixel patches, two GroupNorm-partials slots per patch -> only where that equals the default count
   v.swap_halo_geom = v.swap_can && Hout >= 32 && Wout >= 8 && 2ll * ((Wout + 7) / 8) * ((Hout + 31) / 32) == tiles_img;
   static const int env_swap_halo = [] { const char* e = getenv("SDM_SWAP_HALO"); return e ? atoi(e) : 0; }();
-  v.swap = v.swap_can && force_pair != 1 && force_halo != 1 &&
+  v.swap = v.swap_can && force_halo != 1 &&
            (force_swap >= 1 || (want_gn && v.swap_halo_geom) ||
             (force_swap == 0 && env_swap != 0 && N == 128 && force_block_n == 0 && force_mt == 0));
   v.swap_halo = v.swap && v.swap_halo_geom && (force_swap == 2 || want_gn || (force_swap == 0 && env_swap_halo != 0));
@@ -118,7 +116,7 @@ static ConvVariant conv3x3_variant(int ksize, int stride, int mode, bool light, 
   static const int env_halo = [] { const char* e = getenv("SDM_HALO"); return e ? atoi(e) : 1; }();
   v.halo_geom = conv3 && !v.swap && Hout >= 16 && Wout >= 8 && (long long)((Wout + 7) / 8) * ((Hout + 15) / 16) == tiles_img;
   v.halo_bn = N % 256 == 0 ? 256 : (N % 160 == 0 ? 160 : 0);
-  v.halo_auto = v.halo_geom && v.halo_bn != 0 && force_halo == 0 && env_halo != 0 && force_block_n == 0 && force_mt == 0 && force_pair != 1;
+  v.halo_auto = v.halo_geom && v.halo_bn != 0 && force_halo == 0 && env_halo != 0 && force_block_n == 0 && force_mt == 0;
   return v;
 }
 // 0 = one TMA box per tap (conv_gemm_kernel), 1 / 2 = resident halo with 256- / 160-wide tiles, 3 = swapped operands
@@ -127,11 +125,11 @@ static ConvVariant conv3x3_variant(int ksize, int stride, int mode, bool light, 
 bool conv_gemm_can_fuse_gn(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout) {
   static const int level = [] { const char* e = getenv("SDM_GN_FUSE"); return e ? atoi(e) : 1; }();
   if (level <= 0 || (level == 1 && N != 128)) return false;
-  const ConvVariant v = conv3x3_variant(ksize, stride, mode, false, ups2, false, N, 0, has_res != 0, Hout, Wout, 0, 0, 0, 0, 0, true);
+  const ConvVariant v = conv3x3_variant(ksize, stride, mode, ups2, false, N, 0, has_res != 0, Hout, Wout, 0, 0, 0, 0, true);
   return v.swap && v.swap_halo;
 }
 int conv_gemm_variant_code(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout) {
-  const ConvVariant v = conv3x3_variant(ksize, stride, mode, false, ups2, false, N, 0, has_res != 0, Hout, Wout, 0, 0, 0, 0, 0);
+  const ConvVariant v = conv3x3_variant(ksize, stride, mode, ups2, false, N, 0, has_res != 0, Hout, Wout, 0, 0, 0, 0);
   return v.swap ? 3 : (v.halo_auto ? (v.halo_bn == 256 ? 1 : 2) : 0);
 }
 
@@ -157,41 +155,23 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   p.tiles_y = (Hout + p.th - 1) / p.th;
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * d.B;
   p.N = d.N;
-  // short-K GEMMs (<= 16 K steps, no taps): epilogue-latency bound -> 128-wide tiles, two CTAs per SM ("light" config)
-  const bool light_ok = d.ksize == 1 && cin_total <= 1024 && !d.ups2 && d.N >= 64 &&
-                        (d.mode == EPI_F16 || d.mode == EPI_F16_T || d.mode == EPI_F32) && d.n_store == 0;
-  (void)light_ok;  // measured (r1i): the two-CTAs-per-SM config is slower than 160/256-wide tiles -> only on request
-  const bool light = d.force_light == 1;
-  L->light = light;
   // ---- kernel variant of the 3x3 stride-1 convs: conv3x3_variant() sees the per-sample geometry only
-  const ConvVariant cv = conv3x3_variant(d.ksize, d.stride, d.mode, light, d.ups2, d.w_bstride != 0, d.N, d.n_store, d.res != nullptr, Hout, Wout,
-                                         d.force_swap, d.force_halo, d.force_pair, d.force_block_n, d.force_mt, d.gn_ab != nullptr);
+  const ConvVariant cv = conv3x3_variant(d.ksize, d.stride, d.mode, d.ups2, d.w_bstride != 0, d.N, d.n_store, d.res != nullptr, Hout, Wout,
+                                         d.force_swap, d.force_halo, d.force_block_n, d.force_mt, d.gn_ab != nullptr);
   if (d.force_swap >= 1) SDM_CHECK(cv.swap_can, "force_swap: configuration not supported by the swapped-operand kernel");
   if (d.force_swap == 2) SDM_CHECK(cv.swap_halo, "force_swap = 2: geometry not supported by the resident-halo swapped-operand kernel");
   if (d.gn_ab) SDM_CHECK(cv.swap && cv.swap_halo, "fused GroupNorm needs the resident-halo swapped-operand kernel (conv_gemm_can_fuse_gn)");
   L->swap = cv.swap;
   const bool halo_geom = cv.halo_geom, halo_auto = cv.halo_auto;
   const int halo_bn = cv.halo_bn;
-  const int bn = light ? 128 : (halo_auto ? halo_bn : (d.force_block_n ? d.force_block_n : pick_block_n(d.N, d.mode, m_tiles, num_sms)));
+  const int bn = halo_auto ? halo_bn : (d.force_block_n ? d.force_block_n : pick_block_n(d.N, d.mode, m_tiles, num_sms));
   if (d.mode == EPI_GEGLU) SDM_CHECK(bn == 256 && d.N % 256 == 0, "GEGLU needs N % 256 == 0");
   L->block_n = bn;
   p.n_tiles = (d.N + bn - 1) / bn;
   // 256 x 128 CTA tiles (two M sub-tiles per B tile) when there is enough work to keep every SM busy
-  L->mt = (bn == 128 && !light && d.mode == EPI_F16 && d.force_mt != 1 && (d.force_mt == 2 || (m_tiles / 2) * p.n_tiles >= 2 * num_sms)) ? 2 : 1;
-  // CTA pairs for the 256 x 128 tiles of the long-K convs (SDM_PAIR=1 / force_pair = 1 from the kernel tests; bit-identical to the
-  // single-CTA MT=2 kernel).  Restrictions: one weight set, N % 128 == 0, fp16 epilogue without the 2x scatter.
+  L->mt = (bn == 128 && d.mode == EPI_F16 && d.force_mt != 1 && (d.force_mt == 2 || (m_tiles / 2) * p.n_tiles >= 2 * num_sms)) ? 2 : 1;
   {
-    // measured r1r/r1s: the pair kernel is SLOWER on the 128->128 convs (711 vs 1098 TFLOP/s): those layers are bound by the
-    // operand fetch / L2 -> shared-memory fill, which a CTA pair does not reduce (each CTA still fetches its own activation
-    // tile per tap), and the 2-CTA TMA/MMA round trips add latency -> off by default
-    static const int env_pair = [] { const char* e = getenv("SDM_PAIR"); return e ? atoi(e) : 0; }();
-    const long long ksteps_all = (long long)d.ksize * d.ksize * (cin_total / 64);
-    const bool can = !L->swap && bn == 128 && L->mt == 2 && d.mode == EPI_F16 && !d.ups2 && !d.w_bstride && d.N % 128 == 0 && (d.n_store == 0 || d.n_store == d.N);
-    L->pair = can && (d.force_pair == 1 || (d.force_pair == 0 && env_pair != 0 && ksteps_all > 4));
-    if (d.force_pair == 1) SDM_CHECK(can, "force_pair: configuration not supported by the CTA-pair kernel");
-  }
-  {
-    const bool can = halo_geom && !L->pair && (bn == 256 || bn == 160 || (bn == 128 && L->mt == 2));
+    const bool can = halo_geom && (bn == 256 || bn == 160 || (bn == 128 && L->mt == 2));
     if (d.force_halo == 1) SDM_CHECK(can, "force_halo: configuration not supported by the halo kernel");
     L->halo = can && (d.force_halo == 1 || halo_auto);
     if (L->halo) {
@@ -274,7 +254,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   } else {
     const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d.N};
     const uint64_t strides[1] = {(uint64_t)ktot * 2};
-    const uint32_t bbox[2] = {64u, (uint32_t)(L->swap ? 128 : (L->pair ? bn / 2 : bn))};  // pair: each CTA loads half of the tile's weight rows
+    const uint32_t bbox[2] = {64u, (uint32_t)(L->swap ? 128 : bn)};
     make_tmap(&p.b_map, d.w, 2, dims, strides, bbox);
   }
   // ---- residual: extra K steps  A = residual tile, B = identity columns
@@ -287,7 +267,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
     make_tmap(&p.r_map, d.res, 4, dims, strides, box);
     const uint64_t idims[2] = {(uint64_t)kIdentityN, (uint64_t)kIdentityN};
     const uint64_t istr[1] = {(uint64_t)kIdentityN * 2};
-    const uint32_t ibox[2] = {64u, L->swap ? 128u : (L->pair ? 32u : 64u)};  // swap: 128 channel rows x one 64-column slice
+    const uint32_t ibox[2] = {64u, L->swap ? 128u : 64u};  // swap: 128 channel rows x one 64-column slice
     make_tmap(&p.i_map, identity_matrix(), 2, idims, istr, ibox);
     p.has_res = 1;
   } else {
@@ -327,17 +307,14 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
                (p.mode == EPI_F16 && L->mt == 1 && (bn <= 160 || ksteps <= 16)) ||
                (p.mode == EPI_F16 && L->mt == 2 && ksteps <= 4 && env_mt2 != 0)) ? 2 : 1;
     if (env_ewg == 1 || env_ewg == 2) ewg = env_ewg;
-    if (bn == 16 || light || p.mode == EPI_ALPHA || p.mode == EPI_SKINNY || L->pair) ewg = 1;
+    if (bn == 16 || p.mode == EPI_ALPHA || p.mode == EPI_SKINNY) ewg = 1;
     L->ewg = ewg;
   }
   {
-    static const int env_pf = [] { const char* e = getenv("SDM_PREFETCH"); return e ? atoi(e) : 0; }();
     static const int env_prof = [] { const char* e = getenv("SDM_GEMM_PROF"); return e ? atoi(e) : 0; }();
-    p.prof = env_prof;
-    p.prefetch = env_pf;  // measured (A/B, one box): L2 prefetch of the next tile slows the large convs by 3-9 % -> off by default
+    p.prof = env_prof;  // measurement aid: in-kernel cycle counters of the producer / MMA / epilogue threads
   }
-  L->grid = (int)std::min<long long>(total, light ? 2 * num_sms : num_sms);
-  if (L->pair) L->grid = (int)std::min<long long>(2 * total, (long long)(num_sms & ~1));  // two CTAs per pair tile
+  L->grid = (int)std::min<long long>(total, num_sms);
   L->flops = 2.0 * (double)d.B * Hout * Wout * (double)d.N * (double)ktot;
   return L;
 }
@@ -347,11 +324,10 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
   const int bn = l.block_n, mt = l.mt, g = l.grid;
 #define SDM_GO(BN, MT, MODE, UPS2)                                                  \
   do {                                                                              \
-    if (l.ewg == 2) return conv_gemm_launch<BN, MT, MODE, UPS2, false, 2>(p, g, st); \
-    return conv_gemm_launch<BN, MT, MODE, UPS2, false, 1>(p, g, st);                 \
+    if (l.ewg == 2) return conv_gemm_launch<BN, MT, MODE, UPS2, 2>(p, g, st); \
+    return conv_gemm_launch<BN, MT, MODE, UPS2, 1>(p, g, st);                 \
   } while (0)
   if (l.swap) return l.swap_halo ? conv_swap_halo_launch(p, g, st) : conv_swap_launch(p, g, st);
-  if (l.pair) return conv_gemm_launch_pair<128, EPI_F16>(p, g, st);
   if (l.halo) {
     if (bn == 256 && !p.ups2) return conv_gemm_launch_halo<256, 1, false, 1>(p, g, st);
     if (bn == 256 && p.ups2) return conv_gemm_launch_halo<256, 1, true, 1>(p, g, st);
@@ -359,12 +335,6 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
     if (bn == 160 && p.ups2) return conv_gemm_launch_halo<160, 1, true, 2>(p, g, st);
     if (bn == 128 && mt == 2 && !p.ups2) return conv_gemm_launch_halo<128, 2, false, 1>(p, g, st);
     throw Error{"conv_gemm: no halo instantiation for this configuration"};
-  }
-  if (l.light) {
-    if (p.mode == EPI_F16 && !p.ups2) return conv_gemm_launch<128, 1, EPI_F16, false, true>(p, g, st);
-    if (p.mode == EPI_F16_T) return conv_gemm_launch<128, 1, EPI_F16_T, false, true>(p, g, st);
-    if (p.mode == EPI_F32) return conv_gemm_launch<128, 1, EPI_F32, false, true>(p, g, st);
-    throw Error{"conv_gemm: no light instantiation for this mode"};
   }
   switch (p.mode) {
     case EPI_F16:
@@ -374,7 +344,7 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
         if (bn == 128 && mt == 2) SDM_GO(128, 2, EPI_F16, false);
         if (bn == 128) SDM_GO(128, 1, EPI_F16, false);
         if (bn == 64) SDM_GO(64, 1, EPI_F16, false);
-        if (bn == 16) return conv_gemm_launch<16, 1, EPI_F16, false, false, 1>(p, g, st);
+        if (bn == 16) return conv_gemm_launch<16, 1, EPI_F16, false, 1>(p, g, st);
       } else {
         if (bn == 256) SDM_GO(256, 1, EPI_F16, true);
         if (bn == 160) SDM_GO(160, 1, EPI_F16, true);
@@ -398,10 +368,10 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
       if (bn == 64) SDM_GO(64, 1, EPI_F32, false);
       break;
     case EPI_ALPHA:
-      if (bn == 16) return conv_gemm_launch<16, 1, EPI_ALPHA, false, false, 1>(p, g, st);
+      if (bn == 16) return conv_gemm_launch<16, 1, EPI_ALPHA, false, 1>(p, g, st);
       break;
     case EPI_SKINNY:
-      if (bn == 16) return conv_gemm_launch<16, 1, EPI_SKINNY, false, false, 1>(p, g, st);
+      if (bn == 16) return conv_gemm_launch<16, 1, EPI_SKINNY, false, 1>(p, g, st);
       break;
   }
 #undef SDM_GO

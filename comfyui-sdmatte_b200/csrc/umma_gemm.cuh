@@ -56,7 +56,6 @@ struct alignas(64) ConvGemmParams {
   signed char tap_map[9], tap_dx[9], tap_dy[9];
   int b_batched;      // weight map has a batch coordinate
   int has_res;        // residual K steps present
-  int prefetch;       // L2-prefetch the next tile's activation rows
   int prof;           // SDM_GEMM_PROF=1: CTAs 0/1 print the cycles their producer / MMA / epilogue threads spent waiting
   int mode;
   int ups2;           // EPI_F16 only: write each pixel to the 2x2 block of a (2H,2W) output
@@ -77,15 +76,12 @@ struct alignas(64) ConvGemmParams {
 
 // MT = number of 128-row M sub-tiles a CTA processes against ONE B tile (MT=2 halves the weight traffic per FLOP:
 // the N=128 VAE convs were L2->SM bandwidth bound at 128 B/clk/SM with MT=1, r1c: 545-885 TFLOP/s vs 1300-1440 for N=256)
-// LIGHT: 2 pipeline stages and <= 256 TMEM columns so that TWO CTAs share an SM: short-K GEMMs (linears, 1x1 convs, im2col
-// conv_in) are bound by the per-tile epilogue latency, and a second resident CTA doubles the epilogues in flight.
 // EWG: number of epilogue warpgroups.  With 2, tile i of a CTA is drained by warpgroup i%2 (MT=1) or the two M sub-tiles
 // of a tile are drained concurrently (MT=2): twice the epilogues in flight for the GEMMs whose short K loop cannot hide
 // one (r1i: linears 350-600 TFLOP/s, the N=128 VAE convs ~1000 vs ~1400 for long-K layers).
-// PAIR (r1q): the 256 x BLOCK_N tile is computed by a CTA PAIR (cluster of 2, tcgen05 cta_group::2, MMA M = 256): each CTA stages
-// its own 128-row A sub-tile and HALF of the B rows, and owns 128 accumulator lanes.  Per MMA each SM then reads 4 KB (A) +
-// N/2 x 32 B (B) of shared memory instead of 4 KB + N x 32 B: the N=128 convs sat exactly at the 128 B/clk shared-memory limit
-// (tensor pipe 59-62 %, ncu r1k/r1n) while the N=256 tiles (96 B/clk) reach 80 %+.  MT must be 1 (the pair IS the two sub-tiles).
+// (Round 1 also carried a two-CTAs-per-SM "light" config, an L2 prefetch of the next tile and a CTA-pair (tcgen05 cta_group::2,
+// M = 256) variant of this kernel; all three were measured slower than the configurations below — profiles/r1r_*, r1s_*,
+// DESIGN.md section 3 — and were removed in round 2.)
 // HALO (r1s): 3x3 stride-1 convolutions keep ONE (8+2) x (16+2)-pixel halo tile per M sub-tile and 64-channel slice resident in
 // shared memory and issue all NINE taps from it: the A operand of tap (dy, dx) is the descriptor of the same tile started
 // (dy*10 + dx) pixel rows later with SBO = 10 rows (1280 B) — the 128-byte swizzle is a function of the absolute shared-memory
@@ -94,10 +90,10 @@ struct alignas(64) ConvGemmParams {
 // taps re-fetch the activation tile nine times) and each MMA took 109 clk instead of 64: shared-memory bandwidth = 8 KB operand
 // reads + 6 KB TMA writes per MMA.  With the halo tile the fill traffic per 64-channel slice drops from 9 x 16 KB to 23 KB per
 // sub-tile.  Shared memory = 2 halo slots (x MT) + a ring of weight tiles.
-template <int BLOCK_N, int MT = 1, bool LIGHT = false, int EWG = 1, bool PAIR = false, bool HALO = false>
+template <int BLOCK_N, int MT = 1, int EWG = 1, bool HALO = false>
 struct ConvGemmCfg {
   static constexpr int kABytes = 128 * 128;          // 128 rows x 64 fp16 (per M sub-tile)
-  static constexpr int kBBytes = (PAIR ? BLOCK_N / 2 : BLOCK_N) * 128;  // B rows held by this CTA x 64 fp16
+  static constexpr int kBBytes = BLOCK_N * 128;      // B rows x 64 fp16
   static constexpr int kHaloBytes = 23 * 1024;       // 10 x 18 pixel rows of 128 B (23 040 B) rounded up to the 1024-byte swizzle atom
   static constexpr int kHaloTx = 10 * 18 * 128;      // bytes one halo box delivers
   static constexpr int kASlots = 2;
@@ -105,7 +101,7 @@ struct ConvGemmCfg {
   static constexpr int kBudget = 232448 - 1024 - 256 - kEpiBytes - 512;
   static constexpr int kStageBytes = HALO ? kBBytes : MT * kABytes + kBBytes;
   static constexpr int kRingBudget = HALO ? kBudget - kASlots * MT * kHaloBytes : kBudget;
-  static constexpr int kStages = LIGHT ? 2 : ((kRingBudget / kStageBytes) > 8 ? 8 : (kRingBudget / kStageBytes));
+  static constexpr int kStages = (kRingBudget / kStageBytes) > 8 ? 8 : (kRingBudget / kStageBytes);
   static constexpr int kSubStride = BLOCK_N < 32 ? 32 : BLOCK_N;  // TMEM columns per M sub-tile accumulator
   static constexpr int kAccStride = MT * kSubStride;              // TMEM columns between the two accumulator stages
   static constexpr int kTmemCols = (2 * kAccStride <= 64) ? 64 : (2 * kAccStride <= 128) ? 128 : (2 * kAccStride <= 256) ? 256 : 512;
@@ -124,18 +120,14 @@ __device__ __forceinline__ int residual_steps(int n0, int N) {
   return (min(BLOCK_N, N - n0) + 63) >> 6;
 }
 
-template <int BLOCK_N, int MT, int MODE, bool UPS2, bool LIGHT = false, int EWG = 1, bool PAIR = false, bool HALO = false>
-__global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BLOCK_N, MT, LIGHT, EWG, PAIR, HALO>;
-  static_assert(!HALO || (!PAIR && !LIGHT && MODE == EPI_F16), "halo configuration");
+template <int BLOCK_N, int MT, int MODE, bool UPS2, int EWG = 1, bool HALO = false>
+__global__ void __launch_bounds__(64 + 128 * EWG, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using Cfg = ConvGemmCfg<BLOCK_N, MT, EWG, HALO>;
+  static_assert(!HALO || MODE == EPI_F16, "halo configuration");
   static_assert(EWG == 1 || EWG == 2, "one or two epilogue warpgroups");
-  static_assert(!PAIR || (MT == 1 && EWG == 1 && !LIGHT && MODE == EPI_F16 && BLOCK_N % 128 == 0), "CTA-pair configuration");
-  // PAIR: p.total_tiles counts 256-row pair tiles (as for MT = 2); this CTA works on sub-tile `rank` of every pair tile
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-  const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  constexpr int SUBS = PAIR ? 2 : MT;  // M sub-tiles per (pair) tile
-  static_assert(!LIGHT || Cfg::kTmemCols <= 256, "two CTAs per SM need <= 256 TMEM columns each");
+  const int tile_first = (int)blockIdx.x;
+  const int tile_step = (int)gridDim.x;
+  constexpr int SUBS = MT;  // M sub-tiles per tile
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -163,19 +155,15 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), ((EWG == 2 && MT == 2) || PAIR) ? 8 : 4);  // PAIR: 4 epilogue warps of each CTA (leader's barrier)
+      mbar_init(tempty_bar(a), (EWG == 2 && MT == 2) ? 8 : 4);
       if (HALO) { mbar_init(afull_bar(a), 1); mbar_init(aempty_bar(a), 1); }
     }
     fence_barrier_init();
     fence_proxy_async_smem();
   }
-  if (warp == 1) {
-    if constexpr (PAIR) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
-    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
-  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -194,44 +182,17 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
       uint32_t aphase = 0;
       long long prof_wait = 0;
       const long long prof_t0 = p.prof ? clock64() : 0;
-      // PAIR: every transaction byte of both CTAs is accounted on the LEADER's full barrier
-      uint32_t full_remote[PAIR ? kStages : 1];
-      if constexpr (PAIR) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) full_remote[s] = mapa_shared(full_bar(s), 0);
-      }
       for (int tile = tile_first; tile < p.total_tiles; tile += tile_step) {
         const int nt = tile % p.n_tiles;
         const int n0 = nt * BLOCK_N;
         int x0[MT], y0[MT], bb[MT];
 #pragma unroll
         for (int u = 0; u < MT; ++u) {
-          const int mt = (tile / p.n_tiles) * SUBS + (PAIR ? (int)rank : u);
+          const int mt = (tile / p.n_tiles) * SUBS + u;
           const int tx = mt % p.tiles_x;
           const int ty = (mt / p.tiles_x) % p.tiles_y;
           x0[u] = tx * p.tw; y0[u] = ty * p.th;
           bb[u] = mt < p.m_tiles ? mt / (p.tiles_x * p.tiles_y) : p.B;  // past-the-end sub-tile: batch index out of range -> zero fill
-        }
-        // L2 prefetch of the NEXT tile's activation rows (centre column of every tap row): its cold misses then overlap this
-        // tile's main loop instead of stalling the 4-stage ring (ncu r1i, 128->128 conv: 20 % of the A sectors missed L2,
-        // tensor pipe 64 % busy with L2 at 52 % and DRAM at 22 %: latency, not bandwidth)
-        {
-          const int nxt = tile + tile_step;
-          if (!PAIR && p.prefetch && nxt < p.total_tiles && (nxt % p.n_tiles) == 0) {
-#pragma unroll
-            for (int u = 0; u < MT; ++u) {
-              const int mt = (nxt / p.n_tiles) * MT + u;
-              if (mt < p.m_tiles) {
-                const int ptx = mt % p.tiles_x, pty = (mt / p.tiles_x) % p.tiles_y, pb = mt / (p.tiles_x * p.tiles_y);
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                  if (p.tap_dx[tap] != 0) continue;
-                  for (int s = 0; s < p.nsrc; ++s)
-                    for (int c0 = 0; c0 < p.src_c[s]; c0 += 64)
-                      tma_prefetch_4d(&p.a_map[p.tap_map[tap] + s], c0, ptx * p.tw, pty * p.th + p.tap_dy[tap], pb);
-                }
-              }
-            }
-          }
         }
         if constexpr (HALO) {
           // per 64-channel slice: ONE halo box per M sub-tile (x0-1 .. x0+8, y0-1 .. y0+16; zero fill = conv padding), then the
@@ -282,11 +243,6 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
               else mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
               const uint32_t b_dst = a_dst + MT * Cfg::kABytes;
-              if constexpr (PAIR) {
-                if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-                tma_load_4d_pair(a_dst, amap, full_remote[stage], c0, x0[0] + p.tap_dx[tap], y0[0] + p.tap_dy[tap], bb[0]);
-                tma_load_2d_pair(b_dst, &p.b_map, full_remote[stage], koff + c0, n0 + (int)rank * (BLOCK_N / 2));
-              } else {
               mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
 #pragma unroll
               for (int u = 0; u < MT; ++u)
@@ -295,7 +251,6 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
                 tma_load_3d(b_dst, &p.b_map, full_bar(stage), koff + c0, n0, bb[0]);
               else
                 tma_load_2d(b_dst, &p.b_map, full_bar(stage), koff + c0, n0);
-              }
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
             koff += p.src_c[s];
@@ -307,16 +262,10 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
             const uint32_t b_dst = a_dst + MT * Cfg::kABytes;
-            if constexpr (PAIR) {  // identity block: 32 of its 64 rows per CTA (i_map box = 64 x 32)
-              if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * (Cfg::kABytes + 32 * 128));
-              tma_load_4d_pair(a_dst, &p.r_map, full_remote[stage], n0 + i * 64, x0[0], y0[0], bb[0]);
-              tma_load_2d_pair(b_dst, &p.i_map, full_remote[stage], 0, (int)rank * 32);
-            } else {
             mbar_expect_tx(full_bar(stage), MT * Cfg::kABytes + 64 * 128);
 #pragma unroll
             for (int u = 0; u < MT; ++u) tma_load_4d(a_dst + u * Cfg::kABytes, &p.r_map, full_bar(stage), n0 + i * 64, x0[u], y0[u], bb[u]);
             tma_load_2d(b_dst, &p.i_map, full_bar(stage), 0, 0);
-            }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -327,8 +276,8 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0 && rank == 0) {  // PAIR: only the leader issues (its MMAs drive both CTAs' tensor cores)
-      constexpr uint32_t idesc = PAIR ? umma_idesc_f16_m256(BLOCK_N) : umma_idesc_f16(BLOCK_N);
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -383,7 +332,7 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
           const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
           const uint64_t bdesc = umma_desc_k128(a_addr + MT * Cfg::kABytes);
           const int ri = ks - num_ksteps;  // >= 0: residual slice index
-          const uint32_t id = ri < 0 ? idesc : (PAIR ? umma_idesc_f16_m256(64) : umma_idesc_f16(min(64, BLOCK_N - ri * 64)));
+          const uint32_t id = ri < 0 ? idesc : umma_idesc_f16(min(64, BLOCK_N - ri * 64));
           const uint32_t dcol = ri < 0 ? 0u : (uint32_t)(ri * 64);
 #pragma unroll
           for (int u = 0; u < MT; ++u) {
@@ -391,16 +340,13 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // +32 B per 16-element K step (start-address field is in 16-byte units)
-              if constexpr (PAIR) umma_f16_pair(d_tmem + dcol, adesc + 2 * k, bdesc + 2 * k, id, (ks | k) != 0);
-              else umma_f16(d_tmem + u * Cfg::kSubStride + dcol, adesc + 2 * k, bdesc + 2 * k, id, (ks | k) != 0);
+              umma_f16(d_tmem + u * Cfg::kSubStride + dcol, adesc + 2 * k, bdesc + 2 * k, id, (ks | k) != 0);
             }
           }
-          if constexpr (PAIR) umma_commit_pair(empty_bar(stage));  // frees the stage in both CTAs
-          else umma_commit(empty_bar(stage));
+          umma_commit(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        if constexpr (PAIR) umma_commit_pair(tfull_bar(acc));
-        else umma_commit(tfull_bar(acc));
+        umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
       if (p.prof && blockIdx.x < 2)
@@ -429,8 +375,6 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
     uint32_t acc_phase = 0;
     long long prof_tfull = 0;
     const long long prof_t0 = p.prof ? clock64() : 0;
-    const uint32_t tempty_leader0 = PAIR ? mapa_shared(tempty_bar(0), 0) : 0u;
-    const uint32_t tempty_leader1 = PAIR ? mapa_shared(tempty_bar(1), 0) : 0u;
     for (int tile = tile_first + (kAlternate ? ewg * tile_step : 0); tile < p.total_tiles;
          tile += (kAlternate ? 2 : 1) * tile_step) {
       if (p.prof) { const long long t = clock64(); mbar_wait(tfull_bar(acc), acc_phase); prof_tfull += clock64() - t; }
@@ -440,7 +384,7 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
       const int n0 = nt * BLOCK_N;
 #pragma unroll 1
       for (int u = (EWG == 2 && MT == 2) ? ewg : 0; u < ((EWG == 2 && MT == 2) ? ewg + 1 : MT); ++u) {
-        const int mt = (tile / p.n_tiles) * SUBS + (PAIR ? (int)rank : u);
+        const int mt = (tile / p.n_tiles) * SUBS + u;
         if (mt >= p.m_tiles) break;  // warp-uniform
         const int tx = mt % p.tiles_x;
         const int ty = (mt / p.tiles_x) % p.tiles_y;
@@ -755,10 +699,7 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
       }  // M sub-tile
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if constexpr (PAIR) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);  // the leader's MMA thread waits for both CTAs
-        else mbar_arrive(tempty_bar(acc));
-      }
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (kAlternate) acc_phase ^= 1u;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -767,12 +708,10 @@ __global__ void __launch_bounds__(64 + 128 * EWG, LIGHT ? 2 : 1) conv_gemm_kerne
   }
 
   tc_fence_before();
-  if constexpr (PAIR) cluster_sync_all();  // neither CTA may free tensor memory (or exit) while the pair's MMAs / remote arrives are in flight
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if constexpr (PAIR) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
-    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 

@@ -32,7 +32,7 @@ class sdm_conv_gemm_args(C.Structure):
         ("out", C.c_void_p), ("out_ld", C.c_int64), ("out_bstride", C.c_int64),
         ("bias", C.c_void_p), ("bias_sel", C.c_void_p),
         ("res", C.c_void_p), ("res_ld", C.c_int64), ("res_bstride", C.c_int64),
-        ("scale", C.c_float), ("force_block_n", C.c_int), ("post_div", C.c_float), ("n_store", C.c_int), ("out2", C.c_void_p), ("force_mt", C.c_int), ("force_light", C.c_int), ("stats", C.c_void_p), ("force_pair", C.c_int), ("force_halo", C.c_int), ("force_swap", C.c_int),
+        ("scale", C.c_float), ("force_block_n", C.c_int), ("post_div", C.c_float), ("n_store", C.c_int), ("out2", C.c_void_p), ("force_mt", C.c_int), ("stats", C.c_void_p), ("force_halo", C.c_int), ("force_swap", C.c_int),
         ("gn_ab", C.c_void_p), ("gn_silu", C.c_int),
     ]
 
@@ -456,7 +456,7 @@ def _p(t):
 
 
 def k_conv_gemm(srcs, w, N, out, *, B, Hin, Win, ksize=1, stride=1, pad=0, mode=0, ups2=0, bias=None, bias_sel=None,
-                res=None, scale=1.0, w_bstride=0, out_ld=None, out_bstride=None, force_block_n=0, post_div=1.0, n_store=0, out2=None, force_mt=0, stats=None, force_light=0, force_pair=0, force_halo=0, force_swap=0, gn_ab=None, gn_silu=0):
+                res=None, scale=1.0, w_bstride=0, out_ld=None, out_bstride=None, force_block_n=0, post_div=1.0, n_store=0, out2=None, force_mt=0, stats=None, force_halo=0, force_swap=0, gn_ab=None, gn_silu=0):
     lib = load_library()
     a = sdm_conv_gemm_args()
     a.B, a.Hin, a.Win, a.nsrc = B, Hin, Win, len(srcs)
@@ -471,8 +471,8 @@ def k_conv_gemm(srcs, w, N, out, *, B, Hin, Win, ksize=1, stride=1, pad=0, mode=
     if res is not None:
         a.res, a.res_ld, a.res_bstride = res[0].data_ptr(), res[1], res[2]
     a.scale, a.force_block_n = scale, force_block_n
-    a.post_div, a.n_store, a.out2, a.force_mt, a.stats, a.force_light = post_div, n_store, _p(out2), force_mt, _p(stats), force_light
-    a.force_pair, a.force_halo, a.force_swap = force_pair, force_halo, force_swap
+    a.post_div, a.n_store, a.out2, a.force_mt, a.stats = post_div, n_store, _p(out2), force_mt, _p(stats)
+    a.force_halo, a.force_swap = force_halo, force_swap
     a.gn_ab, a.gn_silu = _p(gn_ab), int(gn_silu)
     _check(lib.sdm_k_conv_gemm(C.byref(a), _stream_ptr(out.device)))
 

@@ -146,9 +146,7 @@ typedef struct {
   int n_store;                  /* mode 0: store only the first n_store (< 8) columns; 0 = all */
   void* out2;                   /* mode 4 (alpha head): optional pre-clip mean */
   int force_mt;                 /* tests: 1 / 2 = force M sub-tiles per CTA tile (BLOCK_N 128 only), 0 = auto */
-  int force_light;              /* tests: 1 = force the 2-CTAs-per-SM short-K config, -1 = forbid it, 0 = auto */
   float* stats;                 /* mode 0 without ups2: GroupNorm partials [B][sdm_k_conv_tiles_per_image][N][2] (sum, sumsq), or NULL */
-  int force_pair;               /* tests: 1 = force the CTA-pair (tcgen05 cta_group::2, M = 256) kernel, -1 = forbid it, 0 = auto */
   int force_halo;               /* tests: 1 = force the resident-halo 3x3 kernel (one halo tile per 64 channels, nine taps from it), -1 = forbid */
   int force_swap;               /* tests: 1 = force the swapped-operand 3x3 kernel (channels on M, 256 pixels on N), 2 = its resident-halo form, -1 = forbid it */
   const float* gn_ab;           /* fused GroupNorm(+SiLU) of the INPUT: [B][c0+c1][2] (scale, shift) as sdm_k_groupnorm leaves them in its scratch

@@ -1,7 +1,8 @@
 #!/bin/bash
-# r2c: fused GroupNorm, second version (8 branch-free transform warps, 3 halo slots / 5 weight stages): kernel parity, then step A/B on one box
+# r2c: fused GroupNorm, second version (8 branch-free transform warps, 3 halo slots / 5 weight stages) + the pruned kernel set
+# (no pair / light / prefetch / split-PV variants): full kernel parity suite, then step A/B on one box
 mkdir -p gpurun_out
-( timeout 900 python -m pytest tests/test_kernels_gpu.py -q -k "fused_groupnorm or can_fuse or swapped" -p no:cacheprovider ) > gpurun_out/r2c_kernels.log 2>&1; echo "kernel pytest exit $?"; tail -5 gpurun_out/r2c_kernels.log
+( timeout 1200 python -m pytest tests/test_kernels_gpu.py -q -p no:cacheprovider ) > gpurun_out/r2c_kernels.log 2>&1; echo "kernel pytest exit $?"; tail -5 gpurun_out/r2c_kernels.log
 for cfg in "0 0" "1 0" "2 0"; do
   set -- $cfg
   SDM_GN_FUSE=$1 SDM_SWAP_HALO=$2 timeout 600 python bench.py --quick --steps 4 --warmup 2 --dump-ops gpurun_out/r2c_ops_f$1_h$2.csv > gpurun_out/r2c_bench_f$1_h$2.json 2> gpurun_out/r2c_bench_f$1_h$2.err; echo "bench GN_FUSE=$1 SWAP_HALO=$2 exit $?"

@@ -472,33 +472,6 @@ def test_groupnorm_two_sources_many_partial_slots(eng_mod):
     assert torch.equal(y3[0], y2[1])
 
 
-@pytest.mark.parametrize("mode", ["f16", "f16_res", "vT", "f32"])
-def test_light_config_two_ctas_per_sm(eng_mod, mode):
-    """Short-K GEMMs run as 128-wide tiles with two CTAs per SM ("light" config)."""
-    B, M, N, K = 2, 1000, 320, 320
-    x = _rand(B, M, K, seed=1).half()
-    w = _rand(N, K, scale=K ** -0.5, seed=2).half()
-    b = _rand(N, seed=3).float()
-    if mode == "f16":
-        out = torch.zeros(B, M, N, dtype=torch.float16, device=DEV)
-        eng_mod.k_conv_gemm([(x, K, K)], w, N, out, B=B, Hin=1, Win=M, bias=b, out_ld=N, out_bstride=M * N, force_light=1)
-        ref = x.float() @ w.float().t() + b
-    elif mode == "f16_res":
-        out = _rand(B, M, N, seed=4).half()
-        ref = x.float() @ w.float().t() + b + out.float()
-        eng_mod.k_conv_gemm([(x, K, K)], w, N, out, B=B, Hin=1, Win=M, bias=b, out_ld=N, out_bstride=M * N, res=(out, N, M * N), force_light=1)
-    elif mode == "vT":
-        out = torch.zeros(B, N, M, dtype=torch.float16, device=DEV)
-        eng_mod.k_conv_gemm([(x, K, K)], w, N, out, B=B, Hin=1, Win=M, mode=1, out_ld=M, out_bstride=N * M, force_light=1)
-        ref = (x.float() @ w.float().t()).transpose(1, 2)
-    else:
-        out = torch.zeros(B, M, N, dtype=torch.float32, device=DEV)
-        eng_mod.k_conv_gemm([(x, K, K)], w, N, out, B=B, Hin=1, Win=M, mode=3, scale=0.5, out_ld=N, out_bstride=M * N, force_light=1)
-        ref = (x.float() @ w.float().t()) * 0.5
-    torch.cuda.synchronize()
-    _close(out, ref, 2e-3, 2e-3, f"light {mode}")
-
-
 # ------------------------------------------------------------------------------------------------ key compaction (attn1)
 def _compact_ref(bias_l2, L):
     """torch restatement of key_compact_kernel for one sample: (idx, cbias, ntiles)."""
@@ -590,34 +563,6 @@ def test_conv1x1_two_m_subtiles_dual_epilogue(eng_mod, B, H, W, Cin, Cout):
     o = out.double().view(B, H * W, Cout)
     assert torch.allclose(tot[..., 0], o.sum(1), rtol=1e-4, atol=1e-2)
     assert torch.allclose(tot[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)
-
-
-@pytest.mark.parametrize("B,H,W,Cin,res", [(2, 32, 32, 128, True), (3, 16, 8, 128, True), (1, 128, 128, 64, False), (2, 64, 64, 256, True),
-                                           (5, 8, 16, 192, False)])
-def test_conv3x3_cta_pair(eng_mod, B, H, W, Cin, res):
-    """256x128 tile computed by a CTA pair (tcgen05 cta_group::2, M = 256): output, residual K steps and GroupNorm partials
-    must equal the single-CTA kernel bit for bit (same K order), incl. an odd number of 128-row M tiles."""
-    Cout = 128
-    x = _rand(B, H, W, Cin, seed=1).half()
-    r = _rand(B, H, W, Cout, seed=5).half() if res else None
-    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2).half()
-    b = _rand(Cout, seed=3).float()
-    slots = eng_mod.conv_tiles_per_image(H, W)
-    outs, stats = [], []
-    for fp in (1, -1):
-        out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
-        st = torch.full((B, slots, Cout, 2), float("nan"), device=DEV)
-        eng_mod.k_conv_gemm([(x, Cin, Cin)], _pack_conv_w(w), Cout, out, B=B, Hin=H, Win=W, ksize=3, bias=b, out_ld=Cout,
-                            out_bstride=H * W * Cout, res=(r, Cout, H * W * Cout) if res else None, force_block_n=128, force_mt=2, stats=st, force_pair=fp, force_swap=-1, force_halo=-1)
-        torch.cuda.synchronize()
-        outs.append(out)
-        stats.append(st)
-    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).half().float().permute(0, 2, 3, 1)
-    if res:
-        ref = ref + r.float()
-    _close(outs[0], ref, 2e-3, 2e-3, "conv3x3 CTA pair")
-    assert torch.equal(outs[0], outs[1]), "pair kernel differs from the single-CTA kernel"
-    assert torch.equal(stats[0], stats[1]), "GroupNorm partials differ"
 
 
 # ------------------------------------------------------------------------------------------------ resident-halo 3x3 convs
