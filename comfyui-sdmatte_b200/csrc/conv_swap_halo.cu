@@ -12,8 +12,8 @@
 // GNF (round 2): the conv of a ResnetBlock2D consumes GroupNorm(32) -> SiLU of its input (reference: diffusers ResnetBlock2D, built at
 // /root/reference/src/utils/replace.py:239,268,321).  As a separate pass that is one full HBM read + write of the activation per
 // conv (27 ms of a 280 ms step).  With the halo tile an activation slice sits in shared memory exactly ONCE per 64 channels, so
-// four TRANSFORM warps apply y = silu(a x + s) in place (per-(sample, channel) (a, s) from gn_finalize_kernel, the same arithmetic
-// as gn_apply_kernel: identical fp16 bits) between the TMA's arrival (xfull) and the MMA's use (xready).  Rows outside the image
+// eight TRANSFORM warps apply y = silu(a x + s) in place (per-(sample, channel) (a, s) from gn_finalize_kernel; the arithmetic of
+// gn_apply_kernel with MUFU.RCP instead of its Newton reciprocal) between the TMA's arrival (xfull) and the MMA's use (xready).  Rows outside the image
 // were zero-filled by the TMA unit and stay zero: the convolution pads the NORMALISED tensor.  The 128-byte swizzle is undone
 // per thread: 16-byte piece j of tile row r holds channel chunk j ^ (r & 7); a thread keeps (piece, r mod 16), hence one fixed
 // chunk and its 16 constants in registers.
@@ -63,7 +63,7 @@ __device__ __forceinline__ void gn_transform_tile(uint8_t* tp, uint32_t inside, 
     for (int j = 0; j < 4; ++j) {
       const int k = g * 4 + j;
       if (k < 11) {
-        uint4 o = gn_piece<SILU>(v[j], ka, ks);
+        uint4 o = gn_piece<SILU, true>(v[j], ka, ks);
         if (!((inside >> k) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);
         if ((exist >> k) & 1u) *reinterpret_cast<uint4*>(tp + k * 4096) = o;
       }
@@ -213,8 +213,13 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
           else gn_load_consts<false>(ab8, ka, ks);
           mbar_wait(xfull_bar(xs), xph);
           uint8_t* tp = smem_raw + (x_base + xs * kXSlot - smem_u32(smem_raw)) + r0 * 128 + piece * 16;
-          if (p.gn_silu) gn_transform_tile<true>(tp, inside, exist, ka, ks);
-          else gn_transform_tile<false>(tp, inside, exist, ka, ks);
+          if (p.gn_silu == 1) gn_transform_tile<true>(tp, inside, exist, ka, ks);
+          else if (p.gn_silu == 0) gn_transform_tile<false>(tp, inside, exist, ka, ks);
+          else if (p.gn_silu == 4) {  // measurement aid (tests/bench_kernels.py): shared-memory traffic of the transform without its math
+#pragma unroll
+            for (int k = 0; k < 11; ++k)
+              if ((exist >> k) & 1u) { uint4* q = reinterpret_cast<uint4*>(tp + k * 4096); uint4 v = *q; v.x ^= inside; *q = v; }
+          }  // gn_silu == 2 (measurement aid): no transform at all, only the extra barrier hop
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
           __syncwarp();
           if (lane == 0) mbar_arrive(xready_bar(xs));

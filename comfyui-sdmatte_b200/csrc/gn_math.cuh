@@ -21,10 +21,21 @@ __device__ __forceinline__ void gn_load_consts(const float* __restrict__ ab8, ui
   }
 }
 
-// y = a x + s, optionally SiLU(y) = y / (1 + 2^(-y log2 e)) with ONE MUFU op per element: the reciprocal of d = 1 + e is the
-// bit-trick guess (negated for free through the magic constant) + two Newton steps,
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// y = a x + s, optionally SiLU(y) = y / (1 + 2^(-y log2 e)).
+// MUFU_RCP = false (the HBM-bound apply pass, which two MUFU ops per element made XU-bound, ncu r1a): ONE MUFU op per element,
+//   the reciprocal of d = 1 + e is the bit-trick guess (negated for free through the magic constant) + two Newton steps,
 //   n0 = -r0,  p1 = n0 (2 + d n0) = -r1,  p2 = p1 (2 + d p1) = -r2,  result = (-y) p2.
-template <bool SILU>
+// MUFU_RCP = true (the transform warps of the fused conv, which are ISSUE-bound, kbench r2d: the arithmetic alone took the fused
+//   128 -> 128 conv from 1.15 to 1.44 ms): MUFU.RCP instead of the Newton chain and no overflow clamp (e = +inf gives d = +inf,
+//   1/d = 0, result -0: the correct limit) — 5.5 instead of 8.5 issue slots per element.  Both forms are accurate to < 1e-5
+//   relative, far below the fp16 rounding of the result; they are not bit-identical to each other.
+template <bool SILU, bool MUFU_RCP = false>
 __device__ __forceinline__ uint4 gn_piece(const uint4& raw, const uint64_t (&ka)[4], const uint64_t (&ks)[4]) {
   const uint64_t kLog2e = pack_f2(1.4426950408889634f, 1.4426950408889634f);
   const uint64_t kOne = pack_f2(1.0f, 1.0f), kTwo = pack_f2(2.0f, 2.0f);
@@ -34,7 +45,13 @@ __device__ __forceinline__ uint4 gn_piece(const uint4& raw, const uint64_t (&ka)
   for (int j = 0; j < 4; ++j) {
     const float2 f = __half22float2(h[j]);
     uint64_t r = fma_f2(pack_f2(f.x, f.y), ka[j], ks[j]);  // y, or -y when SILU
-    if (SILU) {
+    if (SILU && MUFU_RCP) {
+      float t0, t1;
+      unpack_f2(mul_f2(r, kLog2e), t0, t1);                // -y log2(e)
+      float d0, d1;
+      unpack_f2(add_f2(pack_f2(ex2f(t0), ex2f(t1)), kOne), d0, d1);
+      r = mul_f2(r, pack_f2(-rcp_approx(d0), -rcp_approx(d1)));
+    } else if (SILU) {
       float t0, t1;
       unpack_f2(mul_f2(r, kLog2e), t0, t1);                // -y log2(e)
       const uint64_t d = add_f2(pack_f2(ex2f(fminf(t0, 80.0f)), ex2f(fminf(t1, 80.0f))), kOne);

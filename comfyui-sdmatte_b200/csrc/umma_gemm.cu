@@ -120,11 +120,12 @@ static ConvVariant conv3x3_variant(int ksize, int stride, int mode, int ups2, bo
   return v;
 }
 // 0 = one TMA box per tap (conv_gemm_kernel), 1 / 2 = resident halo with 256- / 160-wide tiles, 3 = swapped operands
-// GroupNorm fusion is available where the resident-halo swapped-operand kernel applies.  SDM_GN_FUSE: 0 = never, 1 = the
-// 128-channel convs only, 2 = every N % 128 == 0 conv (A/B switch of round 2)
+// GroupNorm fusion is available where the resident-halo swapped-operand kernel applies.  Every 128-channel N tile of a pixel tile
+// re-normalises the same input slice, so the transform work grows with N / 128 while the apply pass it replaces does not.
+// SDM_GN_FUSE (A/B switch of round 2): 0 = never, 1 = N == 128 only, 2 = every N % 128 == 0 conv, 3 = N <= 256
 bool conv_gemm_can_fuse_gn(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout) {
-  static const int level = [] { const char* e = getenv("SDM_GN_FUSE"); return e ? atoi(e) : 1; }();
-  if (level <= 0 || (level == 1 && N != 128)) return false;
+  static const int level = [] { const char* e = getenv("SDM_GN_FUSE"); return e ? atoi(e) : 2; }();
+  if (level <= 0 || (level == 1 && N != 128) || (level == 3 && N > 256)) return false;
   const ConvVariant v = conv3x3_variant(ksize, stride, mode, ups2, false, N, 0, has_res != 0, Hout, Wout, 0, 0, 0, 0, true);
   return v.swap && v.swap_halo;
 }

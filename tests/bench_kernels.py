@@ -55,6 +55,39 @@ def conv(B, H, W, Cin, Cout, k=3, res=False, stats=False):
     return ms, fl / ms / 1e9
 
 
+def conv_gn(B, H, W, Cin, Cout, variant):
+    """3x3 conv behind a GroupNorm+SiLU: 'apply+swap' / 'apply+swap_halo' = stand-alone apply pass + conv (both timed),
+    'fused' = conv_swap_halo_kernel<true>; 'fused_nomath' / 'fused_hop' isolate the transform's shared-memory traffic / barrier hop."""
+    x = torch.randn(B, H, W, Cin, device=DEV).half()
+    w = (torch.randn(Cout, 9 * Cin, device=DEV) * (9 * Cin) ** -0.5).half()
+    b = torch.randn(Cout, device=DEV)
+    g, bt = torch.ones(Cin, device=DEV), torch.zeros(Cin, device=DEV)
+    out = torch.empty(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    slots = E.conv_tiles_per_image(H, W)
+    st = torch.empty(B, slots, Cout, 2, device=DEV)
+    pre = torch.rand(B, slots, Cin, 2, device=DEV)
+    pre[..., 1] += 1.0
+    xf = x.view(B, H * W, Cin)
+    common = dict(B=B, Hin=H, Win=W, ksize=3, bias=b, out_ld=Cout, out_bstride=H * W * Cout, stats=st)
+    if variant.startswith("apply"):
+        n = torch.empty_like(x)
+        fs = 2 if variant.endswith("halo") else 1
+
+        def run():
+            E.k_groupnorm([(xf, Cin, Cin)], g, bt, n.view(B, H * W, Cin), B=B, HW=H * W, eps=1e-6, silu=1, pre=(pre, None), pre_slots=slots)
+            E.k_conv_gemm([(n, Cin, Cin)], w, Cout, out, force_swap=fs, **common)
+    else:
+        mode = {"fused": 1, "fused_hop": 2, "fused_nomath": 4}[variant]
+        scratch = E.k_groupnorm([(xf, Cin, Cin)], g, bt, None, B=B, HW=H * W, eps=1e-6, silu=1, pre=(pre, None), pre_slots=slots)
+        ab = E.groupnorm_ab(scratch, B, H * W, Cin)
+
+        def run():
+            E.k_groupnorm([(xf, Cin, Cin)], g, bt, None, B=B, HW=H * W, eps=1e-6, silu=1, pre=(pre, None), pre_slots=slots)
+            E.k_conv_gemm([(x, Cin, Cin)], w, Cout, out, gn_ab=ab, gn_silu=mode, **common)
+    ms = timeit(run)
+    return ms, 2.0 * B * H * W * Cout * 9 * Cin / ms / 1e9
+
+
 def linear(B, M, N, K, res=False):
     x = torch.randn(B, M, K, device=DEV).half()
     w = (torch.randn(N, K, device=DEV) * K ** -0.5).half()
@@ -96,6 +129,9 @@ CASES = {
     "attn_cross_L0 (B2 h5 16384x16384)": lambda: attn(2, 5, 16384, 16384, False),
     "attn_cross_L1 (B2 h10 4096x16384)": lambda: attn(2, 10, 4096, 16384, False),
     "attn_self_L2 (B2 h20 1024x1024 bias)": lambda: attn(2, 20, 1024, 1024, True),
+    **{f"gn+conv3x3 128->128 @1024^2 B4 {v}": (lambda v=v: conv_gn(4, 1024, 1024, 128, 128, v)) for v in ("apply+swap", "apply+swap_halo", "fused", "fused_nomath", "fused_hop")},
+    **{f"gn+conv3x3 256->256 @512^2 B4 {v}": (lambda v=v: conv_gn(4, 512, 512, 256, 256, v)) for v in ("apply+swap_halo", "fused", "fused_nomath", "fused_hop")},
+    **{f"gn+conv3x3 512->512 @256^2 B4 {v}": (lambda v=v: conv_gn(4, 256, 256, 512, 512, v)) for v in ("apply+swap_halo", "fused", "fused_nomath", "fused_hop")},
     "conv3x3 128->128 @1024^2 B2": lambda: conv(2, 1024, 1024, 128, 128),
     "conv3x3 128->128 @1024^2 B2 +res+stats": lambda: conv(2, 1024, 1024, 128, 128, res=True, stats=True),
     "conv3x3 256->256 @512^2 B4": lambda: conv(4, 512, 512, 256, 256),

@@ -671,9 +671,10 @@ def test_conv3x3_swapped_operands(eng_mod, B, H, W, C0, C1, Cout, res):
 ])
 def test_conv3x3_fused_groupnorm(eng_mod, B, H, W, C0, C1, Cout, res, silu):
     """GroupNorm(32)(+SiLU) applied to the conv's resident input halo tile by the transform warps of conv_swap_halo_kernel<true>
-    == the stand-alone apply pass followed by the same conv kernel, BIT FOR BIT (same arithmetic on the same fp16 values, same
-    summation order), incl. the zero padding of the NORMALISED tensor; and within fp16 tolerance of the fp32 torch reference
-    (ResnetBlock2D: norm -> silu -> conv, /root/reference/src/utils/replace.py:239,268,321 via diffusers)."""
+    against the stand-alone apply pass followed by the same conv kernel: without SiLU BIT FOR BIT (same arithmetic on the same fp16
+    values, same summation order, incl. the zero padding of the NORMALISED tensor); with SiLU the transform uses MUFU.RCP where the
+    apply pass uses a Newton reciprocal, so a few normalised values differ by one fp16 ulp; and within fp16 tolerance of the fp32
+    torch reference (ResnetBlock2D: norm -> silu -> conv, /root/reference/src/utils/replace.py:239,268,321 via diffusers)."""
     Cin = C0 + C1
     a = (_rand(B, H, W, C0, seed=1) * 1.5 + 0.4).half()
     s2 = (_rand(B, H, W, C1, seed=6) * 0.7 - 0.2).half() if C1 else None
@@ -701,8 +702,12 @@ def test_conv3x3_fused_groupnorm(eng_mod, B, H, W, C0, C1, Cout, res, silu):
     eng_mod.k_conv_gemm(srcs, _pack_conv_w(w), Cout, out_f, B=B, Hin=H, Win=W, ksize=3, bias=bias, out_ld=Cout, out_bstride=H * W * Cout,
                         res=(r, Cout, H * W * Cout) if res else None, stats=st_f, gn_ab=ab, gn_silu=silu)
     torch.cuda.synchronize()
-    assert torch.equal(out_f, out_u), f"fused != unfused: {(out_f.float() - out_u.float()).abs().max().item():.3e}"
-    assert torch.equal(st_f, st_u)
+    if silu:
+        d = (out_f.float() - out_u.float()).abs()
+        assert d.max().item() <= 4e-3 and (d > 0).float().mean().item() < 0.2, (d.max().item(), (d > 0).float().mean().item())
+    else:
+        assert torch.equal(out_f, out_u), f"fused != unfused: {(out_f.float() - out_u.float()).abs().max().item():.3e}"
+        assert torch.equal(st_f, st_u)
     # the raw inputs must not have been modified (the transform works on the shared-memory copy)
     assert torch.equal(a, (_rand(B, H, W, C0, seed=1) * 1.5 + 0.4).half())
     x = torch.cat([a, s2], -1) if C1 else a
