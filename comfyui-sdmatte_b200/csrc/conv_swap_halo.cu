@@ -190,11 +190,20 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
     const uint32_t exist = r0 < kXRows - 320 ? 0x7ffu : 0x3ffu;  // row r0 + 320 exists for r0 < 20
     int xs = 0;
     uint32_t xph = 0;
+    // (scale, shift) of this thread's 8 channels, one slice ahead: ncu r2f — fetched at the top of every slice the constants cost
+    // one exposed L2 round trip per slice (30 % of the kernel's stall samples sat on their first use)
+    auto load_raw = [&](int tile_, int slice, float4 (&raw)[4]) {
+      const int b_ = (tile_ / p.n_tiles) / per_image;
+      const float4* src = reinterpret_cast<const float4*>(p.gn_ab + ((size_t)b_ * p.cin_total + slice * 64 + chunk * 8) * 2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) raw[j] = __ldg(src + j);
+    };
+    float4 raw[4];
+    if ((int)blockIdx.x < p.total_tiles) load_raw(blockIdx.x, 0, raw);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_tiles;
       const int t_img = mt % per_image;
-      const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32, b = mt / per_image;
-      const float* ab_b = p.gn_ab + (size_t)b * p.cin_total * 2;
+      const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32;
       // validity of this thread's rows depends on the tile position only: bit k = row r0 + 32 k lies inside the image
       uint32_t inside = 0;
 #pragma unroll
@@ -204,28 +213,26 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
         if (px >= 0 && px < p.W && py >= 0 && py < p.H) inside |= 1u << k;
       }
       inside &= exist;
-      int coff = 0;
-      for (int s = 0; s < p.nsrc; ++s) {
-        for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
-          uint64_t ka[4], ks[4];
-          const float* ab8 = ab_b + (size_t)(coff + c0 + chunk * 8) * 2;
-          if (p.gn_silu) gn_load_consts<true>(ab8, ka, ks);
-          else gn_load_consts<false>(ab8, ka, ks);
-          mbar_wait(xfull_bar(xs), xph);
-          uint8_t* tp = smem_raw + (x_base + xs * kXSlot - smem_u32(smem_raw)) + r0 * 128 + piece * 16;
-          if (p.gn_silu == 1) gn_transform_tile<true>(tp, inside, exist, ka, ks);
-          else if (p.gn_silu == 0) gn_transform_tile<false>(tp, inside, exist, ka, ks);
-          else if (p.gn_silu == 4) {  // measurement aid (tests/bench_kernels.py): shared-memory traffic of the transform without its math
+      for (int sl = 0; sl < nslices; ++sl) {  // slice sl = channels [64 sl, 64 sl + 64) of the concatenated input
+        uint64_t ka[4], ks[4];
+        if (p.gn_silu == 0) gn_consts_from_raw<false>(raw, ka, ks);
+        else gn_consts_from_raw<true>(raw, ka, ks);
+        // next slice's constants (or the first slice of this CTA's next tile) fly during the transform
+        if (sl + 1 < nslices) load_raw(tile, sl + 1, raw);
+        else if (tile + (int)gridDim.x < p.total_tiles) load_raw(tile + gridDim.x, 0, raw);
+        mbar_wait(xfull_bar(xs), xph);
+        uint8_t* tp = smem_raw + (x_base + xs * kXSlot - smem_u32(smem_raw)) + r0 * 128 + piece * 16;
+        if (p.gn_silu == 1) gn_transform_tile<true>(tp, inside, exist, ka, ks);
+        else if (p.gn_silu == 0) gn_transform_tile<false>(tp, inside, exist, ka, ks);
+        else if (p.gn_silu == 4) {  // measurement aid (tests/bench_kernels.py): shared-memory traffic of the transform without its math
 #pragma unroll
-            for (int k = 0; k < 11; ++k)
-              if ((exist >> k) & 1u) { uint4* q = reinterpret_cast<uint4*>(tp + k * 4096); uint4 v = *q; v.x ^= inside; *q = v; }
-          }  // gn_silu == 2 (measurement aid): no transform at all, only the extra barrier hop
-          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
-          __syncwarp();
-          if (lane == 0) mbar_arrive(xready_bar(xs));
-          if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
-        }
-        coff += p.src_c[s];
+          for (int k = 0; k < 11; ++k)
+            if ((exist >> k) & 1u) { uint4* q = reinterpret_cast<uint4*>(tp + k * 4096); uint4 v = *q; v.x ^= inside; *q = v; }
+        }  // gn_silu == 2 (measurement aid): no transform at all, only the extra barrier hop
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xready_bar(xs));
+        if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
       }
       for (int i = 0; i < nres; ++i) {  // residual boxes pass through untouched
         mbar_wait(xfull_bar(xs), xph);

@@ -27,6 +27,18 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// the same constants from four raw (a0, s0, a1, s1) quads loaded earlier (software-pipelined loads: the transform warps of the
+// fused conv fetch the next slice's constants while they normalise the current one)
+template <bool SILU>
+__device__ __forceinline__ void gn_consts_from_raw(const float4 (&raw)[4], uint64_t (&ka)[4], uint64_t (&ks)[4]) {
+  const float sg = SILU ? -1.0f : 1.0f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    ka[j] = pack_f2(sg * raw[j].x, sg * raw[j].z);
+    ks[j] = pack_f2(sg * raw[j].y, sg * raw[j].w);
+  }
+}
+
 // y = a x + s, optionally SiLU(y) = y / (1 + 2^(-y log2 e)).
 // MUFU_RCP = false (the HBM-bound apply pass, which two MUFU ops per element made XU-bound, ncu r1a): ONE MUFU op per element,
 //   the reciprocal of d = 1 + e is the bit-trick guess (negated for free through the magic constant) + two Newton steps,
