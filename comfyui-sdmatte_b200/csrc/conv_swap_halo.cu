@@ -111,41 +111,54 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
   const int per_image = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
-    // ============================== TMA producer ==============================
+    // ============================== TMA producers ==============================
+    // lane 0 streams the weight tiles, lane 1 the pixel halo tiles, each throttled by its own ring only.  One in-order producer
+    // (round 1) issued halo tile i+1 behind the nine weight taps of slice i, i.e. about half a slice ahead of its use: enough
+    // when the MMA reads the tile as it lands, but with the GroupNorm transform in between (r2g: T + M serialised, the fused conv
+    // 30 % slower than the barrier hop alone) the tile has to arrive a full slice earlier.
     if (lane == 0) {
-      tma_prefetch_desc(&p.a_map[0]); tma_prefetch_desc(&p.a_map[1]); tma_prefetch_desc(&p.b_map);
-      int ws = 0, xs = 0;
-      uint32_t wph = 0, xph = 0;
+      tma_prefetch_desc(&p.b_map);
+      int ws = 0;
+      uint32_t wph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles) * 128;
+        for (int sl = 0; sl < nslices; ++sl) {  // slice sl = K columns [64 sl, 64 sl + 64) of every tap
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(wempty_bar(ws), wph ^ 1u);
+            mbar_expect_tx(wfull_bar(ws), kWBytes);
+            tma_load_2d(smem_base + ws * kWBytes, &p.b_map, wfull_bar(ws), tap * p.cin_total + sl * 64, n0);
+            if (++ws == kWStages) { ws = 0; wph ^= 1u; }
+          }
+        }
+        for (int i = 0; i < nres; ++i) {  // D^T[c][pix] += I[c][64 i + k] . R[pix][n0 + 64 i + k]
+          mbar_wait(wempty_bar(ws), wph ^ 1u);
+          mbar_expect_tx(wfull_bar(ws), kWBytes);
+          tma_load_2d(smem_base + ws * kWBytes, &p.i_map, wfull_bar(ws), 64 * i, 0);
+          if (++ws == kWStages) { ws = 0; wph ^= 1u; }
+        }
+      }
+    } else if (lane == 1) {
+      tma_prefetch_desc(&p.a_map[0]); tma_prefetch_desc(&p.a_map[1]);
+      int xs = 0;
+      uint32_t xph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.n_tiles) * 128;
         const int mt = tile / p.n_tiles;
         const int t_img = mt % per_image;
         const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32, b = mt / per_image;
-        int coff = 0;
         for (int s = 0; s < p.nsrc; ++s) {
           for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
             mbar_wait(xempty_bar(xs), xph ^ 1u);
             mbar_expect_tx(xfull_bar(xs), kXTx);
             tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, x0 - 1, y0 - 1, b);  // zero fill = conv padding
             if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(wempty_bar(ws), wph ^ 1u);
-              mbar_expect_tx(wfull_bar(ws), kWBytes);
-              tma_load_2d(smem_base + ws * kWBytes, &p.b_map, wfull_bar(ws), tap * p.cin_total + coff + c0, n0);
-              if (++ws == kWStages) { ws = 0; wph ^= 1u; }
-            }
           }
-          coff += p.src_c[s];
         }
-        for (int i = 0; i < nres; ++i) {  // D^T[c][pix] += I[c][64 i + k] . R[pix][n0 + 64 i + k]: dense residual box in a halo slot
+        for (int i = 0; i < nres; ++i) {  // dense residual box in a halo slot
           mbar_wait(xempty_bar(xs), xph ^ 1u);
           mbar_expect_tx(xfull_bar(xs), kXDense);
           tma_load_4d(x_base + xs * kXSlot, &p.r_map, xfull_bar(xs), n0 + 64 * i, x0, y0, b);
           if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
-          mbar_wait(wempty_bar(ws), wph ^ 1u);
-          mbar_expect_tx(wfull_bar(ws), kWBytes);
-          tma_load_2d(smem_base + ws * kWBytes, &p.i_map, wfull_bar(ws), 64 * i, 0);
-          if (++ws == kWStages) { ws = 0; wph ^= 1u; }
         }
       }
     }
