@@ -381,7 +381,6 @@ struct Builder {
     float scale = 1.0f;
     float post_div = 1.0f;
     int n_store = 0;
-    bool alpha_slots = false;  // EPI_ALPHA: outputs come from the per-call slots
     T* stats_for = nullptr;    // EPI_F16 (no ups2): attach GroupNorm partial statistics of the output to this tensor
     const float* gn_ab = nullptr;  // fused GroupNorm(+SiLU) of the input (the conv normalises its resident halo tile itself)
     int gn_silu = 0;
@@ -431,12 +430,7 @@ struct Builder {
     std::string kind = o.label ? o.label : (ksize == 3 ? (o.stride == 2 ? "conv3x3_s2" : "conv3x3") : (a.H == 1 ? "linear" : "conv1x1"));
     if (o.mode == EPI_GEGLU) kind = "linear_geglu";
     if (o.mode == EPI_F16_T) kind = "linear_vT";
-    if (o.alpha_slots) {
-      Plan::Slots* slots = &plan->slots;
-      push([l, slots](cudaStream_t st) { conv_gemm_set_outputs(*l, slots->alpha, slots->premean); conv_gemm_run(*l, st); }, 1, "tc:" + kind, fl, by);
-    } else {
-      push([l](cudaStream_t st) { conv_gemm_run(*l, st); }, 1, "tc:" + kind, fl, by);
-    }
+    push([l](cudaStream_t st) { conv_gemm_run(*l, st); }, 1, "tc:" + kind, fl, by);
   }
   // token GEMM: x [B][L][K] -> out [B][L][N]
   void linear(const T& x, const __half* w, int N, const T& out, const GemmOpt& o) {
@@ -982,10 +976,9 @@ struct Builder {
       // r1a-r1o: ONE tcgen05 conv with N = 16 and the alpha math in the epilogue — 3.8 ms at bs=8: the nine shifted TMA boxes
       // re-read the 2.1 GB input nine times through L2 -> shared memory for 0.15 TFLOP of math.  r1p: the 27 per-tap partial
       // products of every input pixel as ONE 1x1 GEMM (input read once, fp32 out), then a col2im sum of the nine shifted
-      // partials + the alpha math (SDM_ALPHA_HEAD=0 selects the old path for A/B).
-      const bool taprows = [] { const char* e = getenv("SDM_ALPHA_HEAD"); return e ? atoi(e) != 0 : true; }();
+      // partials + the alpha math (the EPI_ALPHA conv survives as a kernel-level test only).
       const float* cbias = W.vec(dcd + ".conv_out.bias", 3, 8);
-      if (taprows) {
+      {
         const __half* wt = W.conv_taprows(dcd + ".conv_out", 3, 128);
         size_t yoff;
         const size_t ybytes = (size_t)B * R * R * 32 * sizeof(float);
@@ -1000,10 +993,6 @@ struct Builder {
                (double)B * R * R * (128.0 + 2.0));
         } else n_launches++;
         arena.release(yoff, ybytes);
-      } else {
-        GemmOpt o; o.bias = cbias; o.mode = EPI_ALPHA; o.alpha_slots = true; o.label = "conv3x3_alpha_head";
-        T dummy; dummy.B = B; dummy.H = R; dummy.W = R; dummy.C = 1;
-        conv_tc(n, nullptr, W.conv(dcd + ".conv_out", 3, 128, 3, 0, 8), 8, 3, dummy, o);
       }
       free(n);
     }

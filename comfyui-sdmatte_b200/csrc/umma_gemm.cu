@@ -98,25 +98,24 @@ static ConvVariant conv3x3_variant(int ksize, int stride, int mode, int ups2, bo
   int tw = 128, th = 1;
   pick_patch(Hout, Wout, tw, th);
   const long long tiles_img = (long long)((Wout + tw - 1) / tw) * ((Hout + th - 1) / th);  // default patch, per sample
-  // swapped operands (conv_swap.cu; SDM_SWAP=0 for A/B, force_swap = 1 / -1 from the tests): 16 x 16 pixel patches, two
+  // swapped operands (conv_swap.cu; force_swap = 1 / 2 / -1 from the tests): 16 x 16 pixel patches, two
   // GroupNorm-partials slots per patch -> only where that equals the default slot count
-  static const int env_swap = [] { const char* e = getenv("SDM_SWAP"); return e ? atoi(e) : 1; }();
   v.swap_can = conv3 && !ups2 && !batched_w && N % 128 == 0 && Hout >= 16 && Wout >= 16 &&
                2ll * ((Wout + 15) / 16) * ((Hout + 15) / 16) == tiles_img && (!has_res || N <= kIdentityN);
   // resident-halo form: 8 x 32 pixel patches, two GroupNorm-partials slots per patch -> only where that equals the default count
   v.swap_halo_geom = v.swap_can && Hout >= 32 && Wout >= 8 && 2ll * ((Wout + 7) / 8) * ((Hout + 31) / 32) == tiles_img;
-  static const int env_swap_halo = [] { const char* e = getenv("SDM_SWAP_HALO"); return e ? atoi(e) : 0; }();
   v.swap = v.swap_can && force_halo != 1 &&
            (force_swap >= 1 || (want_gn && v.swap_halo_geom) ||
-            (force_swap == 0 && env_swap != 0 && N == 128 && force_block_n == 0 && force_mt == 0));
-  v.swap_halo = v.swap && v.swap_halo_geom && (force_swap == 2 || want_gn || (force_swap == 0 && env_swap_halo != 0));
-  // resident halo tile (SDM_HALO=0: one TMA box per tap; force_halo = 1 / -1 from the tests): 8 x 16 pixel patches, used where that
+            (force_swap == 0 && N == 128 && force_block_n == 0 && force_mt == 0));
+  // the resident-halo form wherever its patches fit (kbench r2h: 895 vs 823 TFLOP/s on the 128 -> 128 conv at 1024^2, and it
+  // carries the fused GroupNorm); force_swap = 1 keeps the one-box-per-tap form for the kernel tests
+  v.swap_halo = v.swap && v.swap_halo_geom && force_swap != 1;
+  // resident halo tile (force_halo = 1 / -1 from the tests): 8 x 16 pixel patches, used where that
   // gives the default number of M tiles (the slot count conv_gemm_tiles_per_image must not depend on the kernel choice).
   // Tile width by N alone: 256 | 160 (the small-problem narrowing of pick_block_n depends on the batch size).
-  static const int env_halo = [] { const char* e = getenv("SDM_HALO"); return e ? atoi(e) : 1; }();
   v.halo_geom = conv3 && !v.swap && Hout >= 16 && Wout >= 8 && (long long)((Wout + 7) / 8) * ((Hout + 15) / 16) == tiles_img;
   v.halo_bn = N % 256 == 0 ? 256 : (N % 160 == 0 ? 160 : 0);
-  v.halo_auto = v.halo_geom && v.halo_bn != 0 && force_halo == 0 && env_halo != 0 && force_block_n == 0 && force_mt == 0;
+  v.halo_auto = v.halo_geom && v.halo_bn != 0 && force_halo == 0 && force_block_n == 0 && force_mt == 0;
   return v;
 }
 // 0 = one TMA box per tap (conv_gemm_kernel), 1 / 2 = resident halo with 256- / 160-wide tiles, 3 = swapped operands
@@ -296,18 +295,15 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   p.stats = (d.mode == EPI_F16 && !d.ups2) ? d.stats : nullptr;
   if (d.mode == EPI_ALPHA) SDM_CHECK(d.N >= 3 && d.N <= 16 && d.bias != nullptr, "EPI_ALPHA needs 3..16 columns and a bias");
   {
-    // epilogue warpgroups: two for the GEMMs whose K loop is too short to hide one epilogue (SDM_EWG=1|2 overrides, for A/B runs)
-    static const int env_ewg = [] { const char* e = getenv("SDM_EWG"); return e ? atoi(e) : 0; }();
+    // epilogue warpgroups: two for the GEMMs whose K loop is too short to hide one epilogue
     // measured (A/B on one box): 2 warpgroups help short-K tiles (1x1 conv K=128: 170 -> 294 TFLOP/s), cost a pipeline stage on the
     // 256-wide and 256x128 tiles (1337 -> 1299) -> only where the tile is <= 160 wide and single
     const long long ksteps = (long long)p.ntaps * (cin_total / 64);
     // r1p: 256x128 tiles with ONE or a few K steps (im2col conv_in: 1, VAE 1x1 shortcuts: 4) are pure epilogue: drain the two
-    // M sub-tiles concurrently (SDM_EWG_MT2=0 restores the single warpgroup for A/B)
-    static const int env_mt2 = [] { const char* e = getenv("SDM_EWG_MT2"); return e ? atoi(e) : 1; }();
+    // M sub-tiles concurrently
     int ewg = (p.mode == EPI_GEGLU || p.mode == EPI_F32 || p.mode == EPI_F16_T ||
                (p.mode == EPI_F16 && L->mt == 1 && (bn <= 160 || ksteps <= 16)) ||
-               (p.mode == EPI_F16 && L->mt == 2 && ksteps <= 4 && env_mt2 != 0)) ? 2 : 1;
-    if (env_ewg == 1 || env_ewg == 2) ewg = env_ewg;
+               (p.mode == EPI_F16 && L->mt == 2 && ksteps <= 4)) ? 2 : 1;
     if (bn == 16 || p.mode == EPI_ALPHA || p.mode == EPI_SKINNY) ewg = 1;
     L->ewg = ewg;
   }
