@@ -206,6 +206,74 @@ def gpu_baseline(R: int, batches, dev, steps: int = 2):
     return out
 
 
+def run_sweep(args, pkg, nodes, dev, world, rank, local_rank):
+    """BASELINE config 5: the same engine over a list of inference sizes (bs per GPU fixed), device-timed like the headline run,
+    one JSON line with a `sweep` list (value, ms_per_step, path roofline per resolution).  No e2e / baselines here."""
+    import torch
+    import torch.distributed as dist
+    from oracle import synth
+
+    B = args.batch
+    nodes.register_state_dict("SDMatte.safetensors", synth.make_checkpoint(seed=1234))
+    eng = nodes.get_engine("SDMatte.safetensors", dev)
+    peaks = measured_peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = []
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for R in [int(x) for x in args.sweep.split(",")]:
+        lo, _ = shard_range(world * B, rank, world)
+        image, trimap = synth.make_inputs(B, R, seed=1000 + lo)
+        img_d, tri_d = image.to(dev), trimap.to(dev)
+        alpha_d = torch.empty((B, R, R), dtype=torch.float16, device=dev)
+        gathered = torch.empty((world * B, R, R), dtype=torch.float16, device=dev) if world > 1 else None
+
+        def step():
+            flush.zero_()
+            eng.forward(img_d, tri_d, False, out=alpha_d)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, alpha_d)
+
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = t.item() / args.steps
+        tf = world * B * TFLOP_PER_MATTE[R] / (ms_step * 1e-3)
+        out.append({"resolution": R, "value": world * B / (ms_step * 1e-3), "unit": "mattes/s", "ms_per_step": ms_step, "global_batch": world * B,
+                    "algorithmic_tflop_per_matte": TFLOP_PER_MATTE[R], "achieved_tflops_all_gpus": tf,
+                    "frac_of_sustained_peak": tf / (world * peaks["tflops_sustained"]), "launches_per_step": eng.stats()["launches"]})
+        del img_d, tri_d, alpha_d, gathered
+        eng._ws = None
+        torch.cuda.empty_cache()
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        print(json.dumps({"metric": f"mattes/sec resolution sweep bs={B} per GPU", "unit": "mattes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "higher_is_better": True, "scaling": "weak", "dtype": "f16", "data": "synthetic", "clocks": clocks,
+                          "config": {"workload": f"bs={B} per GPU, synthetic RGB+trimap at each resolution, synthetic SDMatte checkpoint (seed 1234)",
+                                     "parallelism": f"dp{world} batch shard + one NCCL all-gather of alpha" if world > 1 else "single GPU",
+                                     "l2": "256 MiB buffer written between timed iterations"},
+                          "peak": peaks, "sweep": out}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -224,6 +292,8 @@ def run_b200(args):
     nodes = pkg.sdmatte_nodes
 
     R, B = args.size, args.batch
+    if args.sweep:
+        return run_sweep(args, pkg, nodes, dev, world, rank, local_rank)
     sd = synth.make_checkpoint(seed=1234)
     nodes.register_state_dict("SDMatte.safetensors", sd)
     nodes.set_devices([dev])
@@ -311,6 +381,7 @@ def run_b200(args):
     for _ in range(0 if args.quick else min(2, args.warmup)):
         step_node()
     ms_e2e = timed(step_node, e2e_steps)
+    node_split = eng.node_call_timing()
 
     if rank != 0:
         if world > 1:
@@ -402,7 +473,7 @@ def run_b200(args):
                            "reference's -10000 bias, so tc:attention_self reports algorithmic TFLOP/s above what it executes; see worst_case"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "mattes/s", "h2d_bytes_per_step": B * R * R * 16, "d2h_bytes_per_step": B * R * R * 2,
-                "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "host_split_last_call_ms": node_split,
                 "api": "SDMatteApply.apply_matte(ckpt, image, trimap, R, False, 'alpha_only', mask_refine=True, 0.8) with pageable host tensors"},
         "gpu_launches": stats["launches"] * args.steps,
         "roofline": {"bound": "tensor", "kernel": "tc:conv3x3 — the tcgen05 implicit-GEMM 3x3 stride-1 convolutions (conv_gemm_kernel<..., HALO>, conv_swap_kernel), all launches of one step",
@@ -440,6 +511,7 @@ def main():
     ap.add_argument("--dump-ops", default=None, help="write the per-op profile of one step to this CSV")
     ap.add_argument("--ref-size", type=int, default=0, choices=[0, 128, 256, 384, 512, 1024], help="--impl reference: resolution of the timed mattes (0 = --size)")
     ap.add_argument("--ref-budget-s", type=float, default=240.0, help="--impl reference: wall-time bound of the whole run")
+    ap.add_argument("--sweep", default="", help="comma-separated inference sizes (BASELINE config 5), e.g. 512,640,768,896,1024: device-timed only")
     ap.add_argument("--quick", action="store_true", help="profiling aid: no e2e repeat / baselines, warm-up as given (not a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":

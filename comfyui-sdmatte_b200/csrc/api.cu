@@ -142,6 +142,11 @@ int sdm_graph_stats(sdm_handle* h, int* captures, int* launches) {
   sdm::engine_graph_stats(reinterpret_cast<sdm::Engine*>(h), captures, launches);
   SDM_API_END
 }
+int sdm_node_call_timing(sdm_handle* h, double* ms4) {
+  SDM_API_BEGIN
+  sdm::engine_node_timing(reinterpret_cast<sdm::Engine*>(h), ms4);
+  SDM_API_END
+}
 int sdm_set_option(sdm_handle* h, const char* name, int value) {
   SDM_API_BEGIN
   sdm::engine_set_option(reinterpret_cast<sdm::Engine*>(h), name, value);

@@ -14,6 +14,7 @@
 #include "umma_gemm.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -308,6 +309,7 @@ struct Engine {
   char* pinned = nullptr;             // page-locked staging of the node call's host tensors (grown on demand, engine_apply_host)
   size_t pinned_bytes = 0;
   int copy_threads = 8;
+  double node_ms[4] = {0, 0, 0, 0};   // last node call: host staging + H2D enqueue, kernel enqueue, wait for the GPU, copy-out
   cudaEvent_t flags_event = nullptr;
   int graph_launches = 0, graph_captures = 0;
   Weights W;
@@ -1311,9 +1313,11 @@ void engine_apply_host(Engine* e, const float* image_host, const float* trimap_h
   }
   char* pin_in = e->pinned;
   char* pin_out = e->pinned + ((in_b + 4095) & ~(size_t)4095);
+  const auto t0 = std::chrono::steady_clock::now();
   // trimap first (the key-bias / compaction kernels need only it), then the image
   stage_h2d(e, pin_in, base + L.tri, trimap_host, hw * 4, st);
   stage_h2d(e, pin_in + hw * 4, base + L.img, image_host, hw * 12, st);
+  const auto t1 = std::chrono::steady_clock::now();
   if (!(H == R && W == R))
     preprocess_run((const float*)(base + L.img), (const float*)(base + L.tri), B, H, W, R, (float*)(base + L.img_r), (float*)(base + L.tri_r), st);
   engine_forward(e, (const float*)(base + L.img_r), (const float*)(base + L.tri_r), B, R, is_trans, base + L.alpha_r, nullptr, ws, L.main_bytes, st);
@@ -1321,9 +1325,14 @@ void engine_apply_host(Engine* e, const float* image_host, const float* trimap_h
                   trimap_constraint, output_mode, (__half*)(base + L.out), L.mch ? (float*)(base + L.matted) : nullptr, st);
   SDM_CUDA_OK(cudaMemcpyAsync(pin_out, base + L.out, hw * 2, cudaMemcpyDeviceToHost, st));
   if (L.mch) SDM_CUDA_OK(cudaMemcpyAsync(pin_out + hw * 2, base + L.matted, hw * 4 * L.mch, cudaMemcpyDeviceToHost, st));
+  const auto t2 = std::chrono::steady_clock::now();
   SDM_CUDA_OK(cudaStreamSynchronize(st));
+  const auto t3 = std::chrono::steady_clock::now();
   parallel_memcpy(e, alpha_out_host_f16, pin_out, hw * 2);
   if (L.mch) parallel_memcpy(e, matted_out_host, pin_out + hw * 2, hw * 4 * L.mch);
+  const auto t4 = std::chrono::steady_clock::now();
+  auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  e->node_ms[0] = ms(t0, t1); e->node_ms[1] = ms(t1, t2); e->node_ms[2] = ms(t2, t3); e->node_ms[3] = ms(t3, t4);
   (void)rr;
 }
 
@@ -1332,6 +1341,7 @@ void engine_stats(Engine* e, int* n_launches, double* tensor_flops) {
   if (tensor_flops) *tensor_flops = e->last_flops;
 }
 
+void engine_node_timing(Engine* e, double* ms4) { for (int i = 0; i < 4; ++i) ms4[i] = e->node_ms[i]; }
 void engine_graph_stats(Engine* e, int* captures, int* launches) {
   if (captures) *captures = e->graph_captures;
   if (launches) *launches = e->graph_launches;

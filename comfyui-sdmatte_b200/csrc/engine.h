@@ -31,4 +31,5 @@ int engine_debug_tensor_count(Engine* e);
 const char* engine_debug_tensor_name(Engine* e, int i);
 void engine_set_option(Engine* e, const char* name, int value);
 void engine_graph_stats(Engine* e, int* captures, int* launches);
+void engine_node_timing(Engine* e, double* ms4);
 }  // namespace sdm

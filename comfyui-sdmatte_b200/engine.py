@@ -68,7 +68,7 @@ class sdm_direct_conv_args(C.Structure):
 EXPORTS = [
     "sdm_version", "sdm_last_error", "sdm_create", "sdm_destroy", "sdm_load_weights", "sdm_load_report",
     "sdm_workspace_bytes", "sdm_forward", "sdm_forward_host", "sdm_node_workspace_bytes", "sdm_apply_matte_host", "sdm_forward_profiled", "sdm_profile_count", "sdm_profile_entry",
-    "sdm_last_forward_stats", "sdm_debug_tensor", "sdm_debug_tensor_count", "sdm_debug_tensor_name", "sdm_set_option", "sdm_graph_stats",
+    "sdm_last_forward_stats", "sdm_debug_tensor", "sdm_debug_tensor_count", "sdm_debug_tensor_name", "sdm_set_option", "sdm_graph_stats", "sdm_node_call_timing",
     "sdm_preprocess", "sdm_postprocess",
     "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_conv_variant", "sdm_k_conv_can_fuse_gn", "sdm_k_groupnorm_ab_offset", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
     "sdm_k_softmax_rows", "sdm_k_direct_conv", "sdm_k_key_compact", "sdm_k_gather_rows", "sdm_k_probe_halo",
@@ -129,6 +129,7 @@ def load_library():
     lib.sdm_debug_tensor_name.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
     lib.sdm_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.sdm_graph_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.sdm_node_call_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.sdm_k_conv_gemm.argtypes = [C.POINTER(sdm_conv_gemm_args), C.c_void_p]
     lib.sdm_k_conv_tiles_per_image.argtypes = [C.c_int, C.c_int]
     lib.sdm_k_attention.argtypes = [C.POINTER(sdm_attn_args), C.c_void_p]
@@ -386,6 +387,12 @@ class Engine:
         c, l = C.c_int(), C.c_int()
         _check(self.lib.sdm_graph_stats(self.h, C.byref(c), C.byref(l)))
         return {"captures": c.value, "launches": l.value}
+
+    def node_call_timing(self):
+        """Host wall-clock split of the last apply_host call (ms): staging + H2D enqueue, kernel enqueue, GPU wait, copy-out."""
+        ms = (C.c_double * 4)()
+        _check(self.lib.sdm_node_call_timing(self.h, ms))
+        return {"stage_in_ms": ms[0], "enqueue_ms": ms[1], "gpu_wait_ms": ms[2], "copy_out_ms": ms[3]}
 
     def tap_names(self):
         """Names of the block taps of the last forward, in graph order (all of them only with set_option("keep_taps", 1))."""

@@ -127,6 +127,10 @@ int sdm_debug_tensor_name(sdm_handle* h, int i, char* name, int name_len);
  * buffers in the workspace).  sdm_graph_stats: graphs captured / graph launches so far. */
 int sdm_set_option(sdm_handle* h, const char* name, int value);
 int sdm_graph_stats(sdm_handle* h, int* captures, int* launches);
+/* Host-side wall-clock split of the LAST sdm_apply_matte_host call, milliseconds: [0] staging memcpy + H2D enqueue, [1] kernel /
+ * D2H enqueue, [2] waiting for the GPU, [3] copy-out of the results (measurement aid for bench.py's e2e line).
+ * Option "copy_threads" (1..64, default 8): host threads of the staging copies. */
+int sdm_node_call_timing(sdm_handle* h, double* ms4);
 
 /* ---- single-kernel entry points (parity tests at the kernel level; all pointers are device pointers) ---- */
 typedef struct {

@@ -185,12 +185,13 @@ def _transformer(c, x, p, heads, ctx, key_bias):
     return c.r(h + res)
 
 
-def unet_forward(c, sample, trans, ctx, bbox_coords_emb, attention_mask, capture=None):
-    """CustomUNet.forward (replace.py:379-549) with timestep=None."""
+def unet_forward(c, sample, trans, ctx, coords_emb, attention_mask, capture=None, point_prompt=False):
+    """CustomUNet.forward (replace.py:379-549) with timestep=None.  `point_prompt`: added_cond_kwargs carries "point_coords"
+    (-> point_embedding, replace.py:446-450) instead of "bbox_mask_coords" (-> bbox_embedding, :451-455)."""
     B = sample.shape[0]
     key_bias = ((1 - attention_mask) * -10000.0).unsqueeze(1)  # replace.py:401-403
     op_emb = _time_mlp(c, timestep_embedding(trans.float(), 320), "unet.time_embedding")  # :430-435
-    aug_emb = _time_mlp(c, bbox_coords_emb.reshape(B, -1), "unet.bbox_embedding")  # :451-455
+    aug_emb = _time_mlp(c, coords_emb.reshape(B, -1), "unet.point_embedding" if point_prompt else "unet.bbox_embedding")
     emb = c.r(op_emb + aug_emb)  # :459
     x = _conv(c, sample, "unet.conv_in")  # :462
     c.tap("unet.conv_in", x)
@@ -296,9 +297,36 @@ def to_device(sd: Dict[str, torch.Tensor], device) -> Dict[str, torch.Tensor]:
 
 
 @torch.no_grad()
+def point_coords_embedding(coor: torch.Tensor) -> torch.Tensor:
+    """meta_arch.py:153-176: N point coordinates per sample are zero-padded to the first i >= N that divides 1680, each embedded
+    with 1680 / i sinusoid channels -> (B, 1680), the input width of point_embedding (meta_arch.py:107-108)."""
+    B, N = coor.shape
+    for i in range(N, 1680):
+        if 1680 % i == 0:
+            num_channels = 1680 // i
+            coor = torch.cat([coor, torch.zeros((B, i - N), dtype=coor.dtype, device=coor.device)], dim=1)
+            break
+    else:
+        raise ValueError("too many point coordinates")
+    half = num_channels // 2
+    # diffusers get_timestep_embedding(dim, flip_sin_to_cos=True, downscale_freq_shift=0); an odd dim is zero-padded by one column
+    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=coor.device) / half
+    emb = coor.flatten()[:, None].float() * torch.exp(exponent)[None, :]
+    emb = torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
+    if num_channels % 2 == 1:
+        emb = F.pad(emb, (0, 1, 0, 0))
+    return emb.reshape(B, -1)
+
+
 def forward(sd: Dict[str, torch.Tensor], image: torch.Tensor, trimap: torch.Tensor, is_transparent=False,
-            mode: str = "fp32", sliced: bool = False, capture: Optional[dict] = None, device="cpu") -> Dict[str, torch.Tensor]:
+            mode: str = "fp32", sliced: bool = False, capture: Optional[dict] = None, device="cpu",
+            prompt: str = "trimap", coords: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """image (B,R,R,3) fp32 in [0,1] and trimap (B,R,R) fp32 in [0,1], both ALREADY at inference size R.
+
+    `prompt` (meta_arch.py:22-28,130-197): which visual prompt the auxiliary image is — "trimap" (the node's
+    case, coords fixed to [0,0,1,1] by sdmatte_nodes.py:353), "mask" / "bbox_mask" (4 coordinates per sample through
+    bbox_embedding) or "point_mask" (N point coordinates per sample through point_embedding); `coords` (B, 4) / (B, N).  The
+    auxiliary image takes the trimap's place everywhere (VAE latent, cross-attention context, attention-mask source).
 
     Returns {"alpha": (B,1,R,R) in [0,1], "label_mean": pre-clip decoder channel mean, + intermediates} on `device`.
     Follows sdmatte_nodes.py:339-360 (pre-processing at native size) then meta_arch.py:127-261.
@@ -308,19 +336,19 @@ def forward(sd: Dict[str, torch.Tensor], image: torch.Tensor, trimap: torch.Tens
     if mode == "autocast":
         assert device.type == "cuda", "mode='autocast' is the reference's CUDA branch (sdmatte_nodes.py:355-358)"
         with torch.autocast(device_type="cuda", dtype=torch.float16):
-            return _forward(sd, image, trimap, is_transparent, mode, True, capture, device)
+            return _forward(sd, image, trimap, is_transparent, mode, True, capture, device, prompt, coords)
     if device.type == "cuda":  # fp32 checker on the GPU: no TF32 anywhere
         old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.backends.cudnn.allow_tf32 = False
         try:
-            return _forward(sd, image, trimap, is_transparent, mode, sliced, capture, device)
+            return _forward(sd, image, trimap, is_transparent, mode, sliced, capture, device, prompt, coords)
         finally:
             torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
-    return _forward(sd, image, trimap, is_transparent, mode, sliced, capture, device)
+    return _forward(sd, image, trimap, is_transparent, mode, sliced, capture, device, prompt, coords)
 
 
-def _forward(sd, image, trimap, is_transparent, mode, sliced, capture, device):
+def _forward(sd, image, trimap, is_transparent, mode, sliced, capture, device, prompt="trimap", coords=None):
     c = _Ctx(sd, mode, sliced, device, capture)
     B = image.shape[0]
     image, trimap = image.to(device), trimap.to(device)
@@ -330,8 +358,17 @@ def _forward(sd, image, trimap, is_transparent, mode, sliced, capture, device):
     is_trans = torch.tensor([1 if f else 0 for f in flags], device=device)
 
     aux_latent = vae_encode(c, tri.repeat(1, 3, 1, 1), "enc_tri")  # meta_arch.py:139-145
-    coor = torch.tensor([[0.0, 0.0, 1.0, 1.0]] * B, device=device)  # sdmatte_nodes.py:353
-    coor_emb = timestep_embedding(coor.flatten(), 320)  # meta_arch.py:181-187
+    assert prompt in ("trimap", "mask", "bbox_mask", "point_mask")
+    if coords is None:
+        assert prompt == "trimap", "mask / bbox / point prompts need their coordinates"
+        coor = torch.tensor([[0.0, 0.0, 1.0, 1.0]] * B, device=device)  # sdmatte_nodes.py:353
+    else:
+        coor = coords.to(device).float()
+    if prompt == "point_mask":
+        coor_emb = point_coords_embedding(coor)  # meta_arch.py:153-176
+    else:
+        assert coor.shape == (B, 4)
+        coor_emb = timestep_embedding(coor.flatten(), 320)  # meta_arch.py:181-187
     attention_mask = (tri + 1) / 2  # meta_arch.py:200-204
     attention_mask = F.interpolate(attention_mask, scale_factor=1 / 8, mode="nearest").flatten(start_dim=1)
     rgb_latent = vae_encode(c, rgb, "enc_rgb")  # meta_arch.py:209-212
@@ -339,7 +376,7 @@ def _forward(sd, image, trimap, is_transparent, mode, sliced, capture, device):
     ehs = ehs.view(B, 1024, -1).permute(0, 2, 1)
     trans = 1 - is_trans  # meta_arch.py:237-238
     unet_input = torch.cat([rgb_latent, aux_latent], dim=1)  # meta_arch.py:244
-    label_latent = unet_forward(c, unet_input, trans, ehs, coor_emb, attention_mask)
+    label_latent = unet_forward(c, unet_input, trans, ehs, coor_emb, attention_mask, point_prompt=(prompt == "point_mask"))
     label_latent = c.r(label_latent / SCALING_FACTOR)  # meta_arch.py:254
     stacked = vae_decode(c, label_latent)
     label_mean = c.r(stacked.mean(dim=1, keepdim=True))  # meta_arch.py:258
