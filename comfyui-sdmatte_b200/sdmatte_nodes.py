@@ -18,6 +18,7 @@ from __future__ import annotations
 import os
 import sys
 import threading
+import time
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -197,8 +198,14 @@ class SDMatteApply:
         zeros_thread = None
         if mode == 0:
             # "alpha_only": zeros_like(image) (sdmatte_nodes.py:384-385).  Clearing 100 MB of host memory takes ~10 ms of one
-            # core: it runs on a helper thread while the GPU works (the library call below releases the GIL)
-            zeros_thread = threading.Thread(target=lambda: zeros_box.append(torch.zeros_like(img)))
+            # core: it runs on a helper thread while the GPU works (the library call below releases the GIL), and it starts
+            # after the input staging, which needs the host memory bandwidth for itself (r2j: 7.2 vs 4.4 ms of staging)
+            def _zeros():
+                if img.numel() * 4 > (32 << 20):
+                    time.sleep(0.015)
+                zeros_box.append(torch.zeros_like(img))
+
+            zeros_thread = threading.Thread(target=_zeros)
             zeros_thread.start()
             matted = None
         else:
