@@ -68,6 +68,22 @@ int sdm_forward(sdm_handle* h, const float* image_dev, const float* trimap_dev, 
                       workspace_dev, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
   SDM_API_END
 }
+size_t sdm_workspace_bytes_prompt(sdm_handle* h, int B, int R, int prompt_kind, int ncoords) {
+  try {
+    return sdm::engine_workspace_bytes_prompt(reinterpret_cast<sdm::Engine*>(h), B, R, prompt_kind, ncoords);
+  } catch (const sdm::Error& e) {
+    sdm::set_last_error(e.msg);
+    return 0;
+  }
+}
+int sdm_forward_prompt(sdm_handle* h, const float* image_dev, const float* aux_dev, int B, int R, const int32_t* is_trans, int prompt_kind,
+                       const float* coords_host, int ncoords, void* alpha_dev, void* premean_dev, void* workspace_dev,
+                       size_t workspace_bytes, uintptr_t stream) {
+  SDM_API_BEGIN
+  sdm::engine_forward_prompt(reinterpret_cast<sdm::Engine*>(h), image_dev, aux_dev, B, R, is_trans, prompt_kind, coords_host, ncoords,
+                             alpha_dev, premean_dev, workspace_dev, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+  SDM_API_END
+}
 int sdm_forward_host(sdm_handle* h, const float* image_host, const float* trimap_host, int B, int R, const int32_t* is_trans,
                      void* alpha_host_f16, void* workspace_dev, size_t workspace_bytes, uintptr_t stream) {
   SDM_API_BEGIN

@@ -290,10 +290,17 @@ struct Plan {
   // CUDA graph of the op list (engine option "cuda_graph"): kernel arguments are baked at capture, so a graph is valid for
   // exactly one set of run-time pointers (`graph_slots`) and one set of per-sample flags
   cudaGraphExec_t graph_exec = nullptr;
-  std::vector<int32_t> flags;   // is_trans values currently resident in d_is_trans
-  bool flags_valid = false;
   int eager_runs = 0;
-  ~Plan() { if (graph_exec) cudaGraphExecDestroy(graph_exec); }
+  // per-sample conditioning (point / bbox / mask prompts): plan-owned device tables, coordinates buffer in the workspace
+  int prompt_kind = -1, prompt_ncoords = 0;
+  int4* d_row_map = nullptr;
+  int* d_iota = nullptr;
+  float* d_coords = nullptr;
+  ~Plan() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (d_row_map) cudaFree(d_row_map);
+    if (d_iota) cudaFree(d_iota);
+  }
   // run-time argument slots (device pointers change per call without rebuilding the plan)
   struct Slots { const float* image; const float* trimap; __half* alpha; __half* premean; } slots{}, graph_slots{}, last_slots{};
   int* d_is_trans = nullptr;
@@ -303,6 +310,11 @@ struct Engine {
   int device = 0;
   int num_sms = 148;
   bool keep_taps = false;  // parity diagnostics: tapped block outputs are never recycled by the arena (bigger workspace)
+  int prompt_kind = -1;    // -1: the node's trimap prompt (embeddings folded at load); 0 bbox-like (4 coords), 1 point coords (n3)
+  int prompt_ncoords = 0;
+  std::vector<std::pair<std::string, int>> temb_order;  // resnets in the order of the stacked time_emb_proj rows, with their C
+  int temb_rows = 0;
+  bool has_point_embedding = false;
   bool use_graph = true;   // replay the plan as one CUDA graph when the caller's pointers repeat (option "cuda_graph")
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream, which cannot capture)
   int32_t* flags_pinned = nullptr;    // staging for the per-sample is_transparent flags (uploaded only when they change)
@@ -333,6 +345,10 @@ struct Builder {
   int n_launches = 0;
   double flops = 0;
   int* d_is_trans = nullptr;
+  // per-sample conditioning (E.prompt_kind >= 0): bias table of every resnet, [B][C] each, selected per sample by d_iota
+  float* dyn_tables = nullptr;
+  const int* d_iota = nullptr;
+  std::map<std::string, size_t> dyn_off;  // resnet -> float offset of its table
 
   Builder(Engine& e, Plan* p, int B_, int R_, void* ws_) : E(e), W(e.W), plan(p), dry(p == nullptr), B(B_), R(R_), S(R_ / 8), ws((char*)ws_) {}
 
@@ -539,7 +555,8 @@ struct Builder {
     T h = alloc(x.B, x.H, x.W, Cout);
     {
       GemmOpt o;
-      if (has_temb) { o.bias = W.raw_vec("temb:" + p, {}); o.bias_sel = d_is_trans; }
+      if (has_temb && E.prompt_kind >= 0) { o.bias = dry ? nullptr : dyn_tables + dyn_off.at(p); o.bias_sel = d_iota; }
+      else if (has_temb) { o.bias = W.raw_vec("temb:" + p, {}); o.bias_sel = d_is_trans; }
       else o.bias = W.vec(p + ".conv1.bias", Cout);
       o.stats_for = &h;  // norm2 statistics come out of this conv's epilogue
       if (fuse1) {
@@ -748,9 +765,27 @@ struct Builder {
       for (int i = 0; i < 1280; ++i) emb[is_trans][i] = op[i] + aug[i];
       emb[is_trans] = silu(emb[is_trans]);  // every resnet applies SiLU to emb before time_emb_proj
     }
+    // n3: the un-folded chain for per-sample coordinates (cond_embed.cu): fp32 embedding MLPs, all time_emb_proj stacked in fp16
+    W.upload("emb:te_w1", te_w1.data(), te_w1.size() * 4); W.upload("emb:te_b1", te_b1.data(), te_b1.size() * 4);
+    W.upload("emb:te_w2", te_w2.data(), te_w2.size() * 4); W.upload("emb:te_b2", te_b2.data(), te_b2.size() * 4);
+    W.upload("emb:bb_w1", bb_w1.data(), bb_w1.size() * 4); W.upload("emb:bb_b1", bb_b1.data(), bb_b1.size() * 4);
+    W.upload("emb:bb_w2", bb_w2.data(), bb_w2.size() * 4); W.upload("emb:bb_b2", bb_b2.data(), bb_b2.size() * 4);
+    E.has_point_embedding = W.find("unet.point_embedding.linear_1.weight") != nullptr;
+    if (E.has_point_embedding) {  // optional: a checkpoint stripped of the unused prompt heads still loads
+      auto w1 = W.fetch("unet.point_embedding.linear_1.weight", 1280 * 1680), b1 = W.fetch("unet.point_embedding.linear_1.bias", 1280);
+      auto w2 = W.fetch("unet.point_embedding.linear_2.weight", 1280 * 1280), b2 = W.fetch("unet.point_embedding.linear_2.bias", 1280);
+      W.upload("emb:pt_w1", w1.data(), w1.size() * 4); W.upload("emb:pt_b1", b1.data(), b1.size() * 4);
+      W.upload("emb:pt_w2", w2.data(), w2.size() * 4); W.upload("emb:pt_b2", b2.data(), b2.size() * 4);
+    }
+    std::vector<__half> tp_w;
+    std::vector<float> tp_b;
+    E.temb_order.clear();
     auto fold = [&](const std::string& p, int C) {
       auto w = W.fetch(p + ".time_emb_proj.weight", (int64_t)C * 1280), b = W.fetch(p + ".time_emb_proj.bias", C);
       auto cb = W.fetch(p + ".conv1.bias", C);
+      E.temb_order.push_back({p, C});
+      for (auto v : w) tp_w.push_back(__float2half_rn(v));
+      for (int i = 0; i < C; ++i) tp_b.push_back(cb[i] + b[i]);
       std::vector<float> out(2 * C);
       for (int v = 0; v < 2; ++v) {
         auto t = matvec(w, b, emb[v], C, 1280);
@@ -765,6 +800,65 @@ struct Builder {
     const int rch[4] = {1280, 1280, 640, 320};
     for (int i = 0; i < 4; ++i)
       for (int j = 0; j < 3; ++j) fold("unet.up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), rch[i]);
+    E.temb_rows = (int)tp_b.size();
+    W.upload("emb:tp_w", tp_w.data(), tp_w.size() * 2);
+    W.upload("emb:tp_b", tp_b.data(), tp_b.size() * 4);
+  }
+
+  // n3: head of the plan for per-sample conditioning — coordinates -> emb -> the [B][C] bias table of every resnet
+  void emit_cond_embed() {
+    SDM_CHECK(E.prompt_kind == 0 || E.prompt_kind == 1, "prompt kind");
+    int npad = 4, dim = 320;
+    if (E.prompt_kind == 0) SDM_CHECK(E.prompt_ncoords == 4, "bbox / mask / trimap prompts carry 4 coordinates per sample");
+    else {
+      SDM_CHECK(E.has_point_embedding, "the checkpoint has no unet.point_embedding.* weights");
+      SDM_CHECK(E.prompt_ncoords >= 1 && E.prompt_ncoords < 1680, "number of point coordinates");
+      npad = 0;
+      for (int i = E.prompt_ncoords; i < 1680; ++i)  // meta_arch.py:153-160: first i >= N that divides 1680
+        if (1680 % i == 0) { npad = i; break; }
+      SDM_CHECK(npad > 0, "point coordinates: no divisor of 1680");
+      dim = 1680 / npad;
+    }
+    const int Kc = npad * dim;
+    size_t off;
+    size_t cum = 0;
+    for (auto& pr : E.temb_order) { dyn_off[pr.first] = cum; cum += (size_t)B * pr.second; }
+    float* coords = (float*)alloc_raw((size_t)B * E.prompt_ncoords * 4, &off);
+    float* xt = (float*)alloc_raw((size_t)B * 320 * 4, &off);
+    float* xc = (float*)alloc_raw((size_t)B * Kc * 4, &off);
+    float* ht = (float*)alloc_raw((size_t)B * 1280 * 4, &off);
+    float* hc = (float*)alloc_raw((size_t)B * 1280 * 4, &off);
+    float* semb = (float*)alloc_raw((size_t)B * 1280 * 4, &off);
+    dyn_tables = (float*)alloc_raw(cum * 4, &off);
+    if (dry) { n_launches += 5; d_iota = (const int*)1; return; }
+    // plan-owned tables (not in the caller's workspace: they must survive whatever the caller does with that memory)
+    std::vector<int4> map((size_t)E.temb_rows);
+    {
+      size_t r = 0;
+      for (auto& pr : E.temb_order)
+        for (int c = 0; c < pr.second; ++c) map[r++] = make_int4((int)dyn_off[pr.first], pr.second, c, 0);
+    }
+    std::vector<int> iota((size_t)B);
+    for (int i = 0; i < B; ++i) iota[(size_t)i] = i;
+    SDM_CUDA_OK(cudaMalloc((void**)&plan->d_row_map, map.size() * sizeof(int4)));
+    SDM_CUDA_OK(cudaMemcpy(plan->d_row_map, map.data(), map.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    SDM_CUDA_OK(cudaMalloc((void**)&plan->d_iota, (size_t)B * 4));
+    SDM_CUDA_OK(cudaMemcpy(plan->d_iota, iota.data(), (size_t)B * 4, cudaMemcpyHostToDevice));
+    d_iota = plan->d_iota;
+    plan->d_coords = coords;
+    CondEmbedDesc d;
+    d.B = B; d.is_trans = d_is_trans; d.coords = coords;
+    d.ncoords = E.prompt_ncoords; d.npad = npad; d.dim = dim; d.Kc = Kc;
+    d.te_w1 = (const float*)W.get("emb:te_w1"); d.te_b1 = (const float*)W.get("emb:te_b1");
+    d.te_w2 = (const float*)W.get("emb:te_w2"); d.te_b2 = (const float*)W.get("emb:te_b2");
+    const char* pre = E.prompt_kind == 1 ? "emb:pt_" : "emb:bb_";
+    d.ce_w1 = (const float*)W.get(std::string(pre) + "w1"); d.ce_b1 = (const float*)W.get(std::string(pre) + "b1");
+    d.ce_w2 = (const float*)W.get(std::string(pre) + "w2"); d.ce_b2 = (const float*)W.get(std::string(pre) + "b2");
+    d.tp_w = (const __half*)W.get("emb:tp_w"); d.tp_b = (const float*)W.get("emb:tp_b");
+    d.rows = E.temb_rows; d.row_map = plan->d_row_map;
+    d.xt = xt; d.xc = xc; d.ht = ht; d.hc = hc; d.semb = semb; d.tables = dyn_tables;
+    SDM_CHECK(d.te_w1 && d.ce_w1 && d.tp_w, "conditioning weights were not packed at load time");
+    push([d](cudaStream_t st) { cond_embed_run(d, st); }, 5, "cond_embed", 0, 0);
   }
 
   // ---------------------------------------------------------------- the whole path
@@ -778,6 +872,7 @@ struct Builder {
     d_is_trans = (int*)alloc_raw((size_t)B * 4, &off);
     if (plan) plan->d_is_trans = d_is_trans;
     Plan::Slots* slots = plan ? &plan->slots : nullptr;
+    if (E.prompt_kind >= 0 && !W.loading) emit_cond_embed();
 
     // ---- a1: input preparation (sdmatte_nodes.py:343,351; meta_arch.py:141)
     T x0 = alloc(B2, R, R, 64);  // im2col rows of the VAE conv_in
@@ -1091,14 +1186,25 @@ size_t engine_workspace_bytes(Engine* e, int B, int R) {
   return b.arena.peak + 4096;
 }
 
+size_t engine_workspace_bytes_prompt(Engine* e, int B, int R, int prompt_kind, int ncoords) {
+  const int k0 = e->prompt_kind, n0 = e->prompt_ncoords;
+  e->prompt_kind = prompt_kind; e->prompt_ncoords = prompt_kind >= 0 ? ncoords : 0;
+  size_t r = 0;
+  try { r = engine_workspace_bytes(e, B, R); } catch (...) { e->prompt_kind = k0; e->prompt_ncoords = n0; throw; }
+  e->prompt_kind = k0; e->prompt_ncoords = n0;
+  return r;
+}
+
 static Plan& get_plan(Engine* e, int B, int R, void* ws, size_t ws_bytes) {
   SDM_CHECK(e->W.loaded, "weights not loaded");
   SDM_CHECK((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "workspace must be 1024-byte aligned");
-  if (e->plan && e->plan->B == B && e->plan->R == R && e->plan->ws == ws && e->plan->ws_bytes == ws_bytes && e->plan->keep_taps == e->keep_taps) return *e->plan;
+  if (e->plan && e->plan->B == B && e->plan->R == R && e->plan->ws == ws && e->plan->ws_bytes == ws_bytes && e->plan->keep_taps == e->keep_taps &&
+      e->plan->prompt_kind == e->prompt_kind && e->plan->prompt_ncoords == e->prompt_ncoords) return *e->plan;
   const size_t need = engine_workspace_bytes(e, B, R);
   if (ws_bytes < need) throw Error{"workspace too small: need " + std::to_string(need) + " bytes, got " + std::to_string(ws_bytes)};
   auto plan = std::make_unique<Plan>();
   plan->B = B; plan->R = R; plan->ws = ws; plan->ws_bytes = ws_bytes; plan->keep_taps = e->keep_taps;
+  plan->prompt_kind = e->prompt_kind; plan->prompt_ncoords = e->prompt_ncoords;
   Builder b(*e, plan.get(), B, R, ws);
   b.build();
   plan->n_launches = b.n_launches;
@@ -1107,33 +1213,57 @@ static Plan& get_plan(Engine* e, int B, int R, void* ws, size_t ws_bytes) {
   return *e->plan;
 }
 
-// per-sample flags: uploaded from a pinned staging buffer, and only when they differ from what the device already holds
-static void upload_flags(Engine* e, Plan& p, const int32_t* is_trans, int B, cudaStream_t st) {
+// per-sample flags (and prompt coordinates): staged through a small page-locked buffer and uploaded at the head of EVERY forward —
+// the workspace is the caller's memory and may have been recycled since the last call, so nothing in it is assumed to persist
+static void upload_flags(Engine* e, Plan& p, const int32_t* is_trans, int B, const float* coords, int ncoords, cudaStream_t st) {
   for (int i = 0; i < B; ++i) SDM_CHECK(is_trans[i] == 0 || is_trans[i] == 1, "is_trans must be 0/1");
-  if (p.flags_valid && (int)p.flags.size() == B && memcmp(p.flags.data(), is_trans, (size_t)B * 4) == 0) return;
-  SDM_CHECK(B <= 1024, "batch too large for the flag staging buffer");
+  const size_t nflag = (size_t)B * 4, ncoor = coords ? (size_t)B * ncoords * 4 : 0;
+  SDM_CHECK(nflag + ncoor <= 64 * 1024, "batch too large for the flag staging buffer");
   if (!e->flags_pinned) {
-    SDM_CUDA_OK(cudaHostAlloc((void**)&e->flags_pinned, 1024 * sizeof(int32_t), cudaHostAllocDefault));
+    SDM_CUDA_OK(cudaHostAlloc((void**)&e->flags_pinned, 64 * 1024, cudaHostAllocDefault));
     SDM_CUDA_OK(cudaEventCreateWithFlags(&e->flags_event, cudaEventDisableTiming));
   } else {
     SDM_CUDA_OK(cudaEventSynchronize(e->flags_event));  // the previous upload has left the staging buffer
   }
-  memcpy(e->flags_pinned, is_trans, (size_t)B * 4);
-  SDM_CUDA_OK(cudaMemcpyAsync(p.d_is_trans, e->flags_pinned, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  memcpy(e->flags_pinned, is_trans, nflag);
+  SDM_CUDA_OK(cudaMemcpyAsync(p.d_is_trans, e->flags_pinned, nflag, cudaMemcpyHostToDevice, st));
+  if (coords) {
+    SDM_CHECK(p.d_coords != nullptr, "plan without a coordinates buffer");
+    memcpy((char*)e->flags_pinned + nflag, coords, ncoor);
+    SDM_CUDA_OK(cudaMemcpyAsync(p.d_coords, (char*)e->flags_pinned + nflag, ncoor, cudaMemcpyHostToDevice, st));
+  }
   SDM_CUDA_OK(cudaEventRecord(e->flags_event, st));
-  p.flags.assign(is_trans, is_trans + B);
-  p.flags_valid = true;
 }
+
+static void forward_impl(Engine* e, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
+                         int prompt_kind, const float* coords_host, int ncoords,
+                         void* alpha_dev, void* premean_dev, void* ws, size_t ws_bytes, cudaStream_t st);
 
 void engine_forward(Engine* e, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
                     void* alpha_dev, void* premean_dev, void* ws, size_t ws_bytes, cudaStream_t st) {
+  forward_impl(e, image_dev, trimap_dev, B, R, is_trans, -1, nullptr, 0, alpha_dev, premean_dev, ws, ws_bytes, st);
+}
+// n3: the auxiliary image is a mask / bbox mask (prompt_kind 0, 4 coordinates per sample) or a point mask (1, n coordinates)
+void engine_forward_prompt(Engine* e, const float* image_dev, const float* aux_dev, int B, int R, const int32_t* is_trans, int prompt_kind,
+                           const float* coords_host, int ncoords, void* alpha_dev, void* premean_dev, void* ws, size_t ws_bytes,
+                           cudaStream_t st) {
+  SDM_CHECK(prompt_kind == 0 || prompt_kind == 1, "prompt_kind: 0 = bbox / mask (4 coordinates), 1 = points");
+  SDM_CHECK(coords_host != nullptr && ncoords >= 1, "coordinates");
+  forward_impl(e, image_dev, aux_dev, B, R, is_trans, prompt_kind, coords_host, ncoords, alpha_dev, premean_dev, ws, ws_bytes, st);
+}
+
+static void forward_impl(Engine* e, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
+                         int prompt_kind, const float* coords_host, int ncoords,
+                         void* alpha_dev, void* premean_dev, void* ws, size_t ws_bytes, cudaStream_t st) {
   SDM_CUDA_OK(cudaSetDevice(e->device));
+  e->prompt_kind = prompt_kind;
+  e->prompt_ncoords = prompt_kind >= 0 ? ncoords : 0;
   Plan& p = get_plan(e, B, R, ws, ws_bytes);
   p.slots.image = image_dev;
   p.slots.trimap = trimap_dev;
   p.slots.alpha = (__half*)alpha_dev;
   p.slots.premean = (__half*)premean_dev;
-  upload_flags(e, p, is_trans, B, st);
+  upload_flags(e, p, is_trans, B, coords_host, ncoords, st);
   e->last_launches = p.n_launches;
   e->last_flops = p.tensor_flops;
   auto same = [](const Plan::Slots& a, const Plan::Slots& b) { return memcmp(&a, &b, sizeof(Plan::Slots)) == 0; };
@@ -1179,7 +1309,7 @@ void engine_forward_profiled(Engine* e, const float* image_dev, const float* tri
   p.slots.trimap = trimap_dev;
   p.slots.alpha = (__half*)alpha_dev;
   p.slots.premean = nullptr;
-  upload_flags(e, p, is_trans, B, st);
+  upload_flags(e, p, is_trans, B, nullptr, 0, st);
   std::vector<cudaEvent_t> ev(p.ops.size() + 1);
   for (auto& x : ev) SDM_CUDA_OK(cudaEventCreate(&x));
   SDM_CUDA_OK(cudaEventRecord(ev[0], st));

@@ -15,6 +15,10 @@ void engine_load_report(Engine* e, int* n_used, int* n_unexpected);
 size_t engine_workspace_bytes(Engine* e, int B, int R);
 void engine_forward(Engine* e, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
                     void* alpha_dev, void* premean_dev, void* ws, size_t ws_bytes, cudaStream_t st);
+void engine_forward_prompt(Engine* e, const float* image_dev, const float* aux_dev, int B, int R, const int32_t* is_trans, int prompt_kind,
+                           const float* coords_host, int ncoords, void* alpha_dev, void* premean_dev, void* ws, size_t ws_bytes,
+                           cudaStream_t st);
+size_t engine_workspace_bytes_prompt(Engine* e, int B, int R, int prompt_kind, int ncoords);
 void engine_forward_host(Engine* e, const float* image_host, const float* trimap_host, int B, int R, const int32_t* is_trans,
                          void* alpha_host_f16, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t engine_node_workspace_bytes(Engine* e, int B, int H, int W, int R, int output_mode);

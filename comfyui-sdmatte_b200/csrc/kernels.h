@@ -113,6 +113,23 @@ void layernorm_run(const __half* x, __half* y, const float* gamma, const float* 
 // rows of fp32 scores -> fp16 probabilities (softmax over the last dim)
 void softmax_rows_run(const float* s, __half* p, long long rows, int L, cudaStream_t st);
 
+// ------------------------------------------------------------------ per-sample conditioning for point / bbox / mask prompts (cond_embed.cu)
+struct CondEmbedDesc {
+  int B = 0;
+  const int* is_trans = nullptr;     // [B] device
+  const float* coords = nullptr;     // [B][ncoords] device
+  int ncoords = 0, npad = 0, dim = 0, Kc = 0;  // coordinates, padded count, sinusoid channels per coordinate, npad * dim
+  const float *te_w1 = nullptr, *te_b1 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr;  // time_embedding (320 -> 1280 -> 1280)
+  const float *ce_w1 = nullptr, *ce_b1 = nullptr, *ce_w2 = nullptr, *ce_b2 = nullptr;  // bbox_ / point_embedding (Kc -> 1280 -> 1280)
+  const __half* tp_w = nullptr;      // [rows][1280]: time_emb_proj of all 22 resnets, stacked
+  const float* tp_b = nullptr;       // [rows]: time_emb_proj.bias + conv1.bias
+  int rows = 0;
+  const int4* row_map = nullptr;     // [rows]: (table offset of the row's resnet, its channel count, channel)
+  float *xt = nullptr, *xc = nullptr, *ht = nullptr, *hc = nullptr, *semb = nullptr;  // scratch: [B][320], [B][Kc], [B][1280] x 3
+  float* tables = nullptr;           // out: per resnet [B][C] bias rows
+};
+void cond_embed_run(const CondEmbedDesc& d, cudaStream_t st);  // 5 launches
+
 // ------------------------------------------------------------------ small direct convs (Cin <= 8 or Cout <= 8)
 struct DirectConvDesc {
   int B = 1, H = 0, W = 0;          // stride 1, pad (k-1)/2

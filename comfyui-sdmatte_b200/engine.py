@@ -67,7 +67,7 @@ class sdm_direct_conv_args(C.Structure):
 
 EXPORTS = [
     "sdm_version", "sdm_last_error", "sdm_create", "sdm_destroy", "sdm_load_weights", "sdm_load_report",
-    "sdm_workspace_bytes", "sdm_forward", "sdm_forward_host", "sdm_node_workspace_bytes", "sdm_apply_matte_host", "sdm_forward_profiled", "sdm_profile_count", "sdm_profile_entry",
+    "sdm_workspace_bytes", "sdm_forward", "sdm_workspace_bytes_prompt", "sdm_forward_prompt", "sdm_forward_host", "sdm_node_workspace_bytes", "sdm_apply_matte_host", "sdm_forward_profiled", "sdm_profile_count", "sdm_profile_entry",
     "sdm_last_forward_stats", "sdm_debug_tensor", "sdm_debug_tensor_count", "sdm_debug_tensor_name", "sdm_set_option", "sdm_graph_stats", "sdm_node_call_timing",
     "sdm_preprocess", "sdm_postprocess",
     "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_conv_variant", "sdm_k_conv_can_fuse_gn", "sdm_k_groupnorm_ab_offset", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
@@ -111,6 +111,10 @@ def load_library():
                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.sdm_forward_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_void_p,
                                      C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.sdm_workspace_bytes_prompt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.sdm_workspace_bytes_prompt.restype = C.c_size_t
+    lib.sdm_forward_prompt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.sdm_node_workspace_bytes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.sdm_node_workspace_bytes.restype = C.c_size_t
     lib.sdm_apply_matte_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32),
@@ -305,6 +309,35 @@ class Engine:
             _check(self.lib.sdm_forward(self.h, image.data_ptr(), trimap.data_ptr(), B, R, it, alpha.data_ptr(),
                                         pre.data_ptr() if pre is not None else None, ws.data_ptr(), ws.numel(),
                                         _stream_ptr(self.device)))
+        return (alpha, pre) if want_premean else alpha
+
+    PROMPT_KINDS = {"trimap": 0, "mask": 0, "bbox_mask": 0, "point_mask": 1}
+
+    def forward_prompt(self, image: torch.Tensor, aux: torch.Tensor, prompt: str, coords: torch.Tensor, is_transparent=False,
+                       want_premean: bool = False):
+        """The model's other visual prompts (include/sdmatte_b200.h: sdm_forward_prompt): `aux` [B,R,R] fp32 cuda is a mask, bbox
+        mask or point mask, `coords` the matching [B,4] box / [B,N] point coordinates (host or device tensor, fp32)."""
+        B, R = image.shape[0], image.shape[1]
+        assert image.shape == (B, R, R, 3) and aux.shape == (B, R, R) and image.is_cuda and aux.is_cuda
+        kind = self.PROMPT_KINDS[prompt]
+        coords = coords.detach().to("cpu", torch.float32).contiguous()
+        assert coords.dim() == 2 and coords.shape[0] == B
+        n = coords.shape[1]
+        image, aux = image.contiguous(), aux.contiguous()
+        need = self.lib.sdm_workspace_bytes_prompt(self.h, B, R, kind, n)
+        if need == 0:
+            _check(1)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        alpha = torch.empty((B, R, R), dtype=torch.float16, device=self.device)
+        pre = torch.empty((B, R, R), dtype=torch.float16, device=self.device) if want_premean else None
+        flags = is_transparent if isinstance(is_transparent, (list, tuple)) else [is_transparent] * B
+        it = (C.c_int32 * B)(*[1 if f else 0 for f in flags])
+        with torch.cuda.device(self.device):
+            _check(self.lib.sdm_forward_prompt(self.h, image.data_ptr(), aux.data_ptr(), B, R, it, kind, coords.data_ptr(), n, alpha.data_ptr(),
+                                               pre.data_ptr() if pre is not None else None, self._ws.data_ptr(), self._ws.numel(),
+                                               _stream_ptr(self.device)))
         return (alpha, pre) if want_premean else alpha
 
     def forward_host(self, image: torch.Tensor, trimap: torch.Tensor, is_transparent=False, out: Optional[torch.Tensor] = None):

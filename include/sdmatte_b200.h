@@ -63,6 +63,19 @@ size_t sdm_workspace_bytes(sdm_handle* h, int B, int R);
 int sdm_forward(sdm_handle* h, const float* image_dev, const float* trimap_dev, int B, int R, const int32_t* is_trans,
                 void* alpha_dev, void* premean_dev, void* workspace_dev, size_t workspace_bytes, uintptr_t stream);
 
+/* The other visual prompts of the SDMatte model (SDMatte.forward meta_arch.py:130-197, CustomUNet.forward
+ * replace.py:446-455) — not reachable from the reference's node, which fixes aux_input="trimap" and coords [0,0,1,1]
+ * (sdmatte_nodes.py:286-296,353): the auxiliary image `aux_dev` [B][R][R] fp32 in [0,1] (it takes the trimap's place: VAE latent,
+ * cross-attention context, attention-mask source) is
+ *   prompt_kind 0: a mask / bbox mask (or a trimap with real coordinates): coords_host [B][4] -> 4 x 320 sinusoids -> bbox_embedding
+ *   prompt_kind 1: a point mask: coords_host [B][ncoords] -> zero-padded to the first divisor of 1680 -> point_embedding
+ * The coordinate -> emb -> time_emb_proj chain, folded into constants for sdm_forward, runs per sample at the head of the plan
+ * (csrc/cond_embed.cu).  Workspace: sdm_workspace_bytes_prompt. */
+size_t sdm_workspace_bytes_prompt(sdm_handle* h, int B, int R, int prompt_kind, int ncoords);
+int sdm_forward_prompt(sdm_handle* h, const float* image_dev, const float* aux_dev, int B, int R, const int32_t* is_trans, int prompt_kind,
+                       const float* coords_host, int ncoords, void* alpha_dev, void* premean_dev, void* workspace_dev,
+                       size_t workspace_bytes, uintptr_t stream);
+
 /* Same, with HOST buffers (pinned or pageable) already at R x R: H2D of image/trimap and D2H of alpha on `stream`, then a
  * stream sync (replaces the .to(device) / .cpu() pair at sdmatte_nodes.py:342,349,363 for pre-sized inputs; bench / tests). */
 int sdm_forward_host(sdm_handle* h, const float* image_host, const float* trimap_host, int B, int R, const int32_t* is_trans,

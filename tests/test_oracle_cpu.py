@@ -280,3 +280,24 @@ def test_flop_model_matches_survey():
     from bench import TFLOP_PER_MATTE
 
     assert TFLOP_PER_MATTE[1024] == 28.785 and TFLOP_PER_MATTE[512] == 5.952
+
+
+def test_point_coordinate_embedding_padding_rule():
+    """meta_arch.py:153-176: N coordinates are zero-padded to the first i >= N dividing 1680, 1680 / i sinusoid channels each
+    (an odd channel count gets one zero column, diffusers get_timestep_embedding), always 1680 values per sample."""
+    from oracle import sdmatte_oracle as orc
+
+    for n, i in ((1, 1), (4, 4), (11, 12), (13, 14), (16, 16), (20, 20), (41, 42), (100, 105)):
+        c = torch.rand(3, n)
+        e = orc.point_coords_embedding(c)
+        assert e.shape == (3, 1680)
+        dim = 1680 // i
+        assert 1680 % i == 0 and all(1680 % j for j in range(n, i))
+        per = e.view(3, i, dim)
+        half = dim // 2
+        # coordinate 0, frequency 0: cos(t), sin(t); padded coordinates embed t = 0: cos = 1, sin = 0
+        assert torch.allclose(per[:, 0, 0], torch.cos(c[:, 0])) and torch.allclose(per[:, 0, half], torch.sin(c[:, 0]))
+        if i > n:
+            assert torch.allclose(per[:, n:, :half], torch.ones(3, i - n, half)) and torch.allclose(per[:, n:, half:2 * half], torch.zeros(3, i - n, half))
+        if dim % 2:
+            assert (per[:, :, -1] == 0).all()
