@@ -425,8 +425,13 @@ def run_b200(args):
     if os.path.exists(tp) and R == 1024 and B == 8:
         try:
             td = json.load(open(tp))
-            traffic = {"dram_bytes_per_launch": td["conv3x3"]["dram_bytes"] / td["conv3x3"]["launches"],
-                       "algorithmic_bytes_per_launch": fam["tc:conv3x3"]["bytes"] / conv_n, "source": "profiles/r2_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one bs=8 1024^2 step)"}
+            # ncu recognises the family by kernel name (conv_swap*_kernel + the HALO instantiations): the 65 big launches of the 98;
+            # the other 33 (small geometries on the tap-per-box kernel) carry 1.6 % of the family's algorithmic bytes
+            traffic = {"dram_bytes_per_launch": td["conv3x3"]["dram_bytes"] / td["conv3x3"]["launches"], "launches_measured": td["conv3x3"]["launches"],
+                       "dram_bytes_per_step_measured_launches": td["conv3x3"]["dram_bytes"],
+                       "algorithmic_bytes_per_step_all_launches": fam["tc:conv3x3"]["bytes"], "launches_per_step": conv_n,
+                       "source": "profiles/r2_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, one bs=8 1024^2 forward, "
+                                 "profiles/scripts/run_r2_traffic.sh): measured traffic is BELOW the read-once/write-once figure (producer outputs still in the 126 MB L2)"}
         except Exception:
             traffic = None
     ms_step = ms_total / args.steps
