@@ -5,6 +5,7 @@ The .so lands next to this file so it travels to the GPU box with the repo snaps
 """
 from __future__ import annotations
 
+import fcntl
 import hashlib
 import os
 import subprocess
@@ -39,7 +40,9 @@ def _digest() -> str:
             h.update(fh.read())
     with open(os.path.join(ROOT, "include", "sdmatte_b200.h"), "rb") as fh:
         h.update(fh.read())
-    h.update(" ".join(FLAGS).encode())
+    # the flags WITHOUT the absolute include paths: the tree is copied to another root on the GPU box, and a digest that
+    # changes with the checkout location would make every process there rebuild (and N ranks race on the output file)
+    h.update(" ".join(f for f in FLAGS if not os.path.isabs(f)).encode())
     return h.hexdigest()
 
 
@@ -47,8 +50,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD, exist_ok=True)
     stamp = os.path.join(BUILD, "digest.txt")
     dig = _digest()
-    if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == dig:
+
+    def fresh() -> bool:
+        return os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == dig
+
+    if not force and fresh():
         return OUT
+    # one builder at a time (torchrun starts N ranks at once); the others wait here and then find a fresh library
+    with open(os.path.join(BUILD, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and fresh():
+            return OUT
+        return _build_locked(dig, stamp, verbose)
+
+
+def _build_locked(dig: str, stamp: str, verbose: bool) -> str:
     if not os.path.exists(NVCC):
         if os.path.exists(OUT):
             return OUT  # GPU box without a toolkit: use the prebuilt library shipped with the snapshot
@@ -68,10 +84,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [NVCC, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+    tmp_out = OUT + f".tmp{os.getpid()}"
+    cmd = [NVCC, "-shared", "-o", tmp_out, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp_out, OUT)  # atomic: a process that dlopens concurrently sees the old or the new file, never a partial one
     with open(stamp, "w") as fh:
         fh.write(dig)
     return OUT
