@@ -168,17 +168,25 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
       constexpr uint32_t idesc = umma_idesc_f16(256);
       int ws = 0, xs = 0, acc = 0;
       uint32_t wph = 0, xph = 0, acc_phase = 0;
+      // SDM_GEMM_PROF=1 (measurement aid): cycles the issuing thread waited for a free accumulator / a (normalised) pixel tile /
+      // a weight tile
+      long long pw_acc = 0, pw_x = 0, pw_w = 0;
+      const long long prof_t0 = p.prof ? clock64() : 0;
+      auto timed_wait = [&](uint32_t bar, uint32_t ph, long long& accum) {
+        if (p.prof) { const long long t = clock64(); mbar_wait(bar, ph); accum += clock64() - t; }
+        else mbar_wait(bar, ph);
+      };
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        timed_wait(tempty_bar(acc), acc_phase ^ 1u, pw_acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int sl = 0; sl < nslices + nres; ++sl) {
-          mbar_wait(GNF ? xready_bar(xs) : xfull_bar(xs), xph);
+          timed_wait(GNF ? xready_bar(xs) : xfull_bar(xs), xph, pw_x);
           const uint32_t x_addr = x_base + xs * kXSlot;
           const bool resid = sl >= nslices;
           const int ntap = resid ? 1 : 9;
           for (int tap = 0; tap < ntap; ++tap) {
-            mbar_wait(wfull_bar(ws), wph);
+            timed_wait(wfull_bar(ws), wph, pw_w);
             tc_fence_after();
             const uint64_t adesc = umma_desc_k128(smem_base + ws * kWBytes);
             const uint64_t bdesc = resid ? umma_desc_k128(x_addr)
@@ -194,6 +202,9 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
         umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
+      if (p.prof && blockIdx.x < 2)
+        printf("sdm prof: swap_halo cta %d MMA issuer total %lld clk, waiting: accumulator %lld, pixel tile %lld, weight tile %lld\n", blockIdx.x,
+               clock64() - prof_t0, pw_acc, pw_x, pw_w);
     }
   } else if (GNF && warp >= 6) {
     // ============================== GroupNorm transform (8 warps) ==============================
