@@ -77,7 +77,7 @@ def conv_gn(B, H, W, Cin, Cout, variant):
             E.k_groupnorm([(xf, Cin, Cin)], g, bt, n.view(B, H * W, Cin), B=B, HW=H * W, eps=1e-6, silu=1, pre=(pre, None), pre_slots=slots)
             E.k_conv_gemm([(n, Cin, Cin)], w, Cout, out, force_swap=fs, **common)
     else:
-        mode = {"fused": 1, "fused_hop": 2, "fused_nomath": 4}[variant]
+        mode = {"fused": 1, "fused_hop": 2, "fused_nomath": 4, "fused_hop_noepilogue": 10, "fused_hop_nostores": 18}[variant]
         scratch = E.k_groupnorm([(xf, Cin, Cin)], g, bt, None, B=B, HW=H * W, eps=1e-6, silu=1, pre=(pre, None), pre_slots=slots)
         ab = E.groupnorm_ab(scratch, B, H * W, Cin)
 
@@ -129,7 +129,7 @@ CASES = {
     "attn_cross_L0 (B2 h5 16384x16384)": lambda: attn(2, 5, 16384, 16384, False),
     "attn_cross_L1 (B2 h10 4096x16384)": lambda: attn(2, 10, 4096, 16384, False),
     "attn_self_L2 (B2 h20 1024x1024 bias)": lambda: attn(2, 20, 1024, 1024, True),
-    **{f"gn+conv3x3 128->128 @1024^2 B4 {v}": (lambda v=v: conv_gn(4, 1024, 1024, 128, 128, v)) for v in ("apply+swap", "apply+swap_halo", "fused", "fused_nomath", "fused_hop")},
+    **{f"gn+conv3x3 128->128 @1024^2 B4 {v}": (lambda v=v: conv_gn(4, 1024, 1024, 128, 128, v)) for v in ("apply+swap", "apply+swap_halo", "fused", "fused_nomath", "fused_hop", "fused_hop_noepilogue", "fused_hop_nostores")},
     **{f"gn+conv3x3 256->256 @512^2 B4 {v}": (lambda v=v: conv_gn(4, 512, 512, 256, 256, v)) for v in ("apply+swap_halo", "fused", "fused_nomath", "fused_hop")},
     **{f"gn+conv3x3 512->512 @256^2 B4 {v}": (lambda v=v: conv_gn(4, 256, 256, 512, 512, v)) for v in ("apply+swap_halo", "fused", "fused_nomath", "fused_hop")},
     "conv3x3 128->128 @1024^2 B2": lambda: conv(2, 1024, 1024, 128, 128),
