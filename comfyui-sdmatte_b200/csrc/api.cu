@@ -220,6 +220,15 @@ int sdm_k_key_compact(const float* bias, float* cbias, int32_t* idx, int32_t* nt
   SDM_API_END
 }
 
+int sdm_k_key_bias(const float* trimap, int B, int R, float* bias0, float* bias1, float* bias2, float* bias3, const int32_t* lpad4,
+                   uintptr_t stream) {
+  SDM_API_BEGIN
+  SDM_CHECK(R % 64 == 0 && R >= 64, "R must be a multiple of 64");
+  const int lp[4] = {lpad4[0], lpad4[1], lpad4[2], lpad4[3]};
+  sdm::key_bias_run(trimap, B, R, bias0, bias1, bias2, bias3, lp, reinterpret_cast<cudaStream_t>(stream));
+  SDM_API_END
+}
+
 int sdm_k_probe_halo(const void* x, const void* eye, float* out, int dy, int dx, int mode, uintptr_t stream) {
   SDM_API_BEGIN
   sdm::probe_halo_run(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(eye), out, dy, dx, mode,

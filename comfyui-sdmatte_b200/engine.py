@@ -71,7 +71,7 @@ EXPORTS = [
     "sdm_last_forward_stats", "sdm_debug_tensor", "sdm_debug_tensor_count", "sdm_debug_tensor_name", "sdm_set_option", "sdm_graph_stats", "sdm_node_call_timing",
     "sdm_preprocess", "sdm_postprocess",
     "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_conv_variant", "sdm_k_conv_can_fuse_gn", "sdm_k_groupnorm_ab_offset", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
-    "sdm_k_softmax_rows", "sdm_k_direct_conv", "sdm_k_key_compact", "sdm_k_gather_rows", "sdm_k_probe_halo",
+    "sdm_k_softmax_rows", "sdm_k_direct_conv", "sdm_k_key_bias", "sdm_k_key_compact", "sdm_k_gather_rows", "sdm_k_probe_halo",
     "sdm_safetensors_open", "sdm_safetensors_count", "sdm_safetensors_entry", "sdm_safetensors_close",
 ]
 
@@ -526,6 +526,20 @@ def k_attention(q, k, vt, out, *, B, heads, Lq, Lk, ldq, ldk, ldvt, ldo, bias=No
     a.out, a.ldo, a.scale = out.data_ptr(), ldo, scale
     a.ntiles = _p(ntiles)
     _check(lib.sdm_k_attention(C.byref(a), _stream_ptr(out.device)))
+
+
+def k_key_bias(trimap, R):
+    """trimap [B,R,R] fp32 cuda -> the four per-level key-bias tensors [B][lpad_l] (log2 domain, -inf padded to 128 keys)."""
+    lib = load_library()
+    lib.sdm_k_key_bias.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
+    B = trimap.shape[0]
+    S = R // 8
+    lpad = [(((S >> l) ** 2 + 127) // 128) * 128 for l in range(4)]
+    outs = [torch.empty((B, lp), dtype=torch.float32, device=trimap.device) for lp in lpad]
+    arr = (C.c_int32 * 4)(*lpad)
+    _check(lib.sdm_k_key_bias(trimap.contiguous().data_ptr(), B, R, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(),
+                              arr, _stream_ptr(trimap.device)))
+    return outs
 
 
 def k_key_compact(bias, cbias, idx, ntiles, *, B, L, lpad):

@@ -195,6 +195,11 @@ int sdm_k_attention(const sdm_attn_args* a, uintptr_t stream);
    bias [B][lpad] (log2 domain, -inf padded) -> idx [B][lpad] kept key indices in order (padded to a multiple of 128 with a
    valid index), cbias [B][lpad] their biases (-inf padding), ntiles [B] = padded count / 128.  L = real key count. */
 int sdm_k_key_compact(const float* bias, float* cbias, int32_t* idx, int32_t* ntiles, int B, int L, int lpad, uintptr_t stream);
+/* Additive attn1 key bias of the four UNet levels from the trimap at R x R (replaces meta_arch.py:200-204: (tri+1)/2, nearest / 8,
+   flatten; replace.py:401-403: (1 - mask) * -10000; replace.py:56-63: nearest resize to each level's grid — the three compose to
+   strided sampling of the trimap): bias_l [B][lpad4[l]] fp32 in the LOG2 domain (x log2 e), -inf beyond the level's (R/8 >> l)^2 keys. */
+int sdm_k_key_bias(const float* trimap, int B, int R, float* bias0, float* bias1, float* bias2, float* bias3, const int32_t* lpad4,
+                   uintptr_t stream);
 /* Hardware probe (tests/probe_halo.py): D = shifted 16x8 window of a TMA-swizzled (18x10) halo tile, as a tcgen05 A operand
    with SBO = 1280 B and an unaligned start; x [16][8][64] fp16, eye [64][64] fp16 identity, out [128][64] fp32;
    mode 0: descriptor base_offset 0, mode 1: base_offset = (start >> 7) & 7 */

@@ -64,7 +64,7 @@ def test_alpha_matches_oracle(engine, ckpt, R, B):
         want = want.permute(0, 2, 3, 1) if name != "ctx" else want.reshape(got.shape)
         rel = ((got - want).abs().max() / want.abs().max()).item()
         print(f"[tap] {name}: max rel-to-range err {rel:.3e}")
-        assert rel < 2e-2, f"{name} diverges: {rel}"
+        assert rel < 6e-3, f"{name} diverges: {rel}"  # measured 1.6e-3 .. 2.8e-3 (profiles/r2i_parity.json: error_growth, max/range column)
     d = (a - ref["alpha"].squeeze(1)).abs()
     dm = (pre.float().cpu() - ref["label_mean"].squeeze(1)).abs()
     print(f"[parity fp32-oracle] R={R} B={B} max|da|={d.max():.3e} mean|da|={d.mean():.3e} max|dmean|={dm.max():.3e}")

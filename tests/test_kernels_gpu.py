@@ -728,3 +728,32 @@ def test_conv_can_fuse_gn_is_geometry_only(eng_mod):
     assert not eng_mod.conv_can_fuse_gn(3, 1, 128, 64, 64, ups2=1)
     assert not eng_mod.conv_can_fuse_gn(3, 1, 320, 64, 64)       # N % 128 != 0
     assert not eng_mod.conv_can_fuse_gn(3, 1, 128, 16, 16)       # too small for 8 x 32 patches
+
+
+# ------------------------------------------------------------------------------------------------ attn1 key bias
+@pytest.mark.parametrize("R,B", [(64, 2), (192, 1), (512, 2)])
+def test_key_bias_kernel(eng_mod, R, B):
+    """key_bias_kernel against the reference chain restated with torch ops: meta_arch.py:200-204 ((tri+1)/2 -> F.interpolate(1/8,
+    nearest) -> flatten), replace.py:401-403 ((1 - m) * -10000) and custom_prepare_attention_mask's nearest resize to each level's
+    grid (replace.py:56-63; pinned to the reference's own function by tests/test_oracle_cpu.py::test_key_bias_matches_reference_mask_functions).
+    Arbitrary trimap values (an antialiased-resized trimap is not 3-valued)."""
+    import math
+
+    g = torch.Generator(device="cpu").manual_seed(R)
+    trimap = torch.rand(B, R, R, generator=g)
+    trimap[:, ::16, ::16] = 1.0
+    trimap[:, 8::16, ::16] = 0.5
+    trimap[:, ::16, 8::16] = 0.0
+    outs = eng_mod.k_key_bias(trimap.to(DEV), R)
+    torch.cuda.synchronize()
+    tri = trimap.unsqueeze(1) * 2 - 1
+    m = F.interpolate((tri + 1) / 2, scale_factor=1 / 8, mode="nearest").flatten(start_dim=1)  # (B, S*S)
+    add = ((1 - m) * -10000.0).unsqueeze(1)
+    S = R // 8
+    for level, got in enumerate(outs):
+        s = S >> level
+        want = add if level == 0 else F.interpolate(add.view(B, 1, S, S), size=(s, s), mode="nearest").view(B, 1, s * s)
+        want = want.squeeze(1) * math.log2(math.e)
+        assert got.shape[1] % 128 == 0 and got.shape[1] >= s * s
+        torch.testing.assert_close(got[:, : s * s].cpu(), want, rtol=1e-6, atol=1e-3)
+        assert torch.isinf(got[:, s * s:]).all() and (got[:, s * s:] < 0).all()
