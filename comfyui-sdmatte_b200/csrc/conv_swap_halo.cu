@@ -105,6 +105,10 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // measurement aids (tests/bench_kernels.py "bisect" cases; the output is garbage with any of them set), bits of gn_silu:
+  //   32: the halo tile always comes from the first patch of the tensor (L2-hot, no zero fill)   64: the MMA issuer does not wait
+  //   for operands   128: the producers issue no TMA loads (implies 64; the transform warps do not wait either)
+  const bool dbg_hot_x = p.gn_silu & 32, dbg_no_tma = p.gn_silu & 128, dbg_no_wait = (p.gn_silu & 64) || dbg_no_tma;
   const int nres = p.has_res ? 2 : 0;
   int nslices = 0;
   for (int s = 0; s < p.nsrc; ++s) nslices += p.src_c[s] >> 6;
@@ -125,8 +129,10 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
         for (int sl = 0; sl < nslices; ++sl) {  // slice sl = K columns [64 sl, 64 sl + 64) of every tap
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(wempty_bar(ws), wph ^ 1u);
-            mbar_expect_tx(wfull_bar(ws), kWBytes);
-            tma_load_2d(smem_base + ws * kWBytes, &p.b_map, wfull_bar(ws), tap * p.cin_total + sl * 64, n0);
+            if (!dbg_no_tma) {
+              mbar_expect_tx(wfull_bar(ws), kWBytes);
+              tma_load_2d(smem_base + ws * kWBytes, &p.b_map, wfull_bar(ws), tap * p.cin_total + sl * 64, n0);
+            }
             if (++ws == kWStages) { ws = 0; wph ^= 1u; }
           }
         }
@@ -149,8 +155,11 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
         for (int s = 0; s < p.nsrc; ++s) {
           for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
             mbar_wait(xempty_bar(xs), xph ^ 1u);
-            mbar_expect_tx(xfull_bar(xs), kXTx);
-            tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, x0 - 1, y0 - 1, b);  // zero fill = conv padding
+            if (!dbg_no_tma) {
+              mbar_expect_tx(xfull_bar(xs), kXTx);
+              if (dbg_hot_x) tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, 0, 0, 0);
+              else tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, x0 - 1, y0 - 1, b);  // zero fill = conv padding
+            }
             if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
           }
         }
@@ -181,12 +190,12 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int sl = 0; sl < nslices + nres; ++sl) {
-          timed_wait(GNF ? xready_bar(xs) : xfull_bar(xs), xph, pw_x);
+          if (!dbg_no_wait) timed_wait(GNF ? xready_bar(xs) : xfull_bar(xs), xph, pw_x);
           const uint32_t x_addr = x_base + xs * kXSlot;
           const bool resid = sl >= nslices;
           const int ntap = resid ? 1 : 9;
           for (int tap = 0; tap < ntap; ++tap) {
-            timed_wait(wfull_bar(ws), wph, pw_w);
+            if (!dbg_no_wait) timed_wait(wfull_bar(ws), wph, pw_w);
             tc_fence_after();
             const uint64_t adesc = umma_desc_k128(smem_base + ws * kWBytes);
             const uint64_t bdesc = resid ? umma_desc_k128(x_addr)
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
         // next slice's constants (or the first slice of this CTA's next tile) fly during the transform
         if (sl + 1 < nslices) load_raw(tile, sl + 1, raw);
         else if (tile + (int)gridDim.x < p.total_tiles) load_raw(tile + gridDim.x, 0, raw);
-        mbar_wait(xfull_bar(xs), xph);
+        if (!dbg_no_tma) mbar_wait(xfull_bar(xs), xph);
         uint8_t* tp = smem_raw + (x_base + xs * kXSlot - smem_u32(smem_raw)) + r0 * 128 + piece * 16;
         if (p.gn_silu == 1) gn_transform_tile<true>(tp, inside, exist, ka, ks);
         else if (p.gn_silu == 0) gn_transform_tile<false>(tp, inside, exist, ka, ks);
