@@ -106,9 +106,9 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   // measurement aids (tests/bench_kernels.py "bisect" cases; the output is garbage with any of them set), bits of gn_silu:
-  //   32: the halo tile always comes from the first patch of the tensor (L2-hot, no zero fill)   64: the MMA issuer does not wait
-  //   for operands   128: the producers issue no TMA loads (implies 64; the transform warps do not wait either)
-  const bool dbg_hot_x = p.gn_silu & 32, dbg_no_tma = p.gn_silu & 128, dbg_no_wait = (p.gn_silu & 64) || dbg_no_tma;
+  //   32: the halo tile always comes from the first patch of the tensor (L2-hot, no zero fill)
+  //   128: no operand traffic at all: the producers stay idle, the MMA issuer and the transform warps do not wait for operands
+  const bool dbg_hot_x = p.gn_silu & 32, dbg_no_tma = p.gn_silu & 128, dbg_no_wait = dbg_no_tma;
   const int nres = p.has_res ? 2 : 0;
   int nslices = 0;
   for (int s = 0; s < p.nsrc; ++s) nslices += p.src_c[s] >> 6;
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
     // (round 1) issued halo tile i+1 behind the nine weight taps of slice i, i.e. about half a slice ahead of its use: enough
     // when the MMA reads the tile as it lands, but with the GroupNorm transform in between (r2g: T + M serialised, the fused conv
     // 30 % slower than the barrier hop alone) the tile has to arrive a full slice earlier.
-    if (lane == 0) {
+    if (lane == 0 && !dbg_no_tma) {
       tma_prefetch_desc(&p.b_map);
       int ws = 0;
       uint32_t wph = 0;
@@ -129,10 +129,8 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
         for (int sl = 0; sl < nslices; ++sl) {  // slice sl = K columns [64 sl, 64 sl + 64) of every tap
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(wempty_bar(ws), wph ^ 1u);
-            if (!dbg_no_tma) {
-              mbar_expect_tx(wfull_bar(ws), kWBytes);
-              tma_load_2d(smem_base + ws * kWBytes, &p.b_map, wfull_bar(ws), tap * p.cin_total + sl * 64, n0);
-            }
+            mbar_expect_tx(wfull_bar(ws), kWBytes);
+            tma_load_2d(smem_base + ws * kWBytes, &p.b_map, wfull_bar(ws), tap * p.cin_total + sl * 64, n0);
             if (++ws == kWStages) { ws = 0; wph ^= 1u; }
           }
         }
@@ -143,7 +141,7 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
           if (++ws == kWStages) { ws = 0; wph ^= 1u; }
         }
       }
-    } else if (lane == 1) {
+    } else if (lane == 1 && !dbg_no_tma) {
       tma_prefetch_desc(&p.a_map[0]); tma_prefetch_desc(&p.a_map[1]);
       int xs = 0;
       uint32_t xph = 0;
@@ -155,11 +153,9 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
         for (int s = 0; s < p.nsrc; ++s) {
           for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
             mbar_wait(xempty_bar(xs), xph ^ 1u);
-            if (!dbg_no_tma) {
-              mbar_expect_tx(xfull_bar(xs), kXTx);
-              if (dbg_hot_x) tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, 0, 0, 0);
-              else tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, x0 - 1, y0 - 1, b);  // zero fill = conv padding
-            }
+            mbar_expect_tx(xfull_bar(xs), kXTx);
+            if (dbg_hot_x) tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, 0, 0, 0);
+            else tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, x0 - 1, y0 - 1, b);  // zero fill = conv padding
             if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
           }
         }

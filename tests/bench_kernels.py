@@ -78,8 +78,7 @@ def conv_gn(B, H, W, Cin, Cout, variant):
             E.k_conv_gemm([(n, Cin, Cin)], w, Cout, out, force_swap=fs, **common)
     else:
         mode = {"fused": 1, "fused_hop": 2, "fused_nomath": 4, "fused_hop_noepilogue": 10, "fused_hop_nostores": 18,
-                "bisect_hotx": 2 + 32, "bisect_nowait": 2 + 64, "bisect_notma": 2 + 128, "bisect_notma_noepilogue": 2 + 128 + 8,
-                "bisect_nowait_noepilogue": 2 + 64 + 8, "bisect_hotx_noepilogue": 2 + 32 + 8}[variant]
+                "bisect_hotx": 2 + 32, "bisect_notma": 2 + 128, "bisect_notma_noepilogue": 2 + 128 + 8, "bisect_hotx_noepilogue": 2 + 32 + 8}[variant]
         scratch = E.k_groupnorm([(xf, Cin, Cin)], g, bt, None, B=B, HW=H * W, eps=1e-6, silu=1, pre=(pre, None), pre_slots=slots)
         ab = E.groupnorm_ab(scratch, B, H * W, Cin)
 
@@ -135,9 +134,9 @@ CASES = {
     **{f"gn+conv3x3 256->256 @512^2 B4 {v}": (lambda v=v: conv_gn(4, 512, 512, 256, 256, v)) for v in ("apply+swap_halo", "fused", "fused_nomath", "fused_hop")},
     **{f"gn+conv3x3 512->512 @256^2 B4 {v}": (lambda v=v: conv_gn(4, 256, 256, 512, 512, v)) for v in ("apply+swap_halo", "fused", "fused_nomath", "fused_hop")},
     **{f"bisect 256->256 @512^2 B4 {v}": (lambda v=v: conv_gn(4, 512, 512, 256, 256, v)) for v in (
-        "fused_hop", "bisect_hotx", "bisect_nowait", "bisect_notma", "fused_hop_noepilogue", "bisect_hotx_noepilogue", "bisect_nowait_noepilogue", "bisect_notma_noepilogue")},
+        "fused_hop", "bisect_hotx", "bisect_notma", "fused_hop_noepilogue", "bisect_hotx_noepilogue", "bisect_notma_noepilogue")},
     **{f"bisect 128->128 @1024^2 B4 {v}": (lambda v=v: conv_gn(4, 1024, 1024, 128, 128, v)) for v in (
-        "fused_hop", "bisect_hotx", "bisect_nowait", "bisect_notma", "fused_hop_noepilogue", "bisect_notma_noepilogue")},
+        "fused_hop", "bisect_hotx", "bisect_notma", "fused_hop_noepilogue", "bisect_notma_noepilogue")},
     "conv3x3 128->128 @1024^2 B2": lambda: conv(2, 1024, 1024, 128, 128),
     "conv3x3 128->128 @1024^2 B2 +res+stats": lambda: conv(2, 1024, 1024, 128, 128, res=True, stats=True),
     "conv3x3 256->256 @512^2 B4": lambda: conv(4, 512, 512, 256, 256),
