@@ -70,43 +70,12 @@ __device__ __forceinline__ void gn_transform_tile(uint8_t* tp, uint32_t inside, 
     }
   }
 }
-// ---- cluster-of-2 helpers (MC): the two CTAs of a cluster work on two pixel tiles of the SAME channel tile in lock step, so every
-// weight tile is fetched from L2 once and multicast into both CTAs' rings
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// 2-D TMA load delivered to the same shared-memory offset (and signalling the mbarrier at the same offset) in every CTA of `mask`
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-// arrive (once the MMAs issued so far have completed) on the mbarrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
-}
 }  // namespace swh
 
-// MC (r2u bisection: with the operand traffic switched off the 256 -> 256 conv runs 1.32x faster, an L2-hot pixel tile buys 3 %:
-// the per-tile re-fetch of the weight taps from L2, 144 KB per slice against 43.5 KB of pixels, is what the kernel waits for):
-// clusters of two CTAs, weight tiles multicast.  Each CTA posts the expected bytes on its own full barrier, the CTA whose turn it
-// is (tap parity) issues the multicast load once BOTH CTAs have released the stage (every MMA commit arrives on both empty barriers).
-template <bool GNF, bool MC>
+template <bool GNF>
 __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_kernel(const __grid_constant__ ConvGemmParams p) {
   using namespace swh;
   constexpr int kWStages = Cfg<GNF>::kWStages, kXSlots = Cfg<GNF>::kXSlots, kPipe = Cfg<GNF>::kPipe;
-  const uint32_t rank = MC ? cluster_rank() : 0u;
-  // work items of this CTA: MC: pair tiles (channel tile, two consecutive pixel tiles) per cluster; else single tiles per CTA
-  const int item_first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int item_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int item_count = MC ? ((p.m_tiles + 1) >> 1) * p.n_tiles : p.total_tiles;
-  auto item_mt = [&](int item) { return MC ? 2 * (item / p.n_tiles) + (int)rank : item / p.n_tiles; };
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t x_base = smem_base + kWStages * kWBytes;
@@ -123,7 +92,7 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWStages; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), MC ? 2 : 1); }
+    for (int s = 0; s < kWStages; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
     for (int s = 0; s < kXSlots; ++s) { mbar_init(xfull_bar(s), 1); mbar_init(xempty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     if (GNF) for (int s = 0; s < kXSlots; ++s) mbar_init(xready_bar(s), Cfg<GNF>::kTWarps);  // one arrive per transform warp
@@ -133,7 +102,6 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -156,30 +124,31 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
       tma_prefetch_desc(&p.b_map);
       int ws = 0;
       uint32_t wph = 0;
-      uint32_t seq = 0;  // MC: the CTAs of the cluster take turns issuing the (multicast) loads
-      auto load_w = [&](const CUtensorMap* map, int c0, int c1) {
-        mbar_wait(wempty_bar(ws), wph ^ 1u);
-        mbar_expect_tx(wfull_bar(ws), kWBytes);
-        if (!MC) tma_load_2d(smem_base + ws * kWBytes, map, wfull_bar(ws), c0, c1);
-        else if ((seq & 1u) == rank) tma_load_2d_mc(smem_base + ws * kWBytes, map, wfull_bar(ws), c0, c1, (uint16_t)3);
-        ++seq;
-        if (++ws == kWStages) { ws = 0; wph ^= 1u; }
-      };
-      for (int item = item_first; item < item_count; item += item_step) {
-        const int n0 = (item % p.n_tiles) * 128;
-        for (int sl = 0; sl < nslices; ++sl)  // slice sl = K columns [64 sl, 64 sl + 64) of every tap
-          for (int tap = 0; tap < 9; ++tap) load_w(&p.b_map, tap * p.cin_total + sl * 64, n0);
-        for (int i = 0; i < nres; ++i) load_w(&p.i_map, 64 * i, 0);  // D^T[c][pix] += I[c][64 i + k] . R[pix][n0 + 64 i + k]
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles) * 128;
+        for (int sl = 0; sl < nslices; ++sl) {  // slice sl = K columns [64 sl, 64 sl + 64) of every tap
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(wempty_bar(ws), wph ^ 1u);
+            mbar_expect_tx(wfull_bar(ws), kWBytes);
+            tma_load_2d(smem_base + ws * kWBytes, &p.b_map, wfull_bar(ws), tap * p.cin_total + sl * 64, n0);
+            if (++ws == kWStages) { ws = 0; wph ^= 1u; }
+          }
+        }
+        for (int i = 0; i < nres; ++i) {  // D^T[c][pix] += I[c][64 i + k] . R[pix][n0 + 64 i + k]
+          mbar_wait(wempty_bar(ws), wph ^ 1u);
+          mbar_expect_tx(wfull_bar(ws), kWBytes);
+          tma_load_2d(smem_base + ws * kWBytes, &p.i_map, wfull_bar(ws), 64 * i, 0);
+          if (++ws == kWStages) { ws = 0; wph ^= 1u; }
+        }
       }
     } else if (lane == 1 && !dbg_no_tma) {
       tma_prefetch_desc(&p.a_map[0]); tma_prefetch_desc(&p.a_map[1]);
       int xs = 0;
       uint32_t xph = 0;
-      for (int item = item_first; item < item_count; item += item_step) {
-        const int n0 = (item % p.n_tiles) * 128;
-        const int mt = item_mt(item);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles) * 128;
+        const int mt = tile / p.n_tiles;
         const int t_img = mt % per_image;
-        // a past-the-end pixel tile (MC, odd tile count) has batch index B: the TMA unit zero-fills it
         const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32, b = mt / per_image;
         for (int s = 0; s < p.nsrc; ++s) {
           for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
@@ -212,7 +181,7 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
         if (p.prof) { const long long t = clock64(); mbar_wait(bar, ph); accum += clock64() - t; }
         else mbar_wait(bar, ph);
       };
-      for (int item = item_first; item < item_count; item += item_step) {
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         timed_wait(tempty_bar(acc), acc_phase ^ 1u, pw_acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
@@ -229,8 +198,7 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
                                          : umma_desc_k128_sbo(x_addr + (uint32_t)((tap / 3) * 10 + tap % 3) * 128u, 1280);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (sl | tap | k) != 0);
-            if (MC) umma_commit_mc(wempty_bar(ws), (uint16_t)3);  // frees the stage in both CTAs' books
-            else umma_commit(wempty_bar(ws));
+            umma_commit(wempty_bar(ws));
             if (++ws == kWStages) { ws = 0; wph ^= 1u; }
           }
           umma_commit(xempty_bar(xs));
@@ -253,17 +221,16 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
     uint32_t xph = 0;
     // (scale, shift) of this thread's 8 channels, one slice ahead: ncu r2f — fetched at the top of every slice the constants cost
     // one exposed L2 round trip per slice (30 % of the kernel's stall samples sat on their first use)
-    auto load_raw = [&](int item_, int slice, float4 (&raw)[4]) {
-      const int b_ = min(item_mt(item_) / per_image, p.B - 1);  // (a past-the-end tile reads some valid constants; its pixels are all zero-filled)
+    auto load_raw = [&](int tile_, int slice, float4 (&raw)[4]) {
+      const int b_ = (tile_ / p.n_tiles) / per_image;
       const float4* src = reinterpret_cast<const float4*>(p.gn_ab + ((size_t)b_ * p.cin_total + slice * 64 + chunk * 8) * 2);
 #pragma unroll
       for (int j = 0; j < 4; ++j) raw[j] = __ldg(src + j);
     };
     float4 raw[4];
-    if (item_first < item_count) load_raw(item_first, 0, raw);
-    for (int item = item_first; item < item_count; item += item_step) {
-      const int tile = item;
-      const int mt = item_mt(item);
+    if ((int)blockIdx.x < p.total_tiles) load_raw(blockIdx.x, 0, raw);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles;
       const int t_img = mt % per_image;
       const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32;
       // validity of this thread's rows depends on the tile position only: bit k = row r0 + 32 k lies inside the image
@@ -275,14 +242,13 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
         if (px >= 0 && px < p.W && py >= 0 && py < p.H) inside |= 1u << k;
       }
       inside &= exist;
-      if (mt >= p.m_tiles) inside = 0;
       for (int sl = 0; sl < nslices; ++sl) {  // slice sl = channels [64 sl, 64 sl + 64) of the concatenated input
         uint64_t ka[4], ks[4];
         if (p.gn_silu == 0) gn_consts_from_raw<false>(raw, ka, ks);
         else gn_consts_from_raw<true>(raw, ka, ks);
         // next slice's constants (or the first slice of this CTA's next tile) fly during the transform
         if (sl + 1 < nslices) load_raw(tile, sl + 1, raw);
-        else if (tile + item_step < item_count) load_raw(tile + item_step, 0, raw);
+        else if (tile + (int)gridDim.x < p.total_tiles) load_raw(tile + gridDim.x, 0, raw);
         if (!dbg_no_tma) mbar_wait(xfull_bar(xs), xph);
         uint8_t* tp = smem_raw + (x_base + xs * kXSlot - smem_u32(smem_raw)) + r0 * 128 + piece * 16;
         if (p.gn_silu == 1) gn_transform_tile<true>(tp, inside, exist, ka, ks);
@@ -311,14 +277,13 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
     uint8_t* stg = smem_raw + (bar_base - smem_u32(smem_raw)) + 256 + (warp - 2) * 2048;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = item_first; item < item_count; item += item_step) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int n0 = (item % p.n_tiles) * 128;
-      const int mt = item_mt(item);
-      const bool live = mt < p.m_tiles;  // MC with an odd number of pixel tiles: the last pair's second tile is computed on zeros, not stored
+      const int n0 = (tile % p.n_tiles) * 128;
+      const int mt = tile / p.n_tiles;
       const int t_img = mt % per_image;
-      const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32, b = live ? mt / per_image : 0;
+      const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32, b = mt / per_image;
       const float bias = p.bias ? p.bias[(p.bias_sel ? (long long)p.bias_sel[b] * p.N : 0) + n0 + m] : 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256;
       __half* obase = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + n0 + quad * 32;
@@ -357,7 +322,7 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
         }
       };
       __syncwarp();
-      if (!(p.gn_silu & 8) && live) {  // (bit 3 of gn_silu: measurement aid of tests/bench_kernels.py — the tile's epilogue is skipped)
+      if (!(p.gn_silu & 8)) {  // (bit 3 of gn_silu: measurement aid of tests/bench_kernels.py — the tile's epilogue is skipped)
         tmem_ld32(taddr, ra);
 #pragma unroll 1
         for (int b2 = 0; b2 < 4; ++b2) {
@@ -374,39 +339,23 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
 
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
 }
 
-template <bool GNF, bool MC>
-static void swap_halo_launch_t(const ConvGemmParams& p, int grid, cudaStream_t st) {
-  static PerDeviceOnce attr;
-  attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<GNF, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::Cfg<GNF>::kSmem)); });
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(swh::Cfg<GNF>::kThreads);
-  cfg.dynamicSmemBytes = swh::Cfg<GNF>::kSmem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = MC ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  SDM_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_swap_halo_kernel<GNF, MC>, p));
-}
-
-// mc: clusters of two CTAs with multicast weight tiles (grid must be even)
-void conv_swap_halo_launch(const ConvGemmParams& p, int grid, bool mc, cudaStream_t st) {
+void conv_swap_halo_launch(const ConvGemmParams& p, int grid, cudaStream_t st) {
   if (p.gn_ab) {
-    if (mc) swap_halo_launch_t<true, true>(p, grid, st);
-    else swap_halo_launch_t<true, false>(p, grid, st);
+    static PerDeviceOnce attr;
+    attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::Cfg<true>::kSmem)); });
+    conv_swap_halo_kernel<true><<<grid, swh::Cfg<true>::kThreads, swh::Cfg<true>::kSmem, st>>>(p);
   } else {
-    if (mc) swap_halo_launch_t<false, true>(p, grid, st);
-    else swap_halo_launch_t<false, false>(p, grid, st);
+    static PerDeviceOnce attr;
+    attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::Cfg<false>::kSmem)); });
+    conv_swap_halo_kernel<false><<<grid, swh::Cfg<false>::kThreads, swh::Cfg<false>::kSmem, st>>>(p);
   }
+  SDM_CUDA_OK(cudaGetLastError());
 }
 
 }  // namespace sdm

@@ -11,7 +11,7 @@
 namespace sdm {
 
 void conv_swap_launch(const ConvGemmParams& p, int grid, cudaStream_t st);       // conv_swap.cu
-void conv_swap_halo_launch(const ConvGemmParams& p, int grid, bool mc, cudaStream_t st);  // conv_swap_halo.cu
+void conv_swap_halo_launch(const ConvGemmParams& p, int grid, cudaStream_t st);  // conv_swap_halo.cu
 
 struct ConvGemmLaunch {
   ConvGemmParams p;
@@ -21,7 +21,6 @@ struct ConvGemmLaunch {
   bool halo = false;  // 3x3 stride-1 conv with a resident halo tile per 64-channel slice
   bool swap = false;  // conv_swap_kernel: channels on M, 256 pixels on N (128-channel 3x3 convs)
   bool swap_halo = false;  // ... with a resident 8 x 32 pixel halo tile (conv_swap_halo.cu; carries the fused GroupNorm)
-  bool swap_mc = false;    // ... in clusters of two CTAs with multicast weight tiles
   int grid = 0;
   double flops = 0;
 };
@@ -313,14 +312,6 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
     p.prof = env_prof;  // measurement aid: in-kernel cycle counters of the producer / MMA / epilogue threads
   }
   L->grid = (int)std::min<long long>(total, num_sms);
-  if (L->swap && L->swap_halo) {
-    // clusters of two CTAs sharing (multicast) weight tiles: the grid counts CTAs, the kernel pairs consecutive pixel tiles.
-    // SDM_SWH_MC=0 keeps single CTAs (A/B switch of round 2)
-    static const int env_mc = [] { const char* e = getenv("SDM_SWH_MC"); return e ? atoi(e) : 1; }();
-    const long long pairs = ((m_tiles_eff + 1) / 2) * p.n_tiles;
-    L->swap_mc = env_mc != 0 && num_sms % 2 == 0 && pairs >= num_sms / 2;
-    if (L->swap_mc) L->grid = (int)std::min<long long>(2 * pairs, num_sms);
-  }
   L->flops = 2.0 * (double)d.B * Hout * Wout * (double)d.N * (double)ktot;
   return L;
 }
@@ -333,7 +324,7 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
     if (l.ewg == 2) return conv_gemm_launch<BN, MT, MODE, UPS2, 2>(p, g, st); \
     return conv_gemm_launch<BN, MT, MODE, UPS2, 1>(p, g, st);                 \
   } while (0)
-  if (l.swap) return l.swap_halo ? conv_swap_halo_launch(p, g, l.swap_mc, st) : conv_swap_launch(p, g, st);
+  if (l.swap) return l.swap_halo ? conv_swap_halo_launch(p, g, st) : conv_swap_launch(p, g, st);
   if (l.halo) {
     if (bn == 256 && !p.ups2) return conv_gemm_launch_halo<256, 1, false, 1>(p, g, st);
     if (bn == 256 && p.ups2) return conv_gemm_launch_halo<256, 1, true, 1>(p, g, st);
