@@ -169,7 +169,13 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // The WHOLE warp runs this loop convergently and one elected lane issues the tcgen05 instructions.  With the loop inside an
+    // `if (lane == 0)` (rounds 1 / 2 up to r2u) the descriptors lived in per-thread registers of a divergent region and the
+    // compiler wrapped EVERY tcgen05.mma in an ELECT / 5 x R2UR.BROADCAST / BRA.U.ANY loop (SASS): ~17 dependent instructions per
+    // MMA on top of the per-tap wait, fence and descriptor arithmetic — the issuing thread, not the tensor core or the operand
+    // supply, was the limit (r2u: with the operand waits removed the same kernel ran 1.3x faster; tests/probe_mma_rate.cu).
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_f16(256);
       int ws = 0, xs = 0, acc = 0;
       uint32_t wph = 0, xph = 0, acc_phase = 0;
@@ -196,18 +202,23 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
             const uint64_t adesc = umma_desc_k128(smem_base + ws * kWBytes);
             const uint64_t bdesc = resid ? umma_desc_k128(x_addr)
                                          : umma_desc_k128_sbo(x_addr + (uint32_t)((tap / 3) * 10 + tap % 3) * 128u, 1280);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (sl | tap | k) != 0);
-            umma_commit(wempty_bar(ws));
+              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (sl | tap | k) != 0);
+              umma_commit(wempty_bar(ws));
+            }
+            __syncwarp();
             if (++ws == kWStages) { ws = 0; wph ^= 1u; }
           }
-          umma_commit(xempty_bar(xs));
+          if (leader) umma_commit(xempty_bar(xs));
+          __syncwarp();
           if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
+        if (leader) umma_commit(tfull_bar(acc));
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      if (p.prof && blockIdx.x < 2)
+      if (p.prof && blockIdx.x < 2 && leader)
         printf("sdm prof: swap_halo cta %d MMA issuer total %lld clk, waiting: accumulator %lld, pixel tile %lld, weight tile %lld\n", blockIdx.x,
                clock64() - prof_t0, pw_acc, pw_x, pw_w);
     }
