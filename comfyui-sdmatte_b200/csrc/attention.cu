@@ -154,25 +154,35 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
     }
   } else if (warp == 9 || warp == 10) {
     // ======================================= MMA issuer(s) ======================================
-    if (lane == 0) {
+    // whole warp, one elected lane issues: inside an `if (lane == 0)` the compiler wrapped every tcgen05.mma in an ELECT /
+    // R2UR.BROADCAST loop (conv_swap_halo.cu, r2w: +10 % on the convs from this change alone)
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc_s = umma_idesc_f16(64);
       constexpr uint32_t idesc_o = umma_idesc_f16(64);
       // S_x half hf = Q_x (128 x 64) . K[hf*64 .. hf*64+63]^T  -> S columns [hf*64, hf*64+64)
       auto issue_s = [&](int x, int hf, int stage) {
         const uint64_t ad = umma_desc_k128(base + kOffQ + x * kQBytes);
         const uint64_t bd = umma_desc_k128(base + kOffStage + stage * kStageBytes + hf * (64 * 128));
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tmem + kColS + x * 128 + hf * 64, ad + 2 * k, bd + 2 * k, idesc_s, k != 0);
-        umma_commit(s_full(x, hf));
+          for (int k = 0; k < 4; ++k) umma_f16(tmem + kColS + x * 128 + hf * 64, ad + 2 * k, bd + 2 * k, idesc_s, k != 0);
+          umma_commit(s_full(x, hf));
+        }
+        __syncwarp();
       };
       // O_x += P_x[:, keys k0*16 .. k1*16) . V[those keys]   (K16 steps k0..k1-1 of the 8 in a 128-key tile)
       auto issue_pv = [&](int x, int stage, int j, int k0, int k1, uint32_t commit_bar) {
         const uint32_t vb = base + kOffStage + stage * kStageBytes + kKBytes;
-        for (int k = k0; k < k1; ++k) {
-          const uint64_t bd = umma_desc_k128(vb + (k >> 2) * (64 * 128)) + 2 * (k & 3);
-          umma_f16_ts(tmem + kColO + x * 64, tmem + kColP + x * 64 + k * 8, bd, idesc_o, (j | k) != 0);
+        if (leader) {
+#pragma unroll
+          for (int k = k0; k < k1; ++k) {
+            const uint64_t bd = umma_desc_k128(vb + (k >> 2) * (64 * 128)) + 2 * (k & 3);
+            umma_f16_ts(tmem + kColO + x * 64, tmem + kColP + x * 64 + k * 8, bd, idesc_o, (j | k) != 0);
+          }
+          umma_commit(commit_bar);
         }
-        umma_commit(commit_bar);
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       {
@@ -199,7 +209,8 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           mbar_wait(p_full(x, 1), (uint32_t)t & 1u);
           tc_fence_after();
           issue_pv(x, st, t, 0, 8, o_full(x, 1));
-          umma_commit(kv_empty(st));  // this tile's MMAs on the stage are done (the barrier counts both issuers)
+          if (leader) umma_commit(kv_empty(st));  // this tile's MMAs on the stage are done (the barrier counts both issuers)
+          __syncwarp();
         }
       }
     }

@@ -90,8 +90,9 @@ __global__ void __launch_bounds__(sw::kThreads, 1) conv_swap_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // ============================== MMA issuer (whole warp, one elected lane issues: see conv_swap_halo.cu) ==============
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_f16(256);
       int chunks = 0;
       for (int s = 0; s < p.nsrc; ++s) chunks += p.src_c[s] >> 6;
@@ -107,12 +108,16 @@ __global__ void __launch_bounds__(sw::kThreads, 1) conv_swap_kernel(const __grid
           tc_fence_after();
           const uint32_t w_addr = smem_base + stage * kStageBytes;
           const uint64_t adesc = umma_desc_k128(w_addr), bdesc = umma_desc_k128(w_addr + kWBytes);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
-          umma_commit(empty_bar(stage));
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0);
+            umma_commit(empty_bar(stage));
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
+        if (leader) umma_commit(tfull_bar(acc));
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }

@@ -276,7 +276,10 @@ __global__ void __launch_bounds__(64 + 128 * EWG, 1) conv_gemm_kernel(const __gr
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // The whole warp runs the loop convergently, one elected lane issues (see conv_swap_halo.cu: inside an `if (lane == 0)` every
+    // tcgen05.mma was wrapped in an ELECT / R2UR.BROADCAST loop by the compiler and the issuing thread became the limit).
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_f16(BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
@@ -311,17 +314,21 @@ __global__ void __launch_bounds__(64 + 128 * EWG, 1) conv_gemm_kernel(const __gr
               tc_fence_after();
               const uint64_t bdesc = umma_desc_k128(smem_base + stage * Cfg::kStageBytes);
               const uint32_t woff = ri < 0 ? (uint32_t)((tap / 3) * 10 + tap % 3) * 128u : 0u;
+              if (leader) {
 #pragma unroll
-              for (int u = 0; u < MT; ++u) {
-                const uint64_t adesc = ri < 0 ? umma_desc_k128_sbo(h_addr + u * Cfg::kHaloBytes + woff, 1280) : umma_desc_k128(h_addr + u * Cfg::kHaloBytes);
+                for (int u = 0; u < MT; ++u) {
+                  const uint64_t adesc = ri < 0 ? umma_desc_k128_sbo(h_addr + u * Cfg::kHaloBytes + woff, 1280) : umma_desc_k128(h_addr + u * Cfg::kHaloBytes);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_f16(d_tmem + u * Cfg::kSubStride + dcol, adesc + 2 * k, bdesc + 2 * k, id, (sl | tap | k) != 0);
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16(d_tmem + u * Cfg::kSubStride + dcol, adesc + 2 * k, bdesc + 2 * k, id, (sl | tap | k) != 0);
+                }
+                umma_commit(empty_bar(stage));
               }
-              umma_commit(empty_bar(stage));
+              __syncwarp();
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
-            umma_commit(aempty_bar(aslot));
+            if (leader) umma_commit(aempty_bar(aslot));
+            __syncwarp();
             if (++aslot == Cfg::kASlots) { aslot = 0; aphase ^= 1u; }
           }
         } else
@@ -334,22 +341,26 @@ __global__ void __launch_bounds__(64 + 128 * EWG, 1) conv_gemm_kernel(const __gr
           const int ri = ks - num_ksteps;  // >= 0: residual slice index
           const uint32_t id = ri < 0 ? idesc : umma_idesc_f16(min(64, BLOCK_N - ri * 64));
           const uint32_t dcol = ri < 0 ? 0u : (uint32_t)(ri * 64);
+          if (leader) {
 #pragma unroll
-          for (int u = 0; u < MT; ++u) {
-            const uint64_t adesc = umma_desc_k128(a_addr + u * Cfg::kABytes);
+            for (int u = 0; u < MT; ++u) {
+              const uint64_t adesc = umma_desc_k128(a_addr + u * Cfg::kABytes);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // +32 B per 16-element K step (start-address field is in 16-byte units)
-              umma_f16(d_tmem + u * Cfg::kSubStride + dcol, adesc + 2 * k, bdesc + 2 * k, id, (ks | k) != 0);
+              for (int k = 0; k < 4; ++k) {
+                // +32 B per 16-element K step (start-address field is in 16-byte units)
+                umma_f16(d_tmem + u * Cfg::kSubStride + dcol, adesc + 2 * k, bdesc + 2 * k, id, (ks | k) != 0);
+              }
             }
+            umma_commit(empty_bar(stage));
           }
-          umma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));
+        if (leader) umma_commit(tfull_bar(acc));
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      if (p.prof && blockIdx.x < 2)
+      if (p.prof && blockIdx.x < 2 && leader)
         printf("sdm prof: cta %d MMA issuer total %lld clk, waiting for operands %lld, for a free accumulator %lld\n", blockIdx.x,
                clock64() - prof_t0, prof_full, prof_tempty);
     }
