@@ -18,8 +18,6 @@
 // per thread: 16-byte piece j of tile row r holds channel chunk j ^ (r & 7); a thread keeps (piece, r mod 16), hence one fixed
 // chunk and its 16 constants in registers.
 #include "gn_math.cuh"
-
-#include <cstdlib>
 #include "umma_gemm.cuh"
 
 namespace sdm {
@@ -35,11 +33,10 @@ constexpr int kXRows = 10 * 34;    // pixel rows of a halo tile
 // GNF: the slot of a halo tile is busy for (TMA flight + transform + nine taps of MMAs) instead of (TMA flight + MMAs): a third
 // slot (paid for with one weight stage) keeps the tensor core fed; 8 transform warps (r2b: 4 warps with a branch per piece made
 // the fused conv 35 % slower than conv + separate apply pass, i.e. no net gain)
-// V: ring-depth variant (A/B switch SDM_SWH_CFG of round 2): 0 = 6 weight stages + 2 halo slots (GNF: 5 + 3), 1 = 8 + 2
-template <bool GNF, int V = 0>
+template <bool GNF>
 struct Cfg {
-  static constexpr int kWStages = V == 1 ? 8 : (GNF ? 5 : 6);
-  static constexpr int kXSlots = V == 1 ? 2 : (GNF ? 3 : 2);
+  static constexpr int kWStages = GNF ? 5 : 6;
+  static constexpr int kXSlots = GNF ? 3 : 2;
   static constexpr int kTWarps = GNF ? 8 : 0;
   static constexpr int kThreads = kBaseThreads + 32 * kTWarps;
   static constexpr int kPipe = kWStages * kWBytes + kXSlots * kXSlot;
@@ -75,10 +72,10 @@ __device__ __forceinline__ void gn_transform_tile(uint8_t* tp, uint32_t inside, 
 }
 }  // namespace swh
 
-template <bool GNF, int V>
-__global__ void __launch_bounds__(swh::Cfg<GNF, V>::kThreads, 1) conv_swap_halo_kernel(const __grid_constant__ ConvGemmParams p) {
+template <bool GNF>
+__global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_kernel(const __grid_constant__ ConvGemmParams p) {
   using namespace swh;
-  constexpr int kWStages = Cfg<GNF, V>::kWStages, kXSlots = Cfg<GNF, V>::kXSlots, kPipe = Cfg<GNF, V>::kPipe;
+  constexpr int kWStages = Cfg<GNF>::kWStages, kXSlots = Cfg<GNF>::kXSlots, kPipe = Cfg<GNF>::kPipe;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t x_base = smem_base + kWStages * kWBytes;
@@ -98,7 +95,7 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, V>::kThreads, 1) conv_swap_halo_
     for (int s = 0; s < kWStages; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
     for (int s = 0; s < kXSlots; ++s) { mbar_init(xfull_bar(s), 1); mbar_init(xempty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
-    if (GNF) for (int s = 0; s < kXSlots; ++s) mbar_init(xready_bar(s), Cfg<GNF, V>::kTWarps);  // one arrive per transform warp
+    if (GNF) for (int s = 0; s < kXSlots; ++s) mbar_init(xready_bar(s), Cfg<GNF>::kTWarps);  // one arrive per transform warp
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -359,18 +356,17 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, V>::kThreads, 1) conv_swap_halo_
   }
 }
 
-template <bool GNF, int V>
-static void swap_halo_launch_t(const ConvGemmParams& p, int grid, cudaStream_t st) {
-  static PerDeviceOnce attr;
-  attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<GNF, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::Cfg<GNF, V>::kSmem)); });
-  conv_swap_halo_kernel<GNF, V><<<grid, swh::Cfg<GNF, V>::kThreads, swh::Cfg<GNF, V>::kSmem, st>>>(p);
-  SDM_CUDA_OK(cudaGetLastError());
-}
-
 void conv_swap_halo_launch(const ConvGemmParams& p, int grid, cudaStream_t st) {
-  static const int v = [] { const char* e = getenv("SDM_SWH_CFG"); return e ? atoi(e) : 0; }();
-  if (p.gn_ab) { if (v == 1) swap_halo_launch_t<true, 1>(p, grid, st); else swap_halo_launch_t<true, 0>(p, grid, st); }
-  else { if (v == 1) swap_halo_launch_t<false, 1>(p, grid, st); else swap_halo_launch_t<false, 0>(p, grid, st); }
+  if (p.gn_ab) {
+    static PerDeviceOnce attr;
+    attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::Cfg<true>::kSmem)); });
+    conv_swap_halo_kernel<true><<<grid, swh::Cfg<true>::kThreads, swh::Cfg<true>::kSmem, st>>>(p);
+  } else {
+    static PerDeviceOnce attr;
+    attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::Cfg<false>::kSmem)); });
+    conv_swap_halo_kernel<false><<<grid, swh::Cfg<false>::kThreads, swh::Cfg<false>::kSmem, st>>>(p);
+  }
+  SDM_CUDA_OK(cudaGetLastError());
 }
 
 }  // namespace sdm
