@@ -160,7 +160,8 @@ def run_reference(args):
     sd = synth.make_checkpoint(seed=1234)
     R = args.ref_size or args.size
     rate, dt, done, desc = cpu_oracle_rate(R, max(1, args.steps), threads, sd, max_seconds=args.ref_budget_s)
-    sample = (f"{desc}; each step = ONE matte of the bs={args.batch} batch at the workload's own resolution; {done} of {args.steps} requested "
+    where = "at the workload's own resolution" if R == args.size else f"at {R}x{R} INSTEAD of the workload's {args.size}x{args.size} (--ref-size; not comparable)"
+    sample = (f"{desc}; each step = ONE matte of the bs={args.batch} batch {where}; {done} of {args.steps} requested "
               f"steps executed (time-bounded at {args.ref_budget_s:.0f} s, no warm-up: a matte takes minutes)")
     line = {
         "impl": "reference", "metric": f"mattes/sec @{args.size}^2 bs={args.batch}", "value": rate, "unit": "mattes/s", "n_gpus": args.gpus,
