@@ -23,7 +23,8 @@
 // exponentials) the shared-memory traffic halves, the 64-register P array disappears (no setmaxnreg, no spills) and the
 // per-tile publication tail is a tcgen05.wait::st.
 // Per key tile a warpgroup pulls S(j) out of TMEM in four 32-column chunks, the next chunk's tcgen05.ld in flight while the
-// current one is exponentiated.  S is produced and released in two 64-key halves: the low half is handed back to the tensor
+// current one is exponentiated (PIPE, the biased kernels: also across tile boundaries — chunk 0 of tile j+1 is requested before
+// chunk 3 of tile j is exponentiated; the other kernels load chunks 0 and 1 together at the top of a tile).  S is produced and released in two 64-key halves: the low half is handed back to the tensor
 // core as soon as chunks 0-1 sit in registers (the very start of the tile), the high half once chunks 2-3 do, so S(j+1) is
 // complete long before the warpgroup needs it.  O_X accumulates in TMEM over all key tiles.
 // Softmax reference (lazy, optimistic): a chunk is exponentiated against the current reference m2 FIRST; its sum doubles as
@@ -39,9 +40,10 @@
 // instead of one thread polling the ~12 barriers of both tiles round-robin.  ncu r1p/r1q: the single poller was the bottleneck
 // (the softmax warps waited 25 % of their time for S_hi(j), issued late): same box, B2 h5 16384 x 16384: 501 -> 622 TFLOP/s;
 // in the step cross attention 54.1 -> 42.4 ms.
-// An FMA-pipe polynomial exp2 (degree 4, packed fp32x2) for 4 / 8 of the 16 column pairs of a chunk was measured twice and
-// removed: under the polling issuer (r1o) 519 -> 494 / 464 TFLOP/s at L0, under the sequenced issuers (r1v) 623 -> 603 / 550:
-// the softmax warps are bound by their dependent instruction chain, not by MUFU throughput (XU pipe 65 % in ncu r1q).
+// An FMA-pipe polynomial exp2 (degree 4, packed fp32x2) for 4 / 8 of the 16 column pairs of a chunk was measured three times
+// and removed: under the polling issuer (r1o) 519 -> 494 / 464 TFLOP/s at L0, under the sequenced issuers (r1v) 623 -> 603 /
+// 550, and again with the warp-uniform issuers (r3a: 690 -> 653 / 619 / 559 for 1/4, 1/3, 1/2 of the pairs): the softmax warps
+// are bound by their dependent instruction chain and issue slots, not by MUFU throughput (XU pipe 65 % in ncu r1q).
 // Self-attention only streams the keys that can have a non-zero probability (p.ntiles, see key_compact_kernel).
 // The per-key bias is expected pre-multiplied by log2(e); scores are handled in the log2 domain, statistics in fp32,
 // and scores are NOT rounded to fp16 before the softmax (the reference does).
@@ -88,7 +90,7 @@ __device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, __half2 s) {
 
 // TAIL: Lk is not a multiple of 128 and there is no bias to carry the -inf padding (never the case inside the engine;
 // kept out of the common instantiations: even skipped, the masking code cost a BSSY/branch per chunk and i-cache misses)
-template <bool HAS_BIAS, bool TAIL>
+template <bool HAS_BIAS, bool TAIL, bool PIPE>
 __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
   using namespace a7;
   extern __shared__ uint8_t smem_raw[];
@@ -229,17 +231,21 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
     int s = 0;
     uint32_t ph = 0;
 
+    uint32_t r0[32], r1[32];  // S chunks: even chunks in r0, odd in r1
     for (int j = 0; j < n; ++j) {
       const bool tail = TAIL && (j == n - 1);
       const int kbase = j * 128;
       if (HAS_BIAS) mbar_wait(kv_full(s), ph);  // bias tile visible to this thread
-      mbar_wait(s_full(x, 0), (uint32_t)j & 1u);
-      tc_fence_after();
+      if (!PIPE || j == 0) {
+        mbar_wait(s_full(x, 0), (uint32_t)j & 1u);
+        tc_fence_after();
+      }
       const uint2* bias2 = reinterpret_cast<const uint2*>(base_ptr + kOffBias + s * 512);
       float rowsum = 0.f;
-      uint32_t r0[32], r1[32];
-      tmem_ld32(t_s, r0);
-      tmem_ld32(t_s + 32, r1);
+      if (!PIPE || j == 0) {
+        tmem_ld32(t_s, r0);
+        if (!PIPE) tmem_ld32(t_s + 32, r1);
+      }
 
       // one 32-key chunk c (runtime, 0..3) held in rr: exponentiate, pack, (rarely) redo, store to P
       auto chunk = [&](uint32_t (&rr)[32], int c) {
@@ -335,6 +341,31 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
         rowsum += csum;
       };
 
+      if (PIPE) {
+        // one S chunk always in flight, across tile boundaries too: chunk g+1 is requested before chunk g is exponentiated
+        tmem_ld_wait();              // chunk 0 (requested during the previous tile's chunk 3)
+        tmem_ld32(t_s + 32, r1);
+        chunk(r0, 0);
+        tmem_ld_wait();              // chunk 1 landed: the low half may be overwritten with S_lo(j+1)
+        tc_fence_before();
+        mbar_arrive(s_free(x, 0));
+        mbar_wait(s_full(x, 1), (uint32_t)j & 1u);
+        tc_fence_after();
+        tmem_ld32(t_s + 64, r0);
+        chunk(r1, 1);
+        tmem_ld_wait();
+        tmem_ld32(t_s + 96, r1);
+        chunk(r0, 2);
+        tmem_ld_wait();              // chunk 3 landed: the high half may be overwritten with S_hi(j+1)
+        tc_fence_before();
+        mbar_arrive(s_free(x, 1));
+        if (j + 1 < n) {
+          mbar_wait(s_full(x, 0), (uint32_t)(j + 1) & 1u);  // S_lo(j+1): issued when the low half was released
+          tc_fence_after();
+          tmem_ld32(t_s, r0);
+        }
+        chunk(r1, 3);
+      } else {
       tmem_ld_wait();
       // chunks 0-1 are in registers: the tensor core may overwrite the low half with S_lo(j+1) already
       tc_fence_before();
@@ -356,6 +387,7 @@ __global__ void __launch_bounds__(a7::kThreads, 1) attention_kernel(const __grid
           tmem_ld_wait();
           tmem_ld32(t_s + 96, r1);   // chunk 3 in flight while chunk 2 is processed
         }
+      }
       }
       l += rowsum;
       tmem_st_wait();
@@ -440,9 +472,11 @@ std::shared_ptr<AttnLaunch> attn_build(const AttnDesc& d) {
 
 template <bool HB, bool TL>
 static void attn_launch(const AttnLaunch& l, cudaStream_t st) {
+  // PIPE = HAS_BIAS: same box (profiles/r3b_attn_pipe.txt) the continuous chunk pipeline is +12 % on the biased self attention
+  // (656 vs 584 TFLOP/s at level 0) and -1 % on cross attention, which keeps the two-chunk form
   static PerDeviceOnce attr;  // function attributes are per device: a second GPU in the same process needs them too
-  attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<HB, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem)); });
-  attention_kernel<HB, TL><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
+  attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(attention_kernel<HB, TL, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, a7::kSmem)); });
+  attention_kernel<HB, TL, HB><<<l.grid, a7::kThreads, a7::kSmem, st>>>(l.p);
 }
 
 void attn_run(const AttnLaunch& l, cudaStream_t st) {
