@@ -24,18 +24,29 @@ namespace sdm {
 
 namespace swh {
 constexpr int kWBytes = 128 * 128;    // weight tile: 128 channels x 64 k (fp16)
-constexpr int kXSlot = 44 * 1024;     // halo tile: 10 x 34 pixel rows of 128 B = 43 520 B, rounded up to the 1024-byte swizzle atom
-constexpr int kXTx = 10 * 34 * 128;   // bytes one halo box delivers
-constexpr int kXDense = 256 * 128;    // residual: dense 8 x 32 box
 constexpr int kStgBytes = 4 * 2048;
 constexpr int kBaseThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
-constexpr int kXRows = 10 * 34;    // pixel rows of a halo tile
 // GNF: the slot of a halo tile is busy for (TMA flight + transform + nine taps of MMAs) instead of (TMA flight + MMAs): a third
 // slot (paid for with one weight stage) keeps the tensor core fed; 8 transform warps (r2b: 4 warps with a branch per piece made
 // the fused conv 35 % slower than conv + separate apply pass, i.e. no net gain)
-template <bool GNF>
+// PAIR (r3d): the 8 x 32 patch x 256 output channels is computed by a CTA PAIR (cluster of two, tcgen05 cta_group::2, M = 256):
+// CTA r holds the weights of channel tile 2g + r, the HALF patch of rows [16 r, 16 r + 16) (its (8+2) x (16+2) halo tile) and
+// the 128 x 256 accumulator of its channels.  Why: the single-CTA kernel is bound by SHARED-MEMORY BANDWIDTH (128 B/clk/SM), not by
+// the tensor pipe, L2 or the issuer: per M128 x N256 x K16 MMA (128 clk) the tensor core reads 12 KB of operands (96 B/clk), the
+// TMA unit writes 41 B/clk (weights 32, halo tile 9.4), the GroupNorm transform reads + writes 19 and the epilogue staging 7:
+// 163 B/clk -> 163 clk per MMA predicted, 156 measured net of all barrier waits (profiles/r3c_kbench_mc_after_fix.txt; the same
+// sum explains the probe's 134-137 clk with TMA streams only and the nominal rate of the no-TMA bisect variant).  In a pair each
+// SM reads 4 KB of A + its 4 KB half of B per MMA (64 B/clk) and fills / transforms half a halo tile: 118 B/clk.
+template <bool GNF, bool PAIR = false>
 struct Cfg {
-  static constexpr int kWStages = GNF ? 5 : 6;
+  static_assert(!PAIR || GNF, "the pair kernel exists in its fused-GroupNorm form only");
+  static constexpr int kTileRows = PAIR ? 16 : 32;              // patch rows whose pixels this CTA holds
+  static constexpr int kXRows = 10 * (kTileRows + 2);           // pixel rows of a halo tile (340 / 180)
+  static constexpr int kXSlot = PAIR ? 23 * 1024 : 44 * 1024;   // 43 520 / 23 040 B rounded up to the 1024-byte swizzle atom
+  static constexpr int kXTx = kXRows * 128;                     // bytes one halo box delivers
+  static constexpr int kXDense = 8 * kTileRows * 128;           // residual: dense 8 x 32 (8 x 16) box
+  static constexpr int kPieces = (kXRows + 31) / 32;            // 16-byte pieces per transform thread (11 / 6)
+  static constexpr int kWStages = PAIR ? 8 : (GNF ? 5 : 6);
   static constexpr int kXSlots = GNF ? 3 : 2;
   static constexpr int kTWarps = GNF ? 8 : 0;
   static constexpr int kThreads = kBaseThreads + 32 * kTWarps;
@@ -48,21 +59,21 @@ struct Cfg {
 // one thread's share of a halo tile: pieces (r0 + 32 k, piece), k = 0..10; `exist` bit k: the row is part of the tile,
 // `inside` bit k: its pixel lies inside the image (rows outside stay / become zero: the conv pads the NORMALISED tensor).
 // Branch-free and unrolled four pieces deep, so that 16 independent channel-pair chains are in flight per thread.
-template <bool SILU>
+template <bool SILU, int NP>
 __device__ __forceinline__ void gn_transform_tile(uint8_t* tp, uint32_t inside, uint32_t exist, const uint64_t (&ka)[4], const uint64_t (&ks)[4]) {
 #pragma unroll
-  for (int g = 0; g < 3; ++g) {
+  for (int g = 0; g < (NP + 3) / 4; ++g) {
     uint4 v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = g * 4 + j;
       v[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (k < 11 && ((exist >> k) & 1u)) v[j] = *reinterpret_cast<const uint4*>(tp + k * 4096);
+      if (k < NP && ((exist >> k) & 1u)) v[j] = *reinterpret_cast<const uint4*>(tp + k * 4096);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = g * 4 + j;
-      if (k < 11) {
+      if (k < NP) {
         uint4 o = gn_piece<SILU, true>(v[j], ka, ks);
         if (!((inside >> k) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);
         if ((exist >> k) & 1u) *reinterpret_cast<uint4*>(tp + k * 4096) = o;
@@ -72,10 +83,20 @@ __device__ __forceinline__ void gn_transform_tile(uint8_t* tp, uint32_t inside, 
 }
 }  // namespace swh
 
-template <bool GNF>
-__global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_kernel(const __grid_constant__ ConvGemmParams p) {
+template <bool GNF, bool PAIR>
+__global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_halo_kernel(const __grid_constant__ ConvGemmParams p) {
   using namespace swh;
-  constexpr int kWStages = Cfg<GNF>::kWStages, kXSlots = Cfg<GNF>::kXSlots, kPipe = Cfg<GNF>::kPipe;
+  using C = Cfg<GNF, PAIR>;
+  constexpr int kWStages = C::kWStages, kXSlots = C::kXSlots, kPipe = C::kPipe, kXSlot = C::kXSlot, kXRows = C::kXRows;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  // work items: (pixel tile, channel tile) per CTA, or (pixel tile, PAIR of channel tiles) per cluster; channel tiles fastest
+  const int item_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_groups = PAIR ? (p.n_tiles >> 1) : p.n_tiles;
+  const int item_count = p.m_tiles * n_groups;
+  auto item_n0 = [&](int item) { return ((item % n_groups) * (PAIR ? 2 : 1) + (int)rank) * 128; };  // this CTA's first output channel
+  auto item_mt = [&](int item) { return item / n_groups; };
+  const int yoff = PAIR ? 16 * (int)rank : 0;  // first patch row of this CTA's half
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t x_base = smem_base + kWStages * kWBytes;
@@ -94,14 +115,19 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWStages; ++s) { mbar_init(wfull_bar(s), 1); mbar_init(wempty_bar(s), 1); }
     for (int s = 0; s < kXSlots; ++s) { mbar_init(xfull_bar(s), 1); mbar_init(xempty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
-    if (GNF) for (int s = 0; s < kXSlots; ++s) mbar_init(xready_bar(s), Cfg<GNF>::kTWarps);  // one arrive per transform warp
+    // PAIR: the leader's MMA thread waits for the epilogue / transform warps of BOTH CTAs
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR ? 8 : 4); }
+    if (GNF) for (int s = 0; s < kXSlots; ++s) mbar_init(xready_bar(s), (PAIR ? 2 : 1) * C::kTWarps);  // one arrive per transform warp
     fence_barrier_init();
     fence_proxy_async_smem();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -109,7 +135,7 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
   //   32: the halo tile always comes from the first patch of the tensor (L2-hot, no zero fill)
   //   128: no operand traffic at all: the producers stay idle, the MMA issuer and the transform warps do not wait for operands
   const bool dbg_hot_x = p.gn_silu & 32, dbg_no_tma = p.gn_silu & 128, dbg_no_wait = dbg_no_tma;
-  const int nres = p.has_res ? 2 : 0;
+  const int nres = p.has_res ? (PAIR ? 4 : 2) : 0;  // residual K slices: 64 of the tile's (pair's) output channels each
   int nslices = 0;
   for (int s = 0; s < p.nsrc; ++s) nslices += p.src_c[s] >> 6;
   const int per_image = p.tiles_x * p.tiles_y;
@@ -124,36 +150,38 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
       tma_prefetch_desc(&p.b_map);
       int ws = 0;
       uint32_t wph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.n_tiles) * 128;
-        for (int sl = 0; sl < nslices; ++sl) {  // slice sl = K columns [64 sl, 64 sl + 64) of every tap
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(wempty_bar(ws), wph ^ 1u);
-            mbar_expect_tx(wfull_bar(ws), kWBytes);
-            tma_load_2d(smem_base + ws * kWBytes, &p.b_map, wfull_bar(ws), tap * p.cin_total + sl * 64, n0);
-            if (++ws == kWStages) { ws = 0; wph ^= 1u; }
-          }
-        }
-        for (int i = 0; i < nres; ++i) {  // D^T[c][pix] += I[c][64 i + k] . R[pix][n0 + 64 i + k]
-          mbar_wait(wempty_bar(ws), wph ^ 1u);
+      // PAIR: every transaction byte of both CTAs' weight tiles is accounted on the LEADER's full barrier
+      auto load_w = [&](const CUtensorMap* map, int c0, int c1) {
+        mbar_wait(wempty_bar(ws), wph ^ 1u);
+        if constexpr (PAIR) {
+          if (rank == 0) mbar_expect_tx(wfull_bar(ws), 2 * kWBytes);
+          tma_load_2d_pair(smem_base + ws * kWBytes, map, mapa_shared(wfull_bar(ws), 0), c0, c1);
+        } else {
           mbar_expect_tx(wfull_bar(ws), kWBytes);
-          tma_load_2d(smem_base + ws * kWBytes, &p.i_map, wfull_bar(ws), 64 * i, 0);
-          if (++ws == kWStages) { ws = 0; wph ^= 1u; }
+          tma_load_2d(smem_base + ws * kWBytes, map, wfull_bar(ws), c0, c1);
         }
+        if (++ws == kWStages) { ws = 0; wph ^= 1u; }
+      };
+      for (int item = item_first; item < item_count; item += item_step) {
+        const int n0 = item_n0(item);
+        for (int sl = 0; sl < nslices; ++sl)  // slice sl = K columns [64 sl, 64 sl + 64) of every tap
+          for (int tap = 0; tap < 9; ++tap) load_w(&p.b_map, tap * p.cin_total + sl * 64, n0);
+        // D^T[c][pix] += I[c][64 i + k] . R[pix][g0 + 64 i + k], g0 = first channel of the tile (pair): rows 128 rank .. of the identity
+        for (int i = 0; i < nres; ++i) load_w(&p.i_map, 64 * i, 128 * (int)rank);
       }
     } else if (lane == 1 && !dbg_no_tma) {
       tma_prefetch_desc(&p.a_map[0]); tma_prefetch_desc(&p.a_map[1]);
       int xs = 0;
       uint32_t xph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % p.n_tiles) * 128;
-        const int mt = tile / p.n_tiles;
+      for (int item = item_first; item < item_count; item += item_step) {
+        const int g0 = item_n0(item) - 128 * (int)rank;  // first output channel of the tile (pair)
+        const int mt = item_mt(item);
         const int t_img = mt % per_image;
-        const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32, b = mt / per_image;
+        const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32 + yoff, b = mt / per_image;
         for (int s = 0; s < p.nsrc; ++s) {
           for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
             mbar_wait(xempty_bar(xs), xph ^ 1u);
-            mbar_expect_tx(xfull_bar(xs), kXTx);
+            mbar_expect_tx(xfull_bar(xs), C::kXTx);
             if (dbg_hot_x) tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, 0, 0, 0);
             else tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, x0 - 1, y0 - 1, b);  // zero fill = conv padding
             if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
@@ -161,22 +189,22 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
         }
         for (int i = 0; i < nres; ++i) {  // dense residual box in a halo slot
           mbar_wait(xempty_bar(xs), xph ^ 1u);
-          mbar_expect_tx(xfull_bar(xs), kXDense);
-          tma_load_4d(x_base + xs * kXSlot, &p.r_map, xfull_bar(xs), n0 + 64 * i, x0, y0, b);
+          mbar_expect_tx(xfull_bar(xs), C::kXDense);
+          tma_load_4d(x_base + xs * kXSlot, &p.r_map, xfull_bar(xs), g0 + 64 * i, x0, y0, b);
           if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
+    // ============================== MMA issuer (PAIR: the leader CTA's only) ==============================
     // The WHOLE warp runs this loop convergently and one elected lane issues the tcgen05 instructions.  With the loop inside an
     // `if (lane == 0)` (rounds 1 / 2 up to r2u) the descriptors lived in per-thread registers of a divergent region and the
     // compiler wrapped EVERY tcgen05.mma in an ELECT / 5 x R2UR.BROADCAST / BRA.U.ANY loop (SASS): ~17 dependent instructions per
     // MMA on top of the per-tap wait, fence and descriptor arithmetic — the issuing thread, not the tensor core or the operand
     // supply, was the limit (r2u: with the operand waits removed the same kernel ran 1.3x faster; tests/probe_mma_rate.cu).
-    {
+    if (!PAIR || rank == 0) {
       const bool leader = elect_one();
-      constexpr uint32_t idesc = umma_idesc_f16(256);
+      constexpr uint32_t idesc = PAIR ? umma_idesc_f16_m256(256) : umma_idesc_f16(256);
       int ws = 0, xs = 0, acc = 0;
       uint32_t wph = 0, xph = 0, acc_phase = 0;
       // SDM_GEMM_PROF=1 (measurement aid): cycles the issuing thread waited for a free accumulator / a (normalised) pixel tile /
@@ -184,10 +212,12 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
       long long pw_acc = 0, pw_x = 0, pw_w = 0;
       const long long prof_t0 = p.prof ? clock64() : 0;
       auto timed_wait = [&](uint32_t bar, uint32_t ph, long long& accum) {
-        if (p.prof) { const long long t = clock64(); mbar_wait(bar, ph); accum += clock64() - t; }
+        const long long t = p.prof ? clock64() : 0;
+        if constexpr (PAIR) mbar_wait_cluster(bar, ph);  // arrivals (and the shared-memory writes behind them) come from the peer CTA too
         else mbar_wait(bar, ph);
+        if (p.prof) accum += clock64() - t;
       };
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int item = item_first; item < item_count; item += item_step) {
         timed_wait(tempty_bar(acc), acc_phase ^ 1u, pw_acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
@@ -203,18 +233,24 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
             const uint64_t bdesc = resid ? umma_desc_k128(x_addr)
                                          : umma_desc_k128_sbo(x_addr + (uint32_t)((tap / 3) * 10 + tap % 3) * 128u, 1280);
             if (leader) {
+              if constexpr (PAIR) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (sl | tap | k) != 0);
-              umma_commit(wempty_bar(ws));
+                for (int k = 0; k < 4; ++k) umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (sl | tap | k) != 0);
+                umma_commit_pair(wempty_bar(ws));  // frees the stage in both CTAs
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (sl | tap | k) != 0);
+                umma_commit(wempty_bar(ws));
+              }
             }
             __syncwarp();
             if (++ws == kWStages) { ws = 0; wph ^= 1u; }
           }
-          if (leader) umma_commit(xempty_bar(xs));
+          if (leader) { if constexpr (PAIR) umma_commit_pair(xempty_bar(xs)); else umma_commit(xempty_bar(xs)); }
           __syncwarp();
           if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
         }
-        if (leader) umma_commit(tfull_bar(acc));
+        if (leader) { if constexpr (PAIR) umma_commit_pair(tfull_bar(acc)); else umma_commit(tfull_bar(acc)); }
         __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
@@ -227,27 +263,32 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
     const int t = threadIdx.x - kBaseThreads;  // 0..255
     const int piece = t & 7, r0 = t >> 3;      // rows r0, r0 + 32, ... of the tile; r & 7 == r0 & 7 for all of them
     const int chunk = piece ^ (r0 & 7);        // channel chunk (8 channels) this thread's pieces hold
-    const uint32_t exist = r0 < kXRows - 320 ? 0x7ffu : 0x3ffu;  // row r0 + 320 exists for r0 < 20
+    constexpr int NP = C::kPieces;
+    const uint32_t exist = r0 < kXRows - 32 * (NP - 1) ? (1u << NP) - 1u : (1u << (NP - 1)) - 1u;  // the last piece row exists for r0 < 20
+    auto publish = [&](int slot) {  // this warp's share of the slot's tile is final (PAIR: tell the leader CTA's MMA thread)
+      if constexpr (PAIR) mbar_arrive_cluster_release(mapa_shared(xready_bar(slot), 0));
+      else mbar_arrive(xready_bar(slot));
+    };
     int xs = 0;
     uint32_t xph = 0;
     // (scale, shift) of this thread's 8 channels, one slice ahead: ncu r2f — fetched at the top of every slice the constants cost
     // one exposed L2 round trip per slice (30 % of the kernel's stall samples sat on their first use)
-    auto load_raw = [&](int tile_, int slice, float4 (&raw)[4]) {
-      const int b_ = (tile_ / p.n_tiles) / per_image;
+    auto load_raw = [&](int item_, int slice, float4 (&raw)[4]) {
+      const int b_ = item_mt(item_) / per_image;
       const float4* src = reinterpret_cast<const float4*>(p.gn_ab + ((size_t)b_ * p.cin_total + slice * 64 + chunk * 8) * 2);
 #pragma unroll
       for (int j = 0; j < 4; ++j) raw[j] = __ldg(src + j);
     };
     float4 raw[4];
-    if ((int)blockIdx.x < p.total_tiles) load_raw(blockIdx.x, 0, raw);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles;
+    if (item_first < item_count) load_raw(item_first, 0, raw);
+    for (int item = item_first; item < item_count; item += item_step) {
+      const int mt = item_mt(item);
       const int t_img = mt % per_image;
-      const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32;
+      const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32 + yoff;
       // validity of this thread's rows depends on the tile position only: bit k = row r0 + 32 k lies inside the image
       uint32_t inside = 0;
 #pragma unroll
-      for (int k = 0; k < 11; ++k) {
+      for (int k = 0; k < NP; ++k) {
         const int r = r0 + 32 * k;
         const int px = x0 - 1 + r % 10, py = y0 - 1 + r / 10;
         if (px >= 0 && px < p.W && py >= 0 && py < p.H) inside |= 1u << k;
@@ -258,26 +299,26 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
         if (p.gn_silu == 0) gn_consts_from_raw<false>(raw, ka, ks);
         else gn_consts_from_raw<true>(raw, ka, ks);
         // next slice's constants (or the first slice of this CTA's next tile) fly during the transform
-        if (sl + 1 < nslices) load_raw(tile, sl + 1, raw);
-        else if (tile + (int)gridDim.x < p.total_tiles) load_raw(tile + gridDim.x, 0, raw);
+        if (sl + 1 < nslices) load_raw(item, sl + 1, raw);
+        else if (item + item_step < item_count) load_raw(item + item_step, 0, raw);
         if (!dbg_no_tma) mbar_wait(xfull_bar(xs), xph);
         uint8_t* tp = smem_raw + (x_base + xs * kXSlot - smem_u32(smem_raw)) + r0 * 128 + piece * 16;
-        if (p.gn_silu == 1) gn_transform_tile<true>(tp, inside, exist, ka, ks);
-        else if (p.gn_silu == 0) gn_transform_tile<false>(tp, inside, exist, ka, ks);
+        if (p.gn_silu == 1) gn_transform_tile<true, NP>(tp, inside, exist, ka, ks);
+        else if (p.gn_silu == 0) gn_transform_tile<false, NP>(tp, inside, exist, ka, ks);
         else if (p.gn_silu == 4) {  // measurement aid (tests/bench_kernels.py): shared-memory traffic of the transform without its math
 #pragma unroll
-          for (int k = 0; k < 11; ++k)
+          for (int k = 0; k < NP; ++k)
             if ((exist >> k) & 1u) { uint4* q = reinterpret_cast<uint4*>(tp + k * 4096); uint4 v = *q; v.x ^= inside; *q = v; }
         }  // gn_silu == 2 (measurement aid): no transform at all, only the extra barrier hop
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(xready_bar(xs));
+        if (lane == 0) publish(xs);
         if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
       }
       for (int i = 0; i < nres; ++i) {  // residual boxes pass through untouched
         mbar_wait(xfull_bar(xs), xph);
         __syncwarp();
-        if (lane == 0) mbar_arrive(xready_bar(xs));
+        if (lane == 0) publish(xs);
         if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
       }
     }
@@ -288,11 +329,11 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
     uint8_t* stg = smem_raw + (bar_base - smem_u32(smem_raw)) + 256 + (warp - 2) * 2048;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int item = item_first; item < item_count; item += item_step) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int n0 = (tile % p.n_tiles) * 128;
-      const int mt = tile / p.n_tiles;
+      const int n0 = item_n0(item);
+      const int mt = item_mt(item);
       const int t_img = mt % per_image;
       const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32, b = mt / per_image;
       const float bias = p.bias ? p.bias[(p.bias_sel ? (long long)p.bias_sel[b] * p.N : 0) + n0 + m] : 0.f;
@@ -343,30 +384,53 @@ __global__ void __launch_bounds__(swh::Cfg<GNF>::kThreads, 1) conv_swap_halo_ker
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));  // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA frees tensor memory (or exits) while the pair's MMAs / remote arrives are in flight
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 
-void conv_swap_halo_launch(const ConvGemmParams& p, int grid, cudaStream_t st) {
-  if (p.gn_ab) {
-    static PerDeviceOnce attr;
-    attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::Cfg<true>::kSmem)); });
-    conv_swap_halo_kernel<true><<<grid, swh::Cfg<true>::kThreads, swh::Cfg<true>::kSmem, st>>>(p);
+template <bool GNF, bool PAIR>
+static void swap_halo_launch_t(const ConvGemmParams& p, int grid, cudaStream_t st) {
+  using C = swh::Cfg<GNF, PAIR>;
+  static PerDeviceOnce attr;
+  attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<GNF, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem)); });
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(C::kThreads);
+  cfg.dynamicSmemBytes = C::kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = PAIR ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  SDM_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_swap_halo_kernel<GNF, PAIR>, p));
+}
+
+// pair: CTA pairs (cta_group::2) over 256 output channels; needs the fused GroupNorm form, N % 256 == 0, an even grid and the
+// half-patch tensor-map boxes (conv_gemm_build)
+void conv_swap_halo_launch(const ConvGemmParams& p, int grid, bool pair, cudaStream_t st) {
+  if (pair) {
+    SDM_CHECK(p.gn_ab != nullptr && (p.n_tiles & 1) == 0 && (grid & 1) == 0, "pair launch preconditions");
+    swap_halo_launch_t<true, true>(p, grid, st);
+  } else if (p.gn_ab) {
+    swap_halo_launch_t<true, false>(p, grid, st);
   } else {
-    static PerDeviceOnce attr;
-    attr([] { SDM_CUDA_OK(cudaFuncSetAttribute(conv_swap_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, swh::Cfg<false>::kSmem)); });
-    conv_swap_halo_kernel<false><<<grid, swh::Cfg<false>::kThreads, swh::Cfg<false>::kSmem, st>>>(p);
+    swap_halo_launch_t<false, false>(p, grid, st);
   }
-  SDM_CUDA_OK(cudaGetLastError());
 }
 
 }  // namespace sdm

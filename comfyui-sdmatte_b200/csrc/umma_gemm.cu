@@ -11,7 +11,7 @@
 namespace sdm {
 
 void conv_swap_launch(const ConvGemmParams& p, int grid, cudaStream_t st);       // conv_swap.cu
-void conv_swap_halo_launch(const ConvGemmParams& p, int grid, cudaStream_t st);  // conv_swap_halo.cu
+void conv_swap_halo_launch(const ConvGemmParams& p, int grid, bool pair, cudaStream_t st);  // conv_swap_halo.cu
 
 struct ConvGemmLaunch {
   ConvGemmParams p;
@@ -21,6 +21,7 @@ struct ConvGemmLaunch {
   bool halo = false;  // 3x3 stride-1 conv with a resident halo tile per 64-channel slice
   bool swap = false;  // conv_swap_kernel: channels on M, 256 pixels on N (128-channel 3x3 convs)
   bool swap_halo = false;  // ... with a resident 8 x 32 pixel halo tile (conv_swap_halo.cu; carries the fused GroupNorm)
+  bool swap_pair = false;  // ... computed by CTA pairs (cta_group::2) over 256 output channels, half a patch per CTA
   int grid = 0;
   double flops = 0;
 };
@@ -191,6 +192,10 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
     L->mt = 1;
     L->block_n = 128;
     p.n_tiles = d.N / 128;
+    // CTA pairs: fused-GroupNorm form, an even number of channel tiles, at least one item per cluster (SDM_SWH_PAIR=0: A/B switch)
+    static const int env_pair = [] { const char* e = getenv("SDM_SWH_PAIR"); return e ? atoi(e) : 1; }();
+    L->swap_pair = L->swap_halo && d.gn_ab != nullptr && d.N % 256 == 0 && env_pair != 0 && num_sms % 2 == 0 &&
+                   m_tiles_eff * (p.n_tiles / 2) >= num_sms / 2;
   }
   p.m_tiles = (int)m_tiles_eff;
   const long long total = ((m_tiles_eff + L->mt - 1) / L->mt) * p.n_tiles;
@@ -208,7 +213,8 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
       const long long bs = d.src_bstride[s] ? d.src_bstride[s] : (long long)d.Hin * d.Win * d.src[s].ld;
       const uint64_t dims[4] = {(uint64_t)d.src[s].C, (uint64_t)d.Win, (uint64_t)d.Hin, (uint64_t)d.B};
       const uint64_t strides[3] = {(uint64_t)d.src[s].ld * 2, (uint64_t)d.Win * d.src[s].ld * 2, (uint64_t)bs * 2};
-      const uint32_t hbox[4] = {64u, (uint32_t)p.tw + 2u, (uint32_t)p.th + 2u, 1u};  // halo: (8+2) x (16+2) pixels, loaded at (x0-1, y0-1)
+      // halo: (8+2) x (16+2) pixels, loaded at (x0-1, y0-1); swapped kernel: (8+2) x (32+2), or per CTA of a pair (8+2) x (16+2)
+      const uint32_t hbox[4] = {64u, (uint32_t)p.tw + 2u, (uint32_t)(L->swap_pair ? p.th / 2 : p.th) + 2u, 1u};
       make_tmap(&p.a_map[s], d.src[s].ptr, 4, dims, strides, (L->halo || L->swap_halo) ? hbox : box);
     }
     for (int s = d.nsrc; s < 4; ++s) p.a_map[s] = p.a_map[0];
@@ -264,7 +270,8 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
     const long long bs = d.res_bstride ? d.res_bstride : (long long)Hout * Wout * d.res_ld;
     const uint64_t dims[4] = {(uint64_t)d.N, (uint64_t)Wout, (uint64_t)Hout, (uint64_t)d.B};
     const uint64_t strides[3] = {(uint64_t)d.res_ld * 2, (uint64_t)Wout * d.res_ld * 2, (uint64_t)bs * 2};
-    make_tmap(&p.r_map, d.res, 4, dims, strides, box);
+    const uint32_t rbox[4] = {64u, (uint32_t)p.tw, (uint32_t)(L->swap_pair ? p.th / 2 : p.th), 1u};  // pair: half a patch per CTA
+    make_tmap(&p.r_map, d.res, 4, dims, strides, rbox);
     const uint64_t idims[2] = {(uint64_t)kIdentityN, (uint64_t)kIdentityN};
     const uint64_t istr[1] = {(uint64_t)kIdentityN * 2};
     const uint32_t ibox[2] = {64u, L->swap ? 128u : 64u};  // swap: 128 channel rows x one 64-column slice
@@ -312,6 +319,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
     p.prof = env_prof;  // measurement aid: in-kernel cycle counters of the producer / MMA / epilogue threads
   }
   L->grid = (int)std::min<long long>(total, num_sms);
+  if (L->swap_pair) L->grid = 2 * (int)std::min<long long>(m_tiles_eff * (p.n_tiles / 2), num_sms / 2);  // whole clusters
   L->flops = 2.0 * (double)d.B * Hout * Wout * (double)d.N * (double)ktot;
   return L;
 }
@@ -324,7 +332,7 @@ void conv_gemm_run(const ConvGemmLaunch& l, cudaStream_t st) {
     if (l.ewg == 2) return conv_gemm_launch<BN, MT, MODE, UPS2, 2>(p, g, st); \
     return conv_gemm_launch<BN, MT, MODE, UPS2, 1>(p, g, st);                 \
   } while (0)
-  if (l.swap) return l.swap_halo ? conv_swap_halo_launch(p, g, st) : conv_swap_launch(p, g, st);
+  if (l.swap) return l.swap_halo ? conv_swap_halo_launch(p, g, l.swap_pair, st) : conv_swap_launch(p, g, st);
   if (l.halo) {
     if (bn == 256 && !p.ups2) return conv_gemm_launch_halo<256, 1, false, 1>(p, g, st);
     if (bn == 256 && p.ups2) return conv_gemm_launch_halo<256, 1, true, 1>(p, g, st);

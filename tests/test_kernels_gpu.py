@@ -668,6 +668,11 @@ def test_conv3x3_swapped_operands(eng_mod, B, H, W, C0, C1, Cout, res):
     (1, 96, 48, 128, 64, 128, True, 1),   # concat input: groups straddle the two sources
     (1, 32, 64, 256, 0, 256, False, 0),   # two N tiles, no SiLU
     (2, 128, 128, 64, 0, 128, False, 1),  # many tiles per CTA: slot ring wraps, per-tile validity masks change
+    # >= 74 (pixel tile, 256-channel) items: the CTA-PAIR form (cta_group::2, half a patch per CTA) is selected
+    (2, 128, 96, 256, 0, 256, False, 0),  # pair, no SiLU: bit for bit against the single-CTA unfused path
+    (4, 96, 64, 128, 0, 256, True, 0),    # pair + residual (four identity K slices, half-patch residual boxes), bit for bit
+    (1, 160, 96, 256, 128, 512, True, 1), # pair, two channel-tile pairs, concat input, residual, SiLU
+    (1, 224, 64, 512, 0, 512, False, 1),  # pair, eight input slices per tile: rings wrap many times inside one tile
 ])
 def test_conv3x3_fused_groupnorm(eng_mod, B, H, W, C0, C1, Cout, res, silu):
     """GroupNorm(32)(+SiLU) applied to the conv's resident input halo tile by the transform warps of conv_swap_halo_kernel<true>
