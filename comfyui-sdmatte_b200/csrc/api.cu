@@ -33,7 +33,7 @@ int device_sm_count() {
 
 extern "C" {
 
-int sdm_version(void) { return 200; }
+int sdm_version(void) { return 201; }
 const char* sdm_last_error(void) { return sdm::g_last_error.c_str(); }
 
 int sdm_create(sdm_handle** out, int device) {
@@ -185,6 +185,7 @@ int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream) {
   d.scale = a->scale; d.force_block_n = a->force_block_n;
   d.post_div = a->post_div == 0.f ? 1.f : a->post_div; d.n_store = a->n_store; d.out2 = a->out2; d.force_mt = a->force_mt; d.stats = a->stats; d.force_halo = a->force_halo; d.force_swap = a->force_swap;
   d.gn_ab = a->gn_ab; d.gn_silu = a->gn_silu;
+  d.poly = a->poly;
   auto l = sdm::conv_gemm_build(d, sdm::device_sm_count());
   sdm::conv_gemm_run(*l, reinterpret_cast<cudaStream_t>(stream));
   SDM_API_END
@@ -198,6 +199,8 @@ int sdm_k_conv_variant(int ksize, int stride, int mode, int ups2, int N, int has
 int sdm_k_conv_can_fuse_gn(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout) {
   return sdm::conv_gemm_can_fuse_gn(ksize, stride, mode, ups2, N, has_res, Hout, Wout) ? 1 : 0;
 }
+
+int sdm_k_conv_can_poly(int N, int Hin, int Win) { return sdm::conv_gemm_can_poly(N, Hin, Win) ? 1 : 0; }
 
 int sdm_k_attention(const sdm_attn_args* a, uintptr_t stream) {
   SDM_API_BEGIN

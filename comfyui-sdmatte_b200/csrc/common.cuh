@@ -300,6 +300,13 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* desc,
       "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const void* desc, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst) {  // the same warp index in BOTH CTAs, same smem offset
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(NCOLS) : "memory");
@@ -335,9 +342,14 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 // erf(z) by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 7 FMA-pipe ops.
 // Used by the GEGLU epilogue (exact-erf GELU of the reference, rounded to fp16 right after).
+// The reciprocal is rcp.approx (1 ulp; the argument lies in [1, inf)): __frcp_rn compiled to a range check + branch + MUFU.RCP +
+// Newton step + out-of-line slow path around EVERY element (SASS of the r2z GEGLU kernel: ~12 extra instructions and a
+// BSSY/BSYNC region per value, which also kept the 32 independent element chains of a slab from overlapping; ncu r3c: 48
+// instructions per output, issue slots 38 % busy, tensor pipe 16 %).
 __device__ __forceinline__ float erf_fast(float z) {
   const float a = fabsf(z);
-  const float t = __frcp_rn(fmaf(0.3275911f, a, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);

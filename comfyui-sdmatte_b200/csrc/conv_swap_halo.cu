@@ -39,7 +39,6 @@ constexpr int kBaseThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogu
 // SM reads 4 KB of A + its 4 KB half of B per MMA (64 B/clk) and fills / transforms half a halo tile: 118 B/clk.
 template <bool GNF, bool PAIR = false>
 struct Cfg {
-  static_assert(!PAIR || GNF, "the pair kernel exists in its fused-GroupNorm form only");
   static constexpr int kTileRows = PAIR ? 16 : 32;              // patch rows whose pixels this CTA holds
   static constexpr int kXRows = 10 * (kTileRows + 2);           // pixel rows of a halo tile (340 / 180)
   static constexpr int kXSlot = PAIR ? 23 * 1024 : 44 * 1024;   // 43 520 / 23 040 B rounded up to the 1024-byte swizzle atom
@@ -47,7 +46,7 @@ struct Cfg {
   static constexpr int kXDense = 8 * kTileRows * 128;           // residual: dense 8 x 32 (8 x 16) box
   static constexpr int kPieces = (kXRows + 31) / 32;            // 16-byte pieces per transform thread (11 / 6)
   static constexpr int kWStages = PAIR ? 8 : (GNF ? 5 : 6);
-  static constexpr int kXSlots = GNF ? 3 : 2;
+  static constexpr int kXSlots = (GNF || PAIR) ? 3 : 2;  // (pair: half-size slots; with four taps per slice — polyphase form — two turn over too fast)
   static constexpr int kTWarps = GNF ? 8 : 0;
   static constexpr int kThreads = kBaseThreads + 32 * kTWarps;
   static constexpr int kPipe = kWStages * kWBytes + kXSlots * kXSlot;
@@ -97,6 +96,10 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_ha
   auto item_n0 = [&](int item) { return ((item % n_groups) * (PAIR ? 2 : 1) + (int)rank) * 128; };  // this CTA's first output channel
   auto item_mt = [&](int item) { return item / n_groups; };
   const int yoff = PAIR ? 16 * (int)rank : 0;  // first patch row of this CTA's half
+  // polyphase form of "nearest x2 upsample -> 3x3 conv" (p.poly = 1 + 2 py + px): four taps (dy, dx) in {0,1}^2 whose windows start
+  // (dy + py, dx + px) halo pixels into the tile; output pixel (y, x) of the grid is stored at (2y + py, 2x + px) of a (2H, 2W) image
+  const int ppy = p.poly ? ((p.poly - 1) >> 1) : 0, ppx = p.poly ? ((p.poly - 1) & 1) : 0;
+  const int ntaps = p.ntaps;  // 9, or 4 (polyphase)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t x_base = smem_base + kWStages * kWBytes;
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_ha
       for (int item = item_first; item < item_count; item += item_step) {
         const int n0 = item_n0(item);
         for (int sl = 0; sl < nslices; ++sl)  // slice sl = K columns [64 sl, 64 sl + 64) of every tap
-          for (int tap = 0; tap < 9; ++tap) load_w(&p.b_map, tap * p.cin_total + sl * 64, n0);
+          for (int tap = 0; tap < ntaps; ++tap) load_w(&p.b_map, tap * p.cin_total + sl * 64, n0);
         // D^T[c][pix] += I[c][64 i + k] . R[pix][g0 + 64 i + k], g0 = first channel of the tile (pair): rows 128 rank .. of the identity
         for (int i = 0; i < nres; ++i) load_w(&p.i_map, 64 * i, 128 * (int)rank);
       }
@@ -181,16 +184,26 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_ha
         for (int s = 0; s < p.nsrc; ++s) {
           for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
             mbar_wait(xempty_bar(xs), xph ^ 1u);
-            mbar_expect_tx(xfull_bar(xs), C::kXTx);
-            if (dbg_hot_x) tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, 0, 0, 0);
-            else tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, x0 - 1, y0 - 1, b);  // zero fill = conv padding
+            if constexpr (PAIR && !GNF) {  // no transform warps in between: the leader's MMA thread waits for both halves directly
+              if (rank == 0) mbar_expect_tx(xfull_bar(xs), 2 * C::kXTx);
+              tma_load_4d_pair(x_base + xs * kXSlot, &p.a_map[s], mapa_shared(xfull_bar(xs), 0), c0, x0 - 1, y0 - 1, b);
+            } else {
+              mbar_expect_tx(xfull_bar(xs), C::kXTx);
+              if (dbg_hot_x) tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, 0, 0, 0);
+              else tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, x0 - 1, y0 - 1, b);  // zero fill = conv padding
+            }
             if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
           }
         }
         for (int i = 0; i < nres; ++i) {  // dense residual box in a halo slot
           mbar_wait(xempty_bar(xs), xph ^ 1u);
-          mbar_expect_tx(xfull_bar(xs), C::kXDense);
-          tma_load_4d(x_base + xs * kXSlot, &p.r_map, xfull_bar(xs), g0 + 64 * i, x0, y0, b);
+          if constexpr (PAIR && !GNF) {
+            if (rank == 0) mbar_expect_tx(xfull_bar(xs), 2 * C::kXDense);
+            tma_load_4d_pair(x_base + xs * kXSlot, &p.r_map, mapa_shared(xfull_bar(xs), 0), g0 + 64 * i, x0, y0, b);
+          } else {
+            mbar_expect_tx(xfull_bar(xs), C::kXDense);
+            tma_load_4d(x_base + xs * kXSlot, &p.r_map, xfull_bar(xs), g0 + 64 * i, x0, y0, b);
+          }
           if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
         }
       }
@@ -225,13 +238,13 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_ha
           if (!dbg_no_wait) timed_wait(GNF ? xready_bar(xs) : xfull_bar(xs), xph, pw_x);
           const uint32_t x_addr = x_base + xs * kXSlot;
           const bool resid = sl >= nslices;
-          const int ntap = resid ? 1 : 9;
+          const int ntap = resid ? 1 : ntaps;
           for (int tap = 0; tap < ntap; ++tap) {
             if (!dbg_no_wait) timed_wait(wfull_bar(ws), wph, pw_w);
             tc_fence_after();
             const uint64_t adesc = umma_desc_k128(smem_base + ws * kWBytes);
-            const uint64_t bdesc = resid ? umma_desc_k128(x_addr)
-                                         : umma_desc_k128_sbo(x_addr + (uint32_t)((tap / 3) * 10 + tap % 3) * 128u, 1280);
+            const int win = p.poly ? ((tap >> 1) + ppy) * 10 + (tap & 1) + ppx : (tap / 3) * 10 + tap % 3;  // first halo pixel of the tap's window
+            const uint64_t bdesc = resid ? umma_desc_k128(x_addr) : umma_desc_k128_sbo(x_addr + (uint32_t)win * 128u, 1280);
             if (leader) {
               if constexpr (PAIR) {
 #pragma unroll
@@ -339,6 +352,7 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_ha
       const float bias = p.bias ? p.bias[(p.bias_sel ? (long long)p.bias_sel[b] * p.N : 0) + n0 + m] : 0.f;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256;
       __half* obase = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + n0 + quad * 32;
+      const int osc = p.poly ? 2 : 1;  // polyphase: this launch writes the pixels (2y + ppy, 2x + ppx) of the (2H, 2W) output
       float sum = 0.f, sq = 0.f;
       uint32_t ra[32], rb[32];
       // one block = 32 pixels = patch rows 4 blk .. 4 blk + 3, held in r; `nxt` receives the following block meanwhile
@@ -364,10 +378,10 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_ha
           const int xx = x0 + (px & 7), yy = ya + (px >> 3);
           const uint4 v = *reinterpret_cast<const uint4*>(stg + px * 64 + piece * 16);
           if (xx < p.W && yy < p.H && !(p.gn_silu & 16))  // (bit 4: measurement aid — no global stores)
-            *reinterpret_cast<uint4*>(obase + ((long long)yy * p.W + xx) * p.out_ld + piece * 8) = v;
+            *reinterpret_cast<uint4*>(obase + ((long long)(yy * osc + ppy) * (p.W * osc) + xx * osc + ppx) * p.out_ld + piece * 8) = v;
         }
         if (p.stats && (blk & 3) == 3) {
-          const long long slot = (long long)b * (2 * per_image) + 2 * t_img + (blk >> 2);
+          const long long slot = (long long)b * p.stats_bslots + p.stats_slot0 + 2 * t_img + (blk >> 2);
           *reinterpret_cast<float2*>(p.stats + (slot * p.N + n0 + m) * 2) = make_float2(sum, sq);
           sum = 0.f;
           sq = 0.f;
@@ -420,12 +434,13 @@ static void swap_halo_launch_t(const ConvGemmParams& p, int grid, cudaStream_t s
   SDM_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_swap_halo_kernel<GNF, PAIR>, p));
 }
 
-// pair: CTA pairs (cta_group::2) over 256 output channels; needs the fused GroupNorm form, N % 256 == 0, an even grid and the
-// half-patch tensor-map boxes (conv_gemm_build)
+// pair: CTA pairs (cta_group::2) over 256 output channels; needs N % 256 == 0, an even grid and the half-patch tensor-map
+// boxes (conv_gemm_build)
 void conv_swap_halo_launch(const ConvGemmParams& p, int grid, bool pair, cudaStream_t st) {
   if (pair) {
-    SDM_CHECK(p.gn_ab != nullptr && (p.n_tiles & 1) == 0 && (grid & 1) == 0, "pair launch preconditions");
-    swap_halo_launch_t<true, true>(p, grid, st);
+    SDM_CHECK((p.n_tiles & 1) == 0 && (grid & 1) == 0, "pair launch preconditions");
+    if (p.gn_ab) swap_halo_launch_t<true, true>(p, grid, st);
+    else swap_halo_launch_t<false, true>(p, grid, st);
   } else if (p.gn_ab) {
     swap_halo_launch_t<true, false>(p, grid, st);
   } else {

@@ -117,6 +117,38 @@ struct Weights {
         for (int t = 0; t < k * k; ++t) pk[((size_t)o * k * k + t) * Ip + i] = __float2half_rn(w[((size_t)o * I + i) * k * k + t]);
     return (const __half*)upload(key, pk.data(), pk.size() * 2);
   }
+  // "nearest x2 upsample -> 3x3 conv" as four polyphase 2x2-tap convs over the LOW-resolution input (Upsample2D of diffusers:
+  // F.interpolate(scale 2, nearest) then conv; reference call sites: the decoder / UNet up blocks built at
+  // /root/reference/src/utils/replace.py via diffusers).  Output pixel (2y + py, 2x + px) sees, through the nearest upsampling, the
+  // low-resolution rows {y - 1, y, y} (py = 0) or {y, y, y + 1} (py = 1) under kernel rows ky = 0, 1, 2 — the taps that land on the same
+  // input pixel are summed: 4 products per input channel instead of 9, and the upsampled tensor is never materialised.  The sums are
+  // formed in fp32 from the fp16-rounded taps and rounded to fp16 once (relative error <= 2^-11 per combined weight, random sign:
+  // below the fp16 rounding of the activations they multiply).  Layout: [parity q = 2 py + px][O][tap t = 2 dy + dx][I].
+  const __half* conv_poly(const std::string& name, int O, int I) {
+    const std::string key = "p:" + name;
+    if (void* p = get(key)) return (const __half*)p;
+    require_loading(key);
+    std::vector<float> w = fetch(name + ".weight", (int64_t)O * I * 9);
+    std::vector<__half> pk((size_t)4 * O * 4 * I);
+    // kernel rows (columns) feeding low-resolution offset d of parity p: p = 0: d = 0 <- {0}, d = 1 <- {1, 2}; p = 1: d = 0 <- {0, 1}, d = 1 <- {2}
+    auto lo = [](int par, int d) { return par == 0 ? (d == 0 ? 0 : 1) : (d == 0 ? 0 : 2); };
+    auto hi = [](int par, int d) { return par == 0 ? (d == 0 ? 0 : 2) : (d == 0 ? 1 : 2); };
+    for (int q = 0; q < 4; ++q) {
+      const int py = q >> 1, px = q & 1;
+      for (int o = 0; o < O; ++o)
+        for (int t = 0; t < 4; ++t) {
+          const int dy = t >> 1, dx = t & 1;
+          for (int i = 0; i < I; ++i) {
+            float acc = 0.f;
+            for (int ky = lo(py, dy); ky <= hi(py, dy); ++ky)
+              for (int kx = lo(px, dx); kx <= hi(px, dx); ++kx)
+                acc += __half2float(__float2half_rn(w[((size_t)o * I + i) * 9 + ky * 3 + kx]));
+            pk[(((size_t)q * O + o) * 4 + t) * I + i] = __float2half_rn(acc);
+          }
+        }
+    }
+    return (const __half*)upload(key, pk.data(), pk.size() * 2);
+  }
   // 3x3 conv with O <= 3 output channels as a 1x1 GEMM producing the 9*O per-tap partial products of every INPUT pixel
   // (rows tap*O + o, padded to 32 rows); alpha_col2im_kernel then sums the 9 shifted partials per output pixel
   const __half* conv_taprows(const std::string& name, int O, int I) {
@@ -723,6 +755,39 @@ struct Builder {
     return out;
   }
 
+  // Upsample2D (nearest x2 + conv3x3) of a LOW-resolution x as four polyphase launches (Weights::conv_poly); the caller checked
+  // conv_gemm_can_poly(Cout, x.H, x.W).  The output carries its GroupNorm partials (4 x the low-resolution slot count).
+  T conv3_poly(const T& x, const std::string& name, int Cout) {
+    T out = alloc(x.B, x.H * 2, x.W * 2, Cout);
+    const __half* w = W.conv_poly(name, Cout, x.C);
+    const float* bias = W.vec(name + ".bias", Cout);
+    out.stat_slots = 4 * conv_gemm_tiles_per_image(x.H, x.W);
+    out.stats_bytes = (size_t)x.B * out.stat_slots * Cout * 2 * sizeof(float);
+    float* stats_ptr = (float*)alloc_raw(out.stats_bytes, &out.stats_off);
+    out.stats = dry ? (float*)1 : stats_ptr;
+    for (int q = 0; q < 4; ++q) {
+      const double fl = 2.0 * x.B * (double)x.HW() * Cout * 4.0 * x.C;
+      flops += fl;
+      if (dry) { n_launches++; continue; }
+      ConvGemmDesc d;
+      d.B = x.B; d.Hin = x.H; d.Win = x.W;
+      d.nsrc = 1;
+      d.src[0] = {x.p, x.C, x.ld()};
+      d.ksize = 3; d.stride = 1; d.pad = PAD_SAME;
+      d.w = w + (size_t)q * Cout * 4 * x.C;
+      d.N = Cout;
+      d.mode = EPI_F16;
+      d.out = out.p; d.out_ld = out.C; d.out_bstride = out.HW() * out.C;
+      d.bias = bias;
+      d.stats = stats_ptr;
+      d.poly = q + 1;
+      auto l = conv_gemm_build(d, E.num_sms);
+      const double by = 2.0 * x.B * ((double)x.HW() * x.C + (double)x.HW() * Cout) + 2.0 * Cout * 4.0 * x.C;
+      push([l](cudaStream_t st) { conv_gemm_run(*l, st); }, 1, "tc:conv3x3_poly", fl, by);
+    }
+    return out;
+  }
+
   // ---------------------------------------------------------------- constant folding of the embeddings
   // emb = time_embedding(time_proj(trans)) + bbox_embedding(emb320([0,0,1,1]))   (replace.py:430-459, meta_arch.py:178-187)
   void fold_embeddings() {
@@ -1011,22 +1076,27 @@ struct Builder {
       for (int i = 0; i < 4; ++i) {
         const std::string bp = "unet.up_blocks." + std::to_string(i);
         const int level = 3 - i;
+        // Upsample2D = nearest x2 + conv3x3: as four polyphase convs over the low-resolution tensor where the geometry allows
+        // (conv3_poly), else nearest x2 fused into the producer's store + a plain 3x3 conv over the upsampled tensor
+        const bool poly = i < 3 && conv_gemm_can_poly(rch[i], h.H, h.W);
         for (int j = 0; j < 3; ++j) {
           T skip = skips.back();
           skips.pop_back();
           const bool last = (j == 2) && (i < 3);
           const bool has_attn = i > 0;
-          T o = resnet(h, &skip, bp + ".resnets." + std::to_string(j), rch[i], 1e-5f, true, (last && !has_attn) ? 1 : 0);
+          T o = resnet(h, &skip, bp + ".resnets." + std::to_string(j), rch[i], 1e-5f, true, (last && !has_attn && !poly) ? 1 : 0);
           free(h); free(skip);
           if (has_attn) {
-            T o2 = transformer(o, bp + ".attentions." + std::to_string(j), rheads[i], ctx, kbl[level], last ? 1 : 0);
+            T o2 = transformer(o, bp + ".attentions." + std::to_string(j), rheads[i], ctx, kbl[level], (last && !poly) ? 1 : 0);
             free(o); o = o2;
           }
           h = o;
-          tap("unet.up" + std::to_string(i) + "." + std::to_string(j), h);  // j == 2, i < 3: already nearest-x2 upsampled
+          // j == 2, i < 3: already nearest-x2 upsampled, unless the polyphase form keeps it at low resolution (".lo")
+          tap("unet.up" + std::to_string(i) + "." + std::to_string(j) + ((last && poly) ? ".lo" : ""), h);
         }
-        if (i < 3) {  // Upsample2D: nearest x2 (fused into the producer's store) + conv3x3
-          T o = conv3_plain(h, bp + ".upsamplers.0.conv", rch[i], 1, PAD_SAME);
+        if (i < 3) {
+          if (W.loading) W.conv_poly(bp + ".upsamplers.0.conv", rch[i], h.C);  // both weight forms are packed: the plan's geometry picks one
+          T o = poly ? conv3_poly(h, bp + ".upsamplers.0.conv", rch[i]) : conv3_plain(h, bp + ".upsamplers.0.conv", rch[i], 1, PAD_SAME);
           free(h); h = o;
           tap("unet.up" + std::to_string(i) + ".us", h);
         }
@@ -1060,11 +1130,16 @@ struct Builder {
       const int ch[4] = {512, 512, 256, 128};
       for (int i = 0; i < 4; ++i) {
         const std::string bp = dcd + ".up_blocks." + std::to_string(i);
+        const bool poly = i < 3 && conv_gemm_can_poly(ch[i], h.H, h.W);  // see the UNet up blocks
         for (int j = 0; j < 3; ++j) {
-          T o = resnet(h, nullptr, bp + ".resnets." + std::to_string(j), ch[i], 1e-6f, false, (j == 2 && i < 3) ? 1 : 0);
+          T o = resnet(h, nullptr, bp + ".resnets." + std::to_string(j), ch[i], 1e-6f, false, (j == 2 && i < 3 && !poly) ? 1 : 0);
           free(h); h = o;
         }
-        if (i < 3) { T o = conv3_plain(h, bp + ".upsamplers.0.conv", ch[i], 1, PAD_SAME); free(h); h = o; }
+        if (i < 3) {
+          if (W.loading) W.conv_poly(bp + ".upsamplers.0.conv", ch[i], h.C);
+          T o = poly ? conv3_poly(h, bp + ".upsamplers.0.conv", ch[i]) : conv3_plain(h, bp + ".upsamplers.0.conv", ch[i], 1, PAD_SAME);
+          free(h); h = o;
+        }
         tap("dec.up" + std::to_string(i), h);
       }
       T n = groupnorm(h, nullptr, dcd + ".conv_norm_out", 1e-6f, 1);

@@ -49,6 +49,12 @@ struct ConvGemmDesc {
   // memory with this [B][cin_total][2] (scale, shift) table (groupnorm_ab); only where conv_gemm_can_fuse_gn() says so
   const float* gn_ab = nullptr;
   int gn_silu = 0;
+  // polyphase component of "nearest x2 upsample -> 3x3 conv" (0 = off, 1 + 2 py + px): a 2x2-tap conv over the LOW-resolution
+  // input (Hin x Win) with the pre-combined weights [N][4][cin] of that parity (conv_poly_weights), stored at the pixels
+  // (2y + py, 2x + px) of a (2 Hin, 2 Win) output; out_bstride / stats describe the full-resolution output: `stats` holds
+  // 4 x conv_gemm_tiles_per_image(Hin, Win) slots per sample, launch (py, px) fills slots [q, q + 1) x that count, q = 2 py + px.
+  // Only where conv_gemm_can_poly() says so (resident-halo swapped-operand kernel).
+  int poly = 0;
 };
 
 struct ConvGemmLaunch;  // opaque: prebuilt tensor maps + params
@@ -62,6 +68,8 @@ int conv_gemm_tiles_per_image(int Hout, int Wout);  // number of 128-pixel M til
 int conv_gemm_variant_code(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout);
 // can a conv of this per-sample geometry take its input GroupNorm fused (ConvGemmDesc::gn_ab)?  Geometry only, like the variant.
 bool conv_gemm_can_fuse_gn(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout);
+// can "nearest x2 upsample -> 3x3 conv to N channels" of a Hin x Win input run as four polyphase 2x2-tap convs (ConvGemmDesc::poly)?
+bool conv_gemm_can_poly(int N, int Hin, int Win);
 
 // ------------------------------------------------------------------ flash attention (d = 64)
 struct AttnDesc {

@@ -119,6 +119,12 @@ static ConvVariant conv3x3_variant(int ksize, int stride, int mode, int ups2, bo
   v.halo_auto = v.halo_geom && v.halo_bn != 0 && force_halo == 0 && force_block_n == 0 && force_mt == 0;
   return v;
 }
+bool conv_gemm_can_poly(int N, int Hin, int Win) {
+  static const int on = [] { const char* e = getenv("SDM_CONV_POLY"); return e ? atoi(e) : 1; }();  // A/B switch
+  if (!on) return false;
+  const ConvVariant v = conv3x3_variant(3, 1, EPI_F16, 0, false, N, 0, false, Hin, Win, 2, 0, 0, 0, false);
+  return v.swap && v.swap_halo;
+}
 // 0 = one TMA box per tap (conv_gemm_kernel), 1 / 2 = resident halo with 256- / 160-wide tiles, 3 = swapped operands
 // GroupNorm fusion is available where the resident-halo swapped-operand kernel applies.  Every 128-channel N tile of a pixel tile
 // re-normalises the same input slice, so the transform work grows with N / 128 while the apply pass it replaces does not.
@@ -157,8 +163,15 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * d.B;
   p.N = d.N;
   // ---- kernel variant of the 3x3 stride-1 convs: conv3x3_variant() sees the per-sample geometry only
+  if (d.poly) {
+    SDM_CHECK(d.poly >= 1 && d.poly <= 4 && d.ksize == 3 && d.stride == 1 && d.mode == EPI_F16 && !d.ups2 && !d.res && d.nsrc == 1 && !d.gn_ab &&
+                  !d.w_bstride && (d.n_store == 0 || d.n_store == d.N),
+              "polyphase conv: plain 3x3-geometry stride-1 fp16 conv of one source only");
+    SDM_CHECK(conv_gemm_can_poly(d.N, Hout, Wout), "polyphase conv: geometry not supported (conv_gemm_can_poly)");
+  }
   const ConvVariant cv = conv3x3_variant(d.ksize, d.stride, d.mode, d.ups2, d.w_bstride != 0, d.N, d.n_store, d.res != nullptr, Hout, Wout,
-                                         d.force_swap, d.force_halo, d.force_block_n, d.force_mt, d.gn_ab != nullptr);
+                                         d.poly ? 2 : d.force_swap, d.force_halo, d.force_block_n, d.force_mt, d.gn_ab != nullptr);
+  if (d.poly) SDM_CHECK(cv.swap && cv.swap_halo, "polyphase conv needs the resident-halo swapped-operand kernel");
   if (d.force_swap >= 1) SDM_CHECK(cv.swap_can, "force_swap: configuration not supported by the swapped-operand kernel");
   if (d.force_swap == 2) SDM_CHECK(cv.swap_halo, "force_swap = 2: geometry not supported by the resident-halo swapped-operand kernel");
   if (d.gn_ab) SDM_CHECK(cv.swap && cv.swap_halo, "fused GroupNorm needs the resident-halo swapped-operand kernel (conv_gemm_can_fuse_gn)");
@@ -194,14 +207,15 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
     p.n_tiles = d.N / 128;
     // CTA pairs: fused-GroupNorm form, an even number of channel tiles, at least one item per cluster (SDM_SWH_PAIR=0: A/B switch)
     static const int env_pair = [] { const char* e = getenv("SDM_SWH_PAIR"); return e ? atoi(e) : 1; }();
-    L->swap_pair = L->swap_halo && d.gn_ab != nullptr && d.N % 256 == 0 && env_pair != 0 && num_sms % 2 == 0 &&
+    L->swap_pair = L->swap_halo && d.N % 256 == 0 && env_pair != 0 && num_sms % 2 == 0 &&
                    m_tiles_eff * (p.n_tiles / 2) >= num_sms / 2;
   }
   p.m_tiles = (int)m_tiles_eff;
   const long long total = ((m_tiles_eff + L->mt - 1) / L->mt) * p.n_tiles;
   SDM_CHECK(total < (1ll << 31), "too many tiles");
   p.total_tiles = (int)total;
-  p.ntaps = d.ksize * d.ksize;
+  p.ntaps = d.poly ? 4 : d.ksize * d.ksize;  // polyphase: taps (dy, dx) in {0,1}^2, weights [N][4][cin]
+  p.poly = d.poly;
   p.nsrc = d.nsrc;
   p.cin_total = cin_total;
   for (int s = 0; s < d.nsrc; ++s) p.src_c[s] = d.src[s].C;
@@ -300,6 +314,11 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   p.gn_ab = d.gn_ab;
   p.gn_silu = d.gn_silu;
   p.stats = (d.mode == EPI_F16 && !d.ups2) ? d.stats : nullptr;
+  {  // GroupNorm-partials slots of the swapped kernels: two per 8 x 32 (16 x 16) patch; a polyphase launch fills its quarter
+    const int per = 2 * p.tiles_x * p.tiles_y;
+    p.stats_bslots = d.poly ? 4 * per : per;
+    p.stats_slot0 = d.poly ? (d.poly - 1) * per : 0;
+  }
   if (d.mode == EPI_ALPHA) SDM_CHECK(d.N >= 3 && d.N <= 16 && d.bias != nullptr, "EPI_ALPHA needs 3..16 columns and a bias");
   {
     // epilogue warpgroups: two for the GEMMs whose K loop is too short to hide one epilogue
@@ -320,7 +339,7 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   }
   L->grid = (int)std::min<long long>(total, num_sms);
   if (L->swap_pair) L->grid = 2 * (int)std::min<long long>(m_tiles_eff * (p.n_tiles / 2), num_sms / 2);  // whole clusters
-  L->flops = 2.0 * (double)d.B * Hout * Wout * (double)d.N * (double)ktot;
+  L->flops = 2.0 * (double)d.B * Hout * Wout * (double)d.N * (double)ktot;  // (polyphase: the work actually done, 4/9 of the 3x3 form's per output pixel)
   return L;
 }
 

@@ -59,6 +59,8 @@ struct alignas(64) ConvGemmParams {
   int prof;           // SDM_GEMM_PROF=1: CTAs 0/1 print the cycles their producer / MMA / epilogue threads spent waiting
   int mode;
   int ups2;           // EPI_F16 only: write each pixel to the 2x2 block of a (2H,2W) output
+  int poly;           // conv_swap_halo only: 0, or 1 + 2 py + px = polyphase component (py, px) of "nearest x2 upsample -> 3x3 conv"
+  int stats_bslots, stats_slot0;  // conv_swap_halo: GroupNorm-partials slots per sample / first slot of this launch
   void* out;
   long long out_ld;       // elements between consecutive pixels (EPI_F16/F32/GEGLU) or row length (EPI_F16_T)
   long long out_bstride;  // elements per batch element
@@ -658,23 +660,36 @@ __global__ void __launch_bounds__(64 + 128 * EWG, 1) conv_gemm_kernel(const __gr
           const bool valid = (x < p.W) && (y < p.H);
           const long long pix = (long long)y * p.W + x;
           if constexpr (MODE == EPI_F16_T) {
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
-              uint32_t r[32];
-              __syncwarp();  // tcgen05.ld is .sync.aligned: re-converge after the (divergent) store code
-              tmem_ld32(taddr + c, r);
-              tmem_ld_wait();
-              if (valid) {
-                __half* out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + pix;
+            // 32-column slabs, the next slab's tcgen05.ld and this slab's bias values in flight while the current one is stored
+            // (r3c ncu of the r2z form — ld, wait, then per element a bias load, a bounds branch and the store —: issue slots
+            // 38 % busy, top stalls long_scoreboard / wait, tensor pipe 21 %)
+            __half* out = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + pix;
+            uint32_t ra[32], rb[32];
+            auto slab = [&](const uint32_t (&r)[32], uint32_t (&nxt)[32], int c) {
+              float bv[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  if (n0 + c + i < p.N) {
-                    float v = __uint_as_float(r[i]) * p.scale;
-                    if (bias) v += bias[n0 + c + i];
-                    out[(long long)(n0 + c + i) * p.out_ld] = __float2half_rn(v);
-                  }
+              for (int i = 0; i < 32; ++i) bv[i] = (bias && n0 + c + i < p.N) ? __ldg(bias + n0 + c + i) : 0.f;
+              tmem_ld_wait();
+              __syncwarp();  // tcgen05.ld is .sync.aligned: re-converge after the (divergent) store code
+              if (c + 32 < BLOCK_N) tmem_ld32(taddr + c + 32, nxt);
+              if (valid) {
+                __half* o = out + (long long)(n0 + c) * p.out_ld;
+                if (n0 + c + 32 <= p.N) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) o[(long long)i * p.out_ld] = __float2half_rn(fmaf(__uint_as_float(r[i]), p.scale, bv[i]));
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (n0 + c + i < p.N) o[(long long)i * p.out_ld] = __float2half_rn(fmaf(__uint_as_float(r[i]), p.scale, bv[i]));
                 }
               }
+            };
+            __syncwarp();
+            tmem_ld32(taddr, ra);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 64) {
+              slab(ra, rb, c);
+              if (c + 32 < BLOCK_N) slab(rb, ra, c + 32);
             }
           } else {
             uint32_t r[32];

@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libsdmatte_b200.so")
 _lib = None
-ABI_VERSION = 200  # sdm_version(): bumped whenever a struct or signature of include/sdmatte_b200.h changes
+ABI_VERSION = 201  # sdm_version(): bumped whenever a struct or signature of include/sdmatte_b200.h changes
 
 
 class sdm_tensor_desc(C.Structure):
@@ -33,7 +33,7 @@ class sdm_conv_gemm_args(C.Structure):
         ("bias", C.c_void_p), ("bias_sel", C.c_void_p),
         ("res", C.c_void_p), ("res_ld", C.c_int64), ("res_bstride", C.c_int64),
         ("scale", C.c_float), ("force_block_n", C.c_int), ("post_div", C.c_float), ("n_store", C.c_int), ("out2", C.c_void_p), ("force_mt", C.c_int), ("stats", C.c_void_p), ("force_halo", C.c_int), ("force_swap", C.c_int),
-        ("gn_ab", C.c_void_p), ("gn_silu", C.c_int),
+        ("gn_ab", C.c_void_p), ("gn_silu", C.c_int), ("poly", C.c_int),
     ]
 
 
@@ -70,7 +70,7 @@ EXPORTS = [
     "sdm_workspace_bytes", "sdm_forward", "sdm_workspace_bytes_prompt", "sdm_forward_prompt", "sdm_forward_host", "sdm_node_workspace_bytes", "sdm_apply_matte_host", "sdm_forward_profiled", "sdm_profile_count", "sdm_profile_entry",
     "sdm_last_forward_stats", "sdm_debug_tensor", "sdm_debug_tensor_count", "sdm_debug_tensor_name", "sdm_set_option", "sdm_graph_stats", "sdm_node_call_timing",
     "sdm_preprocess", "sdm_postprocess",
-    "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_conv_variant", "sdm_k_conv_can_fuse_gn", "sdm_k_groupnorm_ab_offset", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
+    "sdm_k_conv_gemm", "sdm_k_conv_tiles_per_image", "sdm_k_conv_variant", "sdm_k_conv_can_fuse_gn", "sdm_k_conv_can_poly", "sdm_k_groupnorm_ab_offset", "sdm_k_attention", "sdm_k_groupnorm_scratch_floats", "sdm_k_groupnorm", "sdm_k_layernorm",
     "sdm_k_softmax_rows", "sdm_k_direct_conv", "sdm_k_key_bias", "sdm_k_key_compact", "sdm_k_gather_rows", "sdm_k_probe_halo",
     "sdm_safetensors_open", "sdm_safetensors_count", "sdm_safetensors_entry", "sdm_safetensors_close",
 ]
@@ -496,9 +496,10 @@ def _p(t):
 
 
 def k_conv_gemm(srcs, w, N, out, *, B, Hin, Win, ksize=1, stride=1, pad=0, mode=0, ups2=0, bias=None, bias_sel=None,
-                res=None, scale=1.0, w_bstride=0, out_ld=None, out_bstride=None, force_block_n=0, post_div=1.0, n_store=0, out2=None, force_mt=0, stats=None, force_halo=0, force_swap=0, gn_ab=None, gn_silu=0):
+                res=None, scale=1.0, w_bstride=0, out_ld=None, out_bstride=None, force_block_n=0, post_div=1.0, n_store=0, out2=None, force_mt=0, stats=None, force_halo=0, force_swap=0, gn_ab=None, gn_silu=0, poly=0):
     lib = load_library()
     a = sdm_conv_gemm_args()
+    a.poly = int(poly)
     a.B, a.Hin, a.Win, a.nsrc = B, Hin, Win, len(srcs)
     a.src0, a.c0, a.ld0 = srcs[0][0].data_ptr(), srcs[0][1], srcs[0][2]
     if len(srcs) > 1:
@@ -570,6 +571,13 @@ def conv_can_fuse_gn(ksize, stride, N, H, W, *, mode=0, ups2=0, has_res=0):
     lib = load_library()
     lib.sdm_k_conv_can_fuse_gn.argtypes = [C.c_int] * 8
     return bool(lib.sdm_k_conv_can_fuse_gn(ksize, stride, mode, ups2, N, has_res, H, W))
+
+
+def conv_can_poly(N, H, W):
+    """Can "nearest x2 upsample -> 3x3 conv to N channels" of an H x W input run as four polyphase launches (k_conv_gemm(poly=1..4))?"""
+    lib = load_library()
+    lib.sdm_k_conv_can_poly.argtypes = [C.c_int] * 3
+    return bool(lib.sdm_k_conv_can_poly(N, H, W))
 
 
 def conv_tiles_per_image(H, W):

@@ -169,6 +169,10 @@ typedef struct {
   const float* gn_ab;           /* fused GroupNorm(+SiLU) of the INPUT: [B][c0+c1][2] (scale, shift) as sdm_k_groupnorm leaves them in its scratch
                                    (offset sdm_k_groupnorm_ab_offset); the conv then reads the raw tensor.  Only where sdm_k_conv_can_fuse_gn() != 0 */
   int gn_silu;
+  int poly;                     /* 0, or 1 + 2 py + px: polyphase component (py, px) of "nearest x2 upsample -> 3x3 conv": a 2x2-tap conv over the
+                                   LOW-resolution input with the pre-combined weights [N][4][c0] of that parity, stored at the pixels (2y+py, 2x+px) of
+                                   the (2 Hin, 2 Win) output (out_bstride / stats describe that output; stats: 4 x sdm_k_conv_tiles_per_image(Hin, Win)
+                                   slots per sample, this launch fills quarter 2 py + px).  Only where sdm_k_conv_can_poly() != 0 */
 } sdm_conv_gemm_args;
 int sdm_k_conv_gemm(const sdm_conv_gemm_args* a, uintptr_t stream);
 int sdm_k_conv_tiles_per_image(int Hout, int Wout);
@@ -178,6 +182,8 @@ int sdm_k_conv_tiles_per_image(int Hout, int Wout);
 int sdm_k_conv_variant(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout);
 /* 1 if a conv of this per-sample geometry can take its input GroupNorm fused (sdm_conv_gemm_args.gn_ab) */
 int sdm_k_conv_can_fuse_gn(int ksize, int stride, int mode, int ups2, int N, int has_res, int Hout, int Wout);
+/* 1 if "nearest x2 upsample -> 3x3 conv to N channels" of a Hin x Win input can run as four polyphase launches (sdm_conv_gemm_args.poly) */
+int sdm_k_conv_can_poly(int N, int Hin, int Win);
 
 typedef struct {
   int B, heads, Lq, Lk;

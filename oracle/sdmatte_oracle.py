@@ -223,8 +223,9 @@ def unet_forward(c, sample, trans, ctx, coords_emb, attention_mask, capture=None
             if not (i < 3 and j == 2):
                 c.tap(f"unet.up{i}.{j}", x)
         if i < 3:
+            c.tap(f"unet.up{i}.2.lo", x)  # before the nearest x2 (the engine's polyphase upsampler keeps the tensor at low resolution)
             x = F.interpolate(x, scale_factor=2.0, mode="nearest")
-            c.tap(f"unet.up{i}.2", x)  # tapped AFTER the nearest x2 (the engine fuses the upsampling into the block's store)
+            c.tap(f"unet.up{i}.2", x)  # AFTER the nearest x2 (elsewhere the engine fuses the upsampling into the block's store)
             x = _conv(c, x, f"{bp}.upsamplers.0.conv")
             c.tap(f"unet.up{i}.us", x)
     assert not skips

@@ -99,6 +99,25 @@ def linear(B, M, N, K, res=False):
     return ms, 2.0 * B * M * N * K / ms / 1e9
 
 
+def geglu(B, M, C):
+    """GEGLU projection of a transformer block's feed-forward (EPI_GEGLU): [M, C] x [8C, C]^T -> [M, 4C]."""
+    x = torch.randn(B, M, C, device=DEV).half()
+    w = (torch.randn(8 * C, C, device=DEV) * C ** -0.5).half()
+    b = torch.randn(8 * C, device=DEV)
+    out = torch.empty(B, M, 4 * C, device=DEV).half()
+    ms = timeit(lambda: E.k_conv_gemm([(x, C, C)], w, 8 * C, out, B=B, Hin=1, Win=M, mode=2, bias=b, out_ld=4 * C, out_bstride=M * 4 * C))
+    return ms, 2.0 * B * M * 8 * C * C / ms / 1e9
+
+
+def linear_t(B, M, N, K):
+    """to_v with the transposed store (EPI_F16_T): out[b][n][m]."""
+    x = torch.randn(B, M, K, device=DEV).half()
+    w = (torch.randn(N, K, device=DEV) * K ** -0.5).half()
+    out = torch.empty(B, N, M, device=DEV).half()
+    ms = timeit(lambda: E.k_conv_gemm([(x, K, K)], w, N, out, B=B, Hin=1, Win=M, mode=1, out_ld=M, out_bstride=N * M))
+    return ms, 2.0 * B * M * N * K / ms / 1e9
+
+
 def gn(B, H, W, C):
     """GroupNorm(+SiLU) with the statistics arriving as conv-epilogue partials (the in-engine case): reduce + finalize + apply."""
     x = torch.randn(B, H * W, C, device=DEV).half()
@@ -147,6 +166,10 @@ CASES = {
     "conv1x1 64->128 @1024^2 B4 +stats (im2col conv_in)": lambda: conv(4, 1024, 1024, 64, 128, k=1, stats=True),
     "conv1x1 64->128 @1024^2 B4": lambda: conv(4, 1024, 1024, 64, 128, k=1),
     "conv1x1 256->128 @1024^2 B2 (vae shortcut)": lambda: conv(2, 1024, 1024, 256, 128, k=1),
+    "geglu 16384x320 B8": lambda: geglu(8, 16384, 320),
+    "geglu 4096x640 B8": lambda: geglu(8, 4096, 640),
+    "linear_T 16384x320x1024 B8 (cross V^T)": lambda: linear_t(8, 16384, 320, 1024),
+    "linear_T 16384x320x320 B8 (self V^T)": lambda: linear_t(8, 16384, 320, 320),
     "linear 16384x320x320 B8 +res": lambda: linear(8, 16384, 320, 320, res=True),
     "linear 16384x320x1024 B8 (cross K)": lambda: linear(8, 16384, 320, 1024),
     "linear 4096x640x640 B8": lambda: linear(8, 4096, 640, 640),

@@ -725,6 +725,72 @@ def test_conv3x3_fused_groupnorm(eng_mod, B, H, W, C0, C1, Cout, res, silu):
     _close(out_f, y.permute(0, 2, 3, 1), 4e-3, 4e-3, "conv3x3 with fused GroupNorm")
 
 
+# ------------------------------------------------------------------------------------------------ Upsample2D as four polyphase convs
+def _poly_pack(w):
+    """OIHW 3x3 -> [4 parities q = 2 py + px][O][4 taps t = 2 dy + dx][I] fp16: the taps of the 3x3 kernel that land on the same
+    low-resolution pixel under a nearest x2 upsampling, summed in fp32 (of the fp16-rounded taps) and rounded once."""
+    w = w.half().float()
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    out = []
+    for q in range(4):
+        py, px = q >> 1, q & 1
+        taps = []
+        for t in range(4):
+            dy, dx = t >> 1, t & 1
+            acc = 0
+            for ky in rows[py][dy]:
+                for kx in rows[px][dx]:
+                    acc = acc + w[:, :, ky, kx]
+            taps.append(acc)
+        out.append(torch.stack(taps, 1))  # [O][4][I]
+    return torch.stack(out).half().contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [
+    (1, 64, 64, 128, 128),     # single-CTA form
+    (2, 128, 96, 256, 256),    # CTA-pair form (>= 74 (pixel tile, 256-channel) items), no GroupNorm in front
+    (1, 64, 64, 640, 640),     # UNet level-1 upsampler: five channel tiles (no pairs), ten input slices
+    (1, 160, 64, 512, 512),    # pair form, two channel-tile pairs, eight slices
+])
+def test_conv3x3_polyphase_upsample(eng_mod, B, H, W, Cin, Cout):
+    """Upsample2D (F.interpolate(scale 2, nearest) -> conv3x3, diffusers; reached from /root/reference/src/utils/replace.py's
+    up blocks) as four polyphase 2x2-tap launches over the LOW-resolution input (conv_swap_halo_kernel, p.poly): (1) against the
+    same four 2x2 convs in torch with the SAME combined fp16 weights (kernel arithmetic: fp16 conv tolerance), (2) against the
+    reference formulation (upsample, 3x3 conv with the original weights): the combined weights carry one extra fp16 rounding."""
+    assert eng_mod.conv_can_poly(Cout, H, W)
+    x = _rand(B, H, W, Cin, seed=11).half()
+    w = _rand(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=12).half()
+    bias = _rand(Cout, seed=13).float()
+    wq = _poly_pack(w).to(DEV)
+    slots = 4 * eng_mod.conv_tiles_per_image(H, W)
+    out = torch.full((B, 2 * H, 2 * W, Cout), float("nan"), dtype=torch.float16, device=DEV)
+    stats = torch.full((B, slots, Cout, 2), float("nan"), device=DEV)
+    for q in range(4):
+        eng_mod.k_conv_gemm([(x, Cin, Cin)], wq[q], Cout, out, B=B, Hin=H, Win=W, ksize=3, bias=bias, out_ld=Cout,
+                            out_bstride=4 * H * W * Cout, stats=stats, poly=q + 1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all(), "every output pixel is written by exactly one parity launch"
+    xf = x.float().permute(0, 3, 1, 2)
+    # (1) same arithmetic in torch: per parity a 2x2 correlation of the zero-padded low-resolution input
+    ref1 = torch.empty(B, Cout, 2 * H, 2 * W, device=DEV)
+    xp = F.pad(xf, (1, 1, 1, 1))
+    for q in range(4):
+        py, px = q >> 1, q & 1
+        k = wq[q].float().view(Cout, 2, 2, Cin).permute(0, 3, 1, 2).contiguous()
+        y = F.conv2d(xp[:, :, py:py + H + 1, px:px + W + 1], k, bias)
+        ref1[:, :, py::2, px::2] = y
+    _close(out, ref1.permute(0, 2, 3, 1), 2e-3, 2e-3, "polyphase conv vs torch with the same combined weights")
+    # (2) the reference formulation
+    ref2 = F.conv2d(F.interpolate(xf, scale_factor=2.0, mode="nearest"), w.float(), bias, padding=1)
+    _close(out, ref2.permute(0, 2, 3, 1), 4e-3, 4e-3, "polyphase conv vs upsample -> conv3x3")
+    rel = ((out.float() - ref2.permute(0, 2, 3, 1)).norm() / ref2.norm()).item()
+    assert rel < 6e-4, rel  # fp16 output rounding alone is ~2.8e-4 relative RMS
+    tot = stats.double().sum(1)
+    o = out.double().view(B, 4 * H * W, Cout)
+    assert torch.allclose(tot[..., 0], o.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(tot[..., 1], (o * o).sum(1), rtol=1e-4, atol=1e-2)
+
+
 def test_conv_can_fuse_gn_is_geometry_only(eng_mod):
     assert eng_mod.conv_can_fuse_gn(3, 1, 128, 1024, 1024)
     assert eng_mod.conv_can_fuse_gn(3, 1, 128, 64, 64, has_res=1)
