@@ -433,6 +433,7 @@ def run_b200(args):
             traffic = {"dram_bytes_per_launch": td["conv3x3"]["dram_bytes"] / td["conv3x3"]["launches"], "launches_measured": td["conv3x3"]["launches"],
                        "dram_bytes_per_step_measured_launches": td["conv3x3"]["dram_bytes"],
                        "algorithmic_bytes_per_step_all_launches": fam["tc:conv3x3"]["bytes"], "launches_per_step": conv_n,
+                       "measured_at": "r2l: before the CTA-pair form and the polyphase upsamplers (which removed three 3x3 launches over upsampled tensors)",
                        "source": "profiles/r2_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, one bs=8 1024^2 forward, "
                                  "profiles/scripts/run_r2_traffic.sh): measured traffic is BELOW the read-once/write-once figure (producer outputs still in the 126 MB L2)"}
         except Exception:

@@ -142,6 +142,21 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_ha
   int nslices = 0;
   for (int s = 0; s < p.nsrc; ++s) nslices += p.src_c[s] >> 6;
   const int per_image = p.tiles_x * p.tiles_y;
+  // K sequence of a tile: the residual K slices are INTERLEAVED with the first input slices (s0 r0 s1 r1 s2 s3 ...).  A residual box
+  // feeds 4 MMAs, an input slice 36: behind the input slices (r3f and earlier) two of the three halo slots held residual boxes
+  // while the last slice was consumed, the next tile's first slice could only be requested when that finished, and its flight +
+  // GroupNorm transform (~3.5 k clk) was covered by 1 k clk of residual MMAs — 128 -> 128 convs with a residual ran at 760-860
+  // TFLOP/s against 1150 without (r3f_ops.csv).  Interleaved, every input slice is requested a full slice ahead (r3g: 864 -> 948,
+  // 761 -> 882).  Only for an ODD number of channel tiles (N = 128, 384, 640): with N % 256 == 0 the same conv runs as CTA pairs or
+  // single CTAs depending on the batch size, a pair adds FOUR residual slices (two of them zeros for either CTA) and its interleaved
+  // order would differ from the single CTA's — a sample must give the same bits alone and in a batch, so those keep the residual last.
+  const int nseq = nslices + nres, nmix = ((p.n_tiles & 1) && p.res_mix) ? min(nslices, nres) : 0;
+  auto seq_item = [&](int q, bool& resid) {  // q-th K item of a tile -> (residual slice i | input slice sl)
+    if (q < 2 * nmix) { resid = (q & 1) != 0; return q >> 1; }
+    const int r = q - 2 * nmix, rem = nslices - nmix;  // behind the interleaved prefix: the other input slices, then the other residual slices
+    resid = r >= rem;
+    return nmix + (resid ? r - rem : r);
+  };
 
   if (warp == 0) {
     // ============================== TMA producers ==============================
@@ -167,10 +182,15 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_ha
       };
       for (int item = item_first; item < item_count; item += item_step) {
         const int n0 = item_n0(item);
-        for (int sl = 0; sl < nslices; ++sl)  // slice sl = K columns [64 sl, 64 sl + 64) of every tap
-          for (int tap = 0; tap < ntaps; ++tap) load_w(&p.b_map, tap * p.cin_total + sl * 64, n0);
-        // D^T[c][pix] += I[c][64 i + k] . R[pix][g0 + 64 i + k], g0 = first channel of the tile (pair): rows 128 rank .. of the identity
-        for (int i = 0; i < nres; ++i) load_w(&p.i_map, 64 * i, 128 * (int)rank);
+        for (int q = 0; q < nseq; ++q) {
+          bool resid;
+          const int i = seq_item(q, resid);
+          if (!resid) {  // input slice i = K columns [64 i, 64 i + 64) of every tap
+            for (int tap = 0; tap < ntaps; ++tap) load_w(&p.b_map, tap * p.cin_total + i * 64, n0);
+          } else {  // D^T[c][pix] += I[c][64 i + k] . R[pix][g0 + 64 i + k], g0 = first channel of the tile (pair): rows 128 rank .. of the identity
+            load_w(&p.i_map, 64 * i, 128 * (int)rank);
+          }
+        }
       }
     } else if (lane == 1 && !dbg_no_tma) {
       tma_prefetch_desc(&p.a_map[0]); tma_prefetch_desc(&p.a_map[1]);
@@ -181,9 +201,13 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_ha
         const int mt = item_mt(item);
         const int t_img = mt % per_image;
         const int x0 = (t_img % p.tiles_x) * 8, y0 = (t_img / p.tiles_x) * 32 + yoff, b = mt / per_image;
-        for (int s = 0; s < p.nsrc; ++s) {
-          for (int c0 = 0; c0 < p.src_c[s]; c0 += 64) {
-            mbar_wait(xempty_bar(xs), xph ^ 1u);
+        const int s0_slices = p.src_c[0] >> 6;  // input slices of the first source (concatenated inputs: the second follows)
+        for (int q = 0; q < nseq; ++q) {
+          bool resid;
+          const int i = seq_item(q, resid);
+          mbar_wait(xempty_bar(xs), xph ^ 1u);
+          if (!resid) {
+            const int s = i < s0_slices ? 0 : 1, c0 = (i < s0_slices ? i : i - s0_slices) * 64;
             if constexpr (PAIR && !GNF) {  // no transform warps in between: the leader's MMA thread waits for both halves directly
               if (rank == 0) mbar_expect_tx(xfull_bar(xs), 2 * C::kXTx);
               tma_load_4d_pair(x_base + xs * kXSlot, &p.a_map[s], mapa_shared(xfull_bar(xs), 0), c0, x0 - 1, y0 - 1, b);
@@ -192,17 +216,14 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_ha
               if (dbg_hot_x) tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, 0, 0, 0);
               else tma_load_4d(x_base + xs * kXSlot, &p.a_map[s], xfull_bar(xs), c0, x0 - 1, y0 - 1, b);  // zero fill = conv padding
             }
-            if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
-          }
-        }
-        for (int i = 0; i < nres; ++i) {  // dense residual box in a halo slot
-          mbar_wait(xempty_bar(xs), xph ^ 1u);
-          if constexpr (PAIR && !GNF) {
-            if (rank == 0) mbar_expect_tx(xfull_bar(xs), 2 * C::kXDense);
-            tma_load_4d_pair(x_base + xs * kXSlot, &p.r_map, mapa_shared(xfull_bar(xs), 0), g0 + 64 * i, x0, y0, b);
-          } else {
-            mbar_expect_tx(xfull_bar(xs), C::kXDense);
-            tma_load_4d(x_base + xs * kXSlot, &p.r_map, xfull_bar(xs), g0 + 64 * i, x0, y0, b);
+          } else {  // dense residual box in a halo slot
+            if constexpr (PAIR && !GNF) {
+              if (rank == 0) mbar_expect_tx(xfull_bar(xs), 2 * C::kXDense);
+              tma_load_4d_pair(x_base + xs * kXSlot, &p.r_map, mapa_shared(xfull_bar(xs), 0), g0 + 64 * i, x0, y0, b);
+            } else {
+              mbar_expect_tx(xfull_bar(xs), C::kXDense);
+              tma_load_4d(x_base + xs * kXSlot, &p.r_map, xfull_bar(xs), g0 + 64 * i, x0, y0, b);
+            }
           }
           if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
         }
@@ -234,10 +255,11 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_ha
         timed_wait(tempty_bar(acc), acc_phase ^ 1u, pw_acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int sl = 0; sl < nslices + nres; ++sl) {
+        for (int sl = 0; sl < nseq; ++sl) {  // sl = position in the tile's K sequence (seq_item)
           if (!dbg_no_wait) timed_wait(GNF ? xready_bar(xs) : xfull_bar(xs), xph, pw_x);
           const uint32_t x_addr = x_base + xs * kXSlot;
-          const bool resid = sl >= nslices;
+          bool resid;
+          (void)seq_item(sl, resid);
           const int ntap = resid ? 1 : ntaps;
           for (int tap = 0; tap < ntap; ++tap) {
             if (!dbg_no_wait) timed_wait(wfull_bar(ws), wph, pw_w);
@@ -307,7 +329,16 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_ha
         if (px >= 0 && px < p.W && py >= 0 && py < p.H) inside |= 1u << k;
       }
       inside &= exist;
-      for (int sl = 0; sl < nslices; ++sl) {  // slice sl = channels [64 sl, 64 sl + 64) of the concatenated input
+      for (int q = 0; q < nseq; ++q) {
+        bool resid;
+        const int sl = seq_item(q, resid);  // input slice sl = channels [64 sl, 64 sl + 64) of the concatenated input
+        if (resid) {  // residual boxes pass through untouched
+          mbar_wait(xfull_bar(xs), xph);
+          __syncwarp();
+          if (lane == 0) publish(xs);
+          if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
+          continue;
+        }
         uint64_t ka[4], ks[4];
         if (p.gn_silu == 0) gn_consts_from_raw<false>(raw, ka, ks);
         else gn_consts_from_raw<true>(raw, ka, ks);
@@ -324,12 +355,6 @@ __global__ void __launch_bounds__(swh::Cfg<GNF, PAIR>::kThreads, 1) conv_swap_ha
             if ((exist >> k) & 1u) { uint4* q = reinterpret_cast<uint4*>(tp + k * 4096); uint4 v = *q; v.x ^= inside; *q = v; }
         }  // gn_silu == 2 (measurement aid): no transform at all, only the extra barrier hop
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
-        __syncwarp();
-        if (lane == 0) publish(xs);
-        if (++xs == kXSlots) { xs = 0; xph ^= 1u; }
-      }
-      for (int i = 0; i < nres; ++i) {  // residual boxes pass through untouched
-        mbar_wait(xfull_bar(xs), xph);
         __syncwarp();
         if (lane == 0) publish(xs);
         if (++xs == kXSlots) { xs = 0; xph ^= 1u; }

@@ -216,6 +216,10 @@ std::shared_ptr<ConvGemmLaunch> conv_gemm_build(const ConvGemmDesc& d, int num_s
   p.total_tiles = (int)total;
   p.ntaps = d.poly ? 4 : d.ksize * d.ksize;  // polyphase: taps (dy, dx) in {0,1}^2, weights [N][4][cin]
   p.poly = d.poly;
+  {
+    static const int env_mix = [] { const char* e = getenv("SDM_SWH_MIX"); return e ? atoi(e) : 1; }();
+    p.res_mix = env_mix;
+  }
   p.nsrc = d.nsrc;
   p.cin_total = cin_total;
   for (int s = 0; s < d.nsrc; ++s) p.src_c[s] = d.src[s].C;

@@ -61,6 +61,7 @@ struct alignas(64) ConvGemmParams {
   int ups2;           // EPI_F16 only: write each pixel to the 2x2 block of a (2H,2W) output
   int poly;           // conv_swap_halo only: 0, or 1 + 2 py + px = polyphase component (py, px) of "nearest x2 upsample -> 3x3 conv"
   int stats_bslots, stats_slot0;  // conv_swap_halo: GroupNorm-partials slots per sample / first slot of this launch
+  int res_mix;        // conv_swap_halo: interleave the residual K slices with the input slices (SDM_SWH_MIX=0: A/B switch, residual last)
   void* out;
   long long out_ld;       // elements between consecutive pixels (EPI_F16/F32/GEGLU) or row length (EPI_F16_T)
   long long out_bstride;  // elements per batch element
