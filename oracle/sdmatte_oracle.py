@@ -292,6 +292,41 @@ def vae_decode(c, z):
     return _conv(c, F.silu(_gn(c, h, d + ".conv_norm_out", 1e-6)), d + ".conv_out")
 
 
+def polyphase_weights(w: torch.Tensor) -> torch.Tensor:
+    """Checker-side restatement of the engine's upsampler weight packing (csrc/engine.cu Weights::conv_poly): a 3x3 conv over a
+    nearest-x2 upsampled image (diffusers Upsample2D: F.interpolate(scale_factor=2, mode="nearest") then conv) equals, for each
+    output parity (py, px), a 2x2-tap conv over the LOW-resolution image whose taps are the sums of the 3x3 taps that land on the
+    same input pixel: rows {0 | 1,2} for py = 0, {0,1 | 2} for py = 1 (columns alike).  OIHW -> [4 (q = 2 py + px)][O][4 (t = 2 dy + dx)][I],
+    in the dtype of `w` (the engine sums the fp16-rounded taps in fp32 and rounds the sum to fp16 once)."""
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    out = []
+    for q in range(4):
+        py, px = q >> 1, q & 1
+        taps = []
+        for t in range(4):
+            dy, dx = t >> 1, t & 1
+            acc = 0
+            for ky in rows[py][dy]:
+                for kx in rows[px][dx]:
+                    acc = acc + w[:, :, ky, kx]
+            taps.append(acc)
+        out.append(torch.stack(taps, 1))
+    return torch.stack(out)
+
+
+def upsample_conv_polyphase(x: torch.Tensor, wq: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """The four polyphase convs with the weights of polyphase_weights(): x [B][C][H][W] -> [B][O][2H][2W]."""
+    B, C, H, W = x.shape
+    O = wq.shape[1]
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = x.new_empty(B, O, 2 * H, 2 * W)
+    for q in range(4):
+        py, px = q >> 1, q & 1
+        k = wq[q].reshape(O, 2, 2, C).permute(0, 3, 1, 2).contiguous()
+        out[:, :, py::2, px::2] = F.conv2d(xp[:, :, py:py + H + 1, px:px + W + 1], k, bias)
+    return out
+
+
 def to_device(sd: Dict[str, torch.Tensor], device) -> Dict[str, torch.Tensor]:
     """fp32 master copy of the checkpoint on `device` (what `.to(device)` leaves at sdmatte_nodes.py:323)."""
     return {k: v.float().to(device) for k, v in sd.items() if k.startswith(("unet.", "vae."))}

@@ -727,23 +727,11 @@ def test_conv3x3_fused_groupnorm(eng_mod, B, H, W, C0, C1, Cout, res, silu):
 
 # ------------------------------------------------------------------------------------------------ Upsample2D as four polyphase convs
 def _poly_pack(w):
-    """OIHW 3x3 -> [4 parities q = 2 py + px][O][4 taps t = 2 dy + dx][I] fp16: the taps of the 3x3 kernel that land on the same
-    low-resolution pixel under a nearest x2 upsampling, summed in fp32 (of the fp16-rounded taps) and rounded once."""
-    w = w.half().float()
-    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
-    out = []
-    for q in range(4):
-        py, px = q >> 1, q & 1
-        taps = []
-        for t in range(4):
-            dy, dx = t >> 1, t & 1
-            acc = 0
-            for ky in rows[py][dy]:
-                for kx in rows[px][dx]:
-                    acc = acc + w[:, :, ky, kx]
-            taps.append(acc)
-        out.append(torch.stack(taps, 1))  # [O][4][I]
-    return torch.stack(out).half().contiguous()
+    """OIHW 3x3 -> [4 parities q = 2 py + px][O][4 taps t = 2 dy + dx][I] fp16, as Weights::conv_poly packs them: the checker-side
+    restatement (oracle.sdmatte_oracle.polyphase_weights) on the fp16-rounded taps in fp32, rounded once."""
+    from oracle import sdmatte_oracle as orc
+
+    return orc.polyphase_weights(w.half().float()).half().contiguous()
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [
