@@ -17,6 +17,11 @@
 // were zero-filled by the TMA unit and stay zero: the convolution pads the NORMALISED tensor.  The 128-byte swizzle is undone
 // per thread: 16-byte piece j of tile row r holds channel chunk j ^ (r & 7); a thread keeps (piece, r mod 16), hence one fixed
 // chunk and its 16 constants in registers.
+//
+// Round 3: PAIR (tcgen05 cta_group::2 over 256 output channels, half a patch per CTA: see swh::Cfg), the polyphase form of
+// "nearest x2 upsample -> 3x3 conv" (p.poly: four taps, strided output; diffusers Upsample2D as reached from the up blocks of
+// /root/reference/src/utils/replace.py and the VAE decoder, meta_arch.py:255-256), residual K slices interleaved with the input
+// slices (seq_item).  Evidence: profiles/r3c_kbench_mc_after_fix.txt, r3d (run_r3d.sh), r3f_*, r3g_ops.csv, r3z_*.
 #include "gn_math.cuh"
 #include "umma_gemm.cuh"
 
